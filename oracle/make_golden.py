@@ -1,0 +1,325 @@
+"""Pin the oracle against the UNMODIFIED reference and write tests/golden/*.npz.
+
+Runs only in the build container (needs /root/reference; read-only, nothing is written there).
+For every known-answer test it executes the reference's own functions
+(`jacobian.grid_sample`, `LM_S2GP.grd2cam2world2sat`, `LM_S2GP.LM_update`, `LM_S2GP.forward`,
+`LM_S2GP_Ford.*`, `VGGUnet.forward`) and oracle/oracle.py on identical seeded inputs, asserts
+they agree, and stores the REFERENCE outputs (small) as fixtures.  Inputs are regenerated from
+seeds at test time; each fixture carries an input checksum so an RNG drift is detected.
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    """SURVEY 8c obstacles: vgg16(pretrained=True) needs the network -> weights=None."""
+    sys.dont_write_bytecode = True
+    import torchvision
+    orig = torchvision.models.vgg16
+    torchvision.models.vgg16 = lambda pretrained=False, **kw: orig(weights=None)
+    sys.path.insert(0, REF)
+    import jacobian as ref_jac          # noqa
+    import models_kitti as ref_kitti    # noqa
+    import models_ford as ref_ford      # noqa
+    import VGG as ref_vgg               # noqa
+    torch.autograd.set_detect_anomaly(False)
+    return ref_jac, ref_kitti, ref_ford, ref_vgg
+
+
+def ref_args(**kw):
+    d = dict(level=3, N_iters=5, using_weight=0, loss_method=0, rotation_range=10.0, proj="geo", Optimizer="LM",
+             damping=0.1, train_damping=0, shift_range_lat=20.0, shift_range_lon=20.0, use_hessian=0, dropout=0,
+             use_gt_depth=0, visualize=0, coe_shift_lat=100.0, coe_shift_lon=100.0, coe_heading=100.0,
+             coe_L1=100.0, coe_L2=100.0, coe_L3=100.0, coe_L4=100.0, estimate_depth=0, level_first=0)
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def o_args(a) -> O.LMArgs:
+    return O.LMArgs(level=a.level, N_iters=a.N_iters, using_weight=a.using_weight, damping=a.damping,
+                    train_damping=a.train_damping, rotation_range=a.rotation_range,
+                    shift_range_lat=a.shift_range_lat, shift_range_lon=a.shift_range_lon,
+                    use_hessian=a.use_hessian, level_first=a.level_first)
+
+
+def csum(*ts) -> np.ndarray:
+    return np.array([float(t.double().sum()) for t in ts] + [float(t.double().abs().sum()) for t in ts])
+
+
+def close(a, b, tol, what):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    d = float((a - b).abs().max())
+    scale = max(float(b.abs().max()), 1e-30)
+    assert d <= tol * max(scale, 1.0), "%s: oracle vs reference max|d|=%g (scale %g, tol %g)" % (what, d, scale, tol)
+    return d
+
+
+# --------------------------------------------------------------------------------------- KATs
+def kat1_sampler(rj):
+    """jacobian.py:216-239 (the reference's own commented test) + border cases."""
+    g = torch.Generator().manual_seed(11)
+    img = torch.rand(1, 3, 32, 32, generator=g)
+    grid = torch.rand(1, 32, 32, 2, generator=g) * 2 - 1
+    uv = (grid + 1) / 2 * 31
+    edge = torch.tensor([-0.5, 0.0, 1e-3, 15.5, 30.0, 31 - 1e-3, 31.0, 31.5])
+    ex, ey = torch.meshgrid(edge, edge, indexing="ij")
+    uv_edge = torch.stack([ex, ey], dim=-1)[None]
+    jac = torch.randn(3, 1, 32, 32, 2, generator=g)
+    jac_e = torch.randn(3, 1, 8, 8, 2, generator=g)
+    out = {}
+    for name, u, j in (("rand", uv, jac), ("edge", uv_edge, jac_e)):
+        r_out, r_jac = rj.grid_sample(img, u, j)
+        o_out, o_jac = O.bilinear_sample(img, u, j)
+        close(o_out, r_out, 0, "kat1 %s out" % name)
+        close(o_jac, r_jac, 0, "kat1 %s jac" % name)
+        out[name + "_uv"], out[name + "_jacin"] = u.numpy(), j.numpy()
+        out[name + "_out"], out[name + "_jac"] = r_out.numpy(), r_jac.numpy()
+    f_out = torch.nn.functional.grid_sample(img, grid, align_corners=True)
+    close(out["rand_out"], f_out, 1e-6, "kat1 vs F.grid_sample")
+    out["img"] = img.numpy()
+    np.savez_compressed(os.path.join(GOLD, "kat1_sampler.npz"), **out)
+    print("KAT-1 sampler ok")
+
+
+POSES = [(0.0, 0.0, 0.0), (1.0, -1.0, 1.0), (0.3, -0.25, 0.5), (-0.7, 0.9, -0.4)]
+
+
+def kat2_geometry(rk, rf):
+    """models_kitti.py:700-801 and models_ford.py:173-264 at several poses, all levels.
+    Stores a strided subsample of uv + Jacobians (full-field equality is asserted here)."""
+    a = ref_args(shift_range_lat=20.0, shift_range_lon=15.0, level=4)
+    net = rk.LM_S2GP(a); torch.autograd.set_detect_anomaly(False)
+    netf = rf.LM_S2GP_Ford(a); torch.autograd.set_detect_anomaly(False)
+    oa = o_args(a)
+    pose = torch.tensor(POSES, dtype=torch.float32)
+    su, sv, th = pose[:, 0:1], pose[:, 1:2], pose[:, 2:3]
+    B = pose.shape[0]
+    R_FL = torch.tensor([[0., 0., 1.], [1., 0., 0.], [0., 1., 0.]])[None].repeat(B, 1, 1)
+    T_FL = torch.tensor([1.7, -0.3, -1.5])[None].repeat(B, 1)
+    out = {"poses": pose.numpy(), "R_FL": R_FL.numpy(), "T_FL": T_FL.numpy()}
+    for lv in range(4):
+        A = 512 // (2 ** (3 - lv))
+        r = net.grd2cam2world2sat(su, sv, th, lv, A, require_jac=True)
+        tab = O.kitti_ground_table(lv)
+        close(tab[0], net.xyz_grds[lv][0][0], 0, "kitti table")
+        o = O.kitti_sat_uv(tab[0], tab[1], su, sv, th, A, oa)
+        for i, nm in enumerate(["uv", "mask", "ju", "jv", "jt"]):
+            close(o[i], r[i], 0, "kat2 kitti L%d %s" % (lv, nm))
+            out["kitti_L%d_%s" % (lv, nm)] = r[i].detach()[:, ::4, ::8].numpy()
+        out["kitti_L%d_tab" % lv] = tab[0][::4, ::8].numpy()
+        Af = 1280 // (2 ** (3 - lv))
+        side = 1280 * 0.22
+        rfo = netf.cam2body2world2sat(R_FL, T_FL, su, sv, th, lv, side, Af, require_jac=True)
+        tabf = O.ford_ground_table(lv)
+        close(tabf[0], netf.xyz_grds[lv][0][0], 0, "ford table")
+        of = O.ford_sat_uv(tabf[0], tabf[1], R_FL, T_FL, su, sv, th, Af, side, oa)
+        for i, nm in enumerate(["uv", "mask", "ju", "jv", "jt"]):
+            close(of[i], rfo[i], 0, "kat2 ford L%d %s" % (lv, nm))
+            out["ford_L%d_%s" % (lv, nm)] = rfo[i].detach()[:, ::4, ::8].numpy()
+        out["ford_L%d_tab" % lv] = tabf[0][::4, ::8].numpy()
+    np.savez_compressed(os.path.join(GOLD, "kat2_geometry.npz"), **out)
+    print("KAT-2 geometry ok")
+
+
+def run_ref_loop(net, kind, sat, grd, conf, a, ford=None, pose0=None):
+    """Drive the reference's own project_map_to_grd + LM_update exactly as its forward does
+    (models_kitti.py:1176-1260), recording pose_in/pose_out per step."""
+    L = len(sat)
+    B = sat[0].shape[0]
+    if pose0 is None:
+        su = torch.zeros(B, 1); sv = torch.zeros(B, 1); th = torch.zeros(B, 1)
+    else:
+        su, sv, th = [p.clone() for p in pose0]
+    traj = torch.zeros(B, a.N_iters, L, 3)
+    pin = torch.zeros(B, a.N_iters, L, 3)
+    order = O._step_order(a.N_iters, L, a.level_first)
+    for it, lv in order:
+        if kind == "kitti":
+            sp, sc, dj, uv, mask = net.project_map_to_grd(sat[lv], None, su, sv, th, lv)
+        else:
+            sp, sc, dj, uv, mask = net.project_map_to_grd(sat[lv], None, ford["R_FL"], ford["T_FL"], su, sv, th, lv,
+                                                           ford["side_m"], require_jac=True)
+        gf = grd[lv] * mask[:, None]
+        gc = conf[lv] * mask[:, None]
+        h2 = gf.shape[-2] // 2
+        pin[:, it, lv] = torch.cat([su, sv, th], dim=1)
+        su, sv, th = net.LM_update(su, sv, th, sp[:, :, h2:], gc[:, :, h2:], gf[:, :, h2:], gc[:, :, h2:],
+                                   dj[:, :, :, h2:])
+        su, sv, th = su.detach(), sv.detach(), th.detach()
+        traj[:, it, lv] = torch.cat([su, sv, th], dim=1)
+    return traj, pin
+
+
+def stats_arrays(res: O.LoopResult, n_iters, L):
+    ks = ["hessian", "grad", "sat_norm", "grd_norm", "res_sq", "delta"]
+    out = {}
+    for k in ks:
+        out[k] = np.stack([np.stack([getattr(res.stats[it][lv], k).numpy() for lv in range(L)], 0)
+                           for it in range(n_iters)], 0)
+    return out
+
+
+def kat_loop(rk, rf, name, kind, make_inputs, tol=2e-6, pose0=None, **akw):
+    """Whole-loop KAT: reference trajectory vs oracle trajectory on identical inputs and
+    identical CPU-RNG state; stores the reference trajectory + oracle per-step stats."""
+    a = ref_args(**akw)
+    net = (rk.LM_S2GP if kind == "kitti" else rf.LM_S2GP_Ford)(a)
+    torch.autograd.set_detect_anomaly(False)
+    oa = o_args(a)
+    sat, grd, conf, ford, meta = make_inputs(oa)
+    damp = None
+    if a.train_damping:
+        damp = net.damping.detach().clone()
+    torch.manual_seed(4242)
+    with torch.no_grad():
+        r_traj, r_pin = run_ref_loop(net, kind, sat, grd, conf, a, ford, pose0)
+    torch.manual_seed(4242)
+    res = O.lm_loop(kind, sat, grd, conf, oa, damp, None, ford, pose0)
+    # reference loop records (su,sv,th); oracle LoopResult is (lat,lon,theta) in the model's convention
+    if kind == "kitti":
+        o_traj = torch.stack([res.lons, res.lats, res.thetas], dim=-1)
+    else:
+        o_traj = torch.stack([res.lats, res.lons, res.thetas], dim=-1)
+    d = close(o_traj, r_traj, tol, name + " trajectory")
+    out = dict(traj=r_traj.numpy(), pose_in=r_pin.numpy(), in_csum=csum(*sat, *grd), **stats_arrays(res, a.N_iters, len(sat)))
+    out.update(meta)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("%s ok  (oracle vs reference max|d| = %.2e; final pose sample0 = %s)" % (name, d, r_traj[0, -1, -1].tolist()))
+
+
+FORD_EXT = dict(R=[[0., 0., 1.], [1., 0., 0.], [0., 1., 0.]], T=[1.7, -0.3, -1.5])
+
+
+def ford_dict(B, side_m):
+    return dict(R_FL=torch.tensor(FORD_EXT["R"])[None].repeat(B, 1, 1),
+                T_FL=torch.tensor(FORD_EXT["T"])[None].repeat(B, 1), side_m=side_m)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    opt = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    rj, rk, rf, rv = import_reference()
+    want = lambda k: (not opt.only) or (k in opt.only.split(","))
+
+    if want("kat1"):
+        kat1_sampler(rj)
+    if want("kat2"):
+        kat2_geometry(rk, rf)
+
+    GT2 = [[0.3, -0.25, 0.5], [-0.2, 0.4, -0.3]]
+
+    def rand_inputs(seed, B=2, A=512, L=3):
+        def f(oa):
+            sat, grd, conf = O.random_pyramid(B, A, L, seed)
+            return sat, grd, conf, None, dict(seed=seed, B=B, A=A, L=L)
+        return f
+
+    def planted_inputs(kind, seed, gt, A=512, L=3, side_m=None):
+        def f(oa):
+            B = len(gt)
+            fd = ford_dict(B, side_m) if kind == "ford" else None
+            sat, grd = O.planted_case(kind, B, A, L, seed, gt, oa, fd)
+            conf = [torch.ones(B, 1, *g.shape[-2:]) for g in grd]
+            return sat, grd, conf, fd, dict(seed=seed, B=B, A=A, L=L, gt=np.array(gt, dtype=np.float32),
+                                            side_m=np.float32(side_m or 0))
+        return f
+
+    if want("kat3"):   # per-step parity on non-contractive features
+        kat_loop(rk, rf, "kat3_random_kitti", "kitti", rand_inputs(31))
+    if want("kat4"):   # planted pose, whole trajectory
+        kat_loop(rk, rf, "kat4_planted_kitti", "kitti", planted_inputs("kitti", 41, GT2))
+        kat_loop(rk, rf, "kat4_planted_ford", "ford", planted_inputs("ford", 42, GT2, A=512, side_m=512 * 0.22))
+    if want("kat5"):   # modes
+        kat_loop(rk, rf, "kat5_weight", "kitti", rand_inputs(51), using_weight=1)
+        kat_loop(rk, rf, "kat5_hessian", "kitti", rand_inputs(52), use_hessian=1)
+        kat_loop(rk, rf, "kat5_traindamp", "kitti", planted_inputs("kitti", 53, GT2), train_damping=1)
+        kat_loop(rk, rf, "kat5_levelfirst", "kitti", planted_inputs("kitti", 54, GT2), level_first=1)
+        kat_loop(rk, rf, "kat5_shiftonly", "kitti", planted_inputs("kitti", 55, [[0.3, -0.25, 0.0], [-0.2, 0.4, 0.0]]),
+                 rotation_range=0.0)
+        kat_loop(rk, rf, "kat5_rotonly", "kitti", planted_inputs("kitti", 56, [[0.0, 0.0, 0.5], [0.0, 0.0, -0.3]]),
+                 shift_range_lat=0.0, shift_range_lon=0.0)
+        kat_loop(rk, rf, "kat5_level4", "kitti", planted_inputs("kitti", 57, GT2[:1], L=4), level=4, N_iters=2)
+        kat_loop(rk, rf, "kat5_ford1280", "ford", planted_inputs("ford", 58, GT2[:1], A=1280, side_m=1280 * 0.22),
+                 N_iters=3)
+        kat_loop(rk, rf, "kat5_anisotropic", "kitti", planted_inputs("kitti", 59, GT2), shift_range_lat=20.0,
+                 shift_range_lon=12.0, rotation_range=15.0)
+    if want("kat6"):   # forced out-of-range reset (models_kitti.py:1028-1033): start outside (-2.5, 2.5)
+        p0 = torch.tensor([[3.0, 0.1, 0.2], [0.1, -2.8, -0.1]])
+        kat_loop(rk, rf, "kat6_reset", "kitti", rand_inputs(61), N_iters=2,
+                 pose0=(p0[:, 0:1], p0[:, 1:2], p0[:, 2:3]))
+
+    if want("kat7"):   # VGG U-Net: small image, all intermediate activations
+        sd = O.vgg_state_dict(7)
+        for level in (3, 4):
+            net = rv.VGGUnet(level)
+            net.load_state_dict(sd)
+            net.eval()
+            g = torch.Generator().manual_seed(70 + level)
+            x = torch.rand(2, 3, 64, 128, generator=g)
+            with torch.no_grad():
+                rfe, rco = net(x)
+            ofe, oco = O.vgg_unet(sd, x, level)
+            out = {"in_csum": csum(x), "w_csum": csum(*[sd[k] for k in sorted(sd)])}
+            for i in range(len(rfe)):
+                close(ofe[i], rfe[i], 1e-6, "kat7 feat %d" % i)
+                close(oco[i], rco[i], 1e-6, "kat7 conf %d" % i)
+                out["feat%d" % i] = rfe[i].numpy()
+                out["conf%d" % i] = rco[i].numpy()
+            np.savez_compressed(os.path.join(GOLD, "kat7_vgg_level%d.npz" % level), **out)
+        print("KAT-7 VGG ok")
+
+    if want("e2e"):    # whole forward through the reference nn.Module (VGG + LM), KITTI + Ford
+        sd = {}
+        sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+        sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+        sd["damping"] = torch.zeros(1, 3)
+        g = torch.Generator().manual_seed(2022)
+        sat = torch.rand(2, 3, 512, 512, generator=g)
+        grd = torch.rand(2, 3, 256, 1024, generator=g)
+        for kind in ("kitti", "ford"):
+            a = ref_args()
+            net = (rk.LM_S2GP if kind == "kitti" else rf.LM_S2GP_Ford)(a)
+            torch.autograd.set_detect_anomaly(False)
+            net.load_state_dict(sd)
+            net.eval()
+            torch.manual_seed(999)
+            with torch.no_grad():
+                if kind == "kitti":
+                    r = net(sat, grd, mode="test")
+                    torch.manual_seed(999)
+                    o = O.forward_kitti(sd, sat, grd, o_args(a))
+                else:
+                    fd = ford_dict(2, 512 * 0.22)
+                    r = net(sat, grd, fd["side_m"], fd["R_FL"], fd["T_FL"], mode="test")
+                    torch.manual_seed(999)
+                    o = O.forward_ford(sd, sat, grd, fd["side_m"], fd["R_FL"], fd["T_FL"], o_args(a))
+            r = torch.stack(r, dim=-1)
+            of = torch.stack([o.lats[:, -1, -1], o.lons[:, -1, -1], o.thetas[:, -1, -1]], dim=-1)
+            d = close(of, r, 1e-5, "e2e " + kind)
+            np.savez_compressed(os.path.join(GOLD, "e2e_%s.npz" % kind), final=r.numpy(),
+                                lats=o.lats.numpy(), lons=o.lons.numpy(), thetas=o.thetas.numpy(),
+                                in_csum=csum(sat, grd))
+            print("e2e %s ok (max|d| %.2e) final=%s" % (kind, d, r.tolist()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,74 @@
+"""Shared definitions of the known-answer cases (inputs are regenerated from seeds; the
+expected outputs are the REFERENCE's, stored in tests/golden/*.npz by oracle/make_golden.py)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from oracle import oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FORD_R = [[0., 0., 1.], [1., 0., 0.], [0., 1., 0.]]
+FORD_T = [1.7, -0.3, -1.5]
+GT2 = [[0.3, -0.25, 0.5], [-0.2, 0.4, -0.3]]
+
+# name -> (kind, input family, LMArgs overrides, extra)
+LOOP_CASES = {
+    "kat3_random_kitti": ("kitti", "rand", {}, {}),
+    "kat4_planted_kitti": ("kitti", "planted", {}, {}),
+    "kat4_planted_ford": ("ford", "planted", {}, {}),
+    "kat5_weight": ("kitti", "rand", dict(using_weight=1), {}),
+    "kat5_hessian": ("kitti", "rand", dict(use_hessian=1), {}),
+    "kat5_traindamp": ("kitti", "planted", dict(train_damping=1), dict(damping_param=torch.zeros(1, 3))),
+    "kat5_levelfirst": ("kitti", "planted", dict(level_first=1), {}),
+    "kat5_shiftonly": ("kitti", "planted", dict(rotation_range=0.0), {}),
+    "kat5_rotonly": ("kitti", "planted", dict(shift_range_lat=0.0, shift_range_lon=0.0), {}),
+    "kat5_level4": ("kitti", "planted", dict(level=4, N_iters=2), {}),
+    "kat5_ford1280": ("ford", "planted", dict(N_iters=3), {}),
+    "kat5_anisotropic": ("kitti", "planted", dict(shift_range_lat=20.0, shift_range_lon=12.0, rotation_range=15.0), {}),
+    "kat6_reset": ("kitti", "rand", dict(N_iters=2), dict(pose0_from_golden=True)),
+}
+# the cases cheap enough for the CPU suite (the rest are exercised by the gpu parity tests)
+CPU_LOOP_CASES = ["kat3_random_kitti", "kat4_planted_kitti", "kat4_planted_ford", "kat5_weight", "kat5_shiftonly",
+                  "kat5_rotonly", "kat5_level4", "kat6_reset"]
+
+
+def csum(*ts) -> np.ndarray:
+    return np.array([float(t.double().sum()) for t in ts] + [float(t.double().abs().sum()) for t in ts])
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def ford_dict(B, side_m):
+    return dict(R_FL=torch.tensor(FORD_R)[None].repeat(B, 1, 1), T_FL=torch.tensor(FORD_T)[None].repeat(B, 1),
+                side_m=float(side_m))
+
+
+def build_loop_case(name):
+    """Returns dict(kind, args, sat, grd, conf, ford, damping_param, pose0, gold)."""
+    kind, fam, akw, extra = LOOP_CASES[name]
+    gold = load_golden(name)
+    args = O.LMArgs(**akw)
+    seed, B, A, L = int(gold["seed"]), int(gold["B"]), int(gold["A"]), int(gold["L"])
+    ford = None
+    if fam == "rand":
+        sat, grd, conf = O.random_pyramid(B, A, L, seed)
+    else:
+        gt = gold["gt"]
+        ford = ford_dict(B, float(gold["side_m"])) if kind == "ford" else None
+        sat, grd = O.planted_case(kind, B, A, L, seed, gt, args, ford)
+        conf = [torch.ones(B, 1, *g.shape[-2:]) for g in grd]
+    np.testing.assert_allclose(csum(*sat, *grd), gold["in_csum"], rtol=1e-6, err_msg="input regeneration drifted")
+    pose0 = None
+    if extra.get("pose0_from_golden"):
+        p0 = torch.from_numpy(gold["pose_in"][:, 0, 0])
+        pose0 = (p0[:, 0:1].clone(), p0[:, 1:2].clone(), p0[:, 2:3].clone())
+    return dict(kind=kind, args=args, sat=sat, grd=grd, conf=conf, ford=ford,
+                damping_param=extra.get("damping_param"), pose0=pose0, gold=gold, B=B, A=A, L=L)
+
+
+RESET_SEED = 4242    # oracle/make_golden.py seeds the CPU generator with this before every loop
