@@ -1,0 +1,89 @@
+"""Mirror of the reference's VGG.py public surface for the hot path: `VGGUnet` and `L2_norm`.
+
+Same constructor, same parameter names/shapes (so reference checkpoints load unchanged:
+VGG.py:23-81 -> 24 state-dict keys per U-Net), same forward contract (VGG.py:121-203) — but the
+convolutions run in libha_b200.so.  The nn.Conv2d children below are parameter containers only.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import torch
+import torch.nn as nn
+
+from . import engine
+
+
+def _conv(cin, cout, bias):
+    return nn.Conv2d(cin, cout, kernel_size=(3, 3), stride=(1, 1), padding=1, bias=bias)
+
+
+def _dec(cin, cmid, cout):
+    return nn.Sequential(nn.ReLU(inplace=True), _conv(cin, cmid, False), nn.ReLU(inplace=True), _conv(cmid, cout, False))
+
+
+def _conf(cin):
+    return nn.Sequential(nn.ReLU(), _conv(cin, 1, False), nn.Sigmoid())
+
+
+class VGGUnet(nn.Module):
+    """VGG.py:13.  `level` selects the returned pyramid: 3 -> [x15,x18,x21], 4 -> +x24 (VGG.py:192-203)."""
+
+    def __init__(self, level, estimate_depth=0):
+        super().__init__()
+        if estimate_depth:
+            raise NotImplementedError("estimate_depth heads are outside the accelerated path (SURVEY.md section 2, row 1)")
+        self.level = level
+        self.estimate_depth = 0
+        self.conv0 = _conv(3, 64, True)
+        self.conv2 = _conv(64, 64, True)
+        self.conv5 = _conv(64, 128, True)
+        self.conv7 = _conv(128, 128, True)
+        self.conv10 = _conv(128, 256, True)
+        self.conv12 = _conv(256, 256, True)
+        self.conv14 = _conv(256, 256, True)
+        self.conv_dec1 = _dec(384, 128, 128)
+        self.conv_dec2 = _dec(192, 64, 64)
+        self.conv_dec3 = _dec(128, 32, 16)
+        self.conf0, self.conf1, self.conf2, self.conf3 = _conf(256), _conf(128), _conf(64), _conf(16)
+        self._load_pretrained_encoder()
+        self.precision = os.environ.get("HA_VGG_PRECISION", "f16x3")
+        self._runner = engine.VggRunner()
+
+    def _load_pretrained_encoder(self):
+        """VGG.py:20-29 takes the encoder from torchvision's ImageNet VGG16.  Offline boxes have no
+        checkpoint: keep the default initialisation and say so (weights normally come from
+        load_state_dict anyway, train_kitti.py:546)."""
+        path = os.environ.get("HA_VGG16_PTH") or os.path.join(torch.hub.get_dir(), "checkpoints", "vgg16-397923af.pth")
+        if not os.path.exists(path):     # never try to download: no network on the target boxes
+            if os.environ.get("HA_QUIET", "0") != "1":
+                warnings.warn("VGG16 ImageNet checkpoint not found at %s; encoder keeps its random init" % path)
+            return
+        sd = torch.load(path, map_location="cpu")
+        for idx in (0, 2, 5, 7, 10, 12, 14):
+            getattr(self, "conv%d" % idx).load_state_dict({"weight": sd["features.%d.weight" % idx],
+                                                           "bias": sd["features.%d.bias" % idx]})
+
+    def n_levels(self) -> int:
+        if self.level in (3, 4):
+            return self.level
+        raise NotImplementedError("VGGUnet level %r: only 3 and 4 are on the accelerated path" % (self.level,))
+
+    def pyramid(self, x: torch.Tensor, want_conf: bool = True) -> engine.Pyramid:
+        """Engine-layout output (NHWC raw features + lazy L2 scale + confidences)."""
+        named = dict(self.named_parameters())
+        return self._runner(named, x, self.n_levels(), want_conf, self.precision)
+
+    def forward(self, x):
+        """Reference contract: ([B,C,H,W] L2-normalised features], [B,1,H,W] confidences])."""
+        p = self.pyramid(x, want_conf=True)
+        feats = [p.nchw(l, normalised=True) for l in range(len(p.feats))]
+        confs = [c[:, None] for c in p.confs]
+        return feats, confs
+
+
+def L2_norm(x):
+    """VGG.py:511-514."""
+    B = x.shape[0]
+    return torch.nn.functional.normalize(x.reshape(B, -1), p=2, dim=-1).view(x.shape)

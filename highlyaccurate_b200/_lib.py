@@ -1,0 +1,93 @@
+"""ctypes binding of libha_b200.so (the C ABI declared in include/ha_b200.h).
+
+The library is the product: there is no Python/CPU fallback.  If it is missing or cannot be
+loaded, importing this module's `lib()` raises — loudly — instead of degrading.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libha_b200.so")
+
+HA_MAX_LEVELS = 4
+HA_STATS = 24
+HA_VGG_N_CONV = 17
+HA_GEOM_KITTI, HA_GEOM_FORD = 0, 1
+HA_CONV_FP32_SIMT, HA_CONV_F16X3, HA_CONV_F16 = 0, 1, 2
+HA_STATUS_NO_INRANGE, HA_STATUS_NAN_POSE, HA_STATUS_RESET = 1, 2, 4
+STAT_H, STAT_GRAD, STAT_SAT_NORM, STAT_GRD_NORM, STAT_RES_SQ, STAT_DELTA, STAT_N_INRANGE = 0, 9, 12, 13, 14, 15, 18
+
+# every symbol include/ha_b200.h declares (tests check the .so exports all of them)
+EXPORTS = ["ha_version", "ha_error_string", "ha_last_cuda_error", "ha_device_check", "ha_nchw_to_nhwc",
+           "ha_nhwc_to_nchw", "ha_lm_workspace_bytes", "ha_lm_step", "ha_lm_run", "ha_vgg_packed_weight_bytes",
+           "ha_vgg_pack_weights", "ha_vgg_workspace_bytes", "ha_vgg_forward"]
+
+
+class HaLevel(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("scale", C.c_void_p), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
+class HaLmParams(C.Structure):
+    _fields_ = [("geometry", C.c_int32), ("n_levels", C.c_int32), ("n_iters", C.c_int32), ("level_first", C.c_int32),
+                ("dof", C.c_int32), ("using_weight", C.c_int32), ("use_hessian", C.c_int32), ("batch", C.c_int32),
+                ("rotation_range", C.c_float), ("shift_range_lat", C.c_float), ("shift_range_lon", C.c_float),
+                ("damping", C.c_float * 3), ("meter_per_pixel", C.c_float * HA_MAX_LEVELS),
+                ("inv_meter_per_pixel", C.c_float * HA_MAX_LEVELS), ("sat_center", C.c_float * HA_MAX_LEVELS)]
+
+
+class HaVggStateDict(C.Structure):
+    _fields_ = [("weight", C.c_void_p * HA_VGG_N_CONV), ("bias", C.c_void_p * HA_VGG_N_CONV)]
+
+
+class HaError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise HaError("libha_b200.so is not built (%s missing): run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "or `python highlyaccurate_b200/build.py`.  There is no fallback path." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+    L.ha_version.restype = i32
+    L.ha_error_string.restype = C.c_char_p
+    L.ha_error_string.argtypes = [i32]
+    L.ha_last_cuda_error.restype = C.c_char_p
+    L.ha_device_check.argtypes = [i32]
+    for f in (L.ha_nchw_to_nhwc, L.ha_nhwc_to_nchw):
+        f.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.ha_lm_workspace_bytes.restype = sz
+    L.ha_lm_workspace_bytes.argtypes = [i32]
+    L.ha_lm_step.argtypes = [C.POINTER(HaLmParams), i32, C.POINTER(HaLevel), C.POINTER(HaLevel), vp, vp, vp, vp, vp,
+                             vp, vp, vp, sz, vp]
+    L.ha_lm_run.argtypes = [C.POINTER(HaLmParams), C.POINTER(HaLevel), C.POINTER(HaLevel), C.POINTER(vp),
+                            C.POINTER(vp), vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.ha_vgg_packed_weight_bytes.restype = sz
+    L.ha_vgg_pack_weights.argtypes = [C.POINTER(HaVggStateDict), vp, sz, vp]
+    L.ha_vgg_workspace_bytes.restype = sz
+    L.ha_vgg_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.ha_vgg_forward.argtypes = [vp, vp, i32, i32, i32, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, sz, vp]
+    for name in EXPORTS:
+        f = getattr(L, name)
+        if f.restype is C.c_int and name not in ("ha_version",):
+            f.restype = i32
+    _LIB = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    L = lib()
+    msg = L.ha_error_string(rc).decode()
+    if rc == -3:
+        msg += ": " + L.ha_last_cuda_error().decode()
+    raise HaError("%s failed: %s" % (what, msg))

@@ -1,0 +1,408 @@
+"""Host side of the pose-refinement engine: everything between the reference-shaped
+`nn.Module.forward()` mirrors (models_kitti.py / models_ford.py in this package) and the C ABI
+(include/ha_b200.h).  PyTorch is used for device memory, streams and the CPU RNG only — all
+arithmetic of the hot path happens inside libha_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import HaLevel, HaLmParams, HaVggStateDict, check
+
+CAMERA_HEIGHT = 1.65           # utils.py:7
+SAT_PROCESS_SIDE = 512         # utils.py:11
+GROUND_EPS = 1e-7              # utils.py:17
+PYRAMID_CHANNELS = (256, 128, 64, 16)
+KITTI_K = ((582.9802, 0.0, 496.2420), (0.0, 482.7076, 125.0034), (0.0, 0.0, 1.0))   # models_kitti.py:657-659
+FORD_K_FL = (945.391406, 0.0, 855.502825, 0.0, 945.668274, 566.372868, 0.0, 0.0, 1.0)  # models_ford.py:116-118
+
+
+def kitti_meter_per_pixel() -> float:
+    """utils.py:142-146 at the defaults (lat 49.015, zoom 18, scale 1) in python doubles."""
+    mpp = 156543.03392 * np.cos(49.015 * np.pi / 180.0) / (2 ** 18)
+    return float(mpp / 2 / 1.0)
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise _lib.HaError("%s must be a CUDA tensor: the engine has no CPU path" % what)
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------------------- ground tables
+def ground_table(kind: str, level: int, n_levels: int = 3) -> torch.Tensor:
+    """Ground-plane lift of every ground-image pixel at a pyramid level, in the camera frame:
+    [H, W, 4] fp32 = (x, y, z, mask).  Init-time CPU work, same arithmetic as
+    models_kitti.py:655-682 (grd_img2cam) / models_ford.py:110-155 so the values are identical."""
+    if kind == "kitti":
+        top = 3
+        k0 = torch.tensor([KITTI_K], dtype=torch.float32)
+    elif kind == "ford":
+        top = 2 if n_levels == 2 else 3
+        raw = torch.tensor(FORD_K_FL, dtype=torch.float32).reshape(1, 3, 3)
+        k0 = torch.zeros_like(raw)
+        k0[0, 0] = raw[0, 0] / 1656 * 1024        # models_ford.py:121-130: sensor 1656x860 -> 1024x256
+        k0[0, 1] = raw[0, 1] / 860 * 256
+        k0[0, 2] = raw[0, 2]
+    else:
+        raise ValueError(kind)
+    gh, gw = 256 / (2 ** (top - level)), 1024 / (2 ** (top - level))
+    k = k0.clone()
+    k[:, :1, :] = k0[:, :1, :] * gw / 1024
+    k[:, 1:2, :] = k0[:, 1:2, :] * gh / 256
+    kinv = torch.inverse(k)
+    vv, uu = torch.meshgrid(torch.arange(0, gh, dtype=torch.float32), torch.arange(0, gw, dtype=torch.float32),
+                            indexing="ij")
+    pix = torch.stack([uu, vv, torch.ones_like(uu)], dim=-1).unsqueeze(0)
+    ray = torch.sum(kinv[:, None, None, :, :] * pix[:, :, :, None, :], dim=-1)
+    ry = ray[..., 1:2]
+    depth = CAMERA_HEIGHT / torch.where(torch.abs(ry) > GROUND_EPS, ry, GROUND_EPS * torch.ones_like(ry))
+    xyz = ray * depth
+    mask = (xyz[..., -1:] > 0).float()
+    return torch.cat([xyz, mask], dim=-1)[0].contiguous()
+
+
+# ------------------------------------------------------------------------------- pyramids
+@dataclass
+class Pyramid:
+    """One branch's feature pyramid in the engine's layout: NHWC fp32, raw (not L2-normalised)
+    features plus the per-sample 1/||x|| the reference would have applied (VGG.py:172-175)."""
+    feats: List[torch.Tensor]
+    scales: List[Optional[torch.Tensor]]
+    confs: List[Optional[torch.Tensor]] = field(default_factory=list)    # [B,H,W] each
+
+    @property
+    def batch(self) -> int:
+        return self.feats[0].shape[0]
+
+    @staticmethod
+    def from_nchw(feats: Sequence[torch.Tensor], confs: Optional[Sequence[Optional[torch.Tensor]]] = None) -> "Pyramid":
+        """Reference-layout ([B,C,H,W], already normalised) features -> engine layout."""
+        out = [nchw_to_nhwc(f) for f in feats]
+        cf = [None if c is None else c.reshape(c.shape[0], c.shape[-2], c.shape[-1]).contiguous().float()
+              for c in (confs or [None] * len(out))]
+        return Pyramid(out, [None] * len(out), cf)
+
+    def nchw(self, level: int, normalised: bool = True) -> torch.Tensor:
+        f = nhwc_to_nchw(self.feats[level])
+        if normalised and self.scales[level] is not None:
+            f = f * self.scales[level][:, None, None, None]
+        return f
+
+
+def nchw_to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x, "nchw_to_nhwc input")
+    x = x.contiguous().float()
+    B, Cc, H, W = x.shape
+    out = torch.empty(B, H, W, Cc, device=x.device, dtype=torch.float32)
+    check(_lib.lib().ha_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, Cc, H, W, _stream_ptr()), "ha_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x, "nhwc_to_nchw input")
+    x = x.contiguous().float()
+    B, H, W, Cc = x.shape
+    out = torch.empty(B, Cc, H, W, device=x.device, dtype=torch.float32)
+    check(_lib.lib().ha_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), B, Cc, H, W, _stream_ptr()), "ha_nhwc_to_nchw")
+    return out
+
+
+# ------------------------------------------------------------------------------- LM parameters
+@dataclass
+class LmSetup:
+    """Everything about one LM run that does not depend on the batch content."""
+    kind: str                  # 'kitti' | 'ford'
+    n_iters: int
+    level_first: int
+    dof: int
+    using_weight: int
+    use_hessian: int
+    rotation_range: float
+    shift_range_lat: float
+    shift_range_lon: float
+
+
+def dof_of(args, kind: str) -> int:
+    """models_kitti.py:954-957; the Ford model always refines all three (models_ford.py:380)."""
+    if kind == "ford":
+        return 3
+    if args.rotation_range == 0:
+        return 2
+    if args.shift_range_lat == 0 and args.shift_range_lon == 0:
+        return 1
+    return 3
+
+
+def setup_from_args(args, kind: str, level_first: int = 0) -> LmSetup:
+    return LmSetup(kind=kind, n_iters=int(args.N_iters), level_first=int(level_first), dof=dof_of(args, kind),
+                   using_weight=int(bool(args.using_weight)), use_hessian=int(bool(getattr(args, "use_hessian", 0))),
+                   rotation_range=float(args.rotation_range), shift_range_lat=float(args.shift_range_lat),
+                   shift_range_lon=float(args.shift_range_lon))
+
+
+def resolve_damping(args, damping_param: Optional[torch.Tensor], dof: int) -> List[float]:
+    """models_kitti.py:958-966: trained lambda = 10^(-6 + 11*sigmoid(p)) else args.damping."""
+    if getattr(args, "train_damping", 0):
+        lam = (10.0 ** (-6 + damping_param.detach().float().sigmoid() * 11)).reshape(-1).tolist()
+        if len(lam) == 1:
+            lam = lam * dof
+        if len(lam) != dof:
+            raise _lib.HaError("damping parameter has %d entries for %d degrees of freedom" % (len(lam), dof))
+        return [float(v) for v in lam]
+    return [float(np.float32(args.damping))] * dof
+
+
+def execution_order(n_iters: int, n_levels: int, level_first: int) -> List[Tuple[int, int]]:
+    """(iteration, level) in the order the reference executes them (models_kitti.py:1176-1180 / :1349-1353)."""
+    if level_first:
+        return [(it, lv) for lv in range(n_levels) for it in range(n_iters)]
+    return [(it, lv) for it in range(n_iters) for lv in range(n_levels)]
+
+
+def draw_reset_uv(n_steps: int, B: int) -> torch.Tensor:
+    """The reference draws two [B,1] Uniform(-1,1) samples from the CPU default generator on every
+    3-DOF LM step whether or not they are used (models_kitti.py:1028-1029).  Make the same draws in
+    the same order so the global RNG stream (and any reset sample) stays identical."""
+    dist = torch.distributions.uniform.Uniform(-1, 1)
+    out = torch.empty(n_steps, 2, B, dtype=torch.float32)
+    for k in range(n_steps):
+        out[k, 0] = dist.sample([B, 1])[:, 0]
+        out[k, 1] = dist.sample([B, 1])[:, 0]
+    return out
+
+
+def _levels(p: Pyramid, n: int):
+    arr = (HaLevel * n)()
+    for i in range(n):
+        f = p.feats[i]
+        if f.dtype != torch.float32 or not f.is_contiguous():
+            raise _lib.HaError("pyramid level %d must be contiguous fp32 NHWC" % i)
+        arr[i].data = f.data_ptr()
+        arr[i].scale = p.scales[i].data_ptr() if p.scales[i] is not None else None
+        arr[i].H, arr[i].W, arr[i].C = f.shape[1], f.shape[2], f.shape[3]
+    return arr
+
+
+def make_params(setup: LmSetup, sat: Pyramid, damping: Sequence[float], side_m: Optional[float]) -> HaLmParams:
+    n = len(sat.feats)
+    p = HaLmParams()
+    p.geometry = _lib.HA_GEOM_KITTI if setup.kind == "kitti" else _lib.HA_GEOM_FORD
+    p.n_levels, p.n_iters, p.level_first, p.dof = n, setup.n_iters, setup.level_first, setup.dof
+    p.using_weight, p.use_hessian, p.batch = setup.using_weight, setup.use_hessian, sat.batch
+    p.rotation_range, p.shift_range_lat, p.shift_range_lon = setup.rotation_range, setup.shift_range_lat, setup.shift_range_lon
+    for i, v in enumerate(damping):
+        p.damping[i] = v
+    for lv in range(n):
+        A = sat.feats[lv].shape[1]
+        if setup.kind == "kitti":
+            mpp = kitti_meter_per_pixel() * (SAT_PROCESS_SIDE / A)      # models_kitti.py:757-758
+            center = A / 2                                              # :765
+        else:
+            mpp = side_m / A                                            # models_ford.py:230
+            center = A // 2                                             # :231
+        p.meter_per_pixel[lv] = mpp
+        p.inv_meter_per_pixel[lv] = 1.0 / mpp
+        p.sat_center[lv] = center
+    return p
+
+
+class LmWorkspace:
+    """Per-device scratch reused across calls (partials + tickets + status word)."""
+
+    def __init__(self):
+        self.buf = None
+        self.status = None
+
+    def get(self, B: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+        need = _lib.lib().ha_lm_workspace_bytes(B)
+        if self.buf is None or self.buf.numel() < need or self.buf.device != device:
+            self.buf = torch.empty(need, dtype=torch.uint8, device=device)
+        if self.status is None or self.status.device != device:
+            self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        return self.buf, self.status
+
+
+_WS = {}
+
+
+def _workspace(device) -> LmWorkspace:
+    key = (device.type, device.index)
+    if key not in _WS:
+        _WS[key] = LmWorkspace()
+    return _WS[key]
+
+
+@dataclass
+class LmResult:
+    traj: torch.Tensor                    # [B, n_iters, n_levels, 3] (su, sv, theta) after every step
+    pose: torch.Tensor                    # [B, 3] final
+    stats: Optional[torch.Tensor]         # [n_iters, n_levels, B, HA_STATS] or None
+    status: torch.Tensor                  # device int32[1], OR of HA_STATUS_* bits (not synced here)
+
+
+def lm_run(setup: LmSetup, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Tensor], damping: Sequence[float],
+           extrinsics: Optional[torch.Tensor] = None, side_m: Optional[float] = None,
+           pose0: Optional[torch.Tensor] = None, reset_uv: Optional[torch.Tensor] = None,
+           want_stats: bool = False) -> LmResult:
+    """The whole LM loop on the current CUDA stream, no host synchronisation."""
+    L = _lib.lib()
+    n = len(sat.feats)
+    B = sat.batch
+    dev = sat.feats[0].device
+    _require_cuda(sat.feats[0], "satellite features")
+    pose = torch.zeros(B, 3, dtype=torch.float32, device=dev) if pose0 is None else pose0.to(dev, torch.float32).clone()
+    traj = torch.empty(B, setup.n_iters, n, 3, dtype=torch.float32, device=dev)
+    stats = torch.empty(setup.n_iters, n, B, _lib.HA_STATS, dtype=torch.float32, device=dev) if want_stats else None
+    n_steps = setup.n_iters * n
+    if setup.dof == 3:
+        if reset_uv is None:
+            reset_uv = draw_reset_uv(n_steps, B)
+        reset_uv = reset_uv.to(dev, torch.float32, non_blocking=True).contiguous()
+        assert reset_uv.shape == (n_steps, 2, B)
+    else:
+        reset_uv = None
+    if setup.kind == "ford":
+        if extrinsics is None or side_m is None:
+            raise _lib.HaError("Ford geometry needs R_FL/T_FL and satmap_sidelength_meters")
+        extrinsics = extrinsics.to(dev, torch.float32).contiguous()
+    params = make_params(setup, sat, damping, side_m)
+    confs = (C.c_void_p * n)()
+    tabs = (C.c_void_p * n)()
+    for i in range(n):
+        c = grd.confs[i] if grd.confs else None
+        if setup.using_weight and c is None:
+            raise _lib.HaError("using_weight needs ground confidence maps")
+        confs[i] = c.data_ptr() if (c is not None and setup.using_weight) else None
+        assert tables[i].is_cuda and tables[i].shape[:2] == grd.feats[i].shape[1:3], "ground table / feature shape mismatch"
+        tabs[i] = tables[i].data_ptr()
+    ws, status = _workspace(dev).get(B, dev)
+    rc = L.ha_lm_run(C.byref(params), _levels(sat, n), _levels(grd, n), confs, tabs,
+                     extrinsics.data_ptr() if extrinsics is not None else None, pose.data_ptr(),
+                     reset_uv.data_ptr() if reset_uv is not None else None, traj.data_ptr(),
+                     stats.data_ptr() if stats is not None else None, status.data_ptr(), ws.data_ptr(), ws.numel(),
+                     _stream_ptr())
+    check(rc, "ha_lm_run")
+    return LmResult(traj, pose, stats, status)
+
+
+def lm_step(setup: LmSetup, level: int, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Tensor],
+            damping: Sequence[float], pose: torch.Tensor, extrinsics: Optional[torch.Tensor] = None,
+            side_m: Optional[float] = None, reset_uv: Optional[torch.Tensor] = None):
+    """One fused LM step at `level` from `pose` [B,3]; returns (new_pose [B,3], stats [B,HA_STATS])."""
+    L = _lib.lib()
+    n = len(sat.feats)
+    B = sat.batch
+    dev = sat.feats[0].device
+    pose = pose.to(dev, torch.float32).clone().contiguous()
+    stats = torch.empty(B, _lib.HA_STATS, dtype=torch.float32, device=dev)
+    if setup.dof == 3:
+        if reset_uv is None:
+            reset_uv = draw_reset_uv(1, B)[0]
+        reset_uv = reset_uv.to(dev, torch.float32).contiguous()
+    if setup.kind == "ford":
+        extrinsics = extrinsics.to(dev, torch.float32).contiguous()
+    params = make_params(setup, sat, damping, side_m)
+    c = grd.confs[level] if (grd.confs and setup.using_weight) else None
+    ws, status = _workspace(dev).get(B, dev)
+    sl, gl = _levels(sat, n), _levels(grd, n)
+    rc = L.ha_lm_step(C.byref(params), level, C.byref(sl[level]), C.byref(gl[level]),
+                      c.data_ptr() if c is not None else None, tables[level].data_ptr(),
+                      extrinsics.data_ptr() if extrinsics is not None else None, pose.data_ptr(),
+                      reset_uv.data_ptr() if reset_uv is not None else None, stats.data_ptr(), status.data_ptr(),
+                      ws.data_ptr(), ws.numel(), _stream_ptr())
+    check(rc, "ha_lm_step")
+    return pose, stats
+
+
+def ford_extrinsics(R_FL: torch.Tensor, T_FL: torch.Tensor) -> torch.Tensor:
+    """[B,3,3] + [B,3] -> [B,12] in the layout ha_lm_* expects."""
+    B = R_FL.shape[0]
+    return torch.cat([R_FL.reshape(B, 9), T_FL.reshape(B, 3)], dim=1).float().contiguous()
+
+
+# ------------------------------------------------------------------------------- VGG
+VGG_CONV_NAMES = ["conv0", "conv2", "conv5", "conv7", "conv10", "conv12", "conv14", "conv_dec1.1", "conv_dec1.3",
+                  "conv_dec2.1", "conv_dec2.3", "conv_dec3.1", "conv_dec3.3", "conf0.1", "conf1.1", "conf2.1", "conf3.1"]
+PRECISIONS = {"fp32": _lib.HA_CONV_FP32_SIMT, "f16x3": _lib.HA_CONV_F16X3, "f16": _lib.HA_CONV_F16}
+
+
+class VggRunner:
+    """Packs one U-Net's weights for the kernels (re-packed when a parameter changes) and runs the
+    feature extractor through ha_vgg_forward, chunking the batch to bound the workspace."""
+
+    def __init__(self, max_ws_bytes: int = 24 << 30):
+        self.packed = None
+        self.key = None
+        self.ws = None
+        self.max_ws_bytes = max_ws_bytes
+
+    def _pack(self, named: dict, device) -> None:
+        key = tuple((n, named[n].data_ptr(), named[n]._version) for n in sorted(named))
+        if self.packed is not None and key == self.key and self.packed.device == device:
+            return
+        L = _lib.lib()
+        sd = HaVggStateDict()
+        keep = []
+        for i, n in enumerate(VGG_CONV_NAMES):
+            w = named[n + ".weight"].detach()
+            _require_cuda(w, n + ".weight")
+            w = w.float().contiguous()
+            keep.append(w)
+            sd.weight[i] = w.data_ptr()
+            b = named.get(n + ".bias")
+            if b is not None:
+                b = b.detach().float().contiguous()
+                keep.append(b)
+                sd.bias[i] = b.data_ptr()
+        nbytes = L.ha_vgg_packed_weight_bytes()
+        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        check(L.ha_vgg_pack_weights(C.byref(sd), self.packed.data_ptr(), nbytes, _stream_ptr()), "ha_vgg_pack_weights")
+        self.key = key
+        self._keep = keep
+
+    def __call__(self, named: dict, img: torch.Tensor, n_levels: int, want_conf: bool, precision: str) -> Pyramid:
+        _require_cuda(img, "image")
+        L = _lib.lib()
+        dev = img.device
+        img = img.float().contiguous()
+        B, c3, H, W = img.shape
+        if c3 != 3:
+            raise _lib.HaError("image must be [B,3,H,W]")
+        prec = PRECISIONS[precision]
+        self._pack(named, dev)
+        per1 = L.ha_vgg_workspace_bytes(1, H, W, n_levels, prec)
+        if per1 == 0:
+            raise _lib.HaError("unsupported VGG shape B=%d H=%d W=%d levels=%d" % (B, H, W, n_levels))
+        chunk = max(1, min(B, int(self.max_ws_bytes // per1)))
+        need = L.ha_vgg_workspace_bytes(chunk, H, W, n_levels, prec)
+        if self.ws is None or self.ws.numel() < need or self.ws.device != dev:
+            self.ws = None
+            self.ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        feats, scales, confs = [], [], []
+        for l in range(n_levels):
+            h, w, ch = H >> (3 - l), W >> (3 - l), PYRAMID_CHANNELS[l]
+            feats.append(torch.empty(B, h, w, ch, dtype=torch.float32, device=dev))
+            scales.append(torch.empty(B, dtype=torch.float32, device=dev))
+            confs.append(torch.empty(B, h, w, dtype=torch.float32, device=dev) if want_conf else None)
+        st = _stream_ptr()
+        for b0 in range(0, B, chunk):
+            nb = min(chunk, B - b0)
+            pf, ps, pc = (C.c_void_p * n_levels)(), (C.c_void_p * n_levels)(), (C.c_void_p * n_levels)()
+            for l in range(n_levels):
+                pf[l] = feats[l][b0:].data_ptr()
+                ps[l] = scales[l][b0:].data_ptr()
+                pc[l] = confs[l][b0:].data_ptr() if want_conf else None
+            check(L.ha_vgg_forward(self.packed.data_ptr(), img[b0:].data_ptr(), nb, H, W, n_levels, prec, pf, ps, pc,
+                                   self.ws.data_ptr(), self.ws.numel(), st), "ha_vgg_forward")
+        return Pyramid(feats, scales, confs)

@@ -1,0 +1,84 @@
+"""Drop-in for the reference's models_kitti.py on the accelerated path: `LM_S2GP` and `loss_func`
+with the reference's constructor / forward signatures and state-dict keys, running the fused
+sm_100a engine.  Citations are into the upstream models_kitti.py.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import engine
+from .VGG import VGGUnet
+from .models_ford import loss_func, _TrajectoryOutputs  # noqa: F401  (the reference re-exports loss_func too, :16)
+
+
+class LM_S2GP(nn.Module):
+    """models_kitti.py:598.  forward(sat_map, grd_img_left, ..., mode='test') -> (lat, lon, theta)."""
+
+    KIND = "kitti"
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.level = args.level
+        self.N_iters = args.N_iters
+        self.using_weight = args.using_weight
+        self.loss_method = args.loss_method
+        if getattr(args, "Optimizer", "LM") != "LM" or getattr(args, "proj", "geo") != "geo":
+            raise NotImplementedError("only --Optimizer LM --proj geo is on the accelerated path")
+        if getattr(args, "dropout", 0) or getattr(args, "use_gt_depth", 0):
+            raise NotImplementedError("dropout / use_gt_depth are outside the accelerated path")
+        self.SatFeatureNet = VGGUnet(self.level)
+        self.GrdFeatureNet = VGGUnet(self.level)
+        if args.rotation_range > 0:                                   # :615-620
+            self.damping = nn.Parameter(torch.zeros(size=(1, 3), dtype=torch.float32, requires_grad=True))
+        else:
+            self.damping = nn.Parameter(torch.zeros(size=(), dtype=torch.float32, requires_grad=True))
+        self._tables_cpu = [engine.ground_table("kitti", lv) for lv in range(4)]   # :622-635
+        self._tables_dev = {}
+        self.meters_per_pixel = [engine.kitti_meter_per_pixel() * (2 ** (3 - lv)) for lv in range(4)]   # :637-640
+        self.last_result = None
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _tables(self, device):
+        key = (device.type, device.index)
+        if key not in self._tables_dev:
+            self._tables_dev[key] = [t.to(device) for t in self._tables_cpu]
+        return self._tables_dev[key]
+
+    def extract(self, sat_map, grd_img, want_conf):
+        sat = self.SatFeatureNet.pyramid(sat_map, want_conf=False)
+        grd = self.GrdFeatureNet.pyramid(grd_img, want_conf=want_conf)
+        return sat, grd
+
+    def refine(self, sat: engine.Pyramid, grd: engine.Pyramid, level_first=0, pose0=None, reset_uv=None,
+               want_stats=False) -> engine.LmResult:
+        """The LM loop on already-extracted pyramids (used by forward and by the parity tests)."""
+        setup = engine.setup_from_args(self.args, self.KIND, level_first)
+        lam = engine.resolve_damping(self.args, self.damping, setup.dof)
+        res = engine.lm_run(setup, sat, grd, self._tables(sat.feats[0].device), lam, pose0=pose0, reset_uv=reset_uv,
+                            want_stats=want_stats)
+        self.last_result = res
+        return res
+
+    # -- reference surface --------------------------------------------------------------------
+    def forward(self, sat_map, grd_img_left, gt_shiftu=None, gt_shiftv=None, gt_heading=None, mode='train',
+                file_name=None, gt_depth=None, loop=0, level_first=0):
+        """models_kitti.py:1126-1316 (iter-first) / :1318-1492 (level-first)."""
+        want_conf = bool(self.using_weight) or mode == 'train'
+        sat, grd = self.extract(sat_map, grd_img_left, want_conf)
+        res = self.refine(sat, grd, level_first)
+        traj = res.traj
+        # :1281-1283: shift_lats = shift_vs, shift_lons = shift_us
+        shift_lats, shift_lons, thetas = traj[..., 1], traj[..., 0], traj[..., 2]
+        out = _TrajectoryOutputs.apply(self.damping, mode == 'train', shift_lats, shift_lons, thetas)
+        shift_lats, shift_lons, thetas = out
+        if mode == 'train':
+            coe_heading = 0 if self.args.rotation_range == 0 else self.args.coe_heading      # :1298-1301
+            r = loss_func(self.args.loss_method, None, None, None, shift_lats, shift_lons, thetas,
+                          gt_shiftv[:, 0], gt_shiftu[:, 0], gt_heading[:, 0], None, None,
+                          self.args.coe_shift_lat, self.args.coe_shift_lon, coe_heading,
+                          self.args.coe_L1, self.args.coe_L2, self.args.coe_L3, self.args.coe_L4)
+            grd_conf_list = [c[:, None] for c in grd.confs]
+            return (*r, grd_conf_list)
+        return shift_lats[:, -1, -1], shift_lons[:, -1, -1], thetas[:, -1, -1]

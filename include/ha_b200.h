@@ -1,0 +1,162 @@
+/*
+ * ha_b200.h — C ABI of the B200-native cross-view pose-refinement engine.
+ *
+ * One shared library (libha_b200.so, sm_100a only) exports exactly the entry points below.
+ * They are what a binding of the reference's hot path would call; each one names the
+ * reference interface (file:line under the upstream tree) it replaces.  Plain pointers and
+ * sizes only — no torch / C++ types.  All `float*` / `void*` data arguments are DEVICE
+ * pointers unless the name ends in `_host`.  Every function is asynchronous on `stream`
+ * (a cudaStream_t passed as void*), allocates nothing, keeps no mutable global state, and
+ * returns 0 on success or a negative HA_E* code (ha_error_string() describes it).
+ *
+ * Feature layout in HBM: NHWC fp32, i.e. [B][H][W][C] with C contiguous, so that one
+ * bilinear tap of one pixel is one contiguous run of 4*C bytes (128-bit loads).
+ */
+#ifndef HA_B200_H_
+#define HA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HA_MAX_LEVELS 4
+
+enum {
+  HA_OK = 0,
+  HA_EINVAL = -1,      /* bad argument (shape / alignment / unsupported channel count)      */
+  HA_ENOSPACE = -2,    /* workspace too small                                              */
+  HA_ECUDA = -3,       /* a CUDA runtime / driver call failed (see ha_last_cuda_error)     */
+  HA_EUNSUPPORTED = -4 /* device is not sm_100                                              */
+};
+
+/* geometry functors of the satellite->ground warp */
+enum {
+  HA_GEOM_KITTI = 0,   /* models_kitti.py:700-801  LM_S2GP.grd2cam2world2sat               */
+  HA_GEOM_FORD = 1     /* models_ford.py:173-264   LM_S2GP_Ford.cam2body2world2sat         */
+};
+
+/* device status word bits (checked by the host ONCE after the loop, never per step;
+ * replaces the reference's per-step host syncs jacobian.py:172,200 / models_kitti.py:1037) */
+enum {
+  HA_STATUS_NO_INRANGE = 1u, /* some step saw no in-range sample point for some sample     */
+  HA_STATUS_NAN_POSE = 2u,   /* a pose became NaN                                           */
+  HA_STATUS_RESET = 4u       /* an out-of-range shift was re-drawn (models_kitti.py:1030)   */
+};
+
+/* One pyramid level of one branch. */
+typedef struct {
+  const float* data;   /* [B][H][W][C] fp32 NHWC                                           */
+  const float* scale;  /* [B] per-sample multiplier (1/||x||, VGG.py:511-514 L2_norm applied
+                          lazily) or NULL for 1                                            */
+  int32_t C, H, W;
+} HaLevel;
+
+/* Parameters of the LM loop = the fields of the reference's `args` Namespace that the path
+ * reads (train_kitti.py:439-476) plus per-level geometry constants. */
+typedef struct {
+  int32_t geometry;          /* HA_GEOM_*                                                  */
+  int32_t n_levels;          /* pyramid levels used by the loop (<= HA_MAX_LEVELS)          */
+  int32_t n_iters;           /* args.N_iters                                                */
+  int32_t level_first;       /* 0: for iter: for level (models_kitti.py:1176-1180);
+                                1: for level: for iter (:1349-1353)                        */
+  int32_t dof;               /* 3: (su,sv,theta); 2: shifts only (rotation_range==0);
+                                1: theta only (both shift ranges 0) (models_kitti.py:954)  */
+  int32_t using_weight;      /* W = grd_conf (models_kitti.py:994-998)                      */
+  int32_t use_hessian;       /* damping * diag(H) instead of damping * I (:1005-1010)       */
+  int32_t batch;             /* B: samples in every per-sample array of the call             */
+  float rotation_range;      /* degrees                                                    */
+  float shift_range_lat;     /* metres                                                     */
+  float shift_range_lon;     /* metres                                                     */
+  float damping[3];          /* resolved lambda per DOF column (:958-966)                   */
+  float meter_per_pixel[HA_MAX_LEVELS]; /* satellite metres per pixel at each level, already
+                                rounded to fp32 the way the reference's python double is   */
+  float inv_meter_per_pixel[HA_MAX_LEVELS]; /* fp32(1/mpp) with mpp in double (models_kitti.py:795) */
+  float sat_center[HA_MAX_LEVELS];      /* A/2 (KITTI) or A//2 (Ford) added to uv           */
+} HaLmParams;
+
+/* ---- library ---------------------------------------------------------------------- */
+int ha_version(void);                      /* ABI version, currently 1                     */
+const char* ha_error_string(int code);
+const char* ha_last_cuda_error(void);      /* text of the last CUDA failure on this thread  */
+int ha_device_check(int device);           /* HA_OK iff `device` is compute capability 10.x */
+
+/* ---- layout helpers (host wrappers use them at the boundary; reference is NCHW) ---- */
+int ha_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
+int ha_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, void* stream);
+
+/* ---- fused LM step: warp + residual + analytic Jacobian + J^T J / J^T r + 3x3 solve ----
+ * Replaces, per (iteration, level): project_map_to_grd (models_kitti.py:803-937 /
+ * models_ford.py:266-378) -> jacobian.grid_sample (jacobian.py:138-205) -> LM_update
+ * (models_kitti.py:939-1041 / models_ford.py:380-466).
+ *
+ * ground_table: [H][W][4] fp32 = (x, y, z, mask) of the ground-plane lift in the camera
+ *   frame (models_kitti.py:655-682 / models_ford.py:110-155); only rows H/2.. are read.
+ * grd_conf:  [B][H][W] fp32 or NULL (required iff using_weight).
+ * extrinsics: Ford only: [B][12] = R_FL row-major (9) then T_FL (3); NULL for KITTI.
+ * pose:      [B][3] = (shift_u, shift_v, theta) normalised units, updated IN PLACE.
+ * reset_uv:  [2][B] uniform(-1,1) draws for this step (models_kitti.py:1028-1029) or NULL
+ *            (required iff dof == 3).
+ * stats:     NULL or [B][HA_STATS] fp32 diagnostics of this step (see HA_STAT_*).
+ * status:    device uint32, OR-ed with HA_STATUS_* bits.
+ */
+#define HA_STATS 24
+enum { HA_STAT_H = 0 /*9: row-major J~^T W J~*/, HA_STAT_GRAD = 9 /*3: J~^T W r*/, HA_STAT_SAT_NORM = 12,
+       HA_STAT_GRD_NORM = 13, HA_STAT_RES_SQ = 14, HA_STAT_DELTA = 15 /*3*/, HA_STAT_N_INRANGE = 18 };
+
+size_t ha_lm_workspace_bytes(int B);
+int ha_lm_step(const HaLmParams* p, int level, const HaLevel* sat, const HaLevel* grd, const float* grd_conf,
+               const float* ground_table, const float* extrinsics, float* pose, const float* reset_uv,
+               float* stats, uint32_t* status, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- the whole LM loop (forward_iter_first / forward_level_first, mode='test') ----------
+ * Replaces models_kitti.py:1176-1283 / :1349-1459 and models_ford.py:652-825 / :868-1000.
+ * Launches n_iters * n_levels dependent steps back to back on `stream`, no host sync.
+ * sat/grd:   arrays of n_levels HaLevel;  grd_conf / ground_tables: arrays of n_levels ptrs.
+ * reset_uv:  [n_steps][2][B] in EXECUTION order, or NULL when dof != 3.
+ * pose:      [B][3] initial pose in, final pose out.
+ * traj:      [B][n_iters][n_levels][3] pose after every step (the reference's
+ *            shift_us / shift_vs / headings stacks, models_kitti.py:1281-1283).
+ * stats:     NULL or [n_iters][n_levels][B][HA_STATS].
+ */
+int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel* grd, const float* const* grd_conf,
+              const float* const* ground_tables, const float* extrinsics, float* pose,
+              const float* reset_uv, float* traj, float* stats, uint32_t* status, void* ws, size_t ws_bytes,
+              void* stream);
+
+/* ---- VGG16 U-Net feature extractor (VGG.py:13-203, estimate_depth off) ----------------- */
+/* Weights, packed by ha_vgg_pack_weights from the reference's state-dict tensors (OIHW fp32,
+ * host or device pointers are both accepted: they are only read by cudaMemcpyAsync). */
+#define HA_VGG_N_CONV 17
+/* order: conv0 conv2 conv5 conv7 conv10 conv12 conv14 | dec1.1 dec1.3 dec2.1 dec2.3 dec3.1
+ * dec3.3 | conf0 conf1 conf2 conf3 ; bias[i] may be NULL (decoder + conf convs have none) */
+typedef struct {
+  const float* weight[HA_VGG_N_CONV];
+  const float* bias[HA_VGG_N_CONV];
+} HaVggStateDict;
+
+/* precision of the tensor-core convolutions */
+enum {
+  HA_CONV_FP32_SIMT = 0,   /* CUDA-core fp32 direct convolution (validation path)            */
+  HA_CONV_F16X3 = 1,       /* tcgen05 kind::f16, fp16 hi/lo split, 3 MMAs, fp32-grade result */
+  HA_CONV_F16 = 2          /* tcgen05 kind::f16 single pass (fp16 operands, fp32 accumulate) */
+};
+
+size_t ha_vgg_packed_weight_bytes(void);
+int ha_vgg_pack_weights(const HaVggStateDict* sd, void* packed, size_t packed_bytes, void* stream);
+
+/* out_feat[l] : [B][H/2^(3-l)][W/2^(3-l)][C_l] fp32 NHWC, raw (not L2-normalised), C_l =
+ * 256,128,64,16; out_scale[l] : [B] = 1/max(||feat||_2, 1e-12) (VGG.py:511-514);
+ * out_conf[l] : [B][H_l][W_l] fp32 = sigmoid(-sigmoid(conv(relu(feat)))) (VGG.py:160-163)
+ * or NULL to skip the confidence heads.  n_levels = 3 (level 3) or 4 (level 4). */
+size_t ha_vgg_workspace_bytes(int B, int H, int W, int n_levels, int precision);
+int ha_vgg_forward(const void* packed_weights, const float* img_nchw, int B, int H, int W, int n_levels,
+                   int precision, float* const* out_feat, float* const* out_scale, float* const* out_conf,
+                   void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HA_B200_H_ */

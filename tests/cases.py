@@ -72,3 +72,20 @@ def build_loop_case(name):
 
 
 RESET_SEED = 4242    # oracle/make_golden.py seeds the CPU generator with this before every loop
+
+
+def ref_args(**kw):
+    """The argparse Namespace of train_kitti.py:426-485 / train_ford.py:343-412 at its defaults."""
+    import types
+    d = dict(level=3, N_iters=5, using_weight=0, loss_method=0, rotation_range=10.0, proj="geo", Optimizer="LM",
+             damping=0.1, train_damping=0, shift_range_lat=20.0, shift_range_lon=20.0, use_hessian=0, dropout=0,
+             use_gt_depth=0, visualize=0, coe_shift_lat=100.0, coe_shift_lon=100.0, coe_heading=100.0,
+             coe_L1=100.0, coe_L2=100.0, coe_L3=100.0, coe_L4=100.0, estimate_depth=0)
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def args_from_lmargs(a: "O.LMArgs"):
+    return ref_args(level=a.level, N_iters=a.N_iters, using_weight=a.using_weight, damping=a.damping,
+                    train_damping=a.train_damping, rotation_range=a.rotation_range, shift_range_lat=a.shift_range_lat,
+                    shift_range_lon=a.shift_range_lon, use_hessian=a.use_hessian)

@@ -1,0 +1,115 @@
+"""CPU: the C-ABI library loads and exports every symbol the header declares; host-side logic
+(ground tables, execution order, RNG draws, loss, state-dict surface) matches the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+os.environ.setdefault("HA_QUIET", "1")
+from highlyaccurate_b200 import _lib, engine  # noqa: E402
+from highlyaccurate_b200.models_ford import LM_S2GP_Ford, loss_func  # noqa: E402
+from highlyaccurate_b200.models_kitti import LM_S2GP  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from tests import cases as K  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "ha_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ha_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    lib = _lib.lib()
+    names = header_functions()
+    assert len(names) >= 13
+    assert sorted(_lib.EXPORTS) == names
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.ha_version() == 1
+    assert b"workspace" in lib.ha_error_string(-2)
+
+
+def test_struct_layouts_match_header():
+    # sizes implied by include/ha_b200.h (LP64): HaLevel 2 ptr + 3 int32 (+pad), HaLmParams 8 int32 + 18 float
+    assert ctypes.sizeof(_lib.HaLevel) == 32
+    assert ctypes.sizeof(_lib.HaLmParams) == 8 * 4 + (3 + 3 + 4 + 4 + 4) * 4
+    assert ctypes.sizeof(_lib.HaVggStateDict) == 2 * 17 * 8
+
+
+def test_no_cpu_fallback():
+    lib = _lib.lib()
+    with pytest.raises(_lib.HaError):
+        engine.nchw_to_nhwc(torch.zeros(1, 4, 2, 2))          # CPU tensor: refused, not emulated
+    assert lib.ha_lm_workspace_bytes(4) > 0
+
+
+@pytest.mark.parametrize("kind", ["kitti", "ford"])
+def test_ground_tables_equal_oracle(kind):
+    for lv in range(4):
+        t = O.kitti_ground_table(lv) if kind == "kitti" else O.ford_ground_table(lv)
+        e = engine.ground_table(kind, lv)
+        assert torch.equal(t[0], e[..., :3]) and torch.equal(t[1], e[..., 3])
+
+
+def test_execution_order_and_draws():
+    assert engine.execution_order(2, 3, 0) == O._step_order(2, 3, 0)
+    assert engine.execution_order(2, 3, 1) == O._step_order(2, 3, 1)
+    torch.manual_seed(7)
+    mine = engine.draw_reset_uv(3, 5)
+    torch.manual_seed(7)
+    for k in range(3):
+        u, v = O.draw_reset(5)
+        assert torch.equal(mine[k, 0], u[:, 0]) and torch.equal(mine[k, 1], v[:, 0])
+
+
+def test_dof_and_damping_resolution():
+    a = K.ref_args()
+    assert engine.dof_of(a, "kitti") == 3 and engine.dof_of(K.ref_args(rotation_range=0.0), "kitti") == 2
+    assert engine.dof_of(K.ref_args(shift_range_lat=0.0, shift_range_lon=0.0), "kitti") == 1
+    assert engine.dof_of(K.ref_args(rotation_range=0.0), "ford") == 3
+    lam = engine.resolve_damping(K.ref_args(train_damping=1), torch.zeros(1, 3), 3)
+    ref = O.resolve_damping(O.LMArgs(train_damping=1), torch.zeros(1, 3), 3)
+    np.testing.assert_allclose(lam, ref.reshape(-1).numpy(), rtol=1e-7)
+
+
+def test_state_dict_surface():
+    shapes = {"conv0": (64, 3), "conv2": (64, 64), "conv5": (128, 64), "conv7": (128, 128), "conv10": (256, 128),
+              "conv12": (256, 256), "conv14": (256, 256), "conv_dec1.1": (128, 384), "conv_dec1.3": (128, 128),
+              "conv_dec2.1": (64, 192), "conv_dec2.3": (64, 64), "conv_dec3.1": (32, 128), "conv_dec3.3": (16, 32),
+              "conf0.1": (1, 256), "conf1.1": (1, 128), "conf2.1": (1, 64), "conf3.1": (1, 16)}
+    for cls in (LM_S2GP, LM_S2GP_Ford):
+        sd = cls(K.ref_args()).state_dict()
+        assert len(sd) == 49 and tuple(sd["damping"].shape) == (1, 3)
+        for br in ("SatFeatureNet.", "GrdFeatureNet."):
+            for n, (co, ci) in shapes.items():
+                assert tuple(sd[br + n + ".weight"].shape) == (co, ci, 3, 3)
+            assert sum(v.numel() for k, v in sd.items() if k.startswith(br)) == 2518416
+        # a reference-format checkpoint loads unchanged
+        ref_sd = {}
+        ref_sd.update(O.vgg_state_dict(1, "SatFeatureNet."))
+        ref_sd.update(O.vgg_state_dict(2, "GrdFeatureNet."))
+        ref_sd["damping"] = torch.zeros(1, 3)
+        cls(K.ref_args()).load_state_dict(ref_sd)
+    assert tuple(LM_S2GP(K.ref_args(rotation_range=0.0)).state_dict()["damping"].shape) == ()
+
+
+def test_loss_func_method0():
+    g = torch.Generator().manual_seed(3)
+    lat, lon, th = (torch.randn(4, 5, 3, generator=g) for _ in range(3))
+    gl, go, gt = (torch.randn(4, generator=g) for _ in range(3))
+    out = loss_func(0, None, None, None, lat, lon, th, gl, go, gt, None, None, 100, 50, 25)
+    e = [(t - q[:, None, None]).abs().mean(0) for t, q in ((lat, gl), (lon, go), (th, gt))]
+    tot = 100 * e[0] + 50 * e[1] + 25 * e[2]
+    torch.testing.assert_close(out[0], tot.mean())
+    torch.testing.assert_close(out[1], tot[0] - tot[-1])
+    torch.testing.assert_close(out[5], tot[-1])
+    torch.testing.assert_close(out[8], e[2][-1])
+    assert len(out) == 13 and out[9] is None

@@ -1,0 +1,229 @@
+"""GPU: the CUDA path (through the C ABI) against the oracle / the reference's golden outputs.
+
+Tolerances (fp32 path; SURVEY.md section 8c measured the reference's own fp32-vs-fp64 noise):
+  * per-step parity from the reference's pose state: |dpose| <= 2e-6 abs + 1e-4 rel, H / grad 2e-4
+    relative to their norm — the reference's own per-step rounding is 1.8e-7..1.9e-6;
+  * whole-trajectory parity on contractive (planted-pose) inputs: 1e-4 relative on the final pose,
+    the bar BASELINE.json:north_star states;
+  * on non-contractive random features the whole trajectory is compared at 5e-5 abs, the
+    reference's own fp32-vs-fp64 drift after 15 steps.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+os.environ.setdefault("HA_QUIET", "1")
+from highlyaccurate_b200 import _lib, engine  # noqa: E402
+from highlyaccurate_b200.models_ford import LM_S2GP_Ford  # noqa: E402
+from highlyaccurate_b200.models_kitti import LM_S2GP  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from tests import cases as K  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def make_net(c):
+    a = K.args_from_lmargs(c["args"])
+    net = (LM_S2GP if c["kind"] == "kitti" else LM_S2GP_Ford)(a).to(DEV)
+    if c["damping_param"] is not None:
+        with torch.no_grad():
+            net.damping.copy_(c["damping_param"])
+    return net
+
+
+def pyramids(c):
+    sat = engine.Pyramid.from_nchw([s.to(DEV) for s in c["sat"]])
+    grd = engine.Pyramid.from_nchw([g.to(DEV) for g in c["grd"]], [x.to(DEV) for x in c["conf"]])
+    return sat, grd
+
+
+def run_loop(net, c, sat, grd, **kw):
+    if c["kind"] == "ford":
+        f = c["ford"]
+        return net.refine(sat, grd, f["side_m"], f["R_FL"].to(DEV), f["T_FL"].to(DEV), level_first=c["args"].level_first, **kw)
+    return net.refine(sat, grd, level_first=c["args"].level_first, **kw)
+
+
+@pytest.mark.parametrize("name", list(K.LOOP_CASES))
+def test_lm_trajectory_vs_reference(name):
+    c = K.build_loop_case(name)
+    net = make_net(c)
+    sat, grd = pyramids(c)
+    pose0 = torch.cat(c["pose0"], dim=1) if c["pose0"] is not None else None
+    torch.manual_seed(K.RESET_SEED)
+    res = run_loop(net, c, sat, grd, pose0=pose0)
+    got = res.traj.cpu().numpy()
+    want = c["gold"]["traj"]
+    status = int(res.status.item())
+    assert not status & _lib.HA_STATUS_NAN_POSE
+    if name == "kat6_reset":
+        assert status & _lib.HA_STATUS_RESET
+    contractive = "gt" in c["gold"].files
+    if contractive:
+        fin_g, fin_w = got[:, -1, -1], want[:, -1, -1]
+        scale = np.maximum(np.abs(fin_w), 1e-2)           # relative, floored where the planted pose is 0
+        assert np.max(np.abs(fin_g - fin_w) / scale) < 1e-4, (fin_g, fin_w)
+        np.testing.assert_allclose(got, want, atol=1e-4)
+    else:
+        np.testing.assert_allclose(got, want, atol=5e-5)
+
+
+@pytest.mark.parametrize("name", ["kat3_random_kitti", "kat4_planted_kitti", "kat4_planted_ford", "kat5_weight",
+                                  "kat5_hessian", "kat5_shiftonly", "kat5_rotonly", "kat5_level4", "kat5_anisotropic"])
+def test_lm_per_step_vs_reference(name):
+    """Every step restarted from the REFERENCE's pose state, so chaos cannot accumulate."""
+    c = K.build_loop_case(name)
+    net = make_net(c)
+    sat, grd = pyramids(c)
+    g = c["gold"]
+    a = c["args"]
+    setup = engine.setup_from_args(K.args_from_lmargs(a), c["kind"], a.level_first)
+    lam = engine.resolve_damping(K.args_from_lmargs(a), net.damping, setup.dof)
+    tabs = net._tables(torch.device(DEV))
+    ext, side = None, None
+    if c["kind"] == "ford":
+        ext = engine.ford_extrinsics(c["ford"]["R_FL"], c["ford"]["T_FL"]).to(DEV)
+        side = c["ford"]["side_m"]
+    n = setup.dof
+    i0 = 2 if n == 1 else 0
+    zeros = torch.zeros(2, c["B"])
+    for it in range(a.N_iters):
+        for lv in range(c["L"]):
+            pin = torch.from_numpy(g["pose_in"][:, it, lv])
+            pose, st = engine.lm_step(setup, lv, sat, grd, tabs, lam, pin, ext, side, reset_uv=zeros)
+            pose, st = pose.cpu().numpy(), st.cpu().numpy()
+            want = g["traj"][:, it, lv]
+            np.testing.assert_allclose(pose, want, atol=2e-6, rtol=1e-4, err_msg="%s it%d lv%d" % (name, it, lv))
+            Hm = st[:, :9].reshape(-1, 3, 3)[:, i0:i0 + n, i0:i0 + n]
+            Hw = g["hessian"][it, lv]
+            assert np.abs(Hm - Hw).max() <= 2e-4 * np.abs(Hw).max()
+            gr = st[:, 9 + i0:9 + i0 + n]
+            gw = g["grad"][it, lv]
+            assert np.abs(gr - gw).max() <= 2e-4 * max(np.abs(gw).max(), 1e-4 * np.sqrt(np.abs(Hw).max()))
+            np.testing.assert_allclose(st[:, 12], g["sat_norm"][it, lv], rtol=2e-5)
+            np.testing.assert_allclose(st[:, 13], g["grd_norm"][it, lv], rtol=2e-5)
+            np.testing.assert_allclose(st[:, 15:15 + n], g["delta"][it, lv], atol=2e-6, rtol=2e-4)
+
+
+def test_lm_deterministic_and_batch_invariant():
+    """Same inputs -> bit-identical trajectories; a sample's result does not depend on its batch."""
+    c = K.build_loop_case("kat4_planted_kitti")
+    net = make_net(c)
+    sat, grd = pyramids(c)
+    draws = torch.zeros(15, 2, c["B"])
+    r1 = run_loop(net, c, sat, grd, reset_uv=draws).traj.clone()
+    r2 = run_loop(net, c, sat, grd, reset_uv=draws).traj.clone()
+    assert torch.equal(r1, r2)
+    sat1 = engine.Pyramid([f[1:2].contiguous() for f in sat.feats], [None] * 3)
+    grd1 = engine.Pyramid([f[1:2].contiguous() for f in grd.feats], [None] * 3, [x[1:2].contiguous() for x in grd.confs])
+    r3 = net.refine(sat1, grd1, reset_uv=draws[:, :, 1:2].contiguous()).traj
+    np.testing.assert_allclose(r3.cpu().numpy(), r1[1:2].cpu().numpy(), atol=2e-6)
+
+
+def test_lazy_l2_scale_is_equivalent():
+    """Raw features + per-sample scale == pre-normalised features (the scale cancels in the LM
+    normalisation, models_kitti.py:982-989)."""
+    c = K.build_loop_case("kat3_random_kitti")
+    net = make_net(c)
+    sat, grd = pyramids(c)
+    draws = torch.zeros(15, 2, c["B"])
+    base = run_loop(net, c, sat, grd, reset_uv=draws).traj.clone()
+    k_s = torch.tensor([37.0, 0.5], device=DEV)
+    k_g = torch.tensor([0.01, 3.0], device=DEV)
+    sat2 = engine.Pyramid([f * k_s[:, None, None, None] for f in sat.feats], [1 / k_s] * 3)
+    grd2 = engine.Pyramid([f * k_g[:, None, None, None] for f in grd.feats], [1 / k_g] * 3, grd.confs)
+    alt = run_loop(net, c, sat2, grd2, reset_uv=draws).traj
+    np.testing.assert_allclose(alt.cpu().numpy(), base.cpu().numpy(), atol=2e-6)
+
+
+def test_layout_round_trip():
+    x = torch.randn(3, 20, 17, 33, device=DEV)
+    y = engine.nchw_to_nhwc(x)
+    assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(engine.nhwc_to_nchw(y), x)
+
+
+VGG_TOL = {"fp32": 2e-5, "f16x3": 5e-5, "f16": 5e-3}
+
+
+def _vgg_precisions():
+    return [p for p in ("fp32", "f16x3", "f16")]
+
+
+@pytest.mark.parametrize("precision", _vgg_precisions())
+@pytest.mark.parametrize("level", [3, 4])
+def test_vgg_vs_reference(level, precision):
+    from highlyaccurate_b200.VGG import VGGUnet
+    g = K.load_golden("kat7_vgg_level%d" % level)
+    sd = O.vgg_state_dict(7)
+    net = VGGUnet(level).to(DEV)
+    net.load_state_dict(sd)
+    net.precision = precision
+    x = torch.rand(2, 3, 64, 128, generator=torch.Generator().manual_seed(70 + level))
+    np.testing.assert_allclose(K.csum(x), g["in_csum"], rtol=1e-6)
+    feats, confs = net(x.to(DEV))
+    tol = VGG_TOL[precision]
+    for i in range(level):
+        want = g["feat%d" % i]
+        got = feats[i].cpu().numpy()
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= tol * np.abs(want).max(), (i, np.abs(got - want).max() / np.abs(want).max())
+        np.testing.assert_allclose(confs[i].cpu().numpy(), g["conf%d" % i], atol=tol)
+
+
+@pytest.mark.parametrize("kind", ["kitti", "ford"])
+def test_end_to_end_forward_vs_reference(kind):
+    """Whole forward() through the reference-shaped module on the reference's config-1 style input
+    (2 pairs, random-init VGG): final pose vs the reference's own output."""
+    g = K.load_golden("e2e_" + kind)
+    sd = {}
+    sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+    sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+    sd["damping"] = torch.zeros(1, 3)
+    gen = torch.Generator().manual_seed(2022)
+    sat = torch.rand(2, 3, 512, 512, generator=gen)
+    grd = torch.rand(2, 3, 256, 1024, generator=gen)
+    np.testing.assert_allclose(K.csum(sat, grd), g["in_csum"], rtol=1e-6)
+    net = (LM_S2GP if kind == "kitti" else LM_S2GP_Ford)(K.ref_args()).to(DEV)
+    net.load_state_dict(sd)
+    net.eval()
+    torch.manual_seed(999)
+    if kind == "kitti":
+        out = net(sat.to(DEV), grd.to(DEV), mode="test")
+    else:
+        f = K.ford_dict(2, 512 * 0.22)
+        out = net(sat.to(DEV), grd.to(DEV), f["side_m"], f["R_FL"].to(DEV), f["T_FL"].to(DEV), mode="test")
+    assert all(o.requires_grad for o in out)
+    torch.mean(out[0]).backward()                     # train_kitti.py:60-64 "just to release graph"
+    got = torch.stack([o.detach() for o in out], dim=-1).cpu().numpy()
+    # random-init features are not contractive: the reference's own fp32-vs-fp64 end-to-end
+    # deviation is up to 2.6e-4 abs; hold the engine to that noise floor
+    np.testing.assert_allclose(got, g["final"], atol=3e-4)
+    traj = net.last_result.traj.cpu().numpy()
+    ref_traj = np.stack([g["lons"], g["lats"], g["thetas"]] if kind == "kitti" else [g["lats"], g["lons"], g["thetas"]], -1)
+    np.testing.assert_allclose(traj[:, 0], ref_traj[:, 0], atol=5e-5)     # first sweep: before chaos accumulates
+
+
+def test_full_size_properties():
+    """BASELINE config-2 size (B=32, KITTI shapes): planted-pose convergence, determinism, and
+    permutation equivariance over the batch — size-independent properties, no oracle run needed."""
+    B = 32
+    args = O.LMArgs()
+    gen = torch.Generator().manual_seed(5)
+    gt = (torch.rand(B, 3, generator=gen) - 0.5) * 0.8
+    sat, grd = O.planted_case("kitti", B, 512, 3, 77, gt, args)
+    net = LM_S2GP(K.ref_args()).to(DEV)
+    ps = engine.Pyramid.from_nchw([s.to(DEV) for s in sat])
+    pg = engine.Pyramid.from_nchw([x.to(DEV) for x in grd])
+    draws = torch.zeros(15, 2, B)
+    r = net.refine(ps, pg, reset_uv=draws)
+    final = r.pose.cpu()
+    assert float((final - gt).abs().max()) < 2e-4
+    perm = torch.randperm(B, generator=gen)
+    ps2 = engine.Pyramid([f[perm.to(DEV)].contiguous() for f in ps.feats], [None] * 3)
+    pg2 = engine.Pyramid([f[perm.to(DEV)].contiguous() for f in pg.feats], [None] * 3)
+    r2 = net.refine(ps2, pg2, reset_uv=draws)
+    assert torch.equal(r2.pose.cpu(), final[perm])
