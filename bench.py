@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: image-pairs/sec through VGG feature extraction + the 5-iteration,
+3-level LM pose refinement (KITTI shapes, BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's engine (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+
+One "step" = one forward pass (both VGG branches + N_iters x levels LM steps) over one batch of
+synthetic pairs per GPU.  Prints ONE JSON line on rank 0 (see DESIGN.md section "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("HA_QUIET", "1")
+
+import torch  # noqa: E402
+
+METRIC = "image-pairs/sec thru 5-iter LM (KITTI)"
+VGG_FLOP_PER_PX = {3: 520056, 4: 603288}                    # 2*9*Cin*Cout summed over live convs
+SAT_TEXELS_TOUCHED = [372, 1326, 5462, 21880]               # unique sat texels per sample at pose 0
+PYR_C = [256, 128, 64, 16]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def ref_args(n_iters=5, level=3):
+    import types
+    return types.SimpleNamespace(level=level, N_iters=n_iters, using_weight=0, loss_method=0, rotation_range=10.0, proj="geo",
+                                 Optimizer="LM", damping=0.1, train_damping=0, shift_range_lat=20.0, shift_range_lon=20.0,
+                                 use_hessian=0, dropout=0, use_gt_depth=0, visualize=0, coe_shift_lat=100.0,
+                                 coe_shift_lon=100.0, coe_heading=100.0, coe_L1=100.0, coe_L2=100.0, coe_L3=100.0,
+                                 coe_L4=100.0, estimate_depth=0)
+
+
+def lm_bytes_per_pair(n_levels, n_iters):
+    """Algorithmic HBM bytes of the LM loop per pair: ground bottom half read once per
+    step + the unique satellite texels touched, fp32."""
+    per_sweep = 0
+    for l in range(n_levels):
+        h, w = 256 >> (3 - l), 1024 >> (3 - l)
+        per_sweep += 4 * PYR_C[l] * ((h // 2) * w + SAT_TEXELS_TOUCHED[l])
+    return per_sweep * n_iters
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.3] or [r for _, r in self.rows]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in rows)]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].isdigit() else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
+
+
+def time_region(fn, steps, sync):
+    """CUDA events on the current stream around `steps` calls of fn; returns seconds."""
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    sync()
+    return e0.elapsed_time(e1) / 1e3
+
+
+def cpu_reference_run(steps, warmup, n_iters=5, level=3, pairs_per_step=1):
+    """The reference algorithm (oracle port, torch CPU, all host threads) on the same workload
+    shape, one bounded sample (pairs_per_step pairs) per step."""
+    from oracle import oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {}
+    sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+    sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+    sd["damping"] = torch.zeros(1, 3)
+    g = torch.Generator().manual_seed(2022)
+    sat = torch.rand(pairs_per_step, 3, 512, 512, generator=g)
+    grd = torch.rand(pairs_per_step, 3, 256, 1024, generator=g)
+    a = O.LMArgs(level=level, N_iters=n_iters)
+    ts = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.forward_kitti(sd, sat, grd, a)
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    total = sum(ts)
+    return dict(value=pairs_per_step * steps / total, ms_per_step=1e3 * total / steps, cores=torch.get_num_threads(),
+                sample="%d synthetic KITTI pair(s) per step x %d steps (+%d warm-up), VGG level %d + %d LM iters, torch %s CPU"
+                       % (pairs_per_step, steps, warmup, level, n_iters, torch.__version__))
+
+
+def run_reference(opt):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(opt.steps, max(1, min(opt.warmup, 3)), opt.n_iters, opt.level)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": opt.gpus, "steps": opt.steps,
+            "warmup": opt.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(opt, 1, "cpu"),
+            "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(opt, batch, where):
+    return {"workload": "KITTI shapes (sat 512x512, grd 256x1024), batch %d per GPU, %d-level VGG pyramid, %d LM iters"
+                        % (batch, opt.level, opt.n_iters),
+            "batch_per_gpu": batch, "levels": opt.level, "n_iters": opt.n_iters, "device": where,
+            "l2": "inputs (%.0f MB of images + GBs of activations per step) exceed the 126 MB L2" % (batch * 6.29),
+            "vgg_precision": opt.precision}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="pairs per GPU per step (BASELINE configs[1]: 32)")
+    ap.add_argument("--n-iters", dest="n_iters", type=int, default=5)
+    ap.add_argument("--level", type=int, default=3)
+    ap.add_argument("--precision", default=os.environ.get("HA_VGG_PRECISION", "f16x3"), choices=["f16x3", "f16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    opt = ap.parse_args()
+    opt.warmup = max(opt.warmup, 3) if opt.impl == "ours" else opt.warmup
+    if opt.impl == "reference":
+        return run_reference(opt)
+
+    from highlyaccurate_b200 import _lib, engine
+    from highlyaccurate_b200 import dist as hd
+    from highlyaccurate_b200.models_kitti import LM_S2GP
+    import torch.distributed as dist
+
+    rank, world, local = hd.init_from_env()
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = _lib.lib()
+    _lib.check(L.ha_device_check(local), "ha_device_check")
+    B, K, W = opt.batch, opt.steps, opt.warmup
+
+    torch.manual_seed(0)
+    net = LM_S2GP(ref_args(opt.n_iters, opt.level)).to(dev).eval()
+    net.SatFeatureNet.precision = net.GrdFeatureNet.precision = opt.precision
+    g = torch.Generator().manual_seed(1000 + rank)
+    host_sat = [torch.rand(B, 3, 512, 512, generator=g).pin_memory() for _ in range(2)]
+    host_grd = [torch.rand(B, 3, 256, 1024, generator=g).pin_memory() for _ in range(2)]
+    sat_d, grd_d = host_sat[0].to(dev), host_grd[0].to(dev)
+    n_steps_lm = opt.n_iters * opt.level
+    draws = torch.zeros(n_steps_lm, 2, B)            # reset draws are host RNG work outside the device path
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def forward_resident(i):
+        sat, grd = net.extract(sat_d, grd_d, False)
+        res = net.refine(sat, grd, reset_uv=draws)
+        return hd.gather_poses(res.pose, world)
+
+    # ---------------- warm-up + the timed region (inputs resident in HBM)
+    for i in range(W):
+        forward_resident(i)
+    sync()
+    n0 = L.ha_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
+    # short runs are repeated so that nvidia-smi gets samples under load, but only K steps are timed per repeat
+    secs = time_region(forward_resident, K, sync)
+    launches = (L.ha_launch_count() - n0)
+    t_wall1 = time.time()
+    if world > 1:
+        t = torch.tensor([secs], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    if sampler is not None and (t_wall1 - t_wall0) < 1.5:      # keep the GPU busy long enough to be sampled
+        t_end = time.time() + 1.5
+        while time.time() < t_end:
+            forward_resident(0)
+        torch.cuda.synchronize()
+        t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler is not None else None
+    value = world * B * K / secs
+
+    # ---------------- end to end: pinned host images -> device -> forward -> poses back on the host
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(sat_d), torch.empty_like(grd_d)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def stage(i):
+        s = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            bufs[s][0].copy_(host_sat[s], non_blocking=True)
+            bufs[s][1].copy_(host_grd[s], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    out_host = torch.empty(world * B, 3).pin_memory()
+
+    def e2e_loop(n):
+        for s in range(2):
+            freed[s].record(torch.cuda.current_stream())
+        stage(0)
+        for i in range(n):
+            s = i & 1
+            if i + 1 < n:
+                stage(i + 1)                       # overlap the next batch's H2D with this batch's compute
+            torch.cuda.current_stream().wait_event(ready[s])
+            out = net(bufs[s][0], bufs[s][1], mode="test")          # the call a user of the reference makes
+            freed[s].record(torch.cuda.current_stream())
+            poses = hd.gather_poses(torch.stack([o.detach() for o in out], dim=-1), world)
+            out_host.copy_(poses, non_blocking=False)                # device -> host read of the result, every step
+
+    e2e_loop(2)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    e2e_loop(K)
+    e1.record()
+    sync()
+    e2e_secs = max(e0.elapsed_time(e1) / 1e3, 0.0)
+    if world > 1:
+        t = torch.tensor([e2e_secs], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_secs = float(t.item())
+    e2e = {"value": world * B * K / e2e_secs, "unit": "pairs/s",
+           "h2d_bytes_per_step": int(world * B * (3 * 512 * 512 + 3 * 256 * 1024) * 4), "d2h_bytes_per_step": int(world * B * 3 * 4),
+           "how": "pinned host fp32 images -> cudaMemcpyAsync on a copy stream (double buffered) -> LM_S2GP.forward(mode='test') "
+                  "-> poses copied back to host every step"}
+
+    # ---------------- per-kernel-family timings for the rooflines (same process, CUDA events)
+    pk = peaks()
+    sat_p, grd_p = net.extract(sat_d, grd_d, False)
+    vgg_secs = time_region(lambda i: net.extract(sat_d, grd_d, False), K, sync) / K
+    lm_secs = time_region(lambda i: net.refine(sat_p, grd_p, reset_uv=draws), K, sync) / K
+    vgg_flops = VGG_FLOP_PER_PX[opt.level] * 2 * 262144 * B
+    mma_mult = {"f16x3": 3, "f16": 1, "fp32": 0}[opt.precision]
+    tf = vgg_flops / vgg_secs / 1e12
+    roof = {"kernel": "conv3x3_tc_kernel (VGG16 U-Net, both branches; includes conv0 + L2-norm kernels)",
+            "bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
+            "peak_source": pk["src"] + " bf16 sustained", "traffic": None, "ms_per_step": vgg_secs * 1e3,
+            "tensor_pipe_tflops_issued": tf * mma_mult,
+            "note": "achieved counts ALGORITHMIC conv FLOPs (272.7 GFLOP/pair); f16x3 issues 3 MMAs per product for fp32-grade "
+                    "features, so the tensor pipe executes 3x that"}
+    lm_b = lm_bytes_per_pair(opt.level, opt.n_iters) * B
+    gbs = lm_b / lm_secs / 1e9
+    roof_lm = {"kernel": "lm_step_kernel x %d launches" % n_steps_lm, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
+               "unit": "GB/s", "frac": gbs / pk["hbm"], "peak_source": pk["src"], "traffic": None, "ms_per_step": lm_secs * 1e3,
+               "bytes_per_pair": lm_bytes_per_pair(opt.level, opt.n_iters)}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not opt.no_cpu_baseline:
+        r = cpu_reference_run(steps=2, warmup=1, n_iters=opt.n_iters, level=opt.level)
+        cpu = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"f16x3": "f16x3 split on tcgen05 (fp32-grade) + f32 LM", "f16": "f16 tcgen05 + f32 LM", "fp32": "f32"}[opt.precision],
+            "data": "synthetic", "config": workload_config(opt, B, "B200"),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_lm": roof_lm,
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,7 +22,8 @@ STAT_H, STAT_GRAD, STAT_SAT_NORM, STAT_GRD_NORM, STAT_RES_SQ, STAT_DELTA, STAT_N
 # every symbol include/ha_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ["ha_version", "ha_error_string", "ha_last_cuda_error", "ha_device_check", "ha_nchw_to_nhwc",
            "ha_nhwc_to_nchw", "ha_lm_workspace_bytes", "ha_lm_step", "ha_lm_run", "ha_vgg_packed_weight_bytes",
-           "ha_vgg_pack_weights", "ha_vgg_workspace_bytes", "ha_vgg_forward"]
+           "ha_vgg_pack_weights", "ha_vgg_workspace_bytes", "ha_vgg_forward", "ha_conv3x3_workspace_bytes",
+           "ha_conv3x3_nhwc", "ha_launch_count"]
 
 
 class HaLevel(C.Structure):
@@ -62,6 +63,7 @@ def lib() -> C.CDLL:
     L.ha_error_string.argtypes = [i32]
     L.ha_last_cuda_error.restype = C.c_char_p
     L.ha_device_check.argtypes = [i32]
+    L.ha_launch_count.restype = C.c_ulonglong
     for f in (L.ha_nchw_to_nhwc, L.ha_nhwc_to_nchw):
         f.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     L.ha_lm_workspace_bytes.restype = sz
@@ -75,6 +77,9 @@ def lib() -> C.CDLL:
     L.ha_vgg_workspace_bytes.restype = sz
     L.ha_vgg_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.ha_vgg_forward.argtypes = [vp, vp, i32, i32, i32, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, sz, vp]
+    L.ha_conv3x3_workspace_bytes.restype = sz
+    L.ha_conv3x3_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.ha_conv3x3_nhwc.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
     for name in EXPORTS:
         f = getattr(L, name)
         if f.restype is C.c_int and name not in ("ha_version",):

@@ -6,6 +6,9 @@
 namespace ha {
 
 static thread_local char g_cuda_err[512] = "";
+static unsigned long long g_launches = 0;   // statistics only
+
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 void set_cuda_error(cudaError_t e, const char* what) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
@@ -39,12 +42,14 @@ static int transpose(const float* src, float* dst, int B, int C, int H, int W, v
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, B), block(32, 8);
   if (grid.y > 65535 || grid.z > 65535) return HA_EINVAL;
   transpose_kernel<TO_NHWC><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, dst, C, HW);
+  count_launches(1);
   return check_launch("transpose_kernel");
 }
 
 }  // namespace ha
 
 extern "C" int ha_version(void) { return 1; }
+extern "C" unsigned long long ha_launch_count(void) { return __atomic_load_n(&ha::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" const char* ha_error_string(int code) {
   switch (code) {

@@ -9,6 +9,7 @@
 namespace ha {
 
 void set_cuda_error(cudaError_t e, const char* what);
+void count_launches(int n);   // statistics only: kernels launched by this library (ha_launch_count)
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_cuda_error(e, what); return HA_ECUDA; }

@@ -395,6 +395,7 @@ static int launch_by_channels(int C, dim3 grid, cudaStream_t st, const LmStepArg
     case 16: lm_step_kernel<GEOM, 16><<<grid, kLmThreads, 0, st>>>(a); break;
     default: return HA_EINVAL;
   }
+  count_launches(1);
   return check_launch("lm_step_kernel");
 }
 
@@ -475,6 +476,7 @@ extern "C" int ha_lm_step(const HaLmParams* p, int level, const HaLevel* sat, co
                                                  (size_t)B * ha::kLmMaxCtasPerSample * ha::kLmAcc * sizeof(double));
   if (ws_bytes < ha::lm_ws_bytes(B)) return HA_ENOSPACE;
   ha::zero_u32_kernel<<<(B + 255) / 256, 256, 0, st>>>(ticket, B);
+  ha::count_launches(1);
   return ha::lm_step_impl(p, level, sat, grd, grd_conf, ground_table, extrinsics, pose, reset_uv, stats, nullptr, 0,
                           status, ws, ws_bytes, B, st);
 }
@@ -491,6 +493,7 @@ extern "C" int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel*
   uint32_t* ticket = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) +
                                                  (size_t)B * ha::kLmMaxCtasPerSample * ha::kLmAcc * sizeof(double));
   ha::zero_u32_kernel<<<(B + 255) / 256, 256, 0, st>>>(ticket, B);
+  ha::count_launches(1);
   int k = 0;
   const int outer = p->level_first ? L : N, inner = p->level_first ? N : L;
   for (int o = 0; o < outer; ++o) {

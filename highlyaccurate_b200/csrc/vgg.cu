@@ -111,11 +111,12 @@ __global__ void __launch_bounds__(256) conv3x3_simt_kernel(const SimtConvArgs a)
   }
 }
 
-static int conv_simt(const float* in, int in_pitch, int in_coff, int cin, const float* w, const float* bias, float* out,
+int conv_simt(const float* in, int in_pitch, int in_coff, int cin, const float* w, const float* bias, float* out,
                      int out_pitch, int out_coff, int cout, int B, int H, int W, int relu_out, cudaStream_t st) {
   SimtConvArgs a{in, in_pitch, in_coff, cin, w, bias, out, out_pitch, out_coff, cout, B, H, W, relu_out};
   dim3 grid(((W + kSimtTW - 1) / kSimtTW) * ((H + kSimtTH - 1) / kSimtTH), (cout + kSimtTN - 1) / kSimtTN, B);
   conv3x3_simt_kernel<<<grid, 256, 0, st>>>(a);
+  count_launches(1);
   return check_launch("conv3x3_simt_kernel");
 }
 
@@ -224,21 +225,6 @@ static inline int ew_blocks(size_t total) {
   return (int)(b < (size_t)kNumSMs * 16 ? b : (size_t)kNumSMs * 16);
 }
 
-// ---------------------------------------------------------------------------- workspace arena
-struct Arena {
-  char* base; size_t off; size_t cap; bool dry;
-  void* take(size_t bytes) {
-    off = align_up(off, 256);
-    void* p = dry ? nullptr : base + off;
-    off += bytes;
-    return p;
-  }
-};
-
-int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, int B, int H, int W, int n_levels,
-                   int precision, float* const* out_feat, Arena& ar, cudaStream_t st);
-size_t vgg_tc_workspace(int B, int H, int W, int n_levels, int precision);
-
 // fp32 CUDA-core schedule.  Buffers follow the names of VGG.py:121-158.
 static int vgg_forward_simt(const char* packed, const PackedLayout& L, const float* img, int B, int H, int W, int n_levels,
                             float* const* out_feat, Arena& ar, cudaStream_t st) {
@@ -265,22 +251,22 @@ static int vgg_forward_simt(const char* packed, const PackedLayout& L, const flo
   HA_TRY(ha_nchw_to_nhwc(img, nhwc_img, B, 3, H, W, st));
   HA_TRY(conv_simt(nhwc_img, 3, 0, 3, Wf(L_CONV0), Bs(L_CONV0), a1, 64, 0, 64, B, H, W, 1, st));             // x1
   HA_TRY(conv_simt(a1, 64, 0, 64, Wf(L_CONV2), Bs(L_CONV2), cat3, 128, 64, 64, B, H, W, 1, st));             // relu(x2)
-  pool2x2_kernel<<<ew_blocks(px2 * 16), 256, 0, st>>>(cat3, 128, 64, cat2, 192, 128, 64, H, W, px2 * 16);     // x4
+  pool2x2_kernel<<<ew_blocks(px2 * 16), 256, 0, st>>>(cat3, 128, 64, cat2, 192, 128, 64, H, W, px2 * 16); count_launches(1);     // x4
   HA_TRY(conv_simt(cat2, 192, 128, 64, Wf(L_CONV5), Bs(L_CONV5), a5, 128, 0, 128, B, H / 2, W / 2, 1, st));  // x6
   HA_TRY(conv_simt(a5, 128, 0, 128, Wf(L_CONV7), Bs(L_CONV7), x7, 128, 0, 128, B, H / 2, W / 2, 1, st));     // relu(x7)
-  pool2x2_kernel<<<ew_blocks(px4 * 32), 256, 0, st>>>(x7, 128, 0, cat1, 384, 256, 128, H / 2, W / 2, px4 * 32);  // x9
+  pool2x2_kernel<<<ew_blocks(px4 * 32), 256, 0, st>>>(x7, 128, 0, cat1, 384, 256, 128, H / 2, W / 2, px4 * 32); count_launches(1);  // x9
   HA_TRY(conv_simt(cat1, 384, 256, 128, Wf(L_CONV10), Bs(L_CONV10), a10, 256, 0, 256, B, H / 4, W / 4, 1, st));
   HA_TRY(conv_simt(a10, 256, 0, 256, Wf(L_CONV12), Bs(L_CONV12), a12, 256, 0, 256, B, H / 4, W / 4, 1, st));
   HA_TRY(conv_simt(a12, 256, 0, 256, Wf(L_CONV14), Bs(L_CONV14), x14, 256, 0, 256, B, H / 4, W / 4, 0, st)); // x14 (no relu)
-  pool2x2_kernel<<<ew_blocks(px4 / 4 * 64), 256, 0, st>>>(x14, 256, 0, out_feat[0], 256, 0, 256, H / 4, W / 4, px4 / 4 * 64);  // x15
-  relu_up2x_kernel<<<ew_blocks(px4 * 64), 256, 0, st>>>(out_feat[0], cat1, 384, 0, 256, H / 8, W / 8, px4 * 64);
+  pool2x2_kernel<<<ew_blocks(px4 / 4 * 64), 256, 0, st>>>(x14, 256, 0, out_feat[0], 256, 0, 256, H / 4, W / 4, px4 / 4 * 64); count_launches(1);  // x15
+  relu_up2x_kernel<<<ew_blocks(px4 * 64), 256, 0, st>>>(out_feat[0], cat1, 384, 0, 256, H / 8, W / 8, px4 * 64); count_launches(1);
   HA_TRY(conv_simt(cat1, 384, 0, 384, Wf(L_DEC1A), nullptr, d1, 128, 0, 128, B, H / 4, W / 4, 1, st));
   HA_TRY(conv_simt(d1, 128, 0, 128, Wf(L_DEC1B), nullptr, out_feat[1], 128, 0, 128, B, H / 4, W / 4, 0, st));   // x18
-  relu_up2x_kernel<<<ew_blocks(px2 * 32), 256, 0, st>>>(out_feat[1], cat2, 192, 0, 128, H / 4, W / 4, px2 * 32);
+  relu_up2x_kernel<<<ew_blocks(px2 * 32), 256, 0, st>>>(out_feat[1], cat2, 192, 0, 128, H / 4, W / 4, px2 * 32); count_launches(1);
   HA_TRY(conv_simt(cat2, 192, 0, 192, Wf(L_DEC2A), nullptr, d2, 64, 0, 64, B, H / 2, W / 2, 1, st));
   HA_TRY(conv_simt(d2, 64, 0, 64, Wf(L_DEC2B), nullptr, out_feat[2], 64, 0, 64, B, H / 2, W / 2, 0, st));        // x21
   if (n_levels == 4) {
-    relu_up2x_kernel<<<ew_blocks(px1 * 16), 256, 0, st>>>(out_feat[2], cat3, 128, 0, 64, H / 2, W / 2, px1 * 16);
+    relu_up2x_kernel<<<ew_blocks(px1 * 16), 256, 0, st>>>(out_feat[2], cat3, 128, 0, 64, H / 2, W / 2, px1 * 16); count_launches(1);
     HA_TRY(conv_simt(cat3, 128, 0, 128, Wf(L_DEC3A), nullptr, d3, 32, 0, 32, B, H, W, 1, st));
     HA_TRY(conv_simt(d3, 32, 0, 32, Wf(L_DEC3B), nullptr, out_feat[3], 16, 0, 16, B, H, W, 0, st));              // x24
   }
@@ -302,11 +288,13 @@ static int vgg_run(const char* packed, const float* img, int B, int H, int W, in
     if (out_scale && out_scale[l]) {
       sumsq_partial_kernel<<<dim3(kNormChunks, B), 256, 0, st>>>(out_feat[l], (size_t)h * w * C, norm_part);
       norm_scale_kernel<<<(B + 127) / 128, 128, 0, st>>>(norm_part, kNormChunks, out_scale[l], B);
+      count_launches(2);
     }
     if (out_conf && out_conf[l]) {
       const size_t n_px = (size_t)B * h * w;
       conf_head_kernel<<<(unsigned)((n_px * 32 + 255) / 256), 256, 0, st>>>(
           out_feat[l], reinterpret_cast<const float*>(packed + L.c[L_CONF0 + l].f32), out_conf[l], C, h, w, n_px);
+      count_launches(1);
     }
   }
   return check_launch("vgg_run");
@@ -331,6 +319,7 @@ extern "C" int ha_vgg_pack_weights(const HaVggStateDict* sd, void* packed, size_
                                              reinterpret_cast<__half*>(base + p.hi), reinterpret_cast<__half*>(base + p.lo),
                                              reinterpret_cast<float*>(base + p.bias));
   }
+  ha::count_launches(HA_VGG_N_CONV);
   return ha::check_launch("pack_conv_kernel");
 }
 

@@ -43,6 +43,35 @@ inline PackedLayout vgg_packed_layout() {
   return L;
 }
 
+// sequential 256-byte-aligned carve-up of the caller's workspace (dry = size query)
+struct Arena {
+  char* base; size_t off; size_t cap; bool dry;
+  void* take(size_t bytes) {
+    off = align_up(off, 256);
+    void* p = dry ? nullptr : base + off;
+    off += bytes;
+    return p;
+  }
+};
+
+struct TcOut {   // where the tensor-core conv epilogue writes (any subset)
+  __half* act_full = nullptr; int af_pitch = 0, af_coff = 0;   // relu(v), same resolution
+  __half* act_pool = nullptr; int ap_pitch = 0, ap_coff = 0;   // relu(maxpool2x2(v))
+  __half* act_up = nullptr; int au_pitch = 0, au_coff = 0;     // relu(nearest x2 upsample of feat)
+  float* feat = nullptr; int feat_pooled = 0;                  // raw fp32 v or maxpool2x2(v)
+};
+
+__global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ bias, int cin, int cout,
+                                 int cin_pad, int cout_pad, float* __restrict__ f32, __half* __restrict__ hi,
+                                 __half* __restrict__ lo, float* __restrict__ bias_out);
+__global__ void split_act_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, size_t n_px);
+int conv_simt(const float* in, int in_pitch, int in_coff, int cin, const float* w, const float* bias, float* out,
+              int out_pitch, int out_coff, int cout, int B, int H, int W, int relu_out, cudaStream_t st);
+int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* packed, const PackedConv& pc, int cout,
+            bool has_bias, const TcOut& o, int B, int H, int W, bool split, cudaStream_t st);
+int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, int B, int H, int W, int n_levels,
+                   int precision, float* const* out_feat, Arena& ar, cudaStream_t st);
+
 constexpr float kLoScale = 2048.f;          // 2^11
 constexpr float kLoInvScale = 1.f / 2048.f;
 

@@ -1,8 +1,587 @@
-// placeholder until the tcgen05 back end lands
+// tcgen05 / TMA implicit-GEMM 3x3 convolution for the VGG16 U-Net (VGG.py:121-158), sm_100a.
+//
+// GEMM view per layer: M = B*H*W output pixels (tile = 8 rows x 16 cols = 128 pixels = UMMA M),
+// N = Cout (tile BLOCK_N <= 128), K = 9 taps x Cin (k-block = one tap x 64 channels = one
+// 128-byte swizzle atom).  Activations are NHWC fp16 with two planes per pixel,
+// [B][H][W][2][C]: plane 0 = hi = fp16(x), plane 1 = lo = fp16((x - hi) * 2^11).  A shifted
+// (tap) view of the pixel tile is ONE TMA box of the 5-D tensor (C, plane, W, H, B) at signed
+// coordinates — TMA zero-fills the padding ring, so there is no im2col buffer and no halo code.
+// Weights are [9][Cout][Cin] fp16 (K-major B operand), also hi/lo.
+//
+// Precision (HA_CONV_F16X3): x*w ~= hi_x*hi_w + 2^-11 (hi_x*lo_w + lo_x*hi_w): three
+// kind::f16 MMAs per k-step into two fp32 TMEM accumulators, error ~2^-22 per product, i.e.
+// fp32-grade features from the fp16 tensor pipe.  HA_CONV_F16 issues only the first MMA.
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
+// MMA issuer (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM ->
+// registers -> bias / ReLU / 2x2 max-pool by warp shuffles / x2 nearest upsample -> global).
+// smem ring of STAGES k-blocks (full/empty mbarriers), two accumulator stages in TMEM
+// (tmem_full/tmem_empty mbarriers) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
 #include "vgg_common.cuh"
+
 namespace ha {
-struct Arena;
-int vgg_forward_tc(const char*, const PackedLayout&, const float*, int, int, int, int, int, float* const*, Arena&, cudaStream_t) {
-  return HA_EUNSUPPORTED;
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc_512(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(addr) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16, issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address  [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B  [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version 1 (sm_100)      [46,48)
+  d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B           [61,64)
+  return d;
+}
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, A and B K-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------ the kernel
+constexpr int kTileW = 16, kTileH = 8, kBlockM = kTileW * kTileH;   // 128 pixels = UMMA M
+constexpr int kBlockK = 64;                                           // fp16 elements = 128 B
+constexpr int kTcThreads = 256;
+constexpr int kABytes = kBlockM * kBlockK * 2;                        // 16 KB
+
+struct TcConvArgs {
+  const float* bias;                          // [cout] or null
+  __half* act_full; int af_pitch, af_coff;    // relu(v)       -> [B][H][W][2][pitch] + coff
+  __half* act_pool; int ap_pitch, ap_coff;    // relu(pool(v)) -> [B][H/2][W/2][2][pitch] + coff
+  __half* act_up; int au_pitch, au_coff;      // relu(x2 nearest upsample of feat) -> [B][2h][2w][2][pitch] + coff
+  float* feat; int feat_pooled;               // v or pool(v), raw fp32 -> [B][h][w][cout]
+  int B, H, W, cout;
+  int n_kchunks;                              // ceil(cin / 64)
+  int tiles_x, tiles_y, tiles_n, n_tiles;
+};
+
+template <int BLOCK_N, bool SPLIT>
+struct TcCfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = (kABytes + kBBytes) * (SPLIT ? 2 : 1);
+  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void store_split(__half* dst_hi, int pitch, const float (&v)[32], int n) {
+  // v[0..n) -> fp16 hi at dst_hi[0..n), fp16 lo*2^11 at dst_hi[pitch + 0..n); n in {16, 32}
+  for (int j = 0; j < n; j += 8) {
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const __half h = __float2half_rn(v[j + e]);
+      hi[e] = h;
+      lo[e] = __float2half_rn((v[j + e] - __half2float(h)) * kLoScale);
+    }
+    *reinterpret_cast<uint4*>(dst_hi + j) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst_hi + pitch + j) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+template <int BLOCK_N, bool SPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bh,
+                  const __grid_constant__ CUtensorMap tmap_bl, const TcConvArgs a) {
+  using Cfg = TcCfg<BLOCK_N, SPLIT>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int CH = BLOCK_N >= 32 ? 32 : 16;            // accumulator columns per TMEM load
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* full = bars;                    // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + STAGES;          // [STAGES]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * STAGES;  // [2]       MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_bh);
+    if (SPLIT) tma_prefetch_desc(&tmap_bl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_512(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_kb = 9 * a.n_kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int n_idx = tile % a.tiles_n; int pt = tile / a.tiles_n;
+        const int x0 = (pt % a.tiles_x) * kTileW; pt /= a.tiles_x;
+        const int y0 = (pt % a.tiles_y) * kTileH; const int b = pt / a.tiles_y;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          const int tap = kb / a.n_kchunks, kc = kb % a.n_kchunks;
+          const int ky = tap / 3, kx = tap % 3;
+          mbar_wait(empty + stage, phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          mbar_expect_tx(full + stage, Cfg::kStageBytes);
+          tma_load_5d(st, &tmap_a, full + stage, kc * kBlockK, 0, x0 + kx - 1, y0 + ky - 1, b);
+          tma_load_3d(st + kABytes, &tmap_bh, full + stage, kc * kBlockK, n_idx * BLOCK_N, tap);
+          if (SPLIT) {
+            tma_load_5d(st + kABytes + Cfg::kBBytes, &tmap_a, full + stage, kc * kBlockK, 1, x0 + kx - 1, y0 + ky - 1, b);
+            tma_load_3d(st + 2 * kABytes + Cfg::kBBytes, &tmap_bl, full + stage, kc * kBlockK, n_idx * BLOCK_N, tap);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_f16(BLOCK_N);
+    int stage = 0; uint32_t phase = 0; int t = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++t) {
+      const int as = t & 1; const uint32_t aphase = (t >> 1) & 1;
+      mbar_wait(tmem_empty + as, aphase ^ 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + as * 256, acc1 = acc0 + 128;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(full + stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb_hi = sa_hi + kABytes;
+          const uint32_t sa_lo = sb_hi + Cfg::kBBytes;
+          const uint32_t sb_lo = sa_lo + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da_hi = umma_desc_sw128(sa_hi + k * 32), db_hi = umma_desc_sw128(sb_hi + k * 32);
+            umma_f16(acc0, da_hi, db_hi, idesc, (kb | k) != 0);
+            if (SPLIT) {
+              const uint64_t da_lo = umma_desc_sw128(sa_lo + k * 32), db_lo = umma_desc_sw128(sb_lo + k * 32);
+              umma_f16(acc1, da_hi, db_lo, idesc, (kb | k) != 0);
+              umma_f16(acc1, da_lo, db_hi, idesc, 1);
+            }
+          }
+          umma_commit(empty + stage);                       // smem slot reusable once these MMAs retire
+          if (kb == total_kb - 1) umma_commit(tmem_full + as);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int h_loc = q * 2 + (lane >> 4), w_loc = lane & 15;
+    const bool pool_owner = ((lane & 1) == 0) && ((lane & 16) == 0);
+    const bool any_pool = a.act_pool != nullptr || a.feat_pooled;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++t) {
+      const int as = t & 1; const uint32_t aphase = (t >> 1) & 1;
+      const int n_idx = tile % a.tiles_n; int pt = tile / a.tiles_n;
+      const int x0 = (pt % a.tiles_x) * kTileW; pt /= a.tiles_x;
+      const int y0 = (pt % a.tiles_y) * kTileH; const int b = pt / a.tiles_y;
+      const int y = y0 + h_loc, x = x0 + w_loc;
+      mbar_wait(tmem_full + as, aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+        uint32_t r0[32], r1[32];
+        if (CH == 32) { tmem_ld_x32(taddr + c0, r0); if (SPLIT) tmem_ld_x32(taddr + 128 + c0, r1); }
+        else { tmem_ld_x16(taddr + c0, r0); if (SPLIT) tmem_ld_x16(taddr + 128 + c0, r1); }
+        tmem_ld_wait();
+        const int n0 = n_idx * BLOCK_N + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          float acc = __uint_as_float(r0[j]);
+          if (SPLIT) acc += __uint_as_float(r1[j]) * kLoInvScale;
+          if (a.bias) acc += __ldg(a.bias + n0 + j);
+          v[j] = acc;
+        }
+        if (a.feat && !a.feat_pooled) {
+          float* dst = a.feat + (((size_t)b * a.H + y) * a.W + x) * a.cout + n0;
+#pragma unroll
+          for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        float pv[32];
+        if (any_pool) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+            pv[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+          }
+          if (a.feat && a.feat_pooled && pool_owner) {
+            float* dst = a.feat + (((size_t)b * (a.H / 2) + y / 2) * (a.W / 2) + x / 2) * a.cout + n0;
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(pv[j], pv[j + 1], pv[j + 2], pv[j + 3]);
+          }
+        }
+        // everything below stores relu'd fp16 hi/lo activations
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { v[j] = fmaxf(v[j], 0.f); if (any_pool) pv[j] = fmaxf(pv[j], 0.f); }
+        if (a.act_full)
+          store_split(a.act_full + (((size_t)b * a.H + y) * a.W + x) * 2 * a.af_pitch + a.af_coff + n0, a.af_pitch, v, CH);
+        if (a.act_pool && pool_owner)
+          store_split(a.act_pool + (((size_t)b * (a.H / 2) + y / 2) * (a.W / 2) + x / 2) * 2 * a.ap_pitch + a.ap_coff + n0,
+                      a.ap_pitch, pv, CH);
+        if (a.act_up) {
+          if (a.feat_pooled) {
+            // pooled then upsampled x2: lands on this very pixel of the conv-resolution buffer
+            store_split(a.act_up + (((size_t)b * a.H + y) * a.W + x) * 2 * a.au_pitch + a.au_coff + n0, a.au_pitch, pv, CH);
+          } else {
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx)
+                store_split(a.act_up + (((size_t)b * 2 * a.H + 2 * y + dy) * (2 * a.W) + 2 * x + dx) * 2 * a.au_pitch +
+                                a.au_coff + n0, a.au_pitch, v, CH);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_512(tmem_base); }
+}
+
+// ------------------------------------------------------------------------------ conv0 + helpers
+// conv0 (3 -> 64, K = 27) is 0.7 % of the FLOPs: CUDA-core fp32 straight from the NCHW image,
+// fused bias + ReLU, writes the hi/lo activation planes conv2 consumes.  One thread per pixel.
+__global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[9][3][64]*/,
+                                                    const float* __restrict__ bias, __half* __restrict__ out, int H, int W) {
+  __shared__ __align__(16) float w_s[27 * 64];
+  __shared__ float b_s[64];
+  __shared__ float in_s[3][18][18];
+  const int b = blockIdx.z, tx0 = blockIdx.x * 16, ty0 = blockIdx.y * 16;
+  for (int i = threadIdx.x; i < 27 * 64; i += 256) w_s[i] = w[i];
+  if (threadIdx.x < 64) b_s[threadIdx.x] = bias[threadIdx.x];
+  for (int i = threadIdx.x; i < 3 * 18 * 18; i += 256) {
+    const int xx = i % 18, yy = (i / 18) % 18, c = i / 324;
+    const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
+    in_s[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(((size_t)b * 3 + c) * H + gy) * W + gx] : 0.f;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+  const int gx = tx0 + lx, gy = ty0 + ly;
+  if (gx >= W || gy >= H) return;
+  float patch[27];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) patch[tap * 3 + c] = in_s[c][ly + tap / 3][lx + tap % 3];
+  __half* dst = out + (((size_t)b * H + gy) * W + gx) * 2 * 64;
+  for (int n0 = 0; n0 < 64; n0 += 32) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = b_s[n0 + j];
+#pragma unroll
+    for (int k = 0; k < 27; ++k)
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(&w_s[k * 64 + n0 + j]);
+        v[j] += patch[k] * wv.x; v[j + 1] += patch[k] * wv.y; v[j + 2] += patch[k] * wv.z; v[j + 3] += patch[k] * wv.w;
+      }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    store_split(dst + n0, 64, v, 32);
+  }
+}
+
+// fp32 NHWC -> hi/lo activation planes (used by ha_conv3x3_nhwc, the single-layer test entry)
+__global__ void split_act_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, size_t n_px) {
+  const size_t total = n_px * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = i / C; const int c = (int)(i % C);
+    const float v = in[i];
+    const __half h = __float2half_rn(v);
+    out[p * 2 * C + c] = h;
+    out[p * 2 * C + C + c] = __float2half_rn((v - __half2float(h)) * kLoScale);
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// activation tensor [B][H][W][2][pitch] (fp16), channel slice [coff, coff + cin): dims (C, plane, W, H, B)
+static int make_act_map(CUtensorMap* m, const __half* base, int pitch, int coff, int cin, int B, int H, int W) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return HA_ECUDA; }
+  cuuint64_t dims[5] = {(cuuint64_t)cin, 2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 4, (cuuint64_t)W * pitch * 4, (cuuint64_t)H * W * pitch * 4};
+  cuuint32_t box[5] = {kBlockK, 1, kTileW, kTileH, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base + coff), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(activations)"); return HA_ECUDA; }
+  return HA_OK;
+}
+
+// weights [9][cout_pad][cin_pad] fp16: dims (Cin, Cout, tap)
+static int make_weight_map(CUtensorMap* m, const __half* base, int cin_pad, int cout_pad, int block_n) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return HA_ECUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, 9};
+  cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * cout_pad * 2};
+  cuuint32_t box[3] = {kBlockK, (cuuint32_t)block_n, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(weights)"); return HA_ECUDA; }
+  return HA_OK;
+}
+
+template <int BLOCK_N, bool SPLIT>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const TcConvArgs& a, cudaStream_t st) {
+  using Cfg = TcCfg<BLOCK_N, SPLIT>;
+  auto kern = conv3x3_tc_kernel<BLOCK_N, SPLIT>;
+  HA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  const int grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
+  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(ta, tbh, tbl, a);
+  count_launches(1);
+  return check_launch("conv3x3_tc_kernel");
+}
+
+// One 3x3 conv layer on the tensor cores.  in: activation planes (pitch/coff/cin), weights from the packed buffer.
+int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* packed, const PackedConv& pc, int cout,
+            bool has_bias, const TcOut& o, int B, int H, int W, bool split, cudaStream_t st) {
+  if ((W % kTileW) || (H % kTileH) || (cin % 8) || (in_coff % 8) || (in_pitch % 8)) return HA_EINVAL;
+  const int block_n = cout >= 128 ? 128 : cout;
+  if (block_n != 128 && block_n != 64 && block_n != 32 && block_n != 16) return HA_EINVAL;
+  CUtensorMap ta, tbh, tbl;
+  int rc = make_act_map(&ta, in, in_pitch, in_coff, cin, B, H, W);
+  if (rc != HA_OK) return rc;
+  rc = make_weight_map(&tbh, reinterpret_cast<const __half*>(packed + pc.hi), pc.cin_pad, pc.cout_pad, block_n);
+  if (rc != HA_OK) return rc;
+  rc = make_weight_map(&tbl, reinterpret_cast<const __half*>(packed + pc.lo), pc.cin_pad, pc.cout_pad, block_n);
+  if (rc != HA_OK) return rc;
+  TcConvArgs a;
+  a.bias = has_bias ? reinterpret_cast<const float*>(packed + pc.bias) : nullptr;
+  a.act_full = o.act_full; a.af_pitch = o.af_pitch; a.af_coff = o.af_coff;
+  a.act_pool = o.act_pool; a.ap_pitch = o.ap_pitch; a.ap_coff = o.ap_coff;
+  a.act_up = o.act_up; a.au_pitch = o.au_pitch; a.au_coff = o.au_coff;
+  a.feat = o.feat; a.feat_pooled = o.feat_pooled;
+  a.B = B; a.H = H; a.W = W; a.cout = cout;
+  a.n_kchunks = (cin + kBlockK - 1) / kBlockK;
+  a.tiles_x = W / kTileW; a.tiles_y = H / kTileH; a.tiles_n = cout / block_n;
+  a.n_tiles = a.tiles_x * a.tiles_y * a.tiles_n * B;
+#define HA_TC_CASE(N)                                                              \
+  case N: return split ? launch_tc<N, true>(ta, tbh, tbl, a, st) : launch_tc<N, false>(ta, tbh, tbl, a, st);
+  switch (block_n) { HA_TC_CASE(128) HA_TC_CASE(64) HA_TC_CASE(32) HA_TC_CASE(16) }
+#undef HA_TC_CASE
+  return HA_EINVAL;
+}
+
+// Tensor-core schedule of the U-Net; buffer names follow vgg.cu / VGG.py:121-158.
+int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, int B, int H, int W, int n_levels,
+                   int precision, float* const* out_feat, Arena& ar, cudaStream_t st) {
+  const bool split = precision == HA_CONV_F16X3;
+  const size_t px1 = (size_t)B * H * W, px2 = px1 / 4, px4 = px1 / 16;
+  auto act = [&](size_t px, int c) { return (__half*)ar.take(px * 2 * c * sizeof(__half)); };
+  __half* a1 = act(px1, 64);
+  __half* cat3 = n_levels == 4 ? act(px1, 128) : nullptr;
+  __half* cat2 = act(px2, 192);
+  __half* a5 = act(px2, 128);
+  __half* cat1 = act(px4, 384);
+  __half* a10 = act(px4, 256);
+  __half* a12 = act(px4, 256);
+  __half* d1 = act(px4, 128);
+  __half* d2 = act(px2, 64);
+  __half* d3 = n_levels == 4 ? act(px1, 32) : nullptr;
+  if (ar.dry) return HA_OK;
+  if (ar.off > ar.cap) return HA_ENOSPACE;
+  if ((W % (4 * kTileW)) || (H % (4 * kTileH))) return HA_EINVAL;   // tiles must fit down to the 1/4 scale
+  int rc;
+#define HA_TRY(x) do { rc = (x); if (rc != HA_OK) return rc; } while (0)
+  conv0_kernel<<<dim3((W + 15) / 16, (H + 15) / 16, B), 256, 0, st>>>(
+      img, reinterpret_cast<const float*>(packed + L.c[L_CONV0].f32), reinterpret_cast<const float*>(packed + L.c[L_CONV0].bias),
+      a1, H, W);
+  count_launches(1);
+  HA_TRY(check_launch("conv0_kernel"));
+  auto conv = [&](int li, const __half* in, int pitch, int coff, const TcOut& o, int h, int w) {
+    return conv_tc(in, pitch, coff, kVggConvs[li].cin, packed, L.c[li], kVggConvs[li].cout, kVggConvs[li].has_bias != 0, o,
+                   B, h, w, split, st);
+  };
+  TcOut o;
+  o = TcOut(); o.act_pool = cat2; o.ap_pitch = 192; o.ap_coff = 128;                    // x4 = relu(pool(x2))
+  if (n_levels == 4) { o.act_full = cat3; o.af_pitch = 128; o.af_coff = 64; }           // relu(x2) skip for dec3
+  HA_TRY(conv(L_CONV2, a1, 64, 0, o, H, W));
+  o = TcOut(); o.act_full = a5; o.af_pitch = 128;
+  HA_TRY(conv(L_CONV5, cat2, 192, 128, o, H / 2, W / 2));
+  o = TcOut(); o.act_pool = cat1; o.ap_pitch = 384; o.ap_coff = 256;                    // x9 = relu(pool(x7))
+  HA_TRY(conv(L_CONV7, a5, 128, 0, o, H / 2, W / 2));
+  o = TcOut(); o.act_full = a10; o.af_pitch = 256;
+  HA_TRY(conv(L_CONV10, cat1, 384, 256, o, H / 4, W / 4));
+  o = TcOut(); o.act_full = a12; o.af_pitch = 256;
+  HA_TRY(conv(L_CONV12, a10, 256, 0, o, H / 4, W / 4));
+  o = TcOut(); o.feat = out_feat[0]; o.feat_pooled = 1; o.act_up = cat1; o.au_pitch = 384; o.au_coff = 0;   // x15
+  HA_TRY(conv(L_CONV14, a12, 256, 0, o, H / 4, W / 4));
+  o = TcOut(); o.act_full = d1; o.af_pitch = 128;
+  HA_TRY(conv(L_DEC1A, cat1, 384, 0, o, H / 4, W / 4));
+  o = TcOut(); o.feat = out_feat[1]; o.act_up = cat2; o.au_pitch = 192; o.au_coff = 0;                      // x18
+  HA_TRY(conv(L_DEC1B, d1, 128, 0, o, H / 4, W / 4));
+  o = TcOut(); o.act_full = d2; o.af_pitch = 64;
+  HA_TRY(conv(L_DEC2A, cat2, 192, 0, o, H / 2, W / 2));
+  o = TcOut(); o.feat = out_feat[2];                                                                        // x21
+  if (n_levels == 4) { o.act_up = cat3; o.au_pitch = 128; o.au_coff = 0; }
+  HA_TRY(conv(L_DEC2B, d2, 64, 0, o, H / 2, W / 2));
+  if (n_levels == 4) {
+    o = TcOut(); o.act_full = d3; o.af_pitch = 32;
+    HA_TRY(conv(L_DEC3A, cat3, 128, 0, o, H, W));
+    o = TcOut(); o.feat = out_feat[3];                                                                      // x24
+    HA_TRY(conv(L_DEC3B, d3, 32, 0, o, H, W));
+  }
+#undef HA_TRY
+  return HA_OK;
+}
+
 }  // namespace ha
+
+// ------------------------------------------------------------------------------ single-layer entry
+static ha::PackedConv single_layout(int cin, int cout, size_t* total) {
+  ha::PackedConv p;
+  p.cin_pad = (int)ha::align_up(cin, 64);
+  p.cout_pad = (int)ha::align_up(cout, 16);
+  size_t off = 0;
+  p.f32 = off; off = ha::align_up(off + (size_t)9 * cin * cout * 4, 256);
+  p.hi = off; off = ha::align_up(off + (size_t)9 * p.cout_pad * p.cin_pad * 2, 256);
+  p.lo = off; off = ha::align_up(off + (size_t)9 * p.cout_pad * p.cin_pad * 2, 256);
+  p.bias = off; off = ha::align_up(off + (size_t)cout * 4, 256);
+  *total = off;
+  return p;
+}
+
+extern "C" size_t ha_conv3x3_workspace_bytes(int cin, int cout, int B, int H, int W) {
+  if (cin <= 0 || cout <= 0 || B <= 0 || H <= 0 || W <= 0) return 0;
+  size_t wbytes;
+  single_layout(cin, cout, &wbytes);
+  return wbytes + ha::align_up((size_t)B * H * W * 2 * cin * 2, 256) + 256;
+}
+
+extern "C" int ha_conv3x3_nhwc(const float* in_nhwc, int cin, const float* w_oihw, const float* bias, float* out_nhwc, int cout,
+                               int B, int H, int W, int precision, void* ws, size_t ws_bytes, void* stream) {
+  if (!in_nhwc || !w_oihw || !out_nhwc || !ws) return HA_EINVAL;
+  if (ws_bytes < ha_conv3x3_workspace_bytes(cin, cout, B, H, W)) return HA_ENOSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  size_t wbytes;
+  const ha::PackedConv pc = single_layout(cin, cout, &wbytes);
+  char* base = reinterpret_cast<char*>(ws);
+  ha::pack_conv_kernel<<<64, 256, 0, st>>>(w_oihw, bias, cin, cout, pc.cin_pad, pc.cout_pad, reinterpret_cast<float*>(base + pc.f32),
+                                           reinterpret_cast<__half*>(base + pc.hi), reinterpret_cast<__half*>(base + pc.lo),
+                                           reinterpret_cast<float*>(base + pc.bias));
+  ha::count_launches(1);
+  if (precision == HA_CONV_FP32_SIMT)
+    return ha::conv_simt(in_nhwc, cin, 0, cin, reinterpret_cast<const float*>(base + pc.f32),
+                         bias ? reinterpret_cast<const float*>(base + pc.bias) : nullptr, out_nhwc, cout, 0, cout, B, H, W, 0, st);
+  if (precision != HA_CONV_F16X3 && precision != HA_CONV_F16) return HA_EINVAL;
+  __half* act = reinterpret_cast<__half*>(base + wbytes);
+  const size_t n_px = (size_t)B * H * W;
+  ha::split_act_kernel<<<ha::kNumSMs * 8, 256, 0, st>>>(in_nhwc, act, cin, n_px);
+  ha::count_launches(1);
+  ha::TcOut o;
+  o.feat = out_nhwc;
+  return ha::conv_tc(act, cin, 0, cin, base, pc, cout, bias != nullptr, o, B, H, W, precision == HA_CONV_F16X3, st);
+}

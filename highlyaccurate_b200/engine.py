@@ -406,3 +406,20 @@ class VggRunner:
             check(L.ha_vgg_forward(self.packed.data_ptr(), img[b0:].data_ptr(), nb, H, W, n_levels, prec, pf, ps, pc,
                                    self.ws.data_ptr(), self.ws.numel(), st), "ha_vgg_forward")
         return Pyramid(feats, scales, confs)
+
+
+def conv3x3(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: str) -> torch.Tensor:
+    """One 3x3/pad-1 convolution through ha_conv3x3_nhwc: fp32 NHWC in -> fp32 NHWC out (bias, no activation)."""
+    _require_cuda(x_nhwc, "conv3x3 input")
+    L = _lib.lib()
+    x = x_nhwc.float().contiguous()
+    w = weight.detach().float().contiguous().to(x.device)
+    b = None if bias is None else bias.detach().float().contiguous().to(x.device)
+    B, H, W, cin = x.shape
+    cout = w.shape[0]
+    out = torch.empty(B, H, W, cout, dtype=torch.float32, device=x.device)
+    need = L.ha_conv3x3_workspace_bytes(cin, cout, B, H, W)
+    ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+    check(L.ha_conv3x3_nhwc(x.data_ptr(), cin, w.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(), cout,
+                            B, H, W, PRECISIONS[precision], ws.data_ptr(), need, _stream_ptr()), "ha_conv3x3_nhwc")
+    return out

@@ -82,6 +82,8 @@ int ha_version(void);                      /* ABI version, currently 1          
 const char* ha_error_string(int code);
 const char* ha_last_cuda_error(void);      /* text of the last CUDA failure on this thread  */
 int ha_device_check(int device);           /* HA_OK iff `device` is compute capability 10.x */
+unsigned long long ha_launch_count(void);  /* kernels launched by this library since it was loaded
+                                              (statistics for bench.py's gpu_launches; no reference analogue) */
 
 /* ---- layout helpers (host wrappers use them at the boundary; reference is NCHW) ---- */
 int ha_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
@@ -128,7 +130,7 @@ int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel* grd, const
 
 /* ---- VGG16 U-Net feature extractor (VGG.py:13-203, estimate_depth off) ----------------- */
 /* Weights, packed by ha_vgg_pack_weights from the reference's state-dict tensors (OIHW fp32,
- * host or device pointers are both accepted: they are only read by cudaMemcpyAsync). */
+ * DEVICE pointers). */
 #define HA_VGG_N_CONV 17
 /* order: conv0 conv2 conv5 conv7 conv10 conv12 conv14 | dec1.1 dec1.3 dec2.1 dec2.3 dec3.1
  * dec3.3 | conf0 conf1 conf2 conf3 ; bias[i] may be NULL (decoder + conf convs have none) */
@@ -155,6 +157,14 @@ size_t ha_vgg_workspace_bytes(int B, int H, int W, int n_levels, int precision);
 int ha_vgg_forward(const void* packed_weights, const float* img_nchw, int B, int H, int W, int n_levels,
                    int precision, float* const* out_feat, float* const* out_scale, float* const* out_conf,
                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---- one 3x3 / pad 1 / stride 1 convolution layer (the building block of ha_vgg_forward) ----
+ * Replaces a single nn.Conv2d call of VGG.py:123-155.  fp32 NHWC in ([B][H][W][cin]) and out
+ * ([B][H][W][cout], bias added, no activation); weights in torch OIHW layout, device pointers.
+ * Tensor-core precisions need cin % 8 == 0, cout in {16, 32, 64, 128, 256}, W % 16 == 0, H % 8 == 0. */
+size_t ha_conv3x3_workspace_bytes(int cin, int cout, int B, int H, int W);
+int ha_conv3x3_nhwc(const float* in_nhwc, int cin, const float* w_oihw, const float* bias, float* out_nhwc, int cout,
+                    int B, int H, int W, int precision, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -175,6 +175,40 @@ def stats_arrays(res: O.LoopResult, n_iters, L):
     return out
 
 
+def fp64_truth(kind, sat, grd, conf, oa, damp, ford, pose0, r_pin):
+    """The same algorithm in float64 = the truth the fp32 reference itself deviates from
+    (SURVEY 8c noise floor).  traj64: whole loop with the same draws; step64/hess64/grad64/delta64:
+    every step restarted from the REFERENCE's fp32 pose state."""
+    dd = lambda xs: [x.double() for x in xs]
+    s64, g64, c64 = dd(sat), dd(grd), dd(conf)
+    f64 = None if ford is None else dict(R_FL=ford["R_FL"].double(), T_FL=ford["T_FL"].double(), side_m=ford["side_m"])
+    p64 = None if pose0 is None else tuple(p.double() for p in pose0)
+    torch.manual_seed(4242)
+    res = O.lm_loop(kind, s64, g64, c64, oa, None if damp is None else damp.double(), None, f64, p64)
+    if kind == "kitti":
+        traj64 = torch.stack([res.lons, res.lats, res.thetas], dim=-1)
+    else:
+        traj64 = torch.stack([res.lats, res.lons, res.thetas], dim=-1)
+    L, B = len(sat), sat[0].shape[0]
+    nd = O.n_dof(kind, oa)
+    lam = O.resolve_damping(oa, None if damp is None else damp.double(), nd, torch.float64)
+    step = torch.zeros(B, oa.N_iters, L, 3, dtype=torch.float64)
+    hess = torch.zeros(oa.N_iters, L, B, nd, nd, dtype=torch.float64)
+    grad = torch.zeros(oa.N_iters, L, B, nd, dtype=torch.float64)
+    delta = torch.zeros(oa.N_iters, L, B, nd, dtype=torch.float64)
+    zero = (torch.zeros(B, 1, dtype=torch.float64), torch.zeros(B, 1, dtype=torch.float64))
+    for it in range(oa.N_iters):
+        for lv in range(L):
+            pin = r_pin[:, it, lv].double()
+            tab = O.kitti_ground_table(lv) if kind == "kitti" else O.ford_ground_table(lv, L)
+            su, sv, th, st = O.lm_one_step(kind, s64[lv], g64[lv], c64[lv], tab, pin[:, 0:1], pin[:, 1:2], pin[:, 2:3],
+                                           oa, lam, zero, f64)
+            step[:, it, lv] = torch.cat([su, sv, th], dim=1)
+            hess[it, lv], grad[it, lv], delta[it, lv] = st.hessian, st.grad, st.delta
+    return dict(traj64=traj64.numpy(), step64=step.numpy(), hess64=hess.numpy(), grad64=grad.numpy(),
+                delta64=delta.numpy())
+
+
 def kat_loop(rk, rf, name, kind, make_inputs, tol=2e-6, pose0=None, **akw):
     """Whole-loop KAT: reference trajectory vs oracle trajectory on identical inputs and
     identical CPU-RNG state; stores the reference trajectory + oracle per-step stats."""
@@ -198,6 +232,7 @@ def kat_loop(rk, rf, name, kind, make_inputs, tol=2e-6, pose0=None, **akw):
         o_traj = torch.stack([res.lats, res.lons, res.thetas], dim=-1)
     d = close(o_traj, r_traj, tol, name + " trajectory")
     out = dict(traj=r_traj.numpy(), pose_in=r_pin.numpy(), in_csum=csum(*sat, *grd), **stats_arrays(res, a.N_iters, len(sat)))
+    out.update(fp64_truth(kind, sat, grd, conf, oa, damp, ford, pose0, r_pin))
     out.update(meta)
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
     print("%s ok  (oracle vs reference max|d| = %.2e; final pose sample0 = %s)" % (name, d, r_traj[0, -1, -1].tolist()))

@@ -288,6 +288,34 @@ def draw_reset(B: int):
     return u, v
 
 
+def lm_one_step(kind: str, sf, gf, gc, tab, su, sv, th, args: LMArgs, lam, draws, ford: Optional[dict] = None):
+    """One (iteration, level) body of the reference's forward loop: project_map_to_grd ->
+    masking / bottom-half crop -> LM_update (models_kitti.py:1187-1260 / models_ford.py:700-800)."""
+    B = sf.shape[0]
+    dt = sf.dtype
+    A = sf.shape[-1]
+    if kind == "kitti":
+        uv, mask, ju, jv, jt = kitti_sat_uv(tab[0], tab[1], su, sv, th, A, args)
+    else:
+        uv, mask, ju, jv, jt = ford_sat_uv(tab[0], tab[1], ford["R_FL"].to(dt), ford["T_FL"].to(dt),
+                                           su, sv, th, A, ford["side_m"], args)
+    jac = torch.stack([ju, jv, jt], dim=0)
+    sp, dj = bilinear_sample(sf, uv, jac)                       # models_kitti.py:924
+    sp = sp * mask[:, None]                                     # :927
+    dj = dj * mask[None, :, None]                               # :929
+    gfm = gf * mask[:, None]                                    # :1191
+    gcm = (gc * mask[:, None]) if gc is not None else torch.ones(B, 1, *gf.shape[-2:], dtype=dt) * mask[:, None]
+    h2 = gf.shape[-2] // 2                                      # :1195-1199 bottom half only
+    return lm_update(su, sv, th, sp[:, :, h2:], gfm[:, :, h2:], gcm[:, :, h2:], dj[:, :, :, h2:],
+                     args, lam, draws, always_3dof=(kind == "ford"))
+
+
+def n_dof(kind: str, args: LMArgs) -> int:
+    if kind == "ford" or not (args.rotation_range == 0 or (args.shift_range_lat == 0 and args.shift_range_lon == 0)):
+        return 3
+    return 2 if args.rotation_range == 0 else 1
+
+
 # ----------------------------------------------------------------------------- LM loops
 @dataclass
 class LoopResult:
@@ -335,26 +363,12 @@ def lm_loop(kind: str, sat_feats: Sequence[torch.Tensor], grd_feats: Sequence[to
     stats = [[None] * L for _ in range(args.N_iters)]
     pin = [[None] * L for _ in range(args.N_iters)]
     for k, (it, lv) in enumerate(_step_order(args.N_iters, L, args.level_first)):
-        sf, gf, gc = sat_feats[lv], grd_feats[lv], grd_confs[lv]
-        A = sf.shape[-1]
-        if kind == "kitti":
-            uv, mask, ju, jv, jt = kitti_sat_uv(tabs[lv][0], tabs[lv][1], su, sv, th, A, args)
-        else:
-            uv, mask, ju, jv, jt = ford_sat_uv(tabs[lv][0], tabs[lv][1], ford["R_FL"].to(dt), ford["T_FL"].to(dt),
-                                               su, sv, th, A, ford["side_m"], args)
-        jac = torch.stack([ju, jv, jt], dim=0)
-        sp, dj = bilinear_sample(sf, uv, jac)                       # models_kitti.py:924
-        sp = sp * mask[:, None]                                     # :927
-        dj = dj * mask[None, :, None]                               # :929
-        gfm = gf * mask[:, None]                                    # :1191
-        gcm = (gc * mask[:, None]) if gc is not None else torch.ones(B, 1, *gf.shape[-2:], dtype=dt) * mask[:, None]
-        h2 = gf.shape[-2] // 2                                      # :1195-1199 bottom half only
         draws = None
         if ndof == 3:
             draws = reset_draws[k] if reset_draws is not None else draw_reset(B)
         pin[it][lv] = (su.clone(), sv.clone(), th.clone())
-        su, sv, th, st = lm_update(su, sv, th, sp[:, :, h2:], gfm[:, :, h2:], gcm[:, :, h2:], dj[:, :, :, h2:],
-                                   args, lam, draws, always_3dof=always3)
+        su, sv, th, st = lm_one_step(kind, sat_feats[lv], grd_feats[lv], grd_confs[lv], tabs[lv], su, sv, th, args, lam,
+                                     draws, ford)
         stats[it][lv] = st
         rec_u[:, it, lv], rec_v[:, it, lv], rec_t[:, it, lv] = su[:, 0], sv[:, 0], th[:, 0]
     if kind == "kitti":      # models_kitti.py:1281-1283: lats = shift_v, lons = shift_u

@@ -61,14 +61,20 @@ def test_lm_trajectory_vs_reference(name):
     assert not status & _lib.HA_STATUS_NAN_POSE
     if name == "kat6_reset":
         assert status & _lib.HA_STATUS_RESET
+    truth = c["gold"]["traj64"]                           # same algorithm in float64
+    ref_noise = np.abs(want - truth)                      # how far the fp32 reference itself is from it
     contractive = "gt" in c["gold"].files
     if contractive:
-        fin_g, fin_w = got[:, -1, -1], want[:, -1, -1]
+        fin_g, fin_w, fin_t = got[:, -1, -1], want[:, -1, -1], truth[:, -1, -1]
         scale = np.maximum(np.abs(fin_w), 1e-2)           # relative, floored where the planted pose is 0
         assert np.max(np.abs(fin_g - fin_w) / scale) < 1e-4, (fin_g, fin_w)
-        np.testing.assert_allclose(got, want, atol=1e-4)
+        assert np.max(np.abs(fin_g - fin_t) / scale) < 1e-4, (fin_g, fin_t)
+        # whole trajectory: within 1e-4 of the reference, or at least as close to the fp64 truth as it is
+        ok = (np.abs(got - want) <= 1e-4) | (np.abs(got - truth) <= 1.5 * ref_noise + 2e-6)
+        assert ok.all(), (np.abs(got - want).max(), np.abs(got - truth).max())
     else:
-        np.testing.assert_allclose(got, want, atol=5e-5)
+        ok = (np.abs(got - want) <= 5e-5) | (np.abs(got - truth) <= 1.5 * ref_noise + 2e-6)
+        assert ok.all(), (np.abs(got - want).max(), np.abs(got - truth).max())
 
 
 @pytest.mark.parametrize("name", ["kat3_random_kitti", "kat4_planted_kitti", "kat4_planted_ford", "kat5_weight",
@@ -95,17 +101,21 @@ def test_lm_per_step_vs_reference(name):
             pin = torch.from_numpy(g["pose_in"][:, it, lv])
             pose, st = engine.lm_step(setup, lv, sat, grd, tabs, lam, pin, ext, side, reset_uv=zeros)
             pose, st = pose.cpu().numpy(), st.cpu().numpy()
-            want = g["traj"][:, it, lv]
-            np.testing.assert_allclose(pose, want, atol=2e-6, rtol=1e-4, err_msg="%s it%d lv%d" % (name, it, lv))
+            want, truth = g["traj"][:, it, lv], g["step64"][:, it, lv]
+            noise = np.abs(want - truth)                  # the fp32 reference's own rounding on this step
+            ok = (np.abs(pose - want) <= 2e-6 + 1e-4 * np.abs(want)) | (np.abs(pose - truth) <= 1.5 * noise + 1e-6)
+            assert ok.all(), "%s it%d lv%d: %g vs ref, %g vs fp64" % (name, it, lv, np.abs(pose - want).max(),
+                                                                     np.abs(pose - truth).max())
+            assert np.abs(pose - truth).max() <= 2e-5, "step further than 2e-5 from the fp64 truth"
             Hm = st[:, :9].reshape(-1, 3, 3)[:, i0:i0 + n, i0:i0 + n]
-            Hw = g["hessian"][it, lv]
-            assert np.abs(Hm - Hw).max() <= 2e-4 * np.abs(Hw).max()
+            Ht = g["hess64"][it, lv]
+            assert np.abs(Hm - Ht).max() <= 1e-4 * np.abs(Ht).max()
             gr = st[:, 9 + i0:9 + i0 + n]
-            gw = g["grad"][it, lv]
-            assert np.abs(gr - gw).max() <= 2e-4 * max(np.abs(gw).max(), 1e-4 * np.sqrt(np.abs(Hw).max()))
-            np.testing.assert_allclose(st[:, 12], g["sat_norm"][it, lv], rtol=2e-5)
-            np.testing.assert_allclose(st[:, 13], g["grd_norm"][it, lv], rtol=2e-5)
-            np.testing.assert_allclose(st[:, 15:15 + n], g["delta"][it, lv], atol=2e-6, rtol=2e-4)
+            gt_ = g["grad64"][it, lv]
+            assert np.abs(gr - gt_).max() <= 1e-4 * max(np.abs(gt_).max(), 1e-4 * np.sqrt(np.abs(Ht).max()))
+            np.testing.assert_allclose(st[:, 12], g["sat_norm"][it, lv], rtol=1e-4)   # fp32 torch.norm is itself ~3e-5 off
+            np.testing.assert_allclose(st[:, 13], g["grd_norm"][it, lv], rtol=1e-4)
+            np.testing.assert_allclose(st[:, 15:15 + n], g["delta64"][it, lv], atol=2e-6, rtol=2e-4)
 
 
 def test_lm_deterministic_and_batch_invariant():
@@ -144,6 +154,27 @@ def test_layout_round_trip():
     y = engine.nchw_to_nhwc(x)
     assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
     assert torch.equal(engine.nhwc_to_nchw(y), x)
+
+
+CONV_SHAPES = [(64, 64, 2, 16, 32), (64, 128, 1, 8, 16), (128, 128, 1, 24, 48), (128, 256, 1, 8, 16), (256, 256, 1, 8, 32),
+               (384, 128, 1, 8, 16), (192, 64, 2, 8, 16), (128, 32, 1, 16, 16), (32, 16, 1, 8, 16)]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16x3", "f16"])
+@pytest.mark.parametrize("cin,cout,B,H,W", CONV_SHAPES)
+def test_single_conv_layer(cin, cout, B, H, W, precision):
+    """Every (Cin, Cout) the U-Net uses, through the layer entry point, vs an fp64 torch conv."""
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    want = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1)
+    got = engine.conv3x3(x.permute(0, 2, 3, 1).contiguous().to(DEV), w, b, precision).cpu().double()
+    err = float((got - want).abs().max() / want.abs().max())
+    # f16x3: the split keeps ~22 bits per product, but the tensor pipe's fp32 accumulator truncates, so the
+    # error grows with the number of chained MMAs (K = 3456 -> ~5e-6); still fp32-grade, 1000x better than f16
+    tol = {"fp32": 2e-6, "f16x3": 1e-5, "f16": 3e-3}[precision]
+    assert err < tol, err
 
 
 VGG_TOL = {"fp32": 2e-5, "f16x3": 5e-5, "f16": 5e-3}
