@@ -144,9 +144,12 @@ struct TcCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void store_split(__half* dst_hi, int pitch, const float (&v)[32], int n) {
+template <int NV>
+__device__ __forceinline__ void store_split(__half* dst_hi, int pitch, const float (&v)[NV], int n) {
   // v[0..n) -> fp16 hi at dst_hi[0..n), fp16 lo*2^11 at dst_hi[pitch + 0..n); n in {16, 32}
-  for (int j = 0; j < n; j += 8) {
+#pragma unroll
+  for (int j = 0; j < NV; j += 8) {
+    if (j >= n) break;
     __align__(16) __half hi[8];
     __align__(16) __half lo[8];
 #pragma unroll
@@ -334,44 +337,62 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
 // ------------------------------------------------------------------------------ conv0 + helpers
 // conv0 (3 -> 64, K = 27) is 0.7 % of the FLOPs: CUDA-core fp32 straight from the NCHW image,
-// fused bias + ReLU, writes the hi/lo activation planes conv2 consumes.  One thread per pixel.
-__global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[9][3][64]*/,
+// fused bias + ReLU, writes the hi/lo activation planes conv2 consumes.  Each thread owns 4
+// horizontally adjacent pixels x 16 output channels at a time, so one 128-bit weight load from
+// shared memory feeds 16 FMAs (the 1-pixel version was LDS-issue bound at 25 % of the FMA pipe).
+constexpr int kC0TW = 64, kC0TH = 16;     // CTA tile: 64 x 16 pixels, 256 threads
+__global__ void __launch_bounds__(256, 2) conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[9][3][64]*/,
                                                     const float* __restrict__ bias, __half* __restrict__ out, int H, int W) {
   __shared__ __align__(16) float w_s[27 * 64];
   __shared__ float b_s[64];
-  __shared__ float in_s[3][18][18];
-  const int b = blockIdx.z, tx0 = blockIdx.x * 16, ty0 = blockIdx.y * 16;
+  __shared__ float in_s[3][kC0TH + 2][kC0TW + 2];
+  const int b = blockIdx.z, tx0 = blockIdx.x * kC0TW, ty0 = blockIdx.y * kC0TH;
   for (int i = threadIdx.x; i < 27 * 64; i += 256) w_s[i] = w[i];
   if (threadIdx.x < 64) b_s[threadIdx.x] = bias[threadIdx.x];
-  for (int i = threadIdx.x; i < 3 * 18 * 18; i += 256) {
-    const int xx = i % 18, yy = (i / 18) % 18, c = i / 324;
+  for (int i = threadIdx.x; i < 3 * (kC0TH + 2) * (kC0TW + 2); i += 256) {
+    const int xx = i % (kC0TW + 2), yy = (i / (kC0TW + 2)) % (kC0TH + 2), c = i / ((kC0TW + 2) * (kC0TH + 2));
     const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
     in_s[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(((size_t)b * 3 + c) * H + gy) * W + gx] : 0.f;
   }
   __syncthreads();
-  const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
-  const int gx = tx0 + lx, gy = ty0 + ly;
-  if (gx >= W || gy >= H) return;
-  float patch[27];
+  const int lx = (threadIdx.x & 15) * 4, ly = threadIdx.x >> 4;
+  const int gy = ty0 + ly;
+  if (gy >= H) return;
+  float patch[3][3][6];                    // [channel][row][col]: the 3 x 6 window of 4 adjacent pixels
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap)
+  for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) patch[tap * 3 + c] = in_s[c][ly + tap / 3][lx + tap % 3];
-  __half* dst = out + (((size_t)b * H + gy) * W + gx) * 2 * 64;
-  for (int n0 = 0; n0 < 64; n0 += 32) {
-    float v[32];
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = b_s[n0 + j];
+      for (int q = 0; q < 6; ++q) patch[c][r][q] = in_s[c][ly + r][lx + q];
+#pragma unroll 1
+  for (int n0 = 0; n0 < 64; n0 += 16) {
+    float v[4][16];
 #pragma unroll
-    for (int k = 0; k < 27; ++k)
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(&w_s[k * 64 + n0 + j]);
-        v[j] += patch[k] * wv.x; v[j + 1] += patch[k] * wv.y; v[j + 2] += patch[k] * wv.z; v[j + 3] += patch[k] * wv.w;
-      }
+      for (int j = 0; j < 16; ++j) v[p][j] = b_s[n0 + j];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-    store_split(dst + n0, 64, v, 32);
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(&w_s[(tap * 3 + c) * 64 + n0 + j]);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float x = patch[c][tap / 3][p + tap % 3];
+            v[p][j] += x * wv.x; v[p][j + 1] += x * wv.y; v[p][j + 2] += x * wv.z; v[p][j + 3] += x * wv.w;
+          }
+        }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int gx = tx0 + lx + p;
+      if (gx >= W) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[p][j] = fmaxf(v[p][j], 0.f);
+      store_split(out + (((size_t)b * H + gy) * W + gx) * 2 * 64 + n0, 64, v[p], 16);
+    }
   }
 }
 
@@ -496,7 +517,7 @@ int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, 
   if ((W % (4 * kTileW)) || (H % (4 * kTileH))) return HA_EINVAL;   // tiles must fit down to the 1/4 scale
   int rc;
 #define HA_TRY(x) do { rc = (x); if (rc != HA_OK) return rc; } while (0)
-  conv0_kernel<<<dim3((W + 15) / 16, (H + 15) / 16, B), 256, 0, st>>>(
+  conv0_kernel<<<dim3((W + kC0TW - 1) / kC0TW, (H + kC0TH - 1) / kC0TH, B), 256, 0, st>>>(
       img, reinterpret_cast<const float*>(packed + L.c[L_CONV0].f32), reinterpret_cast<const float*>(packed + L.c[L_CONV0].bias),
       a1, H, W);
   count_launches(1);
