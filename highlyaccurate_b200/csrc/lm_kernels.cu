@@ -23,10 +23,11 @@
 
 namespace ha {
 
-constexpr int kLmThreads = 256;
+constexpr int kLmThreads = 128;
 constexpr int kLmWarps = kLmThreads / 32;
 constexpr int kLmAcc = 16;              // per-sample reduced scalars
 constexpr int kLmMaxCtasPerSample = 256;
+constexpr int kLmZeroBytes = 2048;       // zero vector for masked ground pixels (C <= 256 fp32, both halves)
 
 struct LmStepArgs {
   const float* sat;        // [B][A][A][C]
@@ -43,6 +44,7 @@ struct LmStepArgs {
   uint32_t* status;
   double* partial;         // [B][kLmMaxCtasPerSample][kLmAcc]
   uint32_t* ticket;        // [B]
+  const float4* zeros;     // >= 1 KB of zeros (read in place of masked ground pixels)
   int traj_stride;         // floats between consecutive samples in traj
   int B, A, H, W;
   int px_per_cta;          // bottom-half pixels handled by one CTA
@@ -157,36 +159,79 @@ __device__ __forceinline__ PixelWarp warp_ford(const FordPose& f, const LmStepAr
   return w;
 }
 
-// Bilinear taps of jacobian.py:147-193 (clamped corners, inclusive range mask).
-struct Taps {
-  int o_nw, o_ne, o_sw, o_se;          // texel offsets (in pixels) into the sample's sat map
-  float w_nw, w_ne, w_sw, w_se;        // value weights
-  float ax_n, ax_s;                    // d/dx weights: -ax_n*nw + ax_n*ne - ax_s*sw + ax_s*se
-  float ay_w, ay_e;                    // d/dy weights: -ay_w*nw - ay_e*ne + ay_w*sw + ay_e*se
-  bool inr;
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): the kernel is issue-bound, and one
+// packed instruction does the work of two scalar ones on a channel pair.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 dup2(float v) { return pk2(v, v); }
+__device__ __forceinline__ float sum2(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo + hi; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ void acc2(f32x2& acc, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ void inc2(f32x2& acc, f32x2 a) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(a)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+struct V4 { f32x2 lo, hi; };   // one 128-bit load = channels (c, c+1) and (c+2, c+3)
+__device__ __forceinline__ V4 ld_stream(const float4* p) {   // ground features: read once, keep out of L1
+  V4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(r.lo), "=l"(r.hi) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ V4 ld_cached(const float4* p) {   // satellite taps: reused by neighbouring pixels
+  V4 r;
+  asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(r.lo), "=l"(r.hi) : "l"(p));
+  return r;
+}
+
+// Per-pixel scalars, evaluated ONCE per pixel by one lane (phase A) and broadcast by shuffles to
+// the lanes that share the pixel's channels (phase B).  Taps follow jacobian.py:147-193 (clamped
+// corners, inclusive range mask); for a pixel outside the satellite map or behind the camera the
+// weights are zeroed, which reproduces `* mask` (models_kitti.py:927-929) with no control flow.
+struct PixelScalars {
+  float ex, wx, sy, ny;        // xe-x, x-xw, ys-y, y-yn   (0 when the sample point is masked)
+  float tx, ty;                // d(u,v)/dtheta
+  float om;                    // LM weight (grd_conf or 1)
+  float valid;                 // 1 when the sample point is inside the satellite map and in front of the camera
+  int off_n, off_s, east;      // float4 offsets of the north / south tap rows into the sample's map, and of +1 texel
+  int goff;                    // float4 offset of the ground pixel, or -1: read zeros (geometric mask / past the end)
 };
 
-__device__ __forceinline__ Taps make_taps(float x, float y, int A) {
-  Taps t;
-  const float hi = (float)(A - 1);
-  t.inr = (x >= 0.f) && (x <= hi) && (y >= 0.f) && (y <= hi);
-  float x0 = floorf(x), y0 = floorf(y);
-  float xw = fminf(fmaxf(x0, 0.f), hi), xe = fminf(fmaxf(x0 + 1.f, 0.f), hi);
-  float yn = fminf(fmaxf(y0, 0.f), hi), ys = fminf(fmaxf(y0 + 1.f, 0.f), hi);
-  float ex = xe - x, wx = x - xw, sy = ys - y, ny = y - yn;
-  t.w_nw = ex * sy; t.w_ne = wx * sy; t.w_sw = ex * ny; t.w_se = wx * ny;
-  t.ax_n = sy; t.ax_s = ny; t.ay_w = ex; t.ay_e = wx;
-  int ixw = (int)xw, ixe = (int)xe, iyn = (int)yn, iys = (int)ys;
-  t.o_nw = iyn * A + ixw; t.o_ne = iyn * A + ixe; t.o_sw = iys * A + ixw; t.o_se = iys * A + ixe;
-  return t;
+template <int GEOM>
+__device__ __forceinline__ PixelScalars pixel_scalars(const LmStepArgs& a, const KittiPose& kp, const FordPose& fp,
+                                                      const float4* tab, const float* conf, int q, int q_end, int c4) {
+  PixelScalars r;
+  r.ex = r.wx = r.sy = r.ny = 0.f; r.tx = r.ty = 0.f; r.om = 1.f; r.valid = 0.f;
+  r.off_n = r.off_s = r.east = 0; r.goff = -1;
+  if (q >= q_end) return r;
+  const float4 p = __ldg(tab + q);
+  if (p.w == 0.f) return r;                                  // geometric mask: s, J and g all vanish
+  r.goff = q * c4;
+  const PixelWarp w = (GEOM == HA_GEOM_KITTI) ? warp_kitti(kp, a, p) : warp_ford(fp, a, p);
+  const float x = w.u, y = w.v, hi = (float)(a.A - 1);
+  const bool inr = (x >= 0.f) && (x <= hi) && (y >= 0.f) && (y <= hi);
+  if (!inr) return r;                                        // sampler mask: s = 0, J = 0, r = -g~ (taps read texel 0, weights 0)
+  const float x0 = floorf(x), y0 = floorf(y);
+  const float xw = fminf(fmaxf(x0, 0.f), hi), xe = fminf(fmaxf(x0 + 1.f, 0.f), hi);
+  const float yn = fminf(fmaxf(y0, 0.f), hi), ys = fminf(fmaxf(y0 + 1.f, 0.f), hi);
+  const int ixw = (int)xw, ixe = (int)xe, iyn = (int)yn, iys = (int)ys;
+  r.off_n = (iyn * a.A + ixw) * c4; r.off_s = (iys * a.A + ixw) * c4; r.east = (ixe - ixw) * c4;
+  r.ex = xe - x; r.wx = x - xw; r.sy = ys - y; r.ny = y - yn; r.tx = w.jtx; r.ty = w.jty; r.valid = 1.f;
+  if (a.using_weight && conf) r.om = __ldg(conf + q);        // models_kitti.py:994-998
+  return r;
 }
+
+struct PixelLoads {            // one 128-bit channel slice of one pixel: ground vector + the four taps
+  V4 g, nw, ne, sw, se;
+};
 
 template <int GEOM, int C>
 __global__ void __launch_bounds__(kLmThreads) lm_step_kernel(const LmStepArgs a) {
-  constexpr int LPP = (C / 4 >= 32) ? 32 : C / 4;  // lanes per pixel
-  constexpr int V = C / (4 * LPP);                 // float4 per lane per pixel
-  constexpr int PPW = 32 / LPP;                    // pixels per warp per iteration
-  static_assert(C % 4 == 0 && V >= 1 && LPP * V * 4 == C, "channel count");
+  constexpr int LPP = C / 8;                       // lanes per pixel: every lane owns 2 x 4 channels
+  constexpr int PPW = 32 / LPP;                    // pixels processed together by one warp
+  constexpr int IPG = 32 / PPW;                    // iterations per 32-pixel group
+  constexpr int C4 = C / 4;
+  static_assert(C % 8 == 0 && LPP >= 1 && LPP <= 32 && PPW * LPP == 32, "channel count");
 
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -198,81 +243,118 @@ __global__ void __launch_bounds__(kLmThreads) lm_step_kernel(const LmStepArgs a)
   const float su = a.pose[b * 3 + 0], sv = a.pose[b * 3 + 1], th = a.pose[b * 3 + 2];
   KittiPose kp;
   FordPose fp;
-  float jux, juy, jvx, jvy;
-  if (GEOM == HA_GEOM_KITTI) { kp = kitti_pose(a, su, sv, th); jux = kp.jux; juy = kp.juy; jvx = kp.jvx; jvy = kp.jvy; }
-  else { fp = ford_pose(a, b, su, sv, th); jux = fp.jux; juy = fp.juy; jvx = fp.jvx; jvy = fp.jvy; }
+  if (GEOM == HA_GEOM_KITTI) kp = kitti_pose(a, su, sv, th); else fp = ford_pose(a, b, su, sv, th);
 
   const size_t px_base = (size_t)b * a.H * a.W + (size_t)(a.H / 2) * a.W;   // first bottom-half pixel of sample b
-  const float4* grd = reinterpret_cast<const float4*>(a.grd) + px_base * (C / 4);
-  const float4* sat = reinterpret_cast<const float4*>(a.sat) + (size_t)b * a.A * a.A * (C / 4);
+  // half 0 = channels [4*cl, 4*cl+4), half 1 = channels [C/2 + 4*cl, ...): each half of a pixel is one
+  // contiguous 16*LPP-byte run across the pixel's lanes
+  const float4* grd = reinterpret_cast<const float4*>(a.grd) + px_base * C4 + cl;
+  const float4* sat = reinterpret_cast<const float4*>(a.sat) + (size_t)b * a.A * a.A * C4 + cl;
   const float4* tab = a.table + (size_t)(a.H / 2) * a.W;
   const float* conf = a.conf ? a.conf + px_base : nullptr;
 
-  float h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0;
-  float bs0 = 0, bs1 = 0, bs2 = 0, bg0 = 0, bg1 = 0, bg2 = 0;
-  float SS = 0, GG = 0, SG = 0, cnt = 0;
+  // per-warp staging of the per-pixel scalars: phase A writes 32 pixels, phase B broadcasts them
+  __shared__ __align__(16) float4 ps_s[kLmWarps][32][3];
 
-  for (int q = q_begin + warp * PPW + sub; q < q_end; q += kLmWarps * PPW) {
-    const float4 p = __ldg(tab + q);
-    if (p.w == 0.f) continue;                         // geometric mask: s, J and g all vanish
-    float4 g[V];
+  // running sums over this lane's pixels and channels (two partial sums per register pair)
+  f32x2 A_aa = 0, A_ab = 0, A_bb = 0, B_x = 0, B_y = 0, C_tt = 0;
+  f32x2 S_a = 0, S_b = 0, S_t = 0, G_a = 0, G_b = 0, G_t = 0, SS = 0, GG = 0, SG = 0;
+  float cnt = 0.f;
+  // per-pixel channel sums (reset at the first half, consumed at the second)
+  f32x2 p_aa = 0, p_ab = 0, p_bb = 0, p_sa = 0, p_sb = 0, p_ga = 0, p_gb = 0;
+  float4 sc0 = make_float4(0, 0, 0, 0), sc1 = sc0;   // (ex, wx, sy, ny), (tx, ty, om, valid) of the current pixel
+  const float4* zeros = a.zeros;
+
+  auto accumulate = [&](const PixelLoads& L) {
+    const f32x2 ex2 = dup2(sc0.x), wx2 = dup2(sc0.y), sy2 = dup2(sc0.z), ny2 = dup2(sc0.w);
 #pragma unroll
-    for (int i = 0; i < V; ++i) g[i] = ldg_nc_stream(grd + (size_t)q * (C / 4) + cl + i * LPP);
-    PixelWarp w = (GEOM == HA_GEOM_KITTI) ? warp_kitti(kp, a, p) : warp_ford(fp, a, p);
-    Taps t = make_taps(w.u, w.v, a.A);
-    float gg = 0.f;
-#pragma unroll
-    for (int i = 0; i < V; ++i) gg += g[i].x * g[i].x + g[i].y * g[i].y + g[i].z * g[i].z + g[i].w * g[i].w;
-    GG += gg;
-    if (!t.inr) continue;                             // sampler mask: s = 0, J = 0, r = -g~
-    float saa = 0, sab = 0, sbb = 0, ssa = 0, ssb = 0, sga = 0, sgb = 0, ss = 0, sg = 0;
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int co = cl + i * LPP;
-      const float4 nw = ldg_nc(sat + (size_t)t.o_nw * (C / 4) + co);
-      const float4 ne = ldg_nc(sat + (size_t)t.o_ne * (C / 4) + co);
-      const float4 sw = ldg_nc(sat + (size_t)t.o_sw * (C / 4) + co);
-      const float4 se = ldg_nc(sat + (size_t)t.o_se * (C / 4) + co);
-#define HA_CH(f)                                                                            \
-      {                                                                                     \
-        float s_ = nw.f * t.w_nw + ne.f * t.w_ne + sw.f * t.w_sw + se.f * t.w_se;           \
-        float a_ = (ne.f - nw.f) * t.ax_n + (se.f - sw.f) * t.ax_s;                         \
-        float b_ = (sw.f - nw.f) * t.ay_w + (se.f - ne.f) * t.ay_e;                         \
-        float g_ = g[i].f;                                                                  \
-        saa += a_ * a_; sab += a_ * b_; sbb += b_ * b_;                                     \
-        ssa += s_ * a_; ssb += s_ * b_; sga += g_ * a_; sgb += g_ * b_;                     \
-        ss += s_ * s_; sg += s_ * g_;                                                       \
-      }
-      HA_CH(x) HA_CH(y) HA_CH(z) HA_CH(w)
-#undef HA_CH
+    for (int h = 0; h < 2; ++h) {
+      const f32x2 nw = h ? L.nw.hi : L.nw.lo, ne = h ? L.ne.hi : L.ne.lo;
+      const f32x2 sw = h ? L.sw.hi : L.sw.lo, se = h ? L.se.hi : L.se.lo;
+      const f32x2 g = h ? L.g.hi : L.g.lo;
+      const f32x2 top = fma2(ne, wx2, mul2(nw, ex2));          // jacobian.py:174-186, factored
+      const f32x2 bot = fma2(se, wx2, mul2(sw, ex2));
+      const f32x2 s = fma2(bot, ny2, mul2(top, sy2));
+      const f32x2 da = fma2(sub2(se, sw), ny2, mul2(sub2(ne, nw), sy2));   // d/dx  (:190-191)
+      const f32x2 db = fma2(sub2(se, ne), wx2, mul2(sub2(sw, nw), ex2));   // d/dy  (:192-193)
+      acc2(p_aa, da, da); acc2(p_ab, da, db); acc2(p_bb, db, db);
+      acc2(p_sa, s, da); acc2(p_sb, s, db); acc2(p_ga, g, da); acc2(p_gb, g, db);
+      acc2(SS, s, s); acc2(SG, s, g); acc2(GG, g, g);
     }
-    const float om = (a.using_weight && conf) ? __ldg(conf + q) : 1.f;   // models_kitti.py:994-998
-    // D = [ (jux,juy); (jvx,jvy); (jtx,jty) ]; J_k = a*D_kx + b*D_ky
-    const float d0x = jux, d0y = juy, d1x = jvx, d1y = jvy, d2x = w.jtx, d2y = w.jty;
-    const float e0x = saa * d0x + sab * d0y, e0y = sab * d0x + sbb * d0y;   // G * D_0
-    const float e1x = saa * d1x + sab * d1y, e1y = sab * d1x + sbb * d1y;
-    const float e2x = saa * d2x + sab * d2y, e2y = sab * d2x + sbb * d2y;
-    h00 += om * (d0x * e0x + d0y * e0y);
-    h01 += om * (d0x * e1x + d0y * e1y);
-    h02 += om * (d0x * e2x + d0y * e2y);
-    h11 += om * (d1x * e1x + d1y * e1y);
-    h12 += om * (d1x * e2x + d1y * e2y);
-    h22 += om * (d2x * e2x + d2y * e2y);
-    bs0 += om * (ssa * d0x + ssb * d0y);
-    bs1 += om * (ssa * d1x + ssb * d1y);
-    bs2 += om * (ssa * d2x + ssb * d2y);
-    bg0 += om * (sga * d0x + sgb * d0y);
-    bg1 += om * (sga * d1x + sgb * d1y);
-    bg2 += om * (sga * d2x + sgb * d2y);
-    SS += ss; SG += sg;
-    if (cl == 0) cnt += 1.f;
+  };
+  auto finish_pixel = [&]() {
+    if (a.using_weight) {
+      const f32x2 om2 = dup2(sc1.z);
+      p_aa = mul2(p_aa, om2); p_ab = mul2(p_ab, om2); p_bb = mul2(p_bb, om2);
+      p_sa = mul2(p_sa, om2); p_sb = mul2(p_sb, om2); p_ga = mul2(p_ga, om2); p_gb = mul2(p_gb, om2);
+    }
+    // d(u,v)/dsu and /dsv are per-sample constants, only d/dtheta = (tx, ty) varies per pixel, so
+    // J^T J splits into sum(G), sum(G t), sum(t^T G t) and the last CTA applies the constant rows.
+    const f32x2 tx2 = dup2(sc1.x), ty2 = dup2(sc1.y);
+    inc2(A_aa, p_aa); inc2(A_ab, p_ab); inc2(A_bb, p_bb);
+    const f32x2 gx = fma2(p_ab, ty2, mul2(p_aa, tx2)), gy = fma2(p_bb, ty2, mul2(p_ab, tx2));
+    inc2(B_x, gx); inc2(B_y, gy);
+    acc2(C_tt, tx2, gx); acc2(C_tt, ty2, gy);
+    inc2(S_a, p_sa); inc2(S_b, p_sb); acc2(S_t, p_sa, tx2); acc2(S_t, p_sb, ty2);
+    inc2(G_a, p_ga); inc2(G_b, p_gb); acc2(G_t, p_ga, tx2); acc2(G_t, p_gb, ty2);
+    cnt += sc1.w;                                  // every lane of the pixel counts it: divided by LPP below
+    p_aa = p_ab = p_bb = p_sa = p_sb = p_ga = p_gb = 0ull;
+  };
+
+  // Flat software pipeline: every pixel is two half-iterations (channel halves); the loads of one
+  // half are issued before the arithmetic of the previous one (ping-pong buffers A / B), so each
+  // lane always has 5-10 independent 128-bit loads in flight.
+  const int n_groups = (q_end - q_begin + 31) / 32;
+  const int my_groups = (n_groups > warp) ? (n_groups - warp + kLmWarps - 1) / kLmWarps : 0;
+  const int T = my_groups * IPG;                   // pixel-iterations of this warp
+  PixelLoads bufA, bufB;
+  float4 nsc0 = sc0, nsc1 = sc1;                   // scalars of the pixel whose loads are in flight
+
+  auto issue = [&](int t, PixelLoads& A, PixelLoads& B) {       // loads for both halves of pixel-iteration t
+    const int it = t % IPG;
+    const int gbase = q_begin + (warp + (t / IPG) * kLmWarps) * 32;
+    if (it == 0) {                                               // phase A: one lane per pixel, 32 pixels at once
+      __syncwarp();
+      const PixelScalars ps = pixel_scalars<GEOM>(a, kp, fp, tab, conf, gbase + lane, q_end, C4);
+      ps_s[warp][lane][0] = make_float4(ps.ex, ps.wx, ps.sy, ps.ny);
+      ps_s[warp][lane][1] = make_float4(ps.tx, ps.ty, ps.om, ps.valid);
+      ps_s[warp][lane][2] = make_float4(__int_as_float(ps.off_n), __int_as_float(ps.off_s), __int_as_float(ps.east),
+                                        __int_as_float(ps.goff));
+      __syncwarp();
+    }
+    const int src = it * PPW + sub;
+    nsc0 = ps_s[warp][src][0];
+    nsc1 = ps_s[warp][src][1];
+    const float4 o = ps_s[warp][src][2];
+    const int goff = __float_as_int(o.w), east = __float_as_int(o.z);
+    const float4* gp = goff >= 0 ? grd + goff : zeros;           // masked pixels read a zero vector: no predication
+    const float4* s_n = sat + __float_as_int(o.x);
+    const float4* s_s = sat + __float_as_int(o.y);
+    A.g = ld_stream(gp);             B.g = ld_stream(gp + LPP);
+    A.nw = ld_cached(s_n);           B.nw = ld_cached(s_n + LPP);
+    A.ne = ld_cached(s_n + east);    B.ne = ld_cached(s_n + east + LPP);
+    A.sw = ld_cached(s_s);           B.sw = ld_cached(s_s + LPP);
+    A.se = ld_cached(s_s + east);    B.se = ld_cached(s_s + east + LPP);
+  };
+
+  // two buffer pairs so that pixel t+1's loads are in flight while pixel t is being reduced
+  PixelLoads bufC, bufD;
+  if (T > 0) issue(0, bufA, bufB);
+  for (int t = 0; t < T; t += 2) {                 // T is even (IPG is even for every supported C)
+    sc0 = nsc0; sc1 = nsc1;
+    issue(t + 1, bufC, bufD);
+    accumulate(bufA); accumulate(bufB); finish_pixel();
+    sc0 = nsc0; sc1 = nsc1;
+    if (t + 2 < T) issue(t + 2, bufA, bufB);
+    accumulate(bufC); accumulate(bufD); finish_pixel();
   }
 
   // ---- CTA reduction: lanes -> warp (fp64 shuffles) -> shared -> one partial row per CTA
   __shared__ double red[kLmWarps][kLmAcc];
   __shared__ bool is_last;
   {
-    double v[kLmAcc] = {h00, h01, h02, h11, h12, h22, bs0, bs1, bs2, bg0, bg1, bg2, SS, GG, SG, cnt};
+    double v[kLmAcc] = {sum2(A_aa), sum2(A_ab), sum2(A_bb), sum2(B_x), sum2(B_y), sum2(C_tt), sum2(S_a), sum2(S_b),
+                        sum2(S_t), sum2(G_a), sum2(G_b), sum2(G_t), sum2(SS), sum2(GG), sum2(SG), cnt / (float)LPP};
 #pragma unroll
     for (int i = 0; i < kLmAcc; ++i) {
       double r = warp_sum(v[i]);
@@ -309,15 +391,26 @@ __global__ void __launch_bounds__(kLmThreads) lm_step_kernel(const LmStepArgs a)
   if (threadIdx.x != 0) return;
   a.ticket[b] = 0;   // ready for the next step on this stream
 
+  // assemble J^T W J, J^T W s, J^T W g from the split sums with the per-sample constant rows of D
+  const double d0x = (GEOM == HA_GEOM_KITTI) ? kp.jux : fp.jux, d0y = (GEOM == HA_GEOM_KITTI) ? kp.juy : fp.juy;
+  const double d1x = (GEOM == HA_GEOM_KITTI) ? kp.jvx : fp.jvx, d1y = (GEOM == HA_GEOM_KITTI) ? kp.jvy : fp.jvy;
+  const double Gaa = tot[0], Gab = tot[1], Gbb = tot[2], Bx = tot[3], By = tot[4], Ctt = tot[5];
+  const double e0x = Gaa * d0x + Gab * d0y, e0y = Gab * d0x + Gbb * d0y;    // sum(G) * D_0
+  const double e1x = Gaa * d1x + Gab * d1y, e1y = Gab * d1x + Gbb * d1y;
+  const double JtJ[6] = {d0x * e0x + d0y * e0y, d0x * e1x + d0y * e1y, d0x * Bx + d0y * By,
+                         d1x * e1x + d1y * e1y, d1x * Bx + d1y * By, Ctt};
+  const double Jts[3] = {d0x * tot[6] + d0y * tot[7], d1x * tot[6] + d1y * tot[7], tot[8]};
+  const double Jtg[3] = {d0x * tot[9] + d0y * tot[10], d1x * tot[9] + d1y * tot[10], tot[11]};
+
   const double alpha = a.sat_scale ? (double)a.sat_scale[b] : 1.0;
   const double beta = a.grd_scale ? (double)a.grd_scale[b] : 1.0;
   const double ns = fmax(alpha * sqrt(tot[12]), 1e-6);     // models_kitti.py:982-984
   const double ng = fmax(beta * sqrt(tot[13]), 1e-6);      // :987-988
   const double fs = alpha * alpha / (ns * ns), fg = alpha * beta / (ns * ng);
-  double Hm[3][3] = {{tot[0] * fs, tot[1] * fs, tot[2] * fs},
-                     {tot[1] * fs, tot[3] * fs, tot[4] * fs},
-                     {tot[2] * fs, tot[4] * fs, tot[5] * fs}};
-  double gr[3] = {tot[6] * fs - tot[9] * fg, tot[7] * fs - tot[10] * fg, tot[8] * fs - tot[11] * fg};
+  double Hm[3][3] = {{JtJ[0] * fs, JtJ[1] * fs, JtJ[2] * fs},
+                     {JtJ[1] * fs, JtJ[3] * fs, JtJ[4] * fs},
+                     {JtJ[2] * fs, JtJ[4] * fs, JtJ[5] * fs}};
+  double gr[3] = {Jts[0] * fs - Jtg[0] * fg, Jts[1] * fs - Jtg[1] * fg, Jts[2] * fs - Jtg[2] * fg};
   const double res_sq = alpha * alpha * tot[12] / (ns * ns) + beta * beta * tot[13] / (ng * ng) -
                         2.0 * alpha * beta * tot[14] / (ns * ng);
 
@@ -402,15 +495,14 @@ static int launch_by_channels(int C, dim3 grid, cudaStream_t st, const LmStepArg
 static size_t lm_ws_bytes(int B) {
   size_t part = (size_t)B * kLmMaxCtasPerSample * kLmAcc * sizeof(double);
   size_t tick = ((size_t)B * sizeof(uint32_t) + 255) / 256 * 256;
-  return part + tick;
+  return part + tick + kLmZeroBytes;
 }
 
 // One CTA per px_per_cta bottom-half pixels; enough CTAs to fill 148 SMs several times over
 // while keeping at least a few pixels per warp.
 static int choose_ctas_per_sample(int B, int P, int C) {
-  const int lpp = (C / 4 >= 32) ? 32 : C / 4;
-  const int ppw = 32 / lpp;
-  const int min_px = kLmWarps * ppw * 4;                       // >= 4 iterations per warp
+  (void)C;
+  const int min_px = kLmWarps * 32;                            // one 32-pixel group per warp
   int want = (kNumSMs * 8 + B - 1) / B;                        // ~8 CTAs per SM over the batch
   int max_by_px = (P + min_px - 1) / min_px;
   int n = want < max_by_px ? want : max_by_px;
@@ -440,6 +532,7 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   a.status = status;
   a.partial = reinterpret_cast<double*>(ws);
   a.ticket = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + (size_t)B * kLmMaxCtasPerSample * kLmAcc * sizeof(double));
+  a.zeros = reinterpret_cast<const float4*>(reinterpret_cast<char*>(ws) + lm_ws_bytes(B) - kLmZeroBytes);
   a.B = B; a.A = sat->H; a.H = grd->H; a.W = grd->W;
   a.dof = p->dof; a.using_weight = p->using_weight; a.use_hessian = p->use_hessian;
   a.rot = p->rotation_range; a.lat = p->shift_range_lat; a.lon = p->shift_range_lon;
@@ -454,9 +547,10 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   return HA_EINVAL;
 }
 
+// clears the tickets [0, n) and the zero vector that follows them (tickets are padded to 256 B)
 __global__ void zero_u32_kernel(uint32_t* p, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = 0;
+  const int pad = (n * 4 + 255) / 256 * 64, total = pad + kLmZeroBytes / 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) p[i] = 0;
 }
 
 }  // namespace ha
