@@ -23,6 +23,9 @@
 
 namespace ha {
 
+#ifndef HA_LM_MIN_CTAS
+#define HA_LM_MIN_CTAS 4
+#endif
 constexpr int kLmThreads = 128;
 constexpr int kLmWarps = kLmThreads / 32;
 constexpr int kLmAcc = 16;              // per-sample reduced scalars
@@ -45,6 +48,7 @@ struct LmStepArgs {
   double* partial;         // [B][kLmMaxCtasPerSample][kLmAcc]
   uint32_t* ticket;        // [B]
   const float4* zeros;     // >= 1 KB of zeros (read in place of masked ground pixels)
+  double* gg_cache;        // [B] sum g^2 of this level (written by FULL launches, read by the others) or null
   int traj_stride;         // floats between consecutive samples in traj
   int B, A, H, W;
   int px_per_cta;          // bottom-half pixels handled by one CTA
@@ -225,8 +229,8 @@ struct PixelLoads {            // one 128-bit channel slice of one pixel: ground
   V4 g, nw, ne, sw, se;
 };
 
-template <int GEOM, int C>
-__global__ void __launch_bounds__(kLmThreads) lm_step_kernel(const LmStepArgs a) {
+template <int GEOM, int C, bool FULL>
+__global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(const LmStepArgs a) {
   constexpr int LPP = C / 8;                       // lanes per pixel: every lane owns 2 x 4 channels
   constexpr int PPW = 32 / LPP;                    // pixels processed together by one warp
   constexpr int IPG = 32 / PPW;                    // iterations per 32-pixel group
@@ -272,14 +276,15 @@ __global__ void __launch_bounds__(kLmThreads) lm_step_kernel(const LmStepArgs a)
       const f32x2 nw = h ? L.nw.hi : L.nw.lo, ne = h ? L.ne.hi : L.ne.lo;
       const f32x2 sw = h ? L.sw.hi : L.sw.lo, se = h ? L.se.hi : L.se.lo;
       const f32x2 g = h ? L.g.hi : L.g.lo;
-      const f32x2 top = fma2(ne, wx2, mul2(nw, ex2));          // jacobian.py:174-186, factored
-      const f32x2 bot = fma2(se, wx2, mul2(sw, ex2));
+      const f32x2 top = fma2(ne, wx2, mul2(nw, ex2));          // north row interpolated in x  (jacobian.py:174-186, factored)
+      const f32x2 bot = fma2(se, wx2, mul2(sw, ex2));          // south row interpolated in x
       const f32x2 s = fma2(bot, ny2, mul2(top, sy2));
       const f32x2 da = fma2(sub2(se, sw), ny2, mul2(sub2(ne, nw), sy2));   // d/dx  (:190-191)
-      const f32x2 db = fma2(sub2(se, ne), wx2, mul2(sub2(sw, nw), ex2));   // d/dy  (:192-193)
+      const f32x2 db = sub2(bot, top);                         // d/dy = ex (sw - nw) + wx (se - ne)  (:192-193)
       acc2(p_aa, da, da); acc2(p_ab, da, db); acc2(p_bb, db, db);
       acc2(p_sa, s, da); acc2(p_sb, s, db); acc2(p_ga, g, da); acc2(p_gb, g, db);
-      acc2(SS, s, s); acc2(SG, s, g); acc2(GG, g, g);
+      acc2(SS, s, s);
+      if (FULL) { acc2(SG, s, g); acc2(GG, g, g); }          // |g|^2 is pose independent: cached after the first visit
     }
   };
   auto finish_pixel = [&]() {
@@ -310,7 +315,10 @@ __global__ void __launch_bounds__(kLmThreads) lm_step_kernel(const LmStepArgs a)
   PixelLoads bufA, bufB;
   float4 nsc0 = sc0, nsc1 = sc1;                   // scalars of the pixel whose loads are in flight
 
-  auto issue = [&](int t, PixelLoads& A, PixelLoads& B) {       // loads for both halves of pixel-iteration t
+  // addresses of the pixel whose loads are being issued (set by prepare(), used by load_half())
+  const float4 *gp = zeros, *s_n = sat, *s_s = sat;
+  int east = 0;
+  auto prepare = [&](int t) {                                     // per-pixel scalars + addresses of pixel-iteration t
     const int it = t % IPG;
     const int gbase = q_begin + (warp + (t / IPG) * kLmWarps) * 32;
     if (it == 0) {                                               // phase A: one lane per pixel, 32 pixels at once
@@ -326,27 +334,30 @@ __global__ void __launch_bounds__(kLmThreads) lm_step_kernel(const LmStepArgs a)
     nsc0 = ps_s[warp][src][0];
     nsc1 = ps_s[warp][src][1];
     const float4 o = ps_s[warp][src][2];
-    const int goff = __float_as_int(o.w), east = __float_as_int(o.z);
-    const float4* gp = goff >= 0 ? grd + goff : zeros;           // masked pixels read a zero vector: no predication
-    const float4* s_n = sat + __float_as_int(o.x);
-    const float4* s_s = sat + __float_as_int(o.y);
-    A.g = ld_stream(gp);             B.g = ld_stream(gp + LPP);
-    A.nw = ld_cached(s_n);           B.nw = ld_cached(s_n + LPP);
-    A.ne = ld_cached(s_n + east);    B.ne = ld_cached(s_n + east + LPP);
-    A.sw = ld_cached(s_s);           B.sw = ld_cached(s_s + LPP);
-    A.se = ld_cached(s_s + east);    B.se = ld_cached(s_s + east + LPP);
+    const int goff = __float_as_int(o.w);
+    east = __float_as_int(o.z);
+    gp = goff >= 0 ? grd + goff : zeros;                         // masked pixels read a zero vector: no predication
+    s_n = sat + __float_as_int(o.x);
+    s_s = sat + __float_as_int(o.y);
+  };
+  auto load_half = [&](PixelLoads& L, int h) {
+    L.g = ld_stream(gp + h * LPP);
+    L.nw = ld_cached(s_n + h * LPP); L.ne = ld_cached(s_n + east + h * LPP);
+    L.sw = ld_cached(s_s + h * LPP); L.se = ld_cached(s_s + east + h * LPP);
   };
 
-  // two buffer pairs so that pixel t+1's loads are in flight while pixel t is being reduced
-  PixelLoads bufC, bufD;
-  if (T > 0) issue(0, bufA, bufB);
-  for (int t = 0; t < T; t += 2) {                 // T is even (IPG is even for every supported C)
+  // Software pipeline at half-pixel granularity: while one half's five 128-bit loads are reduced, the
+  // other half's (and the next pixel's first half's) are in flight.
+  if (T > 0) { prepare(0); load_half(bufA, 0); load_half(bufB, 1); }
+  for (int t = 0; t < T; ++t) {
     sc0 = nsc0; sc1 = nsc1;
-    issue(t + 1, bufC, bufD);
-    accumulate(bufA); accumulate(bufB); finish_pixel();
-    sc0 = nsc0; sc1 = nsc1;
-    if (t + 2 < T) issue(t + 2, bufA, bufB);
-    accumulate(bufC); accumulate(bufD); finish_pixel();
+    const bool more = t + 1 < T;
+    if (more) prepare(t + 1);
+    accumulate(bufA);
+    if (more) load_half(bufA, 0);
+    accumulate(bufB);
+    finish_pixel();
+    if (more) load_half(bufB, 1);
   }
 
   // ---- CTA reduction: lanes -> warp (fp64 shuffles) -> shared -> one partial row per CTA
@@ -390,6 +401,8 @@ __global__ void __launch_bounds__(kLmThreads) lm_step_kernel(const LmStepArgs a)
   __syncthreads();
   if (threadIdx.x != 0) return;
   a.ticket[b] = 0;   // ready for the next step on this stream
+  if (FULL) { if (a.gg_cache) a.gg_cache[b] = tot[13]; }
+  else tot[13] = a.gg_cache[b];                      // sum g^2 over the unmasked bottom half, from this level's first visit
 
   // assemble J^T W J, J^T W s, J^T W g from the split sums with the per-sample constant rows of D
   const double d0x = (GEOM == HA_GEOM_KITTI) ? kp.jux : fp.jux, d0y = (GEOM == HA_GEOM_KITTI) ? kp.juy : fp.juy;
@@ -411,8 +424,8 @@ __global__ void __launch_bounds__(kLmThreads) lm_step_kernel(const LmStepArgs a)
                      {JtJ[1] * fs, JtJ[3] * fs, JtJ[4] * fs},
                      {JtJ[2] * fs, JtJ[4] * fs, JtJ[5] * fs}};
   double gr[3] = {Jts[0] * fs - Jtg[0] * fg, Jts[1] * fs - Jtg[1] * fg, Jts[2] * fs - Jtg[2] * fg};
-  const double res_sq = alpha * alpha * tot[12] / (ns * ns) + beta * beta * tot[13] / (ng * ng) -
-                        2.0 * alpha * beta * tot[14] / (ns * ng);
+  const double res_sq = FULL ? alpha * alpha * tot[12] / (ns * ns) + beta * beta * tot[13] / (ng * ng) -
+                                   2.0 * alpha * beta * tot[14] / (ns * ng) : 0.0;     // diagnostic, FULL launches only
 
   // DOF selection (models_kitti.py:954-957): 3 -> (0,1,2), 2 -> (0,1), 1 -> (2)
   const int n = a.dof;
@@ -478,14 +491,14 @@ __global__ void __launch_bounds__(kLmThreads) lm_step_kernel(const LmStepArgs a)
   }
 }
 
-template <int GEOM>
+template <int GEOM, bool FULL>
 static int launch_by_channels(int C, dim3 grid, cudaStream_t st, const LmStepArgs& a) {
   switch (C) {
-    case 256: lm_step_kernel<GEOM, 256><<<grid, kLmThreads, 0, st>>>(a); break;
-    case 128: lm_step_kernel<GEOM, 128><<<grid, kLmThreads, 0, st>>>(a); break;
-    case 64: lm_step_kernel<GEOM, 64><<<grid, kLmThreads, 0, st>>>(a); break;
-    case 32: lm_step_kernel<GEOM, 32><<<grid, kLmThreads, 0, st>>>(a); break;
-    case 16: lm_step_kernel<GEOM, 16><<<grid, kLmThreads, 0, st>>>(a); break;
+    case 256: lm_step_kernel<GEOM, 256, FULL><<<grid, kLmThreads, 0, st>>>(a); break;
+    case 128: lm_step_kernel<GEOM, 128, FULL><<<grid, kLmThreads, 0, st>>>(a); break;
+    case 64: lm_step_kernel<GEOM, 64, FULL><<<grid, kLmThreads, 0, st>>>(a); break;
+    case 32: lm_step_kernel<GEOM, 32, FULL><<<grid, kLmThreads, 0, st>>>(a); break;
+    case 16: lm_step_kernel<GEOM, 16, FULL><<<grid, kLmThreads, 0, st>>>(a); break;
     default: return HA_EINVAL;
   }
   count_launches(1);
@@ -495,26 +508,28 @@ static int launch_by_channels(int C, dim3 grid, cudaStream_t st, const LmStepArg
 static size_t lm_ws_bytes(int B) {
   size_t part = (size_t)B * kLmMaxCtasPerSample * kLmAcc * sizeof(double);
   size_t tick = ((size_t)B * sizeof(uint32_t) + 255) / 256 * 256;
-  return part + tick + kLmZeroBytes;
+  return part + tick + kLmZeroBytes + (size_t)HA_MAX_LEVELS * B * sizeof(double);
 }
 
-// One CTA per px_per_cta bottom-half pixels; enough CTAs to fill 148 SMs several times over
-// while keeping at least a few pixels per warp.
-static int choose_ctas_per_sample(int B, int P, int C) {
-  (void)C;
-  const int min_px = kLmWarps * 32;                            // one 32-pixel group per warp
-  int want = (kNumSMs * 8 + B - 1) / B;                        // ~8 CTAs per SM over the batch
-  int max_by_px = (P + min_px - 1) / min_px;
-  int n = want < max_by_px ? want : max_by_px;
-  if (n < 1) n = 1;
-  if (n > kLmMaxCtasPerSample) n = kLmMaxCtasPerSample;
-  return n;
+// Work split: a CTA takes px_per_cta consecutive bottom-half pixels of one sample, a multiple of
+// 32 * warps so that every warp gets the same number of 32-pixel groups (no barrier skew).  Enough
+// CTAs to fill 148 SMs several times over, never more than kLmMaxCtasPerSample per sample.
+static int choose_px_per_cta(int B, int P) {
+  const int unit = kLmWarps * 32;
+  const int units = (P + unit - 1) / unit;                     // whole-CTA units in one sample
+  int want = (kNumSMs * 12 + B - 1) / B;                       // ~12 CTAs per SM over the batch
+  if (want > kLmMaxCtasPerSample) want = kLmMaxCtasPerSample;
+  if (want < 1) want = 1;
+  int upc = (units + want - 1) / want;                         // units per CTA
+  if (upc < 1) upc = 1;
+  while ((units + upc - 1) / upc > kLmMaxCtasPerSample) ++upc;
+  return upc * unit;
 }
 
 static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, const HaLevel* grd, const float* grd_conf,
                         const float* ground_table, const float* extrinsics, float* pose, const float* reset_uv,
                         float* stats, float* traj_step, int traj_stride, uint32_t* status, void* ws, size_t ws_bytes,
-                        int B, cudaStream_t st) {
+                        int B, bool full, cudaStream_t st) {
   if (!p || !sat || !grd || !pose || !status || !ws || !ground_table) return HA_EINVAL;
   if (level < 0 || level >= HA_MAX_LEVELS) return HA_EINVAL;
   if (sat->C != grd->C || sat->H != sat->W || (grd->H & 1)) return HA_EINVAL;
@@ -532,18 +547,21 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   a.status = status;
   a.partial = reinterpret_cast<double*>(ws);
   a.ticket = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + (size_t)B * kLmMaxCtasPerSample * kLmAcc * sizeof(double));
-  a.zeros = reinterpret_cast<const float4*>(reinterpret_cast<char*>(ws) + lm_ws_bytes(B) - kLmZeroBytes);
+  char* tail = reinterpret_cast<char*>(ws) + lm_ws_bytes(B) - kLmZeroBytes - (size_t)HA_MAX_LEVELS * B * sizeof(double);
+  a.zeros = reinterpret_cast<const float4*>(tail);
+  a.gg_cache = reinterpret_cast<double*>(tail + kLmZeroBytes) + (size_t)level * B;
   a.B = B; a.A = sat->H; a.H = grd->H; a.W = grd->W;
   a.dof = p->dof; a.using_weight = p->using_weight; a.use_hessian = p->use_hessian;
   a.rot = p->rotation_range; a.lat = p->shift_range_lat; a.lon = p->shift_range_lon;
   a.mpp = p->meter_per_pixel[level]; a.inv_mpp = p->inv_meter_per_pixel[level]; a.center = p->sat_center[level];
   for (int i = 0; i < 3; ++i) a.damping[i] = p->damping[i];
   const int P = (grd->H - grd->H / 2) * grd->W;
-  const int nc = choose_ctas_per_sample(B, P, grd->C);
-  a.px_per_cta = (P + nc - 1) / nc;
+  a.px_per_cta = choose_px_per_cta(B, P);
   dim3 grid((P + a.px_per_cta - 1) / a.px_per_cta, B);
-  if (p->geometry == HA_GEOM_KITTI) return launch_by_channels<HA_GEOM_KITTI>(grd->C, grid, st, a);
-  if (p->geometry == HA_GEOM_FORD) return launch_by_channels<HA_GEOM_FORD>(grd->C, grid, st, a);
+  if (p->geometry == HA_GEOM_KITTI)
+    return full ? launch_by_channels<HA_GEOM_KITTI, true>(grd->C, grid, st, a) : launch_by_channels<HA_GEOM_KITTI, false>(grd->C, grid, st, a);
+  if (p->geometry == HA_GEOM_FORD)
+    return full ? launch_by_channels<HA_GEOM_FORD, true>(grd->C, grid, st, a) : launch_by_channels<HA_GEOM_FORD, false>(grd->C, grid, st, a);
   return HA_EINVAL;
 }
 
@@ -572,7 +590,7 @@ extern "C" int ha_lm_step(const HaLmParams* p, int level, const HaLevel* sat, co
   ha::zero_u32_kernel<<<(B + 255) / 256, 256, 0, st>>>(ticket, B);
   ha::count_launches(1);
   return ha::lm_step_impl(p, level, sat, grd, grd_conf, ground_table, extrinsics, pose, reset_uv, stats, nullptr, 0,
-                          status, ws, ws_bytes, B, st);
+                          status, ws, ws_bytes, B, /*full=*/true, st);
 }
 
 extern "C" int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel* grd, const float* const* grd_conf,
@@ -596,8 +614,10 @@ extern "C" int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel*
       const float* ruv = (p->dof == 3 && reset_uv) ? reset_uv + (size_t)k * 2 * B : nullptr;
       float* tr = traj ? traj + ((size_t)it * L + lv) * 3 : nullptr;
       float* stp = stats ? stats + ((size_t)it * L + lv) * B * HA_STATS : nullptr;
+      // the first visit of a level also reduces |g|^2 (pose independent) and caches it; later visits skip it
+      const bool full = (it == 0) || stats != nullptr;
       int rc = ha::lm_step_impl(p, lv, sat + lv, grd + lv, grd_conf ? grd_conf[lv] : nullptr, ground_tables[lv],
-                                extrinsics, pose, ruv, stp, tr, N * L * 3, status, ws, ws_bytes, B, st);
+                                extrinsics, pose, ruv, stp, tr, N * L * 3, status, ws, ws_bytes, B, full, st);
       if (rc != HA_OK) return rc;
     }
   }

@@ -45,3 +45,18 @@ for lv in range(L):
     byt = 4 * PYR_C[lv] * ((h // 2) * w + SAT_TEXELS_TOUCHED[lv]) * B
     print("level %d C=%3d: %8.1f us (incl. ~10 us of host-side staging)  %7.1f GB/s  %.3f of %s HBM peak"
           % (lv, PYR_C[lv], t, byt / t / 1e3, byt / t / 1e3 / pk["hbm"], pk["src"]))
+
+# whole loop (5 iterations x L levels): exercises the cached-|g|^2 (FAST) launches too
+for _ in range(2):
+    res = net.refine(sat, grd, reset_uv=torch.zeros(5 * L, 2, B))
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+draws = torch.zeros(5 * L, 2, B, device=dev)
+e0.record()
+for _ in range(reps):
+    res = net.refine(sat, grd, reset_uv=draws)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+byt = sum(4 * PYR_C[l] * (((256 >> (3 - l)) // 2) * (1024 >> (3 - l)) + SAT_TEXELS_TOUCHED[l]) for l in range(L)) * 5 * B
+print("whole LM loop (5 iters x %d levels, B=%d): %.3f ms  -> %.1f GB/s algorithmic = %.3f of HBM peak" % (L, B, ms, byt / ms / 1e6, byt / ms / 1e6 / pk["hbm"]))
