@@ -187,11 +187,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           mbar_wait(empty + stage, phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(full + stage, Cfg::kStageBytes);
+          // stage layout: [A_hi 16 KB][B_hi][B_lo][A_lo 16 KB] — B_hi and B_lo adjacent so that ONE MMA with
+          // N = 2*BLOCK_N multiplies A_hi by both (see the MMA issuer)
           tma_load_5d(st, &tmap_a, full + stage, kc * kBlockK, 0, x0 + kx - 1, y0 + ky - 1, b);
           tma_load_3d(st + kABytes, &tmap_bh, full + stage, kc * kBlockK, n_idx * BLOCK_N, tap);
           if (SPLIT) {
-            tma_load_5d(st + kABytes + Cfg::kBBytes, &tmap_a, full + stage, kc * kBlockK, 1, x0 + kx - 1, y0 + ky - 1, b);
-            tma_load_3d(st + 2 * kABytes + Cfg::kBBytes, &tmap_bl, full + stage, kc * kBlockK, n_idx * BLOCK_N, tap);
+            tma_load_3d(st + kABytes + Cfg::kBBytes, &tmap_bl, full + stage, kc * kBlockK, n_idx * BLOCK_N, tap);
+            tma_load_5d(st + kABytes + 2 * Cfg::kBBytes, &tmap_a, full + stage, kc * kBlockK, 1, x0 + kx - 1, y0 + ky - 1, b);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -199,29 +201,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_f16(BLOCK_N);
+    constexpr uint32_t idesc = umma_idesc_f16(BLOCK_N);             // A x B_hi
+    constexpr uint32_t idesc2 = umma_idesc_f16(2 * BLOCK_N);        // A x [B_hi ; B_lo]
     int stage = 0; uint32_t phase = 0; int t = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++t) {
       const int as = t & 1; const uint32_t aphase = (t >> 1) & 1;
       mbar_wait(tmem_empty + as, aphase ^ 1);
       tc_fence_after();
-      const uint32_t acc0 = tmem_base + as * 256, acc1 = acc0 + 128;
+      // accumulator columns of this stage: [0, BLOCK_N) = hi*hi, [BLOCK_N, 2*BLOCK_N) = hi*lo + lo*hi
+      const uint32_t acc0 = tmem_base + as * 256, acc1 = acc0 + BLOCK_N;
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(full + stage, phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa_hi = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb_hi = sa_hi + kABytes;
-          const uint32_t sa_lo = sb_hi + Cfg::kBBytes;
-          const uint32_t sb_lo = sa_lo + kABytes;
+          const uint32_t sb_hi = sa_hi + kABytes;                    // followed directly by B_lo
+          const uint32_t sa_lo = sb_hi + 2 * Cfg::kBBytes;
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da_hi = umma_desc_sw128(sa_hi + k * 32), db_hi = umma_desc_sw128(sb_hi + k * 32);
-            umma_f16(acc0, da_hi, db_hi, idesc, (kb | k) != 0);
+            const uint64_t da_hi = umma_desc_sw128(sa_hi + k * 32), db = umma_desc_sw128(sb_hi + k * 32);
             if (SPLIT) {
-              const uint64_t da_lo = umma_desc_sw128(sa_lo + k * 32), db_lo = umma_desc_sw128(sb_lo + k * 32);
-              umma_f16(acc1, da_hi, db_lo, idesc, (kb | k) != 0);
-              umma_f16(acc1, da_lo, db_hi, idesc, 1);
+              // one N = 2*BLOCK_N MMA reads A_hi once for both hi_x*hi_w and hi_x*lo_w, then lo_x*hi_w is added
+              umma_f16(acc0, da_hi, db, idesc2, (kb | k) != 0);
+              umma_f16(acc1, umma_desc_sw128(sa_lo + k * 32), db, idesc, 1);
+            } else {
+              umma_f16(acc0, da_hi, db, idesc, (kb | k) != 0);
             }
           }
           umma_commit(empty + stage);                       // smem slot reusable once these MMAs retire
@@ -250,8 +254,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
         uint32_t r0[32], r1[32];
-        if (CH == 32) { tmem_ld_x32(taddr + c0, r0); if (SPLIT) tmem_ld_x32(taddr + 128 + c0, r1); }
-        else { tmem_ld_x16(taddr + c0, r0); if (SPLIT) tmem_ld_x16(taddr + 128 + c0, r1); }
+        if (CH == 32) { tmem_ld_x32(taddr + c0, r0); if (SPLIT) tmem_ld_x32(taddr + BLOCK_N + c0, r1); }
+        else { tmem_ld_x16(taddr + c0, r0); if (SPLIT) tmem_ld_x16(taddr + BLOCK_N + c0, r1); }
         tmem_ld_wait();
         const int n0 = n_idx * BLOCK_N + c0;
         float v[32];
