@@ -222,8 +222,9 @@ def main():
         secs = float(t.item())
     if sampler is not None and (t_wall1 - t_wall0) < 1.5:      # keep the GPU busy long enough to be sampled
         t_end = time.time() + 1.5
-        while time.time() < t_end:
-            forward_resident(0)
+        while time.time() < t_end:                             # rank-local work only: no collective in here
+            sat_w, grd_w = net.extract(sat_d, grd_d, False)
+            net.refine(sat_w, grd_w, reset_uv=draws)
         torch.cuda.synchronize()
         t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler is not None else None
