@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libha_b200.so")
 HA_MAX_LEVELS = 4
 HA_STATS = 24
 HA_VGG_N_CONV = 17
-HA_GEOM_KITTI, HA_GEOM_FORD = 0, 1
+HA_GEOM_KITTI, HA_GEOM_FORD, HA_GEOM_G2SP = 0, 1, 2
 HA_CONV_FP32_SIMT, HA_CONV_F16X3, HA_CONV_F16 = 0, 1, 2
 HA_STATUS_NO_INRANGE, HA_STATUS_NAN_POSE, HA_STATUS_RESET = 1, 2, 4
 STAT_H, STAT_GRAD, STAT_SAT_NORM, STAT_GRD_NORM, STAT_RES_SQ, STAT_DELTA, STAT_N_INRANGE = 0, 9, 12, 13, 14, 15, 18
@@ -35,7 +35,8 @@ class HaLmParams(C.Structure):
                 ("dof", C.c_int32), ("using_weight", C.c_int32), ("use_hessian", C.c_int32), ("batch", C.c_int32),
                 ("rotation_range", C.c_float), ("shift_range_lat", C.c_float), ("shift_range_lon", C.c_float),
                 ("damping", C.c_float * 3), ("meter_per_pixel", C.c_float * HA_MAX_LEVELS),
-                ("inv_meter_per_pixel", C.c_float * HA_MAX_LEVELS), ("sat_center", C.c_float * HA_MAX_LEVELS)]
+                ("inv_meter_per_pixel", C.c_float * HA_MAX_LEVELS), ("sat_center", C.c_float * HA_MAX_LEVELS),
+                ("ori_grd_h", C.c_int32), ("ori_grd_w", C.c_int32)]
 
 
 class HaVggStateDict(C.Structure):

@@ -55,6 +55,7 @@ struct LmStepArgs {
   int dof, using_weight, use_hessian;
   float rot, lat, lon;     // rotation_range (deg), shift_range_lat / lon (m)
   float mpp, inv_mpp, center;  // satellite metres per pixel, fp32(1/mpp), A/2
+  int ori_h, ori_w;        // G2SP: size of the ground IMAGE the camera matrix refers to (models_kitti.py:111-114)
   float damping[3];
 };
 
@@ -123,6 +124,49 @@ __device__ __forceinline__ FordPose ford_pose(const LmStepArgs& a, int b, float 
   f.jvx = __fdiv_rn(dyv, a.mpp);
   f.jvy = __fdiv_rn(-dxv, a.mpp);
   return f;
+}
+
+// G2SP (models_kitti.py:86-160): P = K_l [R(-heading) | T] and the three dP/dpose, per sample.
+struct G2spPose {
+  float P[3][4];        // projection of (X, 0, Z, 1); column 1 multiplies Y = 0 and is dropped
+  float dPt[3][2];      // dP/dtheta columns 0 (X) and 2 (Z); its last column is 0
+  float du[3], dv[3];   // dP/dsu, dP/dsv: only the last column is non-zero -> duv1/dshift are per-sample constants
+};
+
+__device__ __forceinline__ G2spPose g2sp_pose(const LmStepArgs& a, int b, float su, float sv, float th) {
+  G2spPose g;
+  const float pi_f = 3.14159265358979323846f;
+  const float shu = __fmul_rn(a.lon, su), shv = __fmul_rn(a.lat, sv);                  // :92-93
+  const float heading = __fmul_rn(__fdiv_rn(__fmul_rn(th, a.rot), 180.f), pi_f);       // :94
+  float sn, cs;
+  sincosf(-heading, &sn, &cs);                                                          // :96-97
+  float k[3][3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) k[i / 3][i % 3] = a.extr[b * 9 + i];
+  // camera_k rows scaled to this level: row 0 * grd_W / ori_grdW, row 1 * grd_H / ori_grdH  (:111-114)
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    k[0][j] = __fdiv_rn(__fmul_rn(k[0][j], (float)a.W), (float)a.ori_w);
+    k[1][j] = __fdiv_rn(__fmul_rn(k[1][j], (float)a.H), (float)a.ori_h);
+  }
+  const float R[3][3] = {{cs, 0.f, -sn}, {0.f, 1.f, 0.f}, {sn, 0.f, cs}};
+  const float T[3] = {shv, 1.65f, -shu};                                                // :103-105
+  const float kk = (float)((double)a.rot / 180.0 * 3.14159265358979323846);
+  const float dR[3][3] = {{__fmul_rn(kk, sn), 0.f, __fmul_rn(kk, cs)}, {0.f, 0.f, 0.f}, {__fmul_rn(kk, -cs), 0.f, __fmul_rn(kk, sn)}};
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = k[r][0] * R[0][c] + k[r][1] * R[1][c] + k[r][2] * R[2][c];       // P = K [R | T]  (:116)
+      g.P[r][c] = v;
+    }
+    g.P[r][3] = k[r][0] * T[0] + k[r][1] * T[1] + k[r][2] * T[2];
+    g.dPt[r][0] = k[r][0] * dR[0][0] + k[r][1] * dR[1][0] + k[r][2] * dR[2][0];          // dP/dtheta = K [dR | 0]  (:133)
+    g.dPt[r][1] = k[r][0] * dR[0][2] + k[r][1] * dR[1][2] + k[r][2] * dR[2][2];
+    g.du[r] = k[r][2] * (-a.lon);                                                        // K [0 | lon*(0,0,-1)]  (:127,131)
+    g.dv[r] = k[r][0] * a.lat;                                                           // K [0 | lat*(1,0,0)]   (:128,132)
+  }
+  return g;
 }
 
 struct PixelWarp {
@@ -198,30 +242,70 @@ struct PixelScalars {
   float om;                    // LM weight (grd_conf or 1)
   float valid;                 // 1 when the sample point is inside the satellite map and in front of the camera
   int off_n, off_s, east;      // float4 offsets of the north / south tap rows into the sample's map, and of +1 texel
-  int goff;                    // float4 offset of the ground pixel, or -1: read zeros (geometric mask / past the end)
+  int goff;                    // float4 offset of the streamed pixel, or -1: read zeros (masked / past the end)
+  float d0x, d0y, d1x, d1y;    // G2SP only: d(u,v)/dsu and d(u,v)/dsv vary per pixel (quotient rule)
 };
 
 template <int GEOM>
 __device__ __forceinline__ PixelScalars pixel_scalars(const LmStepArgs& a, const KittiPose& kp, const FordPose& fp,
-                                                      const float4* tab, const float* conf, int q, int q_end, int c4) {
+                                                      const G2spPose& gp, const float4* tab, const float* conf, int q,
+                                                      int q_end, int c4) {
   PixelScalars r;
   r.ex = r.wx = r.sy = r.ny = 0.f; r.tx = r.ty = 0.f; r.om = 1.f; r.valid = 0.f;
   r.off_n = r.off_s = r.east = 0; r.goff = -1;
+  r.d0x = r.d0y = r.d1x = r.d1y = 0.f;
   if (q >= q_end) return r;
-  const float4 p = __ldg(tab + q);
-  if (p.w == 0.f) return r;                                  // geometric mask: s, J and g all vanish
-  r.goff = q * c4;
-  const PixelWarp w = (GEOM == HA_GEOM_KITTI) ? warp_kitti(kp, a, p) : warp_ford(fp, a, p);
-  const float x = w.u, y = w.v, hi = (float)(a.A - 1);
-  const bool inr = (x >= 0.f) && (x <= hi) && (y >= 0.f) && (y <= hi);
-  if (!inr) return r;                                        // sampler mask: s = 0, J = 0, r = -g~ (taps read texel 0, weights 0)
+  float x, y;
+  int IW, IH;
+  if (GEOM == HA_GEOM_G2SP) {
+    // satellite pixel (row i, col j) -> ground-plane point (X south, 0, Z east)  (models_kitti.py:54-84)
+    const int i = q / a.A, j = q - i * a.A;
+    const float X = __fmul_rn(a.mpp, (float)(i - (int)a.center)), Z = __fmul_rn(a.mpp, (float)(j - (int)a.center));
+    float uv1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) uv1[k] = gp.P[k][0] * X + gp.P[k][2] * Z + gp.P[k][3];
+    if (!(uv1[2] > 1e-6f)) return r;                           // behind the camera: Jacobian zeroed (:123,146-148)
+    const float w = uv1[2];                                    // == max(w, 1e-6) here
+    x = __fdiv_rn(uv1[0], w); y = __fdiv_rn(uv1[1], w);
+    IW = a.W; IH = a.H;
+    if (!((x >= 0.f) && (x <= (float)(IW - 1)) && (y >= 0.f) && (y <= (float)(IH - 1)))) return r;
+    r.goff = q * c4;                                           // only visible pixels read their satellite vector
+    const float w2 = w * w;
+    float dt1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dt1[k] = gp.dPt[k][0] * X + gp.dPt[k][1] * Z;
+    // quotient rule  d(uv) = d(uv1_xy)/w - uv1_xy * d(w)/w^2   (:139-144)
+    r.d0x = gp.du[0] / w - uv1[0] * gp.du[2] / w2; r.d0y = gp.du[1] / w - uv1[1] * gp.du[2] / w2;
+    r.d1x = gp.dv[0] / w - uv1[0] * gp.dv[2] / w2; r.d1y = gp.dv[1] / w - uv1[1] * gp.dv[2] / w2;
+    r.tx = dt1[0] / w - uv1[0] * dt1[2] / w2; r.ty = dt1[1] / w - uv1[1] * dt1[2] / w2;
+  } else {
+    const float4 p = __ldg(tab + q);
+    if (p.w == 0.f) return r;                                  // geometric mask: s, J and g all vanish
+    r.goff = q * c4;
+    const PixelWarp w = (GEOM == HA_GEOM_KITTI) ? warp_kitti(kp, a, p) : warp_ford(fp, a, p);
+    x = w.u; y = w.v; IW = IH = a.A;
+    if (!((x >= 0.f) && (x <= (float)(IW - 1)) && (y >= 0.f) && (y <= (float)(IH - 1))))
+      return r;                                                // sampler mask: s = 0, J = 0, r = -g~ (taps read texel 0, weights 0)
+    r.tx = w.jtx; r.ty = w.jty;
+  }
+  // bilinear taps of jacobian.py:147-193: four independently clamped corners
+  const float hx = (float)(IW - 1), hy = (float)(IH - 1);
   const float x0 = floorf(x), y0 = floorf(y);
-  const float xw = fminf(fmaxf(x0, 0.f), hi), xe = fminf(fmaxf(x0 + 1.f, 0.f), hi);
-  const float yn = fminf(fmaxf(y0, 0.f), hi), ys = fminf(fmaxf(y0 + 1.f, 0.f), hi);
+  const float xw = fminf(fmaxf(x0, 0.f), hx), xe = fminf(fmaxf(x0 + 1.f, 0.f), hx);
+  const float yn = fminf(fmaxf(y0, 0.f), hy), ys = fminf(fmaxf(y0 + 1.f, 0.f), hy);
   const int ixw = (int)xw, ixe = (int)xe, iyn = (int)yn, iys = (int)ys;
-  r.off_n = (iyn * a.A + ixw) * c4; r.off_s = (iys * a.A + ixw) * c4; r.east = (ixe - ixw) * c4;
-  r.ex = xe - x; r.wx = x - xw; r.sy = ys - y; r.ny = y - yn; r.tx = w.jtx; r.ty = w.jty; r.valid = 1.f;
-  if (a.using_weight && conf) r.om = __ldg(conf + q);        // models_kitti.py:994-998
+  r.off_n = (iyn * IW + ixw) * c4; r.off_s = (iys * IW + ixw) * c4; r.east = (ixe - ixw) * c4;
+  r.ex = xe - x; r.wx = x - xw; r.sy = ys - y; r.ny = y - yn; r.valid = 1.f;
+  if (a.using_weight && conf) {
+    if (GEOM == HA_GEOM_G2SP) {
+      // W = grd_conf warped with the same sampler (models_kitti.py:280-282, :361-362)
+      const int e = ixe - ixw;
+      r.om = conf[iyn * IW + ixw] * (r.ex * r.sy) + conf[iyn * IW + ixw + e] * (r.wx * r.sy) +
+             conf[iys * IW + ixw] * (r.ex * r.ny) + conf[iys * IW + ixw + e] * (r.wx * r.ny);
+    } else {
+      r.om = __ldg(conf + q);                                  // models_kitti.py:994-998
+    }
+  }
   return r;
 }
 
@@ -240,25 +324,34 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPP, cl = lane % LPP;     // pixel slot within the warp, channel lane
-  const int P = (a.H - a.H / 2) * a.W;             // bottom-half pixels (models_kitti.py:1195-1199)
+  constexpr bool G2SP = (GEOM == HA_GEOM_G2SP);
+  // S2GP: the residual lives on the bottom half of the ground image (models_kitti.py:1195-1199), the ground
+  // features are streamed and the satellite map is gathered.  G2SP: the residual lives on the whole satellite
+  // map (:333-379), the satellite features are streamed and the ground features are gathered.
+  const int P = G2SP ? a.A * a.A : (a.H - a.H / 2) * a.W;
   const int q_begin = blockIdx.x * a.px_per_cta;
   const int q_end = min(P, q_begin + a.px_per_cta);
 
   const float su = a.pose[b * 3 + 0], sv = a.pose[b * 3 + 1], th = a.pose[b * 3 + 2];
   KittiPose kp;
   FordPose fp;
-  if (GEOM == HA_GEOM_KITTI) kp = kitti_pose(a, su, sv, th); else fp = ford_pose(a, b, su, sv, th);
+  G2spPose gq;
+  if (GEOM == HA_GEOM_KITTI) kp = kitti_pose(a, su, sv, th);
+  else if (GEOM == HA_GEOM_FORD) fp = ford_pose(a, b, su, sv, th);
+  else gq = g2sp_pose(a, b, su, sv, th);
 
-  const size_t px_base = (size_t)b * a.H * a.W + (size_t)(a.H / 2) * a.W;   // first bottom-half pixel of sample b
+  // first streamed pixel of sample b, in pixels of the streamed tensor
+  const size_t px_base = G2SP ? (size_t)b * a.A * a.A : (size_t)b * a.H * a.W + (size_t)(a.H / 2) * a.W;
   // half 0 = channels [4*cl, 4*cl+4), half 1 = channels [C/2 + 4*cl, ...): each half of a pixel is one
   // contiguous 16*LPP-byte run across the pixel's lanes
-  const float4* grd = reinterpret_cast<const float4*>(a.grd) + px_base * C4 + cl;
-  const float4* sat = reinterpret_cast<const float4*>(a.sat) + (size_t)b * a.A * a.A * C4 + cl;
-  const float4* tab = a.table + (size_t)(a.H / 2) * a.W;
-  const float* conf = a.conf ? a.conf + px_base : nullptr;
+  const float4* grd = reinterpret_cast<const float4*>(G2SP ? a.sat : a.grd) + px_base * C4 + cl;              // streamed
+  const float4* sat = reinterpret_cast<const float4*>(G2SP ? a.grd : a.sat) +
+                      (G2SP ? (size_t)b * a.H * a.W : (size_t)b * a.A * a.A) * C4 + cl;                        // gathered
+  const float4* tab = G2SP ? nullptr : a.table + (size_t)(a.H / 2) * a.W;
+  const float* conf = a.conf ? (G2SP ? a.conf + (size_t)b * a.H * a.W : a.conf + px_base) : nullptr;
 
   // per-warp staging of the per-pixel scalars: phase A writes 32 pixels, phase B broadcasts them
-  __shared__ __align__(16) float4 ps_s[kLmWarps][32][3];
+  __shared__ __align__(16) float4 ps_s[kLmWarps][32][G2SP ? 4 : 3];
 
   // running sums over this lane's pixels and channels (two partial sums per register pair)
   f32x2 A_aa = 0, A_ab = 0, A_bb = 0, B_x = 0, B_y = 0, C_tt = 0;
@@ -267,6 +360,7 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
   // per-pixel channel sums (reset at the first half, consumed at the second)
   f32x2 p_aa = 0, p_ab = 0, p_bb = 0, p_sa = 0, p_sb = 0, p_ga = 0, p_gb = 0;
   float4 sc0 = make_float4(0, 0, 0, 0), sc1 = sc0;   // (ex, wx, sy, ny), (tx, ty, om, valid) of the current pixel
+  float4 sc2 = sc0;                                  // G2SP: (d0x, d0y, d1x, d1y)
   const float4* zeros = a.zeros;
 
   auto accumulate = [&](const PixelLoads& L) {
@@ -283,8 +377,8 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
       const f32x2 db = sub2(bot, top);                         // d/dy = ex (sw - nw) + wx (se - ne)  (:192-193)
       acc2(p_aa, da, da); acc2(p_ab, da, db); acc2(p_bb, db, db);
       acc2(p_sa, s, da); acc2(p_sb, s, db); acc2(p_ga, g, da); acc2(p_gb, g, db);
-      acc2(SS, s, s);
-      if (FULL) { acc2(SG, s, g); acc2(GG, g, g); }          // |g|^2 is pose independent: cached after the first visit
+      if (!G2SP) acc2(SS, s, s);
+      if (FULL && !G2SP) { acc2(SG, s, g); acc2(GG, g, g); }          // |g|^2 is pose independent: cached after the first visit
     }
   };
   auto finish_pixel = [&]() {
@@ -292,6 +386,23 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
       const f32x2 om2 = dup2(sc1.z);
       p_aa = mul2(p_aa, om2); p_ab = mul2(p_ab, om2); p_bb = mul2(p_bb, om2);
       p_sa = mul2(p_sa, om2); p_sb = mul2(p_sb, om2); p_ga = mul2(p_ga, om2); p_gb = mul2(p_gb, om2);
+    }
+    if (G2SP) {
+      // all three rows of D = d(u,v)/d(pose) vary per pixel: accumulate J^T W J (A_aa.. reused as H00,H01,H02,
+      // H11,H12,H22), J^T W s (S_*) and J^T W g (G_*) directly; there is no renormalisation in G2SP (:354)
+      const f32x2 d0x = dup2(sc2.x), d0y = dup2(sc2.y), d1x = dup2(sc2.z), d1y = dup2(sc2.w), d2x = dup2(sc1.x), d2y = dup2(sc1.y);
+      const f32x2 e0x = fma2(p_ab, d0y, mul2(p_aa, d0x)), e0y = fma2(p_bb, d0y, mul2(p_ab, d0x));   // G D_0
+      const f32x2 e1x = fma2(p_ab, d1y, mul2(p_aa, d1x)), e1y = fma2(p_bb, d1y, mul2(p_ab, d1x));
+      const f32x2 e2x = fma2(p_ab, d2y, mul2(p_aa, d2x)), e2y = fma2(p_bb, d2y, mul2(p_ab, d2x));
+      acc2(A_aa, d0x, e0x); acc2(A_aa, d0y, e0y); acc2(A_ab, d0x, e1x); acc2(A_ab, d0y, e1y);
+      acc2(A_bb, d0x, e2x); acc2(A_bb, d0y, e2y); acc2(B_x, d1x, e1x); acc2(B_x, d1y, e1y);
+      acc2(B_y, d1x, e2x); acc2(B_y, d1y, e2y); acc2(C_tt, d2x, e2x); acc2(C_tt, d2y, e2y);
+      // J^T s and J^T g kept apart: the lazy L2-norm scales of the two pyramids differ (applied by the last CTA)
+      acc2(S_a, d0x, p_sa); acc2(S_a, d0y, p_sb); acc2(S_b, d1x, p_sa); acc2(S_b, d1y, p_sb); acc2(S_t, d2x, p_sa); acc2(S_t, d2y, p_sb);
+      acc2(G_a, d0x, p_ga); acc2(G_a, d0y, p_gb); acc2(G_b, d1x, p_ga); acc2(G_b, d1y, p_gb); acc2(G_t, d2x, p_ga); acc2(G_t, d2y, p_gb);
+      cnt += sc1.w;
+      p_aa = p_ab = p_bb = p_sa = p_sb = p_ga = p_gb = 0ull;
+      return;
     }
     // d(u,v)/dsu and /dsv are per-sample constants, only d/dtheta = (tx, ty) varies per pixel, so
     // J^T J splits into sum(G), sum(G t), sum(t^T G t) and the last CTA applies the constant rows.
@@ -313,7 +424,7 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
   const int my_groups = (n_groups > warp) ? (n_groups - warp + kLmWarps - 1) / kLmWarps : 0;
   const int T = my_groups * IPG;                   // pixel-iterations of this warp
   PixelLoads bufA, bufB;
-  float4 nsc0 = sc0, nsc1 = sc1;                   // scalars of the pixel whose loads are in flight
+  float4 nsc0 = sc0, nsc1 = sc1, nsc2 = sc2;       // scalars of the pixel whose loads are in flight
 
   // addresses of the pixel whose loads are being issued (set by prepare(), used by load_half())
   const float4 *gp = zeros, *s_n = sat, *s_s = sat;
@@ -323,7 +434,8 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
     const int gbase = q_begin + (warp + (t / IPG) * kLmWarps) * 32;
     if (it == 0) {                                               // phase A: one lane per pixel, 32 pixels at once
       __syncwarp();
-      const PixelScalars ps = pixel_scalars<GEOM>(a, kp, fp, tab, conf, gbase + lane, q_end, C4);
+      const PixelScalars ps = pixel_scalars<GEOM>(a, kp, fp, gq, tab, conf, gbase + lane, q_end, C4);
+      if (G2SP) ps_s[warp][lane][G2SP ? 3 : 0] = make_float4(ps.d0x, ps.d0y, ps.d1x, ps.d1y);
       ps_s[warp][lane][0] = make_float4(ps.ex, ps.wx, ps.sy, ps.ny);
       ps_s[warp][lane][1] = make_float4(ps.tx, ps.ty, ps.om, ps.valid);
       ps_s[warp][lane][2] = make_float4(__int_as_float(ps.off_n), __int_as_float(ps.off_s), __int_as_float(ps.east),
@@ -333,6 +445,7 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
     const int src = it * PPW + sub;
     nsc0 = ps_s[warp][src][0];
     nsc1 = ps_s[warp][src][1];
+    if (G2SP) nsc2 = ps_s[warp][src][G2SP ? 3 : 0];
     const float4 o = ps_s[warp][src][2];
     const int goff = __float_as_int(o.w);
     east = __float_as_int(o.z);
@@ -350,7 +463,7 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
   // other half's (and the next pixel's first half's) are in flight.
   if (T > 0) { prepare(0); load_half(bufA, 0); load_half(bufB, 1); }
   for (int t = 0; t < T; ++t) {
-    sc0 = nsc0; sc1 = nsc1;
+    sc0 = nsc0; sc1 = nsc1; sc2 = nsc2;
     const bool more = t + 1 < T;
     if (more) prepare(t + 1);
     accumulate(bufA);
@@ -401,31 +514,42 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
   __syncthreads();
   if (threadIdx.x != 0) return;
   a.ticket[b] = 0;   // ready for the next step on this stream
-  if (FULL) { if (a.gg_cache) a.gg_cache[b] = tot[13]; }
-  else tot[13] = a.gg_cache[b];                      // sum g^2 over the unmasked bottom half, from this level's first visit
+  double Hm[3][3], gr[3], ns = 0.0, ng = 0.0, res_sq = 0.0;
+  if (G2SP) {
+    // models_kitti.py:333-379: r = grd_proj - sat with the L2-normalised features (VGG.py:172-175) and no
+    // further normalisation; the sampled (ground) and streamed (satellite) pyramids carry their own scales
+    const double as_ = a.grd_scale ? (double)a.grd_scale[b] : 1.0, bg_ = a.sat_scale ? (double)a.sat_scale[b] : 1.0;
+    const double f2 = as_ * as_, fsg = as_ * bg_;
+    const double h[6] = {tot[0] * f2, tot[1] * f2, tot[2] * f2, tot[3] * f2, tot[4] * f2, tot[5] * f2};
+    Hm[0][0] = h[0]; Hm[0][1] = Hm[1][0] = h[1]; Hm[0][2] = Hm[2][0] = h[2];
+    Hm[1][1] = h[3]; Hm[1][2] = Hm[2][1] = h[4]; Hm[2][2] = h[5];
+    for (int i = 0; i < 3; ++i) gr[i] = tot[6 + i] * f2 - tot[9 + i] * fsg;
+  } else {
+    if (FULL) { if (a.gg_cache) a.gg_cache[b] = tot[13]; }
+    else tot[13] = a.gg_cache[b];                    // sum g^2 over the unmasked bottom half, from this level's first visit
 
-  // assemble J^T W J, J^T W s, J^T W g from the split sums with the per-sample constant rows of D
-  const double d0x = (GEOM == HA_GEOM_KITTI) ? kp.jux : fp.jux, d0y = (GEOM == HA_GEOM_KITTI) ? kp.juy : fp.juy;
-  const double d1x = (GEOM == HA_GEOM_KITTI) ? kp.jvx : fp.jvx, d1y = (GEOM == HA_GEOM_KITTI) ? kp.jvy : fp.jvy;
-  const double Gaa = tot[0], Gab = tot[1], Gbb = tot[2], Bx = tot[3], By = tot[4], Ctt = tot[5];
-  const double e0x = Gaa * d0x + Gab * d0y, e0y = Gab * d0x + Gbb * d0y;    // sum(G) * D_0
-  const double e1x = Gaa * d1x + Gab * d1y, e1y = Gab * d1x + Gbb * d1y;
-  const double JtJ[6] = {d0x * e0x + d0y * e0y, d0x * e1x + d0y * e1y, d0x * Bx + d0y * By,
-                         d1x * e1x + d1y * e1y, d1x * Bx + d1y * By, Ctt};
-  const double Jts[3] = {d0x * tot[6] + d0y * tot[7], d1x * tot[6] + d1y * tot[7], tot[8]};
-  const double Jtg[3] = {d0x * tot[9] + d0y * tot[10], d1x * tot[9] + d1y * tot[10], tot[11]};
+    // assemble J^T W J, J^T W s, J^T W g from the split sums with the per-sample constant rows of D
+    const double d0x = (GEOM == HA_GEOM_KITTI) ? kp.jux : fp.jux, d0y = (GEOM == HA_GEOM_KITTI) ? kp.juy : fp.juy;
+    const double d1x = (GEOM == HA_GEOM_KITTI) ? kp.jvx : fp.jvx, d1y = (GEOM == HA_GEOM_KITTI) ? kp.jvy : fp.jvy;
+    const double Gaa = tot[0], Gab = tot[1], Gbb = tot[2], Bx = tot[3], By = tot[4], Ctt = tot[5];
+    const double e0x = Gaa * d0x + Gab * d0y, e0y = Gab * d0x + Gbb * d0y;    // sum(G) * D_0
+    const double e1x = Gaa * d1x + Gab * d1y, e1y = Gab * d1x + Gbb * d1y;
+    const double JtJ[6] = {d0x * e0x + d0y * e0y, d0x * e1x + d0y * e1y, d0x * Bx + d0y * By,
+                           d1x * e1x + d1y * e1y, d1x * Bx + d1y * By, Ctt};
+    const double Jts[3] = {d0x * tot[6] + d0y * tot[7], d1x * tot[6] + d1y * tot[7], tot[8]};
+    const double Jtg[3] = {d0x * tot[9] + d0y * tot[10], d1x * tot[9] + d1y * tot[10], tot[11]};
 
-  const double alpha = a.sat_scale ? (double)a.sat_scale[b] : 1.0;
-  const double beta = a.grd_scale ? (double)a.grd_scale[b] : 1.0;
-  const double ns = fmax(alpha * sqrt(tot[12]), 1e-6);     // models_kitti.py:982-984
-  const double ng = fmax(beta * sqrt(tot[13]), 1e-6);      // :987-988
-  const double fs = alpha * alpha / (ns * ns), fg = alpha * beta / (ns * ng);
-  double Hm[3][3] = {{JtJ[0] * fs, JtJ[1] * fs, JtJ[2] * fs},
-                     {JtJ[1] * fs, JtJ[3] * fs, JtJ[4] * fs},
-                     {JtJ[2] * fs, JtJ[4] * fs, JtJ[5] * fs}};
-  double gr[3] = {Jts[0] * fs - Jtg[0] * fg, Jts[1] * fs - Jtg[1] * fg, Jts[2] * fs - Jtg[2] * fg};
-  const double res_sq = FULL ? alpha * alpha * tot[12] / (ns * ns) + beta * beta * tot[13] / (ng * ng) -
-                                   2.0 * alpha * beta * tot[14] / (ns * ng) : 0.0;     // diagnostic, FULL launches only
+    const double alpha = a.sat_scale ? (double)a.sat_scale[b] : 1.0;
+    const double beta = a.grd_scale ? (double)a.grd_scale[b] : 1.0;
+    ns = fmax(alpha * sqrt(tot[12]), 1e-6);          // models_kitti.py:982-984
+    ng = fmax(beta * sqrt(tot[13]), 1e-6);           // :987-988
+    const double fs = alpha * alpha / (ns * ns), fg = alpha * beta / (ns * ng);
+    Hm[0][0] = JtJ[0] * fs; Hm[0][1] = Hm[1][0] = JtJ[1] * fs; Hm[0][2] = Hm[2][0] = JtJ[2] * fs;
+    Hm[1][1] = JtJ[3] * fs; Hm[1][2] = Hm[2][1] = JtJ[4] * fs; Hm[2][2] = JtJ[5] * fs;
+    for (int i = 0; i < 3; ++i) gr[i] = Jts[i] * fs - Jtg[i] * fg;
+    res_sq = FULL ? alpha * alpha * tot[12] / (ns * ns) + beta * beta * tot[13] / (ng * ng) -
+                        2.0 * alpha * beta * tot[14] / (ns * ng) : 0.0;     // diagnostic, FULL launches only
+  }
 
   // DOF selection (models_kitti.py:954-957): 3 -> (0,1,2), 2 -> (0,1), 1 -> (2)
   const int n = a.dof;
@@ -463,9 +587,11 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
   uint32_t st = 0;
   if (n == 3) {
     nsu = su + (float)delta[0]; nsv = sv + (float)delta[1]; nth = th + (float)delta[2];
-    // models_kitti.py:1028-1033: shifts outside (-2.5, 2.5) (or NaN) are re-drawn
-    if (!(nsu > -2.5f && nsu < 2.5f)) { nsu = a.reset_uv[b]; st |= HA_STATUS_RESET; }
-    if (!(nsv > -2.5f && nsv < 2.5f)) { nsv = a.reset_uv[a.B + b]; st |= HA_STATUS_RESET; }
+    // models_kitti.py:1028-1033: shifts outside (-2.5, 2.5) (or NaN) are re-drawn (S2GP models only)
+    if (!G2SP) {
+      if (!(nsu > -2.5f && nsu < 2.5f)) { nsu = a.reset_uv[b]; st |= HA_STATUS_RESET; }
+      if (!(nsv > -2.5f && nsv < 2.5f)) { nsv = a.reset_uv[a.B + b]; st |= HA_STATUS_RESET; }
+    }
   } else if (n == 2) {
     nsu = su + (float)delta[0]; nsv = sv + (float)delta[1];
   } else {
@@ -530,15 +656,18 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
                         const float* ground_table, const float* extrinsics, float* pose, const float* reset_uv,
                         float* stats, float* traj_step, int traj_stride, uint32_t* status, void* ws, size_t ws_bytes,
                         int B, bool full, cudaStream_t st) {
-  if (!p || !sat || !grd || !pose || !status || !ws || !ground_table) return HA_EINVAL;
+  const bool g2sp = p && p->geometry == HA_GEOM_G2SP;
+  if (!p || !sat || !grd || !pose || !status || !ws || (!ground_table && !g2sp)) return HA_EINVAL;
   if (level < 0 || level >= HA_MAX_LEVELS) return HA_EINVAL;
   if (sat->C != grd->C || sat->H != sat->W || (grd->H & 1)) return HA_EINVAL;
   if (p->dof < 1 || p->dof > 3) return HA_EINVAL;
-  if (p->dof == 3 && !reset_uv) return HA_EINVAL;
+  if (p->dof == 3 && !reset_uv && !g2sp) return HA_EINVAL;
+  if (g2sp && (p->dof != 3 || !extrinsics || p->ori_grd_h <= 0 || p->ori_grd_w <= 0)) return HA_EINVAL;
   if (p->using_weight && !grd_conf) return HA_EINVAL;
   if (p->geometry == HA_GEOM_FORD && !extrinsics) return HA_EINVAL;
   if (ws_bytes < lm_ws_bytes(B)) return HA_ENOSPACE;
   if (((uintptr_t)sat->data | (uintptr_t)grd->data | (uintptr_t)ground_table) & 15) return HA_EINVAL;
+  if (sat->H * sat->W >= (1 << 24) || grd->H * grd->W >= (1 << 24)) return HA_EINVAL;
 
   LmStepArgs a;
   a.sat = sat->data; a.grd = grd->data; a.sat_scale = sat->scale; a.grd_scale = grd->scale;
@@ -555,13 +684,15 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   a.rot = p->rotation_range; a.lat = p->shift_range_lat; a.lon = p->shift_range_lon;
   a.mpp = p->meter_per_pixel[level]; a.inv_mpp = p->inv_meter_per_pixel[level]; a.center = p->sat_center[level];
   for (int i = 0; i < 3; ++i) a.damping[i] = p->damping[i];
-  const int P = (grd->H - grd->H / 2) * grd->W;
+  a.ori_h = p->ori_grd_h; a.ori_w = p->ori_grd_w;
+  const int P = g2sp ? sat->H * sat->W : (grd->H - grd->H / 2) * grd->W;
   a.px_per_cta = choose_px_per_cta(B, P);
   dim3 grid((P + a.px_per_cta - 1) / a.px_per_cta, B);
   if (p->geometry == HA_GEOM_KITTI)
     return full ? launch_by_channels<HA_GEOM_KITTI, true>(grd->C, grid, st, a) : launch_by_channels<HA_GEOM_KITTI, false>(grd->C, grid, st, a);
   if (p->geometry == HA_GEOM_FORD)
     return full ? launch_by_channels<HA_GEOM_FORD, true>(grd->C, grid, st, a) : launch_by_channels<HA_GEOM_FORD, false>(grd->C, grid, st, a);
+  if (p->geometry == HA_GEOM_G2SP) return launch_by_channels<HA_GEOM_G2SP, false>(grd->C, grid, st, a);
   return HA_EINVAL;
 }
 

@@ -122,7 +122,7 @@ def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
 @dataclass
 class LmSetup:
     """Everything about one LM run that does not depend on the batch content."""
-    kind: str                  # 'kitti' | 'ford'
+    kind: str                  # 'kitti' | 'ford' | 'g2sp'
     n_iters: int
     level_first: int
     dof: int
@@ -135,7 +135,7 @@ class LmSetup:
 
 def dof_of(args, kind: str) -> int:
     """models_kitti.py:954-957; the Ford model always refines all three (models_ford.py:380)."""
-    if kind == "ford":
+    if kind in ("ford", "g2sp"):               # LM_G2SP.LM_update always refines all three (models_kitti.py:375-377)
         return 3
     if args.rotation_range == 0:
         return 2
@@ -151,8 +151,13 @@ def setup_from_args(args, kind: str, level_first: int = 0) -> LmSetup:
                    shift_range_lon=float(args.shift_range_lon))
 
 
-def resolve_damping(args, damping_param: Optional[torch.Tensor], dof: int) -> List[float]:
-    """models_kitti.py:958-966: trained lambda = 10^(-6 + 11*sigmoid(p)) else args.damping."""
+def resolve_damping(args, damping_param: Optional[torch.Tensor], dof: int, kind: str = "kitti") -> List[float]:
+    """models_kitti.py:958-966: trained lambda = 10^(-6 + 11*sigmoid(p)) else args.damping.
+    LM_G2SP uses the trained parameter as is (models_kitti.py:356-359)."""
+    if kind == "g2sp":
+        if getattr(args, "train_damping", 0):
+            return [float(v) for v in damping_param.detach().float().reshape(-1).tolist()]
+        return [float(np.float32(args.damping))] * 3
     if getattr(args, "train_damping", 0):
         lam = (10.0 ** (-6 + damping_param.detach().float().sigmoid() * 11)).reshape(-1).tolist()
         if len(lam) == 1:
@@ -194,10 +199,12 @@ def _levels(p: Pyramid, n: int):
     return arr
 
 
-def make_params(setup: LmSetup, sat: Pyramid, damping: Sequence[float], side_m: Optional[float]) -> HaLmParams:
+def make_params(setup: LmSetup, sat: Pyramid, damping: Sequence[float], side_m: Optional[float],
+                ori_grd_hw: Tuple[int, int] = (256, 1024)) -> HaLmParams:
     n = len(sat.feats)
     p = HaLmParams()
-    p.geometry = _lib.HA_GEOM_KITTI if setup.kind == "kitti" else _lib.HA_GEOM_FORD
+    p.geometry = {"kitti": _lib.HA_GEOM_KITTI, "ford": _lib.HA_GEOM_FORD, "g2sp": _lib.HA_GEOM_G2SP}[setup.kind]
+    p.ori_grd_h, p.ori_grd_w = int(ori_grd_hw[0]), int(ori_grd_hw[1])
     p.n_levels, p.n_iters, p.level_first, p.dof = n, setup.n_iters, setup.level_first, setup.dof
     p.using_weight, p.use_hessian, p.batch = setup.using_weight, setup.use_hessian, sat.batch
     p.rotation_range, p.shift_range_lat, p.shift_range_lon = setup.rotation_range, setup.shift_range_lat, setup.shift_range_lon
@@ -208,6 +215,9 @@ def make_params(setup: LmSetup, sat: Pyramid, damping: Sequence[float], side_m: 
         if setup.kind == "kitti":
             mpp = kitti_meter_per_pixel() * (SAT_PROCESS_SIDE / A)      # models_kitti.py:757-758
             center = A / 2                                              # :765
+        elif setup.kind == "g2sp":
+            mpp = kitti_meter_per_pixel() * (SAT_PROCESS_SIDE / A)      # models_kitti.py:69-70
+            center = A // 2                                             # :65
         else:
             mpp = side_m / A                                            # models_ford.py:230
             center = A // 2                                             # :231
@@ -254,8 +264,9 @@ class LmResult:
 def lm_run(setup: LmSetup, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Tensor], damping: Sequence[float],
            extrinsics: Optional[torch.Tensor] = None, side_m: Optional[float] = None,
            pose0: Optional[torch.Tensor] = None, reset_uv: Optional[torch.Tensor] = None,
-           want_stats: bool = False) -> LmResult:
-    """The whole LM loop on the current CUDA stream, no host synchronisation."""
+           want_stats: bool = False, ori_grd_hw: Tuple[int, int] = (256, 1024)) -> LmResult:
+    """The whole LM loop on the current CUDA stream, no host synchronisation.
+    `extrinsics`: Ford [B,12] (R_FL | T_FL); G2SP [B,9] (left_camera_k); None for KITTI S2GP."""
     L = _lib.lib()
     n = len(sat.feats)
     B = sat.batch
@@ -265,7 +276,7 @@ def lm_run(setup: LmSetup, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Te
     traj = torch.empty(B, setup.n_iters, n, 3, dtype=torch.float32, device=dev)
     stats = torch.empty(setup.n_iters, n, B, _lib.HA_STATS, dtype=torch.float32, device=dev) if want_stats else None
     n_steps = setup.n_iters * n
-    if setup.dof == 3:
+    if setup.dof == 3 and setup.kind != "g2sp":       # LM_G2SP has no out-of-range reset, hence no RNG draws
         if reset_uv is None:
             reset_uv = draw_reset_uv(n_steps, B)
         reset_uv = reset_uv.to(dev, torch.float32, non_blocking=True).contiguous()
@@ -275,8 +286,11 @@ def lm_run(setup: LmSetup, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Te
     if setup.kind == "ford":
         if extrinsics is None or side_m is None:
             raise _lib.HaError("Ford geometry needs R_FL/T_FL and satmap_sidelength_meters")
+    if setup.kind == "g2sp" and extrinsics is None:
+        raise _lib.HaError("G2SP geometry needs left_camera_k")
+    if extrinsics is not None:
         extrinsics = extrinsics.to(dev, torch.float32).contiguous()
-    params = make_params(setup, sat, damping, side_m)
+    params = make_params(setup, sat, damping, side_m, ori_grd_hw)
     confs = (C.c_void_p * n)()
     tabs = (C.c_void_p * n)()
     for i in range(n):
@@ -284,8 +298,11 @@ def lm_run(setup: LmSetup, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Te
         if setup.using_weight and c is None:
             raise _lib.HaError("using_weight needs ground confidence maps")
         confs[i] = c.data_ptr() if (c is not None and setup.using_weight) else None
-        assert tables[i].is_cuda and tables[i].shape[:2] == grd.feats[i].shape[1:3], "ground table / feature shape mismatch"
-        tabs[i] = tables[i].data_ptr()
+        if setup.kind == "g2sp":
+            tabs[i] = None                            # the satellite-plane points are computed in the kernel
+        else:
+            assert tables[i].is_cuda and tables[i].shape[:2] == grd.feats[i].shape[1:3], "ground table / feature shape mismatch"
+            tabs[i] = tables[i].data_ptr()
     ws, status = _workspace(dev).get(B, dev)
     rc = L.ha_lm_run(C.byref(params), _levels(sat, n), _levels(grd, n), confs, tabs,
                      extrinsics.data_ptr() if extrinsics is not None else None, pose.data_ptr(),
@@ -298,7 +315,8 @@ def lm_run(setup: LmSetup, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Te
 
 def lm_step(setup: LmSetup, level: int, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Tensor],
             damping: Sequence[float], pose: torch.Tensor, extrinsics: Optional[torch.Tensor] = None,
-            side_m: Optional[float] = None, reset_uv: Optional[torch.Tensor] = None):
+            side_m: Optional[float] = None, reset_uv: Optional[torch.Tensor] = None,
+            ori_grd_hw: Tuple[int, int] = (256, 1024)):
     """One fused LM step at `level` from `pose` [B,3]; returns (new_pose [B,3], stats [B,HA_STATS])."""
     L = _lib.lib()
     n = len(sat.feats)
@@ -306,18 +324,21 @@ def lm_step(setup: LmSetup, level: int, sat: Pyramid, grd: Pyramid, tables: Sequ
     dev = sat.feats[0].device
     pose = pose.to(dev, torch.float32).clone().contiguous()
     stats = torch.empty(B, _lib.HA_STATS, dtype=torch.float32, device=dev)
-    if setup.dof == 3:
+    if setup.dof == 3 and setup.kind != "g2sp":
         if reset_uv is None:
             reset_uv = draw_reset_uv(1, B)[0]
         reset_uv = reset_uv.to(dev, torch.float32).contiguous()
-    if setup.kind == "ford":
+    else:
+        reset_uv = None
+    if extrinsics is not None:
         extrinsics = extrinsics.to(dev, torch.float32).contiguous()
-    params = make_params(setup, sat, damping, side_m)
+    params = make_params(setup, sat, damping, side_m, ori_grd_hw)
     c = grd.confs[level] if (grd.confs and setup.using_weight) else None
     ws, status = _workspace(dev).get(B, dev)
     sl, gl = _levels(sat, n), _levels(grd, n)
     rc = L.ha_lm_step(C.byref(params), level, C.byref(sl[level]), C.byref(gl[level]),
-                      c.data_ptr() if c is not None else None, tables[level].data_ptr(),
+                      c.data_ptr() if c is not None else None,
+                      tables[level].data_ptr() if setup.kind != "g2sp" else None,
                       extrinsics.data_ptr() if extrinsics is not None else None, pose.data_ptr(),
                       reset_uv.data_ptr() if reset_uv is not None else None, stats.data_ptr(), status.data_ptr(),
                       ws.data_ptr(), ws.numel(), _stream_ptr())

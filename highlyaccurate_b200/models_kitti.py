@@ -82,3 +82,58 @@ class LM_S2GP(nn.Module):
             grd_conf_list = [c[:, None] for c in grd.confs]
             return (*r, grd_conf_list)
         return shift_lats[:, -1, -1], shift_lons[:, -1, -1], thetas[:, -1, -1]
+
+
+class LM_G2SP(nn.Module):
+    """models_kitti.py:22.  Ground features are warped onto the satellite plane with the full K[R|T]
+    projection (:86-160) and the residual lives on the whole satellite map (:333-379).
+    forward(sat_map, grd_img_left, left_camera_k, ..., mode='test') -> (lat, lon, theta)."""
+
+    KIND = "g2sp"
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.level = args.level
+        self.N_iters = args.N_iters
+        self.using_weight = args.using_weight
+        self.loss_method = args.loss_method
+        if getattr(args, "proj", "geo") != "geo":
+            raise NotImplementedError("LM_G2SP: only --proj geo is on the accelerated path (VGGUnet_G2S / 'nn' is out of scope)")
+        self.SatFeatureNet = VGGUnet(self.level)
+        self.GrdFeatureNet = VGGUnet(self.level)
+        self.damping = nn.Parameter(args.damping * torch.ones(size=(1, 3), dtype=torch.float32, requires_grad=True))   # :41
+        self.meters_per_pixel = [engine.kitti_meter_per_pixel() * (2 ** (3 - lv)) for lv in range(4)]                     # :43-46
+        self.last_result = None
+
+    def extract(self, sat_map, grd_img, want_conf):
+        sat = self.SatFeatureNet.pyramid(sat_map, want_conf=False)
+        grd = self.GrdFeatureNet.pyramid(grd_img, want_conf=want_conf)
+        return sat, grd
+
+    def refine(self, sat: engine.Pyramid, grd: engine.Pyramid, left_camera_k, ori_grd_hw=(256, 1024), pose0=None,
+               want_stats=False) -> engine.LmResult:
+        setup = engine.setup_from_args(self.args, self.KIND, 0)
+        lam = engine.resolve_damping(self.args, self.damping, 3, self.KIND)
+        B = sat.batch
+        res = engine.lm_run(setup, sat, grd, [None] * len(sat.feats), lam, extrinsics=left_camera_k.reshape(B, 9),
+                            pose0=pose0, want_stats=want_stats, ori_grd_hw=ori_grd_hw)
+        self.last_result = res
+        return res
+
+    def forward(self, sat_map, grd_img_left, left_camera_k, gt_shift_u=None, gt_shift_v=None, gt_heading=None,
+                mode='train', file_name=None, gt_depth=None):
+        """models_kitti.py:381-499."""
+        want_conf = bool(self.using_weight) or mode == 'train'
+        sat, grd = self.extract(sat_map, grd_img_left, want_conf)
+        res = self.refine(sat, grd, left_camera_k, ori_grd_hw=tuple(grd_img_left.shape[-2:]))
+        traj = res.traj
+        shift_lats, shift_lons, thetas = _TrajectoryOutputs.apply(self.damping, mode == 'train', traj[..., 1], traj[..., 0],
+                                                                  traj[..., 2])       # :472-474
+        if mode == 'train':
+            r = loss_func(self.args.loss_method, None, None, None, shift_lats, shift_lons, thetas,
+                          gt_shift_v[:, 0], gt_shift_u[:, 0], gt_heading[:, 0], None, None,
+                          self.args.coe_shift_lat, self.args.coe_shift_lon, self.args.coe_heading,
+                          self.args.coe_L1, self.args.coe_L2, self.args.coe_L3, self.args.coe_L4)
+            return (*r, [c[:, None] for c in grd.confs])
+        return shift_lats[:, -1, -1], shift_lons[:, -1, -1], thetas[:, -1, -1]

@@ -35,7 +35,10 @@ enum {
 /* geometry functors of the satellite->ground warp */
 enum {
   HA_GEOM_KITTI = 0,   /* models_kitti.py:700-801  LM_S2GP.grd2cam2world2sat               */
-  HA_GEOM_FORD = 1     /* models_ford.py:173-264   LM_S2GP_Ford.cam2body2world2sat         */
+  HA_GEOM_FORD = 1,    /* models_ford.py:173-264   LM_S2GP_Ford.cam2body2world2sat         */
+  HA_GEOM_G2SP = 2     /* models_kitti.py:54-160   LM_G2SP.get_warp_sat2real + seq_warp_real2camera:
+                          ground features warped onto the satellite plane, residual over the
+                          whole satellite map, LM_update of :333-379 (no renormalisation)     */
 };
 
 /* device status word bits (checked by the host ONCE after the loop, never per step;
@@ -74,7 +77,9 @@ typedef struct {
   float meter_per_pixel[HA_MAX_LEVELS]; /* satellite metres per pixel at each level, already
                                 rounded to fp32 the way the reference's python double is   */
   float inv_meter_per_pixel[HA_MAX_LEVELS]; /* fp32(1/mpp) with mpp in double (models_kitti.py:795) */
-  float sat_center[HA_MAX_LEVELS];      /* A/2 (KITTI) or A//2 (Ford) added to uv           */
+  float sat_center[HA_MAX_LEVELS];      /* A/2 (KITTI) or A//2 (Ford, G2SP)                  */
+  int32_t ori_grd_h, ori_grd_w;         /* G2SP: size of the ground image `left_camera_k` refers to
+                                           (models_kitti.py:111-114); ignored otherwise              */
 } HaLmParams;
 
 /* ---- library ---------------------------------------------------------------------- */
@@ -97,7 +102,8 @@ int ha_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, vo
  * ground_table: [H][W][4] fp32 = (x, y, z, mask) of the ground-plane lift in the camera
  *   frame (models_kitti.py:655-682 / models_ford.py:110-155); only rows H/2.. are read.
  * grd_conf:  [B][H][W] fp32 or NULL (required iff using_weight).
- * extrinsics: Ford only: [B][12] = R_FL row-major (9) then T_FL (3); NULL for KITTI.
+ * extrinsics: Ford: [B][12] = R_FL row-major (9) then T_FL (3); G2SP: [B][9] = left_camera_k
+ *            row-major (models_kitti.py:381); NULL for KITTI S2GP.  ground_table may be NULL for G2SP.
  * pose:      [B][3] = (shift_u, shift_v, theta) normalised units, updated IN PLACE.
  * reset_uv:  [2][B] uniform(-1,1) draws for this step (models_kitti.py:1028-1029) or NULL
  *            (required iff dof == 3).

@@ -238,6 +238,57 @@ def kat_loop(rk, rf, name, kind, make_inputs, tol=2e-6, pose0=None, **akw):
     print("%s ok  (oracle vs reference max|d| = %.2e; final pose sample0 = %s)" % (name, d, r_traj[0, -1, -1].tolist()))
 
 
+
+def kat_g2sp(rk, name, make_inputs, **akw):
+    """LM_G2SP (models_kitti.py:22-499): the reference hard-codes .cuda() (:59,68,73); run it on CPU
+    with Tensor.cuda patched to the identity (SURVEY 8c obstacle 2).  Reference trajectory + fp64 truth."""
+    a = ref_args(**akw)
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *x, **k: self
+    try:
+        net = rk.LM_G2SP(a)
+        torch.autograd.set_detect_anomaly(False)
+        oa = o_args(a)
+        sat, grd, conf, meta = make_inputs(oa)
+        B, L = sat[0].shape[0], len(sat)
+        cam_k = torch.tensor([O._KITTI_K], dtype=torch.float32).repeat(B, 1, 1)
+        su = torch.zeros(B, 1); sv = torch.zeros(B, 1); th = torch.zeros(B, 1)
+        traj = torch.zeros(B, a.N_iters, L, 3)
+        pin = torch.zeros(B, a.N_iters, L, 3)
+        with torch.no_grad():
+            for it in range(a.N_iters):
+                for lv in range(L):
+                    A = sat[lv].shape[-1]
+                    gp, gcp, dj = net.project_grd_to_map(grd[lv], conf[lv], su, sv, th, cam_k, A, 256, 1024)
+                    pin[:, it, lv] = torch.cat([su, sv, th], dim=1)
+                    su, sv, th = net.LM_update(su, sv, th, gp, gcp, sat[lv], None, dj)
+                    traj[:, it, lv] = torch.cat([su, sv, th], dim=1)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    res = O.lm_loop_g2sp(sat, grd, conf, cam_k, oa)
+    o_traj = torch.stack([res.lons, res.lats, res.thetas], dim=-1)
+    d = close(o_traj, traj, 2e-6, name + " trajectory")
+    dd = lambda xs: [x.double() for x in xs]
+    r64 = O.lm_loop_g2sp(dd(sat), dd(grd), dd(conf), cam_k.double(), oa)
+    traj64 = torch.stack([r64.lons, r64.lats, r64.thetas], dim=-1)
+    lam = oa.damping * torch.ones(1, 3, dtype=torch.float64)
+    step64 = torch.zeros(B, a.N_iters, L, 3, dtype=torch.float64)
+    hess64 = torch.zeros(a.N_iters, L, B, 3, 3, dtype=torch.float64)
+    grad64 = torch.zeros(a.N_iters, L, B, 3, dtype=torch.float64)
+    for it in range(a.N_iters):
+        for lv in range(L):
+            p = pin[:, it, lv].double()
+            u, v, t, st = O.g2sp_one_step(sat[lv].double(), grd[lv].double(), conf[lv].double(), cam_k.double(),
+                                          p[:, 0:1], p[:, 1:2], p[:, 2:3], 256, 1024, oa, lam)
+            step64[:, it, lv] = torch.cat([u, v, t], dim=1)
+            hess64[it, lv], grad64[it, lv] = st.hessian, st.grad
+    out = dict(traj=traj.numpy(), pose_in=pin.numpy(), in_csum=csum(*sat, *grd), traj64=traj64.numpy(), step64=step64.numpy(),
+               hess64=hess64.numpy(), grad64=grad64.numpy(), cam_k=cam_k.numpy(), **stats_arrays(res, a.N_iters, L))
+    out.update(meta)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("%s ok  (oracle vs reference max|d| = %.2e; final pose sample0 = %s)" % (name, d, traj[0, -1, -1].tolist()))
+
+
 FORD_EXT = dict(R=[[0., 0., 1.], [1., 0., 0.], [0., 1., 0.]], T=[1.7, -0.3, -1.5])
 
 
@@ -301,6 +352,25 @@ def main():
         p0 = torch.tensor([[3.0, 0.1, 0.2], [0.1, -2.8, -0.1]])
         kat_loop(rk, rf, "kat6_reset", "kitti", rand_inputs(61), N_iters=2,
                  pose0=(p0[:, 0:1], p0[:, 1:2], p0[:, 2:3]))
+
+    if want("g2sp"):   # LM_G2SP: ground features warped to the satellite plane
+        def g2sp_planted(seed, gt, using_conf=False):
+            def f(oa):
+                B = len(gt)
+                sat, grd = O.planted_case("kitti", B, 512, 3, seed, gt, oa)
+                g = torch.Generator().manual_seed(seed + 1)
+                conf = [torch.sigmoid(-torch.sigmoid(torch.randn(B, 1, *x.shape[-2:], generator=g))) for x in grd]
+                return sat, grd, conf, dict(seed=seed, B=B, A=512, L=3, gt=np.array(gt, dtype=np.float32))
+            return f
+
+        def g2sp_rand(seed, B=2):
+            def f(oa):
+                sat, grd, conf = O.random_pyramid(B, 512, 3, seed)
+                return sat, grd, conf, dict(seed=seed, B=B, A=512, L=3)
+            return f
+        kat_g2sp(rk, "g2sp_planted", g2sp_planted(81, GT2), N_iters=3)
+        kat_g2sp(rk, "g2sp_random", g2sp_rand(82), N_iters=2)
+        kat_g2sp(rk, "g2sp_weight", g2sp_planted(83, GT2), N_iters=2, using_weight=1)
 
     if want("kat7"):   # VGG U-Net: small image, all intermediate activations
         sd = O.vgg_state_dict(7)

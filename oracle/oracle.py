@@ -376,6 +376,113 @@ def lm_loop(kind: str, sat_feats: Sequence[torch.Tensor], grd_feats: Sequence[to
     return LoopResult(rec_u, rec_v, rec_t, stats, pin)               # models_ford.py:823-825
 
 
+
+# ----------------------------------------------------------------------------- G2SP (ground -> satellite plane)
+def g2sp_sat_table(A: int, dtype=torch.float32) -> torch.Tensor:
+    """models_kitti.py:54-84 (get_warp_sat2real): homogeneous ground-plane point of every satellite
+    pixel, [A, A, 4] = (X south, Y = 0, Z east, 1); the map centre is A // 2."""
+    i = torch.arange(0, A)
+    ii, jj = torch.meshgrid(i, i, indexing="ij")
+    uv = torch.stack([jj, ii], dim=-1).float()
+    uv_c = uv - torch.tensor([A // 2, A // 2])
+    mpp = meter_per_pixel_base()
+    mpp *= SAT_PROCESS_SIDE / A
+    aff = mpp * torch.tensor([[0, 1], [1, 0]]).float()
+    xz = torch.einsum("ij, hwj -> hwi", aff, uv_c)
+    y = torch.zeros_like(xz[..., 0:1])
+    return torch.cat([xz[:, :, :1], y, xz[:, :, 1:], torch.ones_like(y)], dim=-1).to(dtype)
+
+
+def g2sp_cam_uv(xyz1: torch.Tensor, su, sv, th, cam_k: torch.Tensor, gh: int, gw: int, ori_h: int, ori_w: int,
+                args: LMArgs):
+    """models_kitti.py:86-160 (seq_warp_real2camera): project the satellite-plane points into the
+    ground camera, P = K_l [R(-heading) | T], perspective divide with max(w, 1e-6), quotient-rule
+    Jacobians zeroed where w <= 1e-6.  Returns uv[B,A,A,2], (duv/dsu, duv/dsv, duv/dth), mask[B,A,A,1]."""
+    dt = su.dtype
+    B = th.shape[0]
+    shu = args.shift_range_lon * su
+    shv = args.shift_range_lat * sv
+    heading = th * args.rotation_range / 180 * np.pi
+    c, s = torch.cos(-heading), torch.sin(-heading)
+    z0, o1 = torch.zeros_like(c), torch.ones_like(c)
+    R = torch.cat([c, z0, -s, z0, o1, z0, s, z0, c], dim=-1).view(B, 3, 3)
+    T = torch.cat([shv, CAMERA_HEIGHT * torch.ones_like(shu), -shu], dim=-1).unsqueeze(-1)
+    k = cam_k.clone()
+    k[:, :1, :] = cam_k[:, :1, :] * gw / ori_w
+    k[:, 1:2, :] = cam_k[:, 1:2, :] * gh / ori_h
+    P = k @ torch.cat([R, T], dim=-1)
+    uv1 = torch.sum(P[:, None, None, :, :] * xyz1[None, :, :, None, :], dim=-1)
+    w = torch.maximum(uv1[..., 2:], torch.ones_like(uv1[..., 2:]) * 1e-6)
+    uv = uv1[..., :2] / w
+    mask = torch.greater(w, torch.ones_like(w) * 1e-6)
+    kk = args.rotation_range / 180 * np.pi
+    dT_u = args.shift_range_lon * torch.tensor([0.0, 0.0, -1.0], dtype=dt).view(1, 3, 1).repeat(B, 1, 1)
+    dT_v = args.shift_range_lat * torch.tensor([1.0, 0.0, 0.0], dtype=dt).view(1, 3, 1).repeat(B, 1, 1)
+    dR = (kk * torch.cat([s, z0, c, z0, z0, z0, -c, z0, s], dim=-1)).view(B, 3, 3)
+    Rz, Tz = torch.zeros(B, 3, 3, dtype=dt), torch.zeros(B, 3, 1, dtype=dt)
+    out = []
+    for dP in (k @ torch.cat([Rz, dT_u], dim=-1), k @ torch.cat([Rz, dT_v], dim=-1), k @ torch.cat([dR, Tz], dim=-1)):
+        d1 = torch.sum(dP[:, None, None, :, :] * xyz1[None, :, :, None, :], dim=-1)
+        d = d1[..., 0:2] / w - uv1[..., :2] * d1[..., 2:] / (w ** 2)
+        out.append(torch.where(mask, d, torch.zeros_like(d)))
+    return uv, out[0], out[1], out[2], mask
+
+
+def g2sp_lm_update(su, sv, th, grd_proj, grd_conf_proj, sat_feat, dfeat, args: LMArgs, damping: torch.Tensor):
+    """models_kitti.py:333-379 (LM_G2SP.LM_update): r = grd_proj - sat, NO renormalisation, identity
+    damping, always 3 DOF, no out-of-range reset."""
+    N, B, C, H, W = dfeat.shape
+    r = grd_proj - sat_feat
+    if args.using_weight:
+        w = grd_conf_proj.repeat(1, C, 1, 1).reshape(B, C * H * W)
+    else:
+        w = torch.ones([B, C * H * W], dtype=sat_feat.dtype)
+    J = dfeat.flatten(start_dim=2).permute(1, 2, 0)
+    JtW = J.transpose(1, 2) * w.unsqueeze(1)
+    Hm = JtW @ J
+    eye = torch.eye(N, dtype=sat_feat.dtype).unsqueeze(0).repeat(B, 1, 1)
+    grad = JtW @ r.reshape(B, C * H * W, 1)
+    delta = -torch.inverse(Hm + damping * eye) @ JtW @ r.reshape(B, C * H * W, 1)
+    st = StepStats(Hm, grad[:, :, 0], torch.zeros(B), torch.zeros(B), torch.sum(r.reshape(B, -1) ** 2, dim=-1), delta[:, :, 0])
+    return su + delta[:, 0:1, 0], sv + delta[:, 1:2, 0], th + delta[:, 2:, 0], st
+
+
+def g2sp_one_step(sf, gf, gc, cam_k, su, sv, th, ori_h: int, ori_w: int, args: LMArgs, lam):
+    """One (iteration, level) body of LM_G2SP.forward (models_kitti.py:432-470):
+    project_grd_to_map (:163-177,276-287) -> LM_update."""
+    A = sf.shape[-1]
+    gh, gw = gf.shape[-2:]
+    xyz1 = g2sp_sat_table(A, sf.dtype)
+    uv, ju, jv, jt, mask = g2sp_cam_uv(xyz1, su, sv, th, cam_k.to(sf.dtype), gh, gw, ori_h, ori_w, args)
+    gp, dj = bilinear_sample(gf, uv, torch.stack([ju, jv, jt], dim=0))
+    gcp = bilinear_sample(gc, uv)[0] if gc is not None else None
+    return g2sp_lm_update(su, sv, th, gp, gcp, sf, dj, args, lam)
+
+
+def lm_loop_g2sp(sat_feats, grd_feats, grd_confs, cam_k, args: LMArgs, damping_param=None, ori_hw=(256, 1024),
+                 pose0=None) -> LoopResult:
+    """models_kitti.py:381-499 (LM_G2SP.forward, mode='test'), iteration-first only."""
+    L = len(sat_feats)
+    B = sat_feats[0].shape[0]
+    dt = sat_feats[0].dtype
+    if pose0 is None:
+        su = torch.zeros([B, 1], dtype=dt); sv = torch.zeros([B, 1], dtype=dt); th = torch.zeros([B, 1], dtype=dt)
+    else:
+        su, sv, th = [p.clone().to(dt) for p in pose0]
+    lam = damping_param.to(dt) if args.train_damping else args.damping * torch.ones(1, 3, dtype=dt)   # :356-359
+    rec = torch.zeros(3, B, args.N_iters, L, dtype=dt)
+    stats = [[None] * L for _ in range(args.N_iters)]
+    pin = [[None] * L for _ in range(args.N_iters)]
+    for it in range(args.N_iters):
+        for lv in range(L):
+            pin[it][lv] = (su.clone(), sv.clone(), th.clone())
+            su, sv, th, st = g2sp_one_step(sat_feats[lv], grd_feats[lv], grd_confs[lv], cam_k, su, sv, th, ori_hw[0],
+                                           ori_hw[1], args, lam)
+            stats[it][lv] = st
+            rec[0][:, it, lv], rec[1][:, it, lv], rec[2][:, it, lv] = su[:, 0], sv[:, 0], th[:, 0]
+    return LoopResult(rec[1], rec[0], rec[2], stats, pin)           # :472-474: lats = shift_v, lons = shift_u
+
+
 # ----------------------------------------------------------------------------- VGG U-Net
 def l2_norm(x: torch.Tensor) -> torch.Tensor:
     """VGG.py:511-514: per-sample L2 normalisation over C*H*W (F.normalize, eps 1e-12)."""

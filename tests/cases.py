@@ -89,3 +89,22 @@ def args_from_lmargs(a: "O.LMArgs"):
     return ref_args(level=a.level, N_iters=a.N_iters, using_weight=a.using_weight, damping=a.damping,
                     train_damping=a.train_damping, rotation_range=a.rotation_range, shift_range_lat=a.shift_range_lat,
                     shift_range_lon=a.shift_range_lon, use_hessian=a.use_hessian)
+
+
+G2SP_CASES = {"g2sp_planted": ("planted", dict(N_iters=3)), "g2sp_random": ("rand", dict(N_iters=2)),
+              "g2sp_weight": ("planted", dict(N_iters=2, using_weight=1))}
+
+
+def build_g2sp_case(name):
+    fam, akw = G2SP_CASES[name]
+    gold = load_golden(name)
+    args = O.LMArgs(**akw)
+    seed, B, A, L = int(gold["seed"]), int(gold["B"]), int(gold["A"]), int(gold["L"])
+    if fam == "rand":
+        sat, grd, conf = O.random_pyramid(B, A, L, seed)
+    else:
+        sat, grd = O.planted_case("kitti", B, A, L, seed, gold["gt"], args)
+        g = torch.Generator().manual_seed(seed + 1)
+        conf = [torch.sigmoid(-torch.sigmoid(torch.randn(B, 1, *x.shape[-2:], generator=g))) for x in grd]
+    np.testing.assert_allclose(csum(*sat, *grd), gold["in_csum"], rtol=1e-6, err_msg="input regeneration drifted")
+    return dict(args=args, sat=sat, grd=grd, conf=conf, cam_k=torch.from_numpy(gold["cam_k"]), gold=gold, B=B, A=A, L=L)

@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # sizes implied by include/ha_b200.h (LP64): HaLevel 2 ptr + 3 int32 (+pad), HaLmParams 8 int32 + 18 float
     assert ctypes.sizeof(_lib.HaLevel) == 32
-    assert ctypes.sizeof(_lib.HaLmParams) == 8 * 4 + (3 + 3 + 4 + 4 + 4) * 4
+    assert ctypes.sizeof(_lib.HaLmParams) == 8 * 4 + (3 + 3 + 4 + 4 + 4) * 4 + 2 * 4
     assert ctypes.sizeof(_lib.HaVggStateDict) == 2 * 17 * 8
 
 

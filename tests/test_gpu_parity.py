@@ -17,7 +17,7 @@ import torch
 os.environ.setdefault("HA_QUIET", "1")
 from highlyaccurate_b200 import _lib, engine  # noqa: E402
 from highlyaccurate_b200.models_ford import LM_S2GP_Ford  # noqa: E402
-from highlyaccurate_b200.models_kitti import LM_S2GP  # noqa: E402
+from highlyaccurate_b200.models_kitti import LM_G2SP, LM_S2GP  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 from tests import cases as K  # noqa: E402
 
@@ -118,6 +118,35 @@ def test_lm_per_step_vs_reference(name):
             np.testing.assert_allclose(st[:, 12], g["sat_norm"][it, lv], rtol=1e-4)   # fp32 torch.norm is itself ~3e-5 off
             np.testing.assert_allclose(st[:, 13], g["grd_norm"][it, lv], rtol=1e-4)
             assert near(st[:, 15:15 + n], g["delta"][it, lv], g["delta64"][it, lv], 2e-6)
+
+
+@pytest.mark.parametrize("name", list(K.G2SP_CASES))
+def test_g2sp_vs_reference(name):
+    """LM_G2SP (ground -> satellite plane): whole trajectory and every step restarted from the
+    reference's pose state, against the reference's outputs and the float64 truth."""
+    c = K.build_g2sp_case(name)
+    g = c["gold"]
+    net = LM_G2SP(K.args_from_lmargs(c["args"])).to(DEV)
+    sat = engine.Pyramid.from_nchw([s.to(DEV) for s in c["sat"]])
+    grd = engine.Pyramid.from_nchw([x.to(DEV) for x in c["grd"]], [x.to(DEV) for x in c["conf"]])
+    res = net.refine(sat, grd, c["cam_k"].to(DEV))
+    got, want, truth = res.traj.cpu().numpy(), g["traj"], g["traj64"]
+    assert not int(res.status.item()) & _lib.HA_STATUS_NAN_POSE
+    ok = (np.abs(got - want) <= 5e-5) | (np.abs(got - truth) <= 1.5 * np.abs(want - truth) + 2e-6)
+    assert ok.all(), (np.abs(got - want).max(), np.abs(got - truth).max())
+    setup = engine.setup_from_args(K.args_from_lmargs(c["args"]), "g2sp", 0)
+    kmat = c["cam_k"].reshape(-1, 9).to(DEV)
+    for it in range(c["args"].N_iters):
+        for lv in range(c["L"]):
+            pin = torch.from_numpy(g["pose_in"][:, it, lv])
+            pose, st = engine.lm_step(setup, lv, sat, grd, [None] * c["L"], [c["args"].damping] * 3, pin, kmat)
+            pose, st = pose.cpu().numpy(), st.cpu().numpy()
+            w_, t_ = g["traj"][:, it, lv], g["step64"][:, it, lv]
+            ok = (np.abs(pose - w_) <= 2e-6 + 1e-4 * np.abs(w_)) | (np.abs(pose - t_) <= 1.5 * np.abs(w_ - t_) + 1e-6)
+            assert ok.all(), "%s it%d lv%d: %g vs ref, %g vs fp64" % (name, it, lv, np.abs(pose - w_).max(), np.abs(pose - t_).max())
+            Ht = g["hess64"][it, lv]
+            Hm = st[:, :9].reshape(-1, 3, 3)
+            assert np.abs(Hm - Ht).max() <= 2e-4 * np.abs(Ht).max()
 
 
 def test_lm_deterministic_and_batch_invariant():

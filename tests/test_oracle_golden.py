@@ -79,3 +79,11 @@ def test_kat7_vgg(level):
     for i in range(len(feats)):
         np.testing.assert_allclose(feats[i].numpy(), g["feat%d" % i], atol=1e-6)
         np.testing.assert_allclose(confs[i].numpy(), g["conf%d" % i], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["g2sp_random", "g2sp_weight"])
+def test_g2sp_loop_matches_reference(name):
+    c = K.build_g2sp_case(name)
+    res = O.lm_loop_g2sp(c["sat"], c["grd"], c["conf"], c["cam_k"], c["args"])
+    traj = torch.stack([res.lons, res.lats, res.thetas], dim=-1)
+    np.testing.assert_allclose(traj.numpy(), c["gold"]["traj"], rtol=0, atol=2e-6)
