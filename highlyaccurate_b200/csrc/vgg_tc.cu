@@ -12,9 +12,10 @@
 // kind::f16 MMAs per k-step into two fp32 TMEM accumulators, error ~2^-22 per product, i.e.
 // fp32-grade features from the fp16 tensor pipe.  HA_CONV_F16 issues only the first MMA.
 //
-// Warp roles (256 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
-// MMA issuer (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM ->
-// registers -> bias / ReLU / 2x2 max-pool by warp shuffles / x2 nearest upsample -> global).
+// Warp roles (384 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
+// MMA issuer (one elected lane), warp 2 = TMEM allocator, warps 4-11 = epilogue, two warps per TMEM
+// lane quarter alternating 32-column chunks (TMEM -> registers -> bias / ReLU / 2x2 max-pool by warp
+// shuffles / x2 nearest upsample -> global): short-K layers (conv0, conv2, dec2) are epilogue-bound.
 // smem ring of STAGES k-blocks (full/empty mbarriers), two accumulator stages in TMEM
 // (tmem_full/tmem_empty mbarriers) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
@@ -99,7 +100,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
 // ------------------------------------------------------------------------------ the kernel
 constexpr int kTileW = 16, kTileH = 8, kBlockM = kTileW * kTileH;   // 128 pixels = UMMA M
 constexpr int kBlockK = 64;                                           // fp16 elements = 128 B
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 384;                                       // 4 control warps + 8 epilogue warps
 constexpr int kABytes = kBlockM * kBlockK * 2;                        // 16 KB
 
 struct TcConvArgs {
@@ -110,6 +111,7 @@ struct TcConvArgs {
   float* feat; int feat_pooled;               // v or pool(v), raw fp32 -> [B][h][w][cout]
   int B, H, W, cout;
   int n_kchunks;                              // ceil(cin / 64)
+  int n_taps;                                 // 9 (3x3, pad 1) or 1 (1x1: conv0 over im2col channels)
   int tiles_x, tiles_y, tiles_n, n_tiles;
 };
 
@@ -123,20 +125,23 @@ struct TcCfg {
 
 template <int NV>
 __device__ __forceinline__ void store_split(__half* dst_hi, int pitch, const float (&v)[NV], int n) {
-  // v[0..n) -> fp16 hi at dst_hi[0..n), fp16 lo*2^11 at dst_hi[pitch + 0..n); n in {16, 32}
+  // v[0..n) -> fp16 hi at dst_hi[0..n), fp16 lo*2^11 at dst_hi[pitch + 0..n); n in {16, 32}.
+  // Two elements per conversion: cvt.rn.f16x2.f32 for hi, one FFMA each for (v - hi) * 2^11, cvt again for lo.
 #pragma unroll
   for (int j = 0; j < NV; j += 8) {
     if (j >= n) break;
-    __align__(16) __half hi[8];
-    __align__(16) __half lo[8];
+    uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const __half h = __float2half_rn(v[j + e]);
-      hi[e] = h;
-      lo[e] = __float2half_rn((v[j + e] - __half2float(h)) * kLoScale);
+    for (int e = 0; e < 4; ++e) {
+      const float v0 = v[j + 2 * e], v1 = v[j + 2 * e + 1];
+      const __half2 h = __floats2half2_rn(v0, v1);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(__fmaf_rn(v0, kLoScale, -hf.x * kLoScale), __fmaf_rn(v1, kLoScale, -hf.y * kLoScale));
+      hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[e] = *reinterpret_cast<const uint32_t*>(&l);
     }
-    *reinterpret_cast<uint4*>(dst_hi + j) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(dst_hi + pitch + j) = *reinterpret_cast<const uint4*>(lo);
+    *reinterpret_cast<uint4*>(dst_hi + j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst_hi + pitch + j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -163,7 +168,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_512(tmem_slot);
@@ -171,7 +176,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_kb = 9 * a.n_kchunks;
+  const int total_kb = a.n_taps * a.n_kchunks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -183,7 +188,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int y0 = (pt % a.tiles_y) * kTileH; const int b = pt / a.tiles_y;
         for (int kb = 0; kb < total_kb; ++kb) {
           const int tap = kb / a.n_kchunks, kc = kb % a.n_kchunks;
-          const int ky = tap / 3, kx = tap % 3;
+          const int ky = a.n_taps == 1 ? 1 : tap / 3, kx = a.n_taps == 1 ? 1 : tap % 3;
           mbar_wait(empty + stage, phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(full + stage, Cfg::kStageBytes);
@@ -238,6 +243,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int egrp = (warp - 4) >> 2;                     // two warps share a quarter: they alternate column chunks
     const int h_loc = q * 2 + (lane >> 4), w_loc = lane & 15;
     const bool pool_owner = ((lane & 1) == 0) && ((lane & 16) == 0);
     const bool any_pool = a.act_pool != nullptr || a.feat_pooled;
@@ -252,7 +258,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+      for (int c0 = egrp * CH; c0 < BLOCK_N; c0 += 2 * CH) {
         uint32_t r0[32], r1[32];
         if (CH == 32) { tmem_ld_x32(taddr + c0, r0); if (SPLIT) tmem_ld_x32(taddr + BLOCK_N + c0, r1); }
         else { tmem_ld_x16(taddr + c0, r0); if (SPLIT) tmem_ld_x16(taddr + BLOCK_N + c0, r1); }
@@ -422,10 +428,10 @@ static int make_act_map(CUtensorMap* m, const __half* base, int pitch, int coff,
 }
 
 // weights [9][cout_pad][cin_pad] fp16: dims (Cin, Cout, tap)
-static int make_weight_map(CUtensorMap* m, const __half* base, int cin_pad, int cout_pad, int block_n) {
+static int make_weight_map(CUtensorMap* m, const __half* base, int cin_pad, int cout_pad, int block_n, int n_taps) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return HA_ECUDA; }
-  cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, 9};
+  cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)n_taps};
   cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * cout_pad * 2};
   cuuint32_t box[3] = {kBlockK, (cuuint32_t)block_n, 1};
   cuuint32_t es[3] = {1, 1, 1};
@@ -449,16 +455,16 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtens
 
 // One 3x3 conv layer on the tensor cores.  in: activation planes (pitch/coff/cin), weights from the packed buffer.
 int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* packed, const PackedConv& pc, int cout,
-            bool has_bias, const TcOut& o, int B, int H, int W, bool split, cudaStream_t st) {
+            bool has_bias, const TcOut& o, int B, int H, int W, bool split, cudaStream_t st, int n_taps) {
   if ((W % kTileW) || (H % kTileH) || (cin % 8) || (in_coff % 8) || (in_pitch % 8)) return HA_EINVAL;
   const int block_n = cout >= 128 ? 128 : cout;
   if (block_n != 128 && block_n != 64 && block_n != 32 && block_n != 16) return HA_EINVAL;
   CUtensorMap ta, tbh, tbl;
   int rc = make_act_map(&ta, in, in_pitch, in_coff, cin, B, H, W);
   if (rc != HA_OK) return rc;
-  rc = make_weight_map(&tbh, reinterpret_cast<const __half*>(packed + pc.hi), pc.cin_pad, pc.cout_pad, block_n);
+  rc = make_weight_map(&tbh, reinterpret_cast<const __half*>(packed + pc.hi), pc.cin_pad, pc.cout_pad, block_n, n_taps);
   if (rc != HA_OK) return rc;
-  rc = make_weight_map(&tbl, reinterpret_cast<const __half*>(packed + pc.lo), pc.cin_pad, pc.cout_pad, block_n);
+  rc = make_weight_map(&tbl, reinterpret_cast<const __half*>(packed + pc.lo), pc.cin_pad, pc.cout_pad, block_n, n_taps);
   if (rc != HA_OK) return rc;
   TcConvArgs a;
   a.bias = has_bias ? reinterpret_cast<const float*>(packed + pc.bias) : nullptr;
@@ -468,6 +474,7 @@ int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* pa
   a.feat = o.feat; a.feat_pooled = o.feat_pooled;
   a.B = B; a.H = H; a.W = W; a.cout = cout;
   a.n_kchunks = (cin + kBlockK - 1) / kBlockK;
+  a.n_taps = n_taps;
   a.tiles_x = W / kTileW; a.tiles_y = H / kTileH; a.tiles_n = cout / block_n;
   a.n_tiles = a.tiles_x * a.tiles_y * a.tiles_n * B;
 #define HA_TC_CASE(N)                                                              \
@@ -498,6 +505,8 @@ int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, 
   if ((W % (4 * kTileW)) || (H % (4 * kTileH))) return HA_EINVAL;   // tiles must fit down to the 1/4 scale
   int rc;
 #define HA_TRY(x) do { rc = (x); if (rc != HA_OK) return rc; } while (0)
+  // conv0 stays on the CUDA cores: a tensor-core variant (im2col channels + 1x1 tcgen05 conv, n_taps = 1) was
+  // measured at 1.39 ms vs 1.30 ms for this kernel at B = 32 (one k-block per tile: L2->smem and epilogue bound)
   conv0_kernel<<<dim3((W + kC0TW - 1) / kC0TW, (H + kC0TH - 1) / kC0TH, B), 256, 0, st>>>(
       img, reinterpret_cast<const float*>(packed + L.c[L_CONV0].f32), reinterpret_cast<const float*>(packed + L.c[L_CONV0].bias),
       a1, H, W);

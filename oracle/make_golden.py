@@ -392,6 +392,9 @@ def main():
             np.savez_compressed(os.path.join(GOLD, "kat7_vgg_level%d.npz" % level), **out)
         print("KAT-7 VGG ok")
 
+    if want("e2eg2sp"):
+        e2e_g2sp(rk)
+
     if want("e2e"):    # whole forward through the reference nn.Module (VGG + LM), KITTI + Ford
         sd = {}
         sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
@@ -424,6 +427,39 @@ def main():
                                 lats=o.lats.numpy(), lons=o.lons.numpy(), thetas=o.thetas.numpy(),
                                 in_csum=csum(sat, grd))
             print("e2e %s ok (max|d| %.2e) final=%s" % (kind, d, r.tolist()))
+
+
+def e2e_g2sp(rk):
+    """Whole LM_G2SP.forward (VGG + LM) through the reference nn.Module on CPU (Tensor.cuda patched)."""
+    sd = {}
+    sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+    sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+    g = torch.Generator().manual_seed(2022)
+    sat = torch.rand(2, 3, 512, 512, generator=g)
+    grd = torch.rand(2, 3, 256, 1024, generator=g)
+    cam_k = torch.tensor([O._KITTI_K], dtype=torch.float32).repeat(2, 1, 1)
+    a = ref_args()
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *x, **k: self
+    try:
+        net = rk.LM_G2SP(a)
+        torch.autograd.set_detect_anomaly(False)
+        sd["damping"] = net.damping.detach().clone()
+        net.load_state_dict(sd)
+        net.eval()
+        with torch.no_grad():
+            r = torch.stack(net(sat, grd, cam_k, mode="test"), dim=-1)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    oa = o_args(a)
+    sf, _ = O.vgg_unet(sd, sat, 3, "SatFeatureNet.")
+    gf, gc = O.vgg_unet(sd, grd, 3, "GrdFeatureNet.")
+    res = O.lm_loop_g2sp(sf, gf, gc, cam_k, oa)
+    of = torch.stack([res.lats[:, -1, -1], res.lons[:, -1, -1], res.thetas[:, -1, -1]], dim=-1)
+    d = close(of, r, 1e-5, "e2e g2sp")
+    np.savez_compressed(os.path.join(GOLD, "e2e_g2sp.npz"), final=r.numpy(), lats=res.lats.numpy(), lons=res.lons.numpy(),
+                        thetas=res.thetas.numpy(), in_csum=csum(sat, grd), cam_k=cam_k.numpy())
+    print("e2e g2sp ok (max|d| %.2e) final=%s" % (d, r.tolist()))
 
 
 if __name__ == "__main__":

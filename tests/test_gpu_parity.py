@@ -269,6 +269,27 @@ def test_end_to_end_forward_vs_reference(kind):
     np.testing.assert_allclose(traj[:, 0], ref_traj[:, 0], atol=5e-5)     # first sweep: before chaos accumulates
 
 
+def test_end_to_end_g2sp_forward_vs_reference():
+    g = K.load_golden("e2e_g2sp")
+    sd = {}
+    sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+    sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+    gen = torch.Generator().manual_seed(2022)
+    sat = torch.rand(2, 3, 512, 512, generator=gen)
+    grd = torch.rand(2, 3, 256, 1024, generator=gen)
+    np.testing.assert_allclose(K.csum(sat, grd), g["in_csum"], rtol=1e-6)
+    net = LM_G2SP(K.ref_args()).to(DEV)
+    sd["damping"] = net.damping.detach().clone()
+    net.load_state_dict(sd)
+    out = net(sat.to(DEV), grd.to(DEV), torch.from_numpy(g["cam_k"]).to(DEV), mode="test")
+    assert all(o.requires_grad for o in out)
+    got = torch.stack([o.detach() for o in out], dim=-1).cpu().numpy()
+    np.testing.assert_allclose(got, g["final"], atol=3e-4)       # same chaos bound as the S2GP end-to-end test
+    traj = net.last_result.traj.cpu().numpy()
+    ref_traj = np.stack([g["lons"], g["lats"], g["thetas"]], -1)
+    np.testing.assert_allclose(traj[:, 0], ref_traj[:, 0], atol=5e-5)
+
+
 def test_full_size_properties():
     """BASELINE config-2 size (B=32, KITTI shapes): planted-pose convergence, determinism, and
     permutation equivariance over the batch — size-independent properties, no oracle run needed."""
