@@ -140,7 +140,8 @@ def run_reference(opt):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": opt.gpus, "steps": opt.steps,
             "warmup": opt.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(opt, 1, "cpu"),
+            "config": dict(workload_config(opt, opt.batch, "host CPU"), vgg_precision="f32 (torch CPU)",
+                           sample="1 pair per step (bounded sample of the batch-%d workload)" % opt.batch),
             "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -192,7 +193,8 @@ def main():
     host_grd = [torch.rand(B, 3, 256, 1024, generator=g).pin_memory() for _ in range(2)]
     sat_d, grd_d = host_sat[0].to(dev), host_grd[0].to(dev)
     n_steps_lm = opt.n_iters * opt.level
-    draws = torch.zeros(n_steps_lm, 2, B)            # reset draws are host RNG work outside the device path
+    draws = torch.zeros(n_steps_lm, 2, B, device=dev)   # reset draws resident on the device (the host RNG draws of the
+                                                          # reference are made by forward() itself in the e2e loop)
 
     def sync():
         torch.cuda.synchronize()
