@@ -12,10 +12,10 @@
 // kind::f16 MMAs per k-step into two fp32 TMEM accumulators, error ~2^-22 per product, i.e.
 // fp32-grade features from the fp16 tensor pipe.  HA_CONV_F16 issues only the first MMA.
 //
-// Warp roles (384 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
-// MMA issuer (one elected lane), warp 2 = TMEM allocator, warps 4-11 = epilogue, two warps per TMEM
-// lane quarter alternating 32-column chunks (TMEM -> registers -> bias / ReLU / 2x2 max-pool by warp
-// shuffles / x2 nearest upsample -> global): short-K layers (conv0, conv2, dec2) are epilogue-bound.
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 =
+// MMA issuer (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue, one per TMEM lane
+// quarter (TMEM -> registers -> bias / ReLU / 2x2 max-pool by warp shuffles -> swizzled smem staging
+// row per pixel -> coalesced 64/128-byte segments to global, incl. the x2 nearest upsample).
 // smem ring of STAGES k-blocks (full/empty mbarriers), two accumulator stages in TMEM
 // (tmem_full/tmem_empty mbarriers) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
@@ -100,7 +100,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
 // ------------------------------------------------------------------------------ the kernel
 constexpr int kTileW = 16, kTileH = 8, kBlockM = kTileW * kTileH;   // 128 pixels = UMMA M
 constexpr int kBlockK = 64;                                           // fp16 elements = 128 B
-constexpr int kTcThreads = 384;                                       // 4 control warps + 8 epilogue warps
+constexpr int kTcThreads = 256;                                       // 4 control warps + 4 epilogue warps
 constexpr int kABytes = kBlockM * kBlockK * 2;                        // 16 KB
 
 struct TcConvArgs {
@@ -119,9 +119,27 @@ template <int BLOCK_N, bool SPLIT>
 struct TcCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = (kABytes + kBBytes) * (SPLIT ? 2 : 1);
-  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStages = (192 * 1024 / kStageBytes) > 8 ? 8 : (192 * 1024 / kStageBytes);
+  static constexpr int kStagingBytes = 4 * 32 * 128;     // epilogue: one 32-row x 128-byte staging tile per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
 };
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+// two fp32 values -> packed fp16 hi pair and packed fp16 (v - hi) * 2^11 pair
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(__fmaf_rn(v0, kLoScale, -hf.x * kLoScale), __fmaf_rn(v1, kLoScale, -hf.y * kLoScale));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 template <int NV>
 __device__ __forceinline__ void store_split(__half* dst_hi, int pitch, const float (&v)[NV], int n) {
@@ -160,6 +178,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* tmem_full = bars + 2 * STAGES;  // [2]       MMA -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;     // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* staging = smem + STAGES * Cfg::kStageBytes + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -168,7 +187,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_512(tmem_slot);
@@ -243,9 +262,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
-    const int egrp = (warp - 4) >> 2;                     // two warps share a quarter: they alternate column chunks
-    const int h_loc = q * 2 + (lane >> 4), w_loc = lane & 15;
-    const bool pool_owner = ((lane & 1) == 0) && ((lane & 16) == 0);
+    const uint32_t stg = smem_u32(staging) + (warp - 4) * (32 * 128);
     const bool any_pool = a.act_pool != nullptr || a.feat_pooled;
     int t = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++t) {
@@ -253,12 +270,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int n_idx = tile % a.tiles_n; int pt = tile / a.tiles_n;
       const int x0 = (pt % a.tiles_x) * kTileW; pt /= a.tiles_x;
       const int y0 = (pt % a.tiles_y) * kTileH; const int b = pt / a.tiles_y;
-      const int y = y0 + h_loc, x = x0 + w_loc;
       mbar_wait(tmem_full + as, aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
 #pragma unroll 1
-      for (int c0 = egrp * CH; c0 < BLOCK_N; c0 += 2 * CH) {
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
         uint32_t r0[32], r1[32];
         if (CH == 32) { tmem_ld_x32(taddr + c0, r0); if (SPLIT) tmem_ld_x32(taddr + BLOCK_N + c0, r1); }
         else { tmem_ld_x16(taddr + c0, r0); if (SPLIT) tmem_ld_x16(taddr + BLOCK_N + c0, r1); }
@@ -272,11 +288,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (a.bias) acc += __ldg(a.bias + n0 + j);
           v[j] = acc;
         }
-        if (a.feat && !a.feat_pooled) {
-          float* dst = a.feat + (((size_t)b * a.H + y) * a.W + x) * a.cout + n0;
-#pragma unroll
-          for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
         float pv[32];
         if (any_pool) {
 #pragma unroll
@@ -284,32 +295,85 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
             pv[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
           }
-          if (a.feat && a.feat_pooled && pool_owner) {
-            float* dst = a.feat + (((size_t)b * (a.H / 2) + y / 2) * (a.W / 2) + x / 2) * a.cout + n0;
+        }
+        // Every lane owns one pixel, and pixels are >= 2*CH bytes apart in every destination, so direct stores
+        // touch 32 lines per instruction.  Instead each lane parks its 128-byte row in a warp-private,
+        // XOR-swizzled staging tile and the warp writes it out with N16 lanes per row (whole 64 / 128-byte segments).
+        constexpr int N16 = CH / 4;                    // 16-byte pieces per staged row (fp32: CH floats; fp16: hi | lo)
+        constexpr int RPI = 32 / N16;                  // rows written per store instruction
+        const int rsub = lane / N16, piece = lane % N16;
+        auto stage_f32 = [&](const float (&x)[32]) {
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(pv[j], pv[j + 1], pv[j + 2], pv[j + 3]);
+          for (int j = 0; j < N16; ++j)
+            st_shared_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
+                         __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
+          __syncwarp();
+        };
+        auto stage_f16 = [&](const float (&x)[32]) {   // relu'd values -> [hi (N16/2 pieces) | lo (N16/2 pieces)]
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < N16 / 2; ++j) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split2(x[8 * j + 2 * e], x[8 * j + 2 * e + 1], hi[e], lo[e]);
+            st_shared_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(stg + lane * 128 + (((j + N16 / 2) ^ (lane & 7)) << 4), lo[0], lo[1], lo[2], lo[3]);
           }
+          __syncwarp();
+        };
+        // rows: 0 = all 32 pixels of the warp (2 tile rows x 16), 1 = the 8 pool-window owners (rows 0,2,..,14)
+        auto row_of = [&](int i, bool owners) { const int r = i * RPI + rsub; return owners ? 2 * r : r; };
+        auto write_f32 = [&](float* base, int hh, int ww, bool owners) {     // base: [B][hh][ww][cout]
+          const int n_rows = owners ? 8 : 32;
+#pragma unroll 1
+          for (int i = 0; i < (n_rows + RPI - 1) / RPI; ++i) {
+            const int r = row_of(i, owners);
+            if (i * RPI + rsub >= n_rows) continue;
+            const int yy = y0 + q * 2 + (r >> 4), xx = x0 + (r & 15);
+            const size_t px = owners ? ((size_t)b * hh + yy / 2) * ww + xx / 2 : ((size_t)b * hh + yy) * ww + xx;
+            const uint4 d = ld_shared_v4(stg + r * 128 + ((piece ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(base + px * a.cout + n0 + piece * 4) = d;
+          }
+        };
+        // mode 0: same pixel; 1: pooled pixel (owners only); 2: x2 upsample position (dy, dx)
+        auto write_f16 = [&](__half* base, int pitch, int coff, int hh, int ww, int mode, int dy, int dx) {
+          const bool owners = mode == 1;
+          const int n_rows = owners ? 8 : 32;
+          const int plane = piece / (N16 / 2), pc = piece % (N16 / 2);
+#pragma unroll 2
+          for (int i = 0; i < (n_rows + RPI - 1) / RPI; ++i) {
+            const int r = row_of(i, owners);
+            if (i * RPI + rsub >= n_rows) continue;
+            const int yy = y0 + q * 2 + (r >> 4), xx = x0 + (r & 15);
+            size_t px;
+            if (mode == 0) px = ((size_t)b * hh + yy) * ww + xx;
+            else if (mode == 1) px = ((size_t)b * hh + yy / 2) * ww + xx / 2;
+            else px = ((size_t)b * hh + 2 * yy + dy) * ww + 2 * xx + dx;
+            const uint4 d = ld_shared_v4(stg + r * 128 + ((piece ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(base + (px * 2 + plane) * pitch + coff + n0 + pc * 8) = d;
+          }
+        };
+        if (a.feat) {
+          if (a.feat_pooled) { stage_f32(pv); write_f32(a.feat, a.H / 2, a.W / 2, true); }
+          else { stage_f32(v); write_f32(a.feat, a.H, a.W, false); }
         }
         // everything below stores relu'd fp16 hi/lo activations
 #pragma unroll
         for (int j = 0; j < CH; ++j) { v[j] = fmaxf(v[j], 0.f); if (any_pool) pv[j] = fmaxf(pv[j], 0.f); }
-        if (a.act_full)
-          store_split(a.act_full + (((size_t)b * a.H + y) * a.W + x) * 2 * a.af_pitch + a.af_coff + n0, a.af_pitch, v, CH);
-        if (a.act_pool && pool_owner)
-          store_split(a.act_pool + (((size_t)b * (a.H / 2) + y / 2) * (a.W / 2) + x / 2) * 2 * a.ap_pitch + a.ap_coff + n0,
-                      a.ap_pitch, pv, CH);
-        if (a.act_up) {
-          if (a.feat_pooled) {
-            // pooled then upsampled x2: lands on this very pixel of the conv-resolution buffer
-            store_split(a.act_up + (((size_t)b * a.H + y) * a.W + x) * 2 * a.au_pitch + a.au_coff + n0, a.au_pitch, pv, CH);
-          } else {
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-              for (int dx = 0; dx < 2; ++dx)
-                store_split(a.act_up + (((size_t)b * 2 * a.H + 2 * y + dy) * (2 * a.W) + 2 * x + dx) * 2 * a.au_pitch +
-                                a.au_coff + n0, a.au_pitch, v, CH);
+        if (a.act_full || (a.act_up && !a.feat_pooled)) {
+          stage_f16(v);
+          if (a.act_full) write_f16(a.act_full, a.af_pitch, a.af_coff, a.H, a.W, 0, 0, 0);
+          if (a.act_up && !a.feat_pooled) {
+#pragma unroll 1
+            for (int dd = 0; dd < 4; ++dd) write_f16(a.act_up, a.au_pitch, a.au_coff, 2 * a.H, 2 * a.W, 2, dd >> 1, dd & 1);
           }
+        }
+        if ((a.act_pool) || (a.act_up && a.feat_pooled)) {
+          stage_f16(pv);
+          if (a.act_pool) write_f16(a.act_pool, a.ap_pitch, a.ap_coff, a.H / 2, a.W / 2, 1, 0, 0);
+          // pooled then upsampled x2: lands on this very pixel of the conv-resolution buffer
+          if (a.act_up && a.feat_pooled) write_f16(a.act_up, a.au_pitch, a.au_coff, a.H, a.W, 0, 0, 0);
         }
       }
       tc_fence_before();
@@ -324,10 +388,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
 // ------------------------------------------------------------------------------ conv0 + helpers
 // conv0 (3 -> 64, K = 27) is 0.7 % of the FLOPs: CUDA-core fp32 straight from the NCHW image,
-// fused bias + ReLU, writes the hi/lo activation planes conv2 consumes.  Each thread owns 4
-// horizontally adjacent pixels x 16 output channels at a time, so one 128-bit weight load from
-// shared memory feeds 16 FMAs (the 1-pixel version was LDS-issue bound at 25 % of the FMA pipe).
-constexpr int kC0TW = 64, kC0TH = 16;     // CTA tile: 64 x 16 pixels, 256 threads
+// fused bias + ReLU, writes the hi/lo activation planes conv2 consumes.  A thread owns 4 horizontally
+// adjacent pixels x 16 output channels (one 128-bit weight load from shared memory feeds 16 FMAs); the
+// four threads that share a pixel group hold its four channel chunks, so their 32-byte stores fall
+// into the same 128-byte line (8 lines per warp-wide store instead of 32).
+constexpr int kC0TW = 64, kC0TH = 4;      // CTA tile: 64 x 4 pixels, 256 threads = 64 pixel groups x 4 chunks
 __global__ void __launch_bounds__(256, 2) conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[9][3][64]*/,
                                                     const float* __restrict__ bias, __half* __restrict__ out, int H, int W) {
   __shared__ __align__(16) float w_s[27 * 64];
@@ -342,7 +407,9 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const float* __restrict__
     in_s[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(((size_t)b * 3 + c) * H + gy) * W + gx] : 0.f;
   }
   __syncthreads();
-  const int lx = (threadIdx.x & 15) * 4, ly = threadIdx.x >> 4;
+  const int n0 = (threadIdx.x & 3) * 16;                       // this thread's 16-channel chunk
+  const int grp = threadIdx.x >> 2;                            // pixel group: 16 per tile row
+  const int lx = (grp & 15) * 4, ly = grp >> 4;
   const int gy = ty0 + ly;
   if (gy >= H) return;
   float patch[3][3][6];                    // [channel][row][col]: the 3 x 6 window of 4 adjacent pixels
@@ -352,34 +419,31 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const float* __restrict__
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int q = 0; q < 6; ++q) patch[c][r][q] = in_s[c][ly + r][lx + q];
-#pragma unroll 1
-  for (int n0 = 0; n0 < 64; n0 += 16) {
-    float v[4][16];
+  float v[4][16];
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+  for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[p][j] = b_s[n0 + j];
+    for (int j = 0; j < 16; ++j) v[p][j] = b_s[n0 + j];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap)
+  for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 wv = *reinterpret_cast<const float4*>(&w_s[(tap * 3 + c) * 64 + n0 + j]);
+      for (int j = 0; j < 16; j += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(&w_s[(tap * 3 + c) * 64 + n0 + j]);
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const float x = patch[c][tap / 3][p + tap % 3];
-            v[p][j] += x * wv.x; v[p][j + 1] += x * wv.y; v[p][j + 2] += x * wv.z; v[p][j + 3] += x * wv.w;
-          }
+        for (int p = 0; p < 4; ++p) {
+          const float x = patch[c][tap / 3][p + tap % 3];
+          v[p][j] += x * wv.x; v[p][j + 1] += x * wv.y; v[p][j + 2] += x * wv.z; v[p][j + 3] += x * wv.w;
         }
+      }
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int gx = tx0 + lx + p;
-      if (gx >= W) continue;
+  for (int p = 0; p < 4; ++p) {
+    const int gx = tx0 + lx + p;
+    if (gx >= W) continue;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[p][j] = fmaxf(v[p][j], 0.f);
-      store_split(out + (((size_t)b * H + gy) * W + gx) * 2 * 64 + n0, 64, v[p], 16);
-    }
+    for (int j = 0; j < 16; ++j) v[p][j] = fmaxf(v[p][j], 0.f);
+    store_split(out + (((size_t)b * H + gy) * W + gx) * 2 * 64 + n0, 64, v[p], 16);
   }
 }
 
