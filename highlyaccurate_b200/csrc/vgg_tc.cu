@@ -388,11 +388,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
 // ------------------------------------------------------------------------------ conv0 + helpers
 // conv0 (3 -> 64, K = 27) is 0.7 % of the FLOPs: CUDA-core fp32 straight from the NCHW image,
-// fused bias + ReLU, writes the hi/lo activation planes conv2 consumes.  A thread owns 4 horizontally
-// adjacent pixels x 16 output channels (one 128-bit weight load from shared memory feeds 16 FMAs); the
-// four threads that share a pixel group hold its four channel chunks, so their 32-byte stores fall
-// into the same 128-byte line (8 lines per warp-wide store instead of 32).
-constexpr int kC0TW = 64, kC0TH = 4;      // CTA tile: 64 x 4 pixels, 256 threads = 64 pixel groups x 4 chunks
+// fused bias + ReLU, writes the hi/lo activation planes conv2 consumes.  Each thread owns 4
+// horizontally adjacent pixels x 16 output channels at a time, so one 128-bit weight load from
+// shared memory feeds 16 FMAs (the 1-pixel version was LDS-issue bound at 25 % of the FMA pipe).
+// (A remap with the four channel chunks of a pixel group on four adjacent threads, so that their stores
+// share 128-byte lines, measured slower: 1.55 ms vs 1.30-1.40 ms at B = 32.)
+constexpr int kC0TW = 64, kC0TH = 16;     // CTA tile: 64 x 16 pixels, 256 threads
 __global__ void __launch_bounds__(256, 2) conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[9][3][64]*/,
                                                     const float* __restrict__ bias, __half* __restrict__ out, int H, int W) {
   __shared__ __align__(16) float w_s[27 * 64];
@@ -407,9 +408,7 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const float* __restrict__
     in_s[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(((size_t)b * 3 + c) * H + gy) * W + gx] : 0.f;
   }
   __syncthreads();
-  const int n0 = (threadIdx.x & 3) * 16;                       // this thread's 16-channel chunk
-  const int grp = threadIdx.x >> 2;                            // pixel group: 16 per tile row
-  const int lx = (grp & 15) * 4, ly = grp >> 4;
+  const int lx = (threadIdx.x & 15) * 4, ly = threadIdx.x >> 4;
   const int gy = ty0 + ly;
   if (gy >= H) return;
   float patch[3][3][6];                    // [channel][row][col]: the 3 x 6 window of 4 adjacent pixels
@@ -419,31 +418,34 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const float* __restrict__
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int q = 0; q < 6; ++q) patch[c][r][q] = in_s[c][ly + r][lx + q];
-  float v[4][16];
+#pragma unroll 1
+  for (int n0 = 0; n0 < 64; n0 += 16) {
+    float v[4][16];
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[p][j] = b_s[n0 + j];
+      for (int j = 0; j < 16; ++j) v[p][j] = b_s[n0 + j];
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap)
+    for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+      for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(&w_s[(tap * 3 + c) * 64 + n0 + j]);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(&w_s[(tap * 3 + c) * 64 + n0 + j]);
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const float x = patch[c][tap / 3][p + tap % 3];
-          v[p][j] += x * wv.x; v[p][j + 1] += x * wv.y; v[p][j + 2] += x * wv.z; v[p][j + 3] += x * wv.w;
+          for (int p = 0; p < 4; ++p) {
+            const float x = patch[c][tap / 3][p + tap % 3];
+            v[p][j] += x * wv.x; v[p][j + 1] += x * wv.y; v[p][j + 2] += x * wv.z; v[p][j + 3] += x * wv.w;
+          }
         }
-      }
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int gx = tx0 + lx + p;
-    if (gx >= W) continue;
+    for (int p = 0; p < 4; ++p) {
+      const int gx = tx0 + lx + p;
+      if (gx >= W) continue;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[p][j] = fmaxf(v[p][j], 0.f);
-    store_split(out + (((size_t)b * H + gy) * W + gx) * 2 * 64 + n0, 64, v[p], 16);
+      for (int j = 0; j < 16; ++j) v[p][j] = fmaxf(v[p][j], 0.f);
+      store_split(out + (((size_t)b * H + gy) * W + gx) * 2 * 64 + n0, 64, v[p], 16);
+    }
   }
 }
 
