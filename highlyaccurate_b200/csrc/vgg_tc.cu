@@ -205,9 +205,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int n_idx = tile % a.tiles_n; int pt = tile / a.tiles_n;
         const int x0 = (pt % a.tiles_x) * kTileW; pt /= a.tiles_x;
         const int y0 = (pt % a.tiles_y) * kTileH; const int b = pt / a.tiles_y;
+        // nested tap / channel-chunk loops: no integer division on the producer's critical path
+        int tap = 0, kc = 0, ky = a.n_taps == 1 ? 1 : 0, kx = ky;
         for (int kb = 0; kb < total_kb; ++kb) {
-          const int tap = kb / a.n_kchunks, kc = kb % a.n_kchunks;
-          const int ky = a.n_taps == 1 ? 1 : tap / 3, kx = a.n_taps == 1 ? 1 : tap % 3;
           mbar_wait(empty + stage, phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(full + stage, Cfg::kStageBytes);
@@ -219,6 +219,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tma_load_3d(st + kABytes + Cfg::kBBytes, &tmap_bl, full + stage, kc * kBlockK, n_idx * BLOCK_N, tap);
             tma_load_5d(st + kABytes + 2 * Cfg::kBBytes, &tmap_a, full + stage, kc * kBlockK, 1, x0 + kx - 1, y0 + ky - 1, b);
           }
+          if (++kc == a.n_kchunks) { kc = 0; ++tap; if (++kx == 3) { kx = 0; ++ky; } }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -227,6 +228,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_f16(BLOCK_N);             // A x B_hi
     constexpr uint32_t idesc2 = umma_idesc_f16(2 * BLOCK_N);        // A x [B_hi ; B_lo]
+    // stage layout [A_hi][B_hi][B_lo][A_lo]: descriptors of stage 0, K advance = +32 B = +2 in the address field
+    const uint64_t desc_a_hi = umma_desc_sw128(smem_u32(smem));
+    const uint64_t desc_b = umma_desc_sw128(smem_u32(smem) + kABytes);
+    const uint64_t desc_a_lo = umma_desc_sw128(smem_u32(smem) + kABytes + 2 * Cfg::kBBytes);
     int stage = 0; uint32_t phase = 0; int t = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++t) {
       const int as = t & 1; const uint32_t aphase = (t >> 1) & 1;
@@ -238,19 +243,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         mbar_wait(full + stage, phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa_hi = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb_hi = sa_hi + kABytes;                    // followed directly by B_lo
-          const uint32_t sa_lo = sb_hi + 2 * Cfg::kBBytes;
+          // The single issuing thread is the critical path of short-K (N = 64) layers: descriptors are one
+          // 64-bit add away from precomputed bases (the 14-bit address field cannot carry: smem < 256 KB).
+          const uint64_t so = (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
+          const uint64_t da0 = desc_a_hi + so, db0 = desc_b + so, dl0 = desc_a_lo + so;
+          if (SPLIT) {
+            // one N = 2*BLOCK_N MMA reads A_hi once for both hi_x*hi_w and hi_x*lo_w, then lo_x*hi_w is added
+            umma_f16(acc0, da0, db0, idesc2, kb != 0);
+            umma_f16(acc1, dl0, db0, idesc, 1);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da_hi = umma_desc_sw128(sa_hi + k * 32), db = umma_desc_sw128(sb_hi + k * 32);
-            if (SPLIT) {
-              // one N = 2*BLOCK_N MMA reads A_hi once for both hi_x*hi_w and hi_x*lo_w, then lo_x*hi_w is added
-              umma_f16(acc0, da_hi, db, idesc2, (kb | k) != 0);
-              umma_f16(acc1, umma_desc_sw128(sa_lo + k * 32), db, idesc, 1);
-            } else {
-              umma_f16(acc0, da_hi, db, idesc, (kb | k) != 0);
+            for (int k = 1; k < kBlockK / 16; ++k) {
+              umma_f16(acc0, da0 + 2 * k, db0 + 2 * k, idesc2, 1);
+              umma_f16(acc1, dl0 + 2 * k, db0 + 2 * k, idesc, 1);
             }
+          } else {
+            umma_f16(acc0, da0, db0, idesc, kb != 0);
+#pragma unroll
+            for (int k = 1; k < kBlockK / 16; ++k) umma_f16(acc0, da0 + 2 * k, db0 + 2 * k, idesc, 1);
           }
           umma_commit(empty + stage);                       // smem slot reusable once these MMAs retire
           if (kb == total_kb - 1) umma_commit(tmem_full + as);
@@ -282,11 +291,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int n0 = n_idx * BLOCK_N + c0;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          float acc = __uint_as_float(r0[j]);
-          if (SPLIT) acc += __uint_as_float(r1[j]) * kLoInvScale;
-          if (a.bias) acc += __ldg(a.bias + n0 + j);
-          v[j] = acc;
+        for (int j = 0; j < CH; j += 4) {
+          const float4 bz = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float bb[4] = {bz.x, bz.y, bz.z, bz.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float acc = __uint_as_float(r0[j + e]);
+            if (SPLIT) acc = fmaf(__uint_as_float(r1[j + e]), kLoInvScale, acc);
+            v[j + e] = acc + bb[e];
+          }
         }
         float pv[32];
         if (any_pool) {
