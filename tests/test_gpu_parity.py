@@ -310,3 +310,38 @@ def test_full_size_properties():
     pg2 = engine.Pyramid([f[perm.to(DEV)].contiguous() for f in pg.feats], [None] * 3)
     r2 = net.refine(ps2, pg2, reset_uv=draws)
     assert torch.equal(r2.pose.cpu(), final[perm])
+
+
+def test_ford_config3_shapes_run_and_are_deterministic():
+    """BASELINE config-3 shapes (Ford geometry, satellite 1280 x 1280, ground 256 x 1024) through the whole
+    forward on the tensor-core path: finite poses, bit-identical on a re-run, per-sample independence."""
+    torch.manual_seed(0)
+    net = LM_S2GP_Ford(K.ref_args()).to(DEV).eval()
+    gen = torch.Generator().manual_seed(7)
+    B = 3
+    sat = torch.rand(B, 3, 1280, 1280, generator=gen).to(DEV)
+    grd = torch.rand(B, 3, 256, 1024, generator=gen).to(DEV)
+    f = K.ford_dict(B, 1280 * 0.22)
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(5)
+        o = net(sat, grd, f["side_m"], f["R_FL"].to(DEV), f["T_FL"].to(DEV), mode="test")
+        outs.append(torch.stack([x.detach() for x in o], dim=-1))
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
+    assert not int(net.last_result.status.item()) & _lib.HA_STATUS_NAN_POSE
+    torch.manual_seed(5)
+    o1 = net(sat[1:2], grd[1:2], f["side_m"], f["R_FL"][1:2].to(DEV), f["T_FL"][1:2].to(DEV), mode="test")
+    np.testing.assert_allclose(torch.stack([x.detach() for x in o1], -1).cpu().numpy(), outs[0][1:2].cpu().numpy(), atol=1e-5)
+
+
+def test_level4_forward_runs():
+    """level = 4 (adds the C = 16 full-resolution level, BASELINE config 5) end to end on the tensor-core path."""
+    torch.manual_seed(0)
+    net = LM_S2GP(K.ref_args(level=4, N_iters=2)).to(DEV).eval()
+    gen = torch.Generator().manual_seed(9)
+    sat = torch.rand(2, 3, 512, 512, generator=gen).to(DEV)
+    grd = torch.rand(2, 3, 256, 1024, generator=gen).to(DEV)
+    out = net(sat, grd, mode="test")
+    assert all(torch.isfinite(o).all() for o in out)
+    assert net.last_result.traj.shape == (2, 2, 4, 3)
