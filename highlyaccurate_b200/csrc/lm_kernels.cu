@@ -18,6 +18,7 @@
 // and finalises  H = JtJ/ns^2,  grad = Jts/ns^2 - Jtg/(ns*ng)  with ns = max(|s|,1e-6),
 // ng = max(|g|,1e-6)  — identical to normalising s, J and g first (models_kitti.py:982-992).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -25,6 +26,9 @@ namespace ha {
 
 #ifndef HA_LM_MIN_CTAS
 #define HA_LM_MIN_CTAS 4
+#endif
+#ifndef HA_LM_DEFAULT_VARIANT
+#define HA_LM_DEFAULT_VARIANT 1
 #endif
 constexpr int kLmThreads = 128;
 constexpr int kLmWarps = kLmThreads / 32;
@@ -309,9 +313,164 @@ __device__ __forceinline__ PixelScalars pixel_scalars(const LmStepArgs& a, const
   return r;
 }
 
+__device__ __forceinline__ V4 ld_ring(uint32_t saddr) {      // ground features staged in shared memory by the bulk-copy ring
+  V4 r;
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(r.lo), "=l"(r.hi) : "r"(saddr));
+  return r;
+}
+
 struct PixelLoads {            // one 128-bit channel slice of one pixel: ground vector + the four taps
   V4 g, nw, ne, sw, se;
 };
+
+// CTA reduction + (last CTA of the sample) ordered combine, damped solve and pose update; shared by both step kernels.
+// v[]: this lane's sixteen running sums {Gaa, Gab, Gbb, Bx, By, Ctt, Sa, Sb, St, Ga, Gb, Gt, SS, GG, SG, count}.
+template <int GEOM, bool FULL>
+__device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const int b, const double (&v)[kLmAcc], const KittiPose& kp,
+                                                    const FordPose& fp, const float su, const float sv, const float th) {
+  constexpr bool G2SP = (GEOM == HA_GEOM_G2SP);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- CTA reduction: lanes -> warp (fp64 shuffles) -> shared -> one partial row per CTA
+  __shared__ double red[kLmWarps][kLmAcc];
+  __shared__ bool is_last;
+  {
+#pragma unroll
+    for (int i = 0; i < kLmAcc; ++i) {
+      double r = warp_sum(v[i]);
+      if (lane == 0) red[warp][i] = r;
+    }
+  }
+  __syncthreads();
+  double* part = a.partial + ((size_t)b * kLmMaxCtasPerSample + blockIdx.x) * kLmAcc;
+  if (threadIdx.x < kLmAcc) {
+    double r = 0;
+#pragma unroll
+    for (int w = 0; w < kLmWarps; ++w) r += red[w][threadIdx.x];
+    part[threadIdx.x] = r;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t prev = atomicAdd(a.ticket + b, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+
+  // ---- last CTA of this sample: ordered combine of the partials, damped solve, pose update
+  __threadfence();
+  __shared__ double tot[kLmAcc];
+  if (threadIdx.x < kLmAcc) {
+    const volatile double* pp = a.partial + (size_t)b * kLmMaxCtasPerSample * kLmAcc + threadIdx.x;
+    double r = 0;
+    for (unsigned c = 0; c < gridDim.x; ++c) r += pp[(size_t)c * kLmAcc];
+    tot[threadIdx.x] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  a.ticket[b] = 0;   // ready for the next step on this stream
+  double Hm[3][3], gr[3], ns = 0.0, ng = 0.0, res_sq = 0.0;
+  if (G2SP) {
+    // models_kitti.py:333-379: r = grd_proj - sat with the L2-normalised features (VGG.py:172-175) and no
+    // further normalisation; the sampled (ground) and streamed (satellite) pyramids carry their own scales
+    const double as_ = a.grd_scale ? (double)a.grd_scale[b] : 1.0, bg_ = a.sat_scale ? (double)a.sat_scale[b] : 1.0;
+    const double f2 = as_ * as_, fsg = as_ * bg_;
+    const double h[6] = {tot[0] * f2, tot[1] * f2, tot[2] * f2, tot[3] * f2, tot[4] * f2, tot[5] * f2};
+    Hm[0][0] = h[0]; Hm[0][1] = Hm[1][0] = h[1]; Hm[0][2] = Hm[2][0] = h[2];
+    Hm[1][1] = h[3]; Hm[1][2] = Hm[2][1] = h[4]; Hm[2][2] = h[5];
+    for (int i = 0; i < 3; ++i) gr[i] = tot[6 + i] * f2 - tot[9 + i] * fsg;
+  } else {
+    if (FULL) { if (a.gg_cache) a.gg_cache[b] = tot[13]; }
+    else tot[13] = a.gg_cache[b];                    // sum g^2 over the unmasked bottom half, from this level's first visit
+
+    // assemble J^T W J, J^T W s, J^T W g from the split sums with the per-sample constant rows of D
+    const double d0x = (GEOM == HA_GEOM_KITTI) ? kp.jux : fp.jux, d0y = (GEOM == HA_GEOM_KITTI) ? kp.juy : fp.juy;
+    const double d1x = (GEOM == HA_GEOM_KITTI) ? kp.jvx : fp.jvx, d1y = (GEOM == HA_GEOM_KITTI) ? kp.jvy : fp.jvy;
+    const double Gaa = tot[0], Gab = tot[1], Gbb = tot[2], Bx = tot[3], By = tot[4], Ctt = tot[5];
+    const double e0x = Gaa * d0x + Gab * d0y, e0y = Gab * d0x + Gbb * d0y;    // sum(G) * D_0
+    const double e1x = Gaa * d1x + Gab * d1y, e1y = Gab * d1x + Gbb * d1y;
+    const double JtJ[6] = {d0x * e0x + d0y * e0y, d0x * e1x + d0y * e1y, d0x * Bx + d0y * By,
+                           d1x * e1x + d1y * e1y, d1x * Bx + d1y * By, Ctt};
+    const double Jts[3] = {d0x * tot[6] + d0y * tot[7], d1x * tot[6] + d1y * tot[7], tot[8]};
+    const double Jtg[3] = {d0x * tot[9] + d0y * tot[10], d1x * tot[9] + d1y * tot[10], tot[11]};
+
+    const double alpha = a.sat_scale ? (double)a.sat_scale[b] : 1.0;
+    const double beta = a.grd_scale ? (double)a.grd_scale[b] : 1.0;
+    ns = fmax(alpha * sqrt(tot[12]), 1e-6);          // models_kitti.py:982-984
+    ng = fmax(beta * sqrt(tot[13]), 1e-6);           // :987-988
+    const double fs = alpha * alpha / (ns * ns), fg = alpha * beta / (ns * ng);
+    Hm[0][0] = JtJ[0] * fs; Hm[0][1] = Hm[1][0] = JtJ[1] * fs; Hm[0][2] = Hm[2][0] = JtJ[2] * fs;
+    Hm[1][1] = JtJ[3] * fs; Hm[1][2] = Hm[2][1] = JtJ[4] * fs; Hm[2][2] = JtJ[5] * fs;
+    for (int i = 0; i < 3; ++i) gr[i] = Jts[i] * fs - Jtg[i] * fg;
+    res_sq = FULL ? alpha * alpha * tot[12] / (ns * ns) + beta * beta * tot[13] / (ng * ng) -
+                        2.0 * alpha * beta * tot[14] / (ns * ng) : 0.0;     // diagnostic, FULL launches only
+  }
+
+  // DOF selection (models_kitti.py:954-957): 3 -> (0,1,2), 2 -> (0,1), 1 -> (2)
+  const int n = a.dof;
+  const int i0 = (n == 1) ? 2 : 0;
+  double Am[3][3], rhs[3], delta[3] = {0, 0, 0};
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) Am[i][j] = Hm[i0 + i][i0 + j];
+    const double lam = (double)a.damping[i];
+    Am[i][i] += a.use_hessian ? lam * Hm[i0 + i][i0 + i] : lam;    // :1005-1012 (column-wise lambda on a diagonal)
+    rhs[i] = gr[i0 + i];
+  }
+  if (n == 1) {
+    delta[0] = -rhs[0] / Am[0][0];
+  } else if (n == 2) {
+    const double det = Am[0][0] * Am[1][1] - Am[0][1] * Am[1][0];
+    delta[0] = -(Am[1][1] * rhs[0] - Am[0][1] * rhs[1]) / det;
+    delta[1] = -(-Am[1][0] * rhs[0] + Am[0][0] * rhs[1]) / det;
+  } else {
+    const double c00 = Am[1][1] * Am[2][2] - Am[1][2] * Am[2][1];
+    const double c01 = Am[1][2] * Am[2][0] - Am[1][0] * Am[2][2];
+    const double c02 = Am[1][0] * Am[2][1] - Am[1][1] * Am[2][0];
+    const double det = Am[0][0] * c00 + Am[0][1] * c01 + Am[0][2] * c02;
+    const double c10 = Am[0][2] * Am[2][1] - Am[0][1] * Am[2][2];
+    const double c11 = Am[0][0] * Am[2][2] - Am[0][2] * Am[2][0];
+    const double c12 = Am[0][1] * Am[2][0] - Am[0][0] * Am[2][1];
+    const double c20 = Am[0][1] * Am[1][2] - Am[0][2] * Am[1][1];
+    const double c21 = Am[0][2] * Am[1][0] - Am[0][0] * Am[1][2];
+    const double c22 = Am[0][0] * Am[1][1] - Am[0][1] * Am[1][0];
+    // inverse = adj / det, adj[i][j] = cofactor[j][i]
+    delta[0] = -(c00 * rhs[0] + c10 * rhs[1] + c20 * rhs[2]) / det;
+    delta[1] = -(c01 * rhs[0] + c11 * rhs[1] + c21 * rhs[2]) / det;
+    delta[2] = -(c02 * rhs[0] + c12 * rhs[1] + c22 * rhs[2]) / det;
+  }
+  float nsu = su, nsv = sv, nth = th;
+  uint32_t st = 0;
+  if (n == 3) {
+    nsu = su + (float)delta[0]; nsv = sv + (float)delta[1]; nth = th + (float)delta[2];
+    // models_kitti.py:1028-1033: shifts outside (-2.5, 2.5) (or NaN) are re-drawn (S2GP models only)
+    if (!G2SP) {
+      if (!(nsu > -2.5f && nsu < 2.5f)) { nsu = a.reset_uv[b]; st |= HA_STATUS_RESET; }
+      if (!(nsv > -2.5f && nsv < 2.5f)) { nsv = a.reset_uv[a.B + b]; st |= HA_STATUS_RESET; }
+    }
+  } else if (n == 2) {
+    nsu = su + (float)delta[0]; nsv = sv + (float)delta[1];
+  } else {
+    nth = th + (float)delta[0];
+  }
+  if (isnan(nsu) || isnan(nsv) || isnan(nth)) st |= HA_STATUS_NAN_POSE;
+  if (tot[15] == 0.0) st |= HA_STATUS_NO_INRANGE;
+  if (st) atomicOr(a.status, st);
+  a.pose[b * 3 + 0] = nsu; a.pose[b * 3 + 1] = nsv; a.pose[b * 3 + 2] = nth;
+  if (a.traj) {
+    float* tr = a.traj + (size_t)b * a.traj_stride;
+    tr[0] = nsu; tr[1] = nsv; tr[2] = nth;
+  }
+  if (a.stats) {
+    float* s = a.stats + (size_t)b * HA_STATS;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) s[HA_STAT_H + i * 3 + j] = (float)Hm[i][j];
+    for (int i = 0; i < 3; ++i) s[HA_STAT_GRAD + i] = (float)gr[i];
+    s[HA_STAT_SAT_NORM] = (float)ns; s[HA_STAT_GRD_NORM] = (float)ng; s[HA_STAT_RES_SQ] = (float)res_sq;
+    for (int i = 0; i < 3; ++i) s[HA_STAT_DELTA + i] = (i < n) ? (float)delta[i] : 0.f;
+    s[HA_STAT_N_INRANGE] = (float)tot[15];
+    for (int i = HA_STAT_N_INRANGE + 1; i < HA_STATS; ++i) s[i] = 0.f;
+  }
+}
 
 template <int GEOM, int C, bool FULL>
 __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(const LmStepArgs a) {
@@ -473,160 +632,294 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
     if (more) load_half(bufB, 1);
   }
 
-  // ---- CTA reduction: lanes -> warp (fp64 shuffles) -> shared -> one partial row per CTA
-  __shared__ double red[kLmWarps][kLmAcc];
-  __shared__ bool is_last;
   {
     double v[kLmAcc] = {sum2(A_aa), sum2(A_ab), sum2(A_bb), sum2(B_x), sum2(B_y), sum2(C_tt), sum2(S_a), sum2(S_b),
                         sum2(S_t), sum2(G_a), sum2(G_b), sum2(G_t), sum2(SS), sum2(GG), sum2(SG), cnt / (float)LPP};
+    lm_reduce_and_solve<GEOM, FULL>(a, b, v, kp, fp, su, sv, th);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// v4 step kernel (S2GP geometries).  What changed against the kernel above and why (B200 measurements):
+//  * HBM latency x bandwidth needs ~40 KB of streamed loads in flight per SM; register-staged loads hold 16 KB
+//    (2 x 512 B per warp), which pinned v3 at 0.4 of the HBM roofline.  Here every warp owns a ring of NSLOT
+//    chunks in shared memory; lane 0 keeps NSLOT-1 chunks of the ground stream in flight with 1-D bulk async copies
+//    (cp.async.bulk -> SASS UBLKCP, completion on a per-slot mbarrier) and re-arms a slot as soon as the warp has
+//    reduced it.  Producer and consumer of a ring are the same warp: no cross-warp synchronisation at all.
+//  * The FMA pipe issues one packed FFMA2 per two cycles per SM sub-partition, which capped v3 at ~0.85 of the
+//    roofline even at 100 % pipe utilisation (19 packed ops per channel pair + 19 per pixel and lane).  Here a lane
+//    owns 16 channels of a pixel (the per-pixel work is amortised over twice the channels) and the interpolation
+//    uses wx + ex = 1, ny + sy = 1 (16 ops per pair).  Pixels where that identity fails — a corner clamped at the
+//    last row / column (jacobian.py:147-166: all weights vanish there) — and masked pixels read their taps from a
+//    zero vector instead, which reproduces the reference's zeros exactly.
+//  * The satellite taps stay on the L1/L2 path (gathers with heavy reuse between neighbouring pixels).
+extern __shared__ __align__(128) uint8_t lm_dyn_smem[];
+
+constexpr int kLmIterBytes = 2048;   // one warp pixel-iteration streams PPW pixels x C channels x 4 B = 2 KB for every C
+
+template <int NSLOT, int CHUNK_IT>
+constexpr int lm_ring_bytes() { return kLmWarps * NSLOT * CHUNK_IT * kLmIterBytes + kLmWarps * NSLOT * 8 + 16; }
+
+template <int GEOM, int C, bool FULL, int NSLOT, int CHUNK_IT_REQ>
+__global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_v4_kernel(const LmStepArgs a) {
+  constexpr int LPP = C / 16;                      // lanes per pixel: every lane owns 4 x 4 channels
+  constexpr int PPW = 32 / LPP;                    // pixels processed together by one warp
+  constexpr int IPG = LPP;                         // pixel-iterations per 32-pixel group
+  constexpr int C4 = C / 4;
+  constexpr int QF4 = C / 16;                      // float4s between the four channel quarters of a lane
+  static_assert(C % 16 == 0 && LPP >= 1 && LPP <= 32 && PPW * LPP == 32, "channel count");
+  static_assert(GEOM != HA_GEOM_G2SP, "G2SP streams only the visible satellite pixels: it stays on lm_step_kernel");
+  constexpr int CHUNK_IT = CHUNK_IT_REQ < IPG ? CHUNK_IT_REQ : IPG;   // a chunk never straddles two 32-pixel groups
+  constexpr int CHUNK_PX = CHUNK_IT * PPW;
+  constexpr int SLOT_BYTES = CHUNK_IT_REQ * kLmIterBytes;             // ring geometry follows the host-side smem size
+  constexpr int CPG = IPG / CHUNK_IT;              // chunks per 32-pixel group
+  static_assert(IPG % CHUNK_IT == 0, "chunk size");
+
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPP, cl = lane % LPP;     // pixel slot within the warp, channel lane
+  const int P = (a.H - a.H / 2) * a.W;             // the residual lives on the bottom half (models_kitti.py:1195-1199)
+  const int q_begin = blockIdx.x * a.px_per_cta;
+  const int q_end = min(P, q_begin + a.px_per_cta);
+
+  const float su = a.pose[b * 3 + 0], sv = a.pose[b * 3 + 1], th = a.pose[b * 3 + 2];
+  KittiPose kp;
+  FordPose fp;
+  G2spPose gq;                                     // unused (pixel_scalars signature)
+  if (GEOM == HA_GEOM_KITTI) kp = kitti_pose(a, su, sv, th);
+  else fp = ford_pose(a, b, su, sv, th);
+
+  const size_t px_base = (size_t)b * a.H * a.W + (size_t)(a.H / 2) * a.W;
+  const float4* grd0 = reinterpret_cast<const float4*>(a.grd) + px_base * C4;                   // streamed (bulk copies)
+  const float4* sat = reinterpret_cast<const float4*>(a.sat) + (size_t)b * a.A * a.A * C4 + cl; // gathered
+  const float4* zeros = a.zeros + cl;              // masked / clamped pixels read this zero vector (all quarters at the same address)
+  const float4* tab = a.table + (size_t)(a.H / 2) * a.W;
+  const float* conf = a.conf ? a.conf + px_base : nullptr;
+
+  // per-warp staging of the per-pixel scalars: phase A writes 32 pixels, phase B reads them back per pixel slot
+  __shared__ __align__(16) float4 ps_s[kLmWarps][32][2];
+
+  // bulk-copy ring of this warp: [NSLOT][SLOT_BYTES], then NSLOT mbarriers per warp, then one 16-byte zero vector
+  const uint32_t dyn = smem_u32(lm_dyn_smem);
+  const uint32_t ring = dyn + warp * (NSLOT * SLOT_BYTES);
+  const uint32_t ring_bar = dyn + kLmWarps * NSLOT * SLOT_BYTES + warp * (NSLOT * 8);
+  const uint32_t zero_s = dyn + kLmWarps * NSLOT * SLOT_BYTES + kLmWarps * NSLOT * 8;
+  if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < kLmAcc; ++i) {
-      double r = warp_sum(v[i]);
-      if (lane == 0) red[warp][i] = r;
-    }
+    for (int s = 0; s < NSLOT; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring_bar + s * 8));
+    fence_barrier_init();
   }
+  if (threadIdx.x == 0) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(zero_s), "r"(0) : "memory");
   __syncthreads();
-  double* part = a.partial + ((size_t)b * kLmMaxCtasPerSample + blockIdx.x) * kLmAcc;
-  if (threadIdx.x < kLmAcc) {
-    double r = 0;
+
+  const int n_groups = (q_end - q_begin + 31) / 32;
+  const int my_groups = (n_groups > warp) ? (n_groups - warp + kLmWarps - 1) / kLmWarps : 0;
+  const int T = my_groups * IPG;                   // pixel-iterations of this warp
+  const int n_chunks = T / CHUNK_IT;
+
+  // ring producer (lane 0): chunk j = CHUNK_PX consecutive pixels of this warp's pixel stream -> slot j % NSLOT
+  auto chunk_start = [&](int j) { return q_begin + (warp + (j / CPG) * kLmWarps) * 32 + (j % CPG) * CHUNK_PX; };
+  auto issue_chunk = [&](int j) {
+    const int start = chunk_start(j);
+    const int n = min(q_end - start, CHUNK_PX);
+    if (n > 0) {
+      const uint32_t bar = ring_bar + (j % NSLOT) * 8, bytes = (uint32_t)n * (C * 4);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(ring + (j % NSLOT) * SLOT_BYTES), "l"(grd0 + (size_t)start * C4), "r"(bytes), "r"(bar) : "memory");
+    }
+  };
+  auto wait_chunk = [&](int j) {
+    if (chunk_start(j) < q_end) {
+      const uint32_t bar = ring_bar + (j % NSLOT) * 8, parity = (j / NSLOT) & 1;
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "LM_WAIT:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra LM_DONE;\n"
+          "bra LM_WAIT;\n"
+          "LM_DONE:\n"
+          "}\n" ::"r"(bar), "r"(parity) : "memory");
+    }
+  };
+  if (lane == 0) {
+    for (int j = 0; j < NSLOT && j < n_chunks; ++j) issue_chunk(j);
+  }
+
+  // running sums over this lane's pixels and channels (two partial sums per register pair)
+  f32x2 A_aa = 0, A_ab = 0, A_bb = 0, B_x = 0, B_y = 0, C_tt = 0;
+  f32x2 S_a = 0, S_b = 0, S_t = 0, G_a = 0, G_b = 0, G_t = 0, SS = 0, GG = 0, SG = 0;
+  float cnt = 0.f;
+  f32x2 p_aa = 0, p_ab = 0, p_bb = 0, p_sa = 0, p_sb = 0, p_ga = 0, p_gb = 0;   // per-pixel channel sums
+  float4 sc = make_float4(0, 0, 0, 0);             // (wx, ny, tx, ty) of the pixel being reduced
+  float om = 1.f, valid = 0.f;
+
+  auto accumulate = [&](const PixelLoads& L) {
+    const f32x2 wx2 = dup2(sc.x), ny2 = dup2(sc.y);
 #pragma unroll
-    for (int w = 0; w < kLmWarps; ++w) r += red[w][threadIdx.x];
-    part[threadIdx.x] = r;
-    __threadfence();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t prev = atomicAdd(a.ticket + b, 1u);
-    is_last = (prev == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-
-  // ---- last CTA of this sample: ordered combine of the partials, damped solve, pose update
-  __threadfence();
-  __shared__ double tot[kLmAcc];
-  if (threadIdx.x < kLmAcc) {
-    const volatile double* pp = a.partial + (size_t)b * kLmMaxCtasPerSample * kLmAcc + threadIdx.x;
-    double r = 0;
-    for (unsigned c = 0; c < gridDim.x; ++c) r += pp[(size_t)c * kLmAcc];
-    tot[threadIdx.x] = r;
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  a.ticket[b] = 0;   // ready for the next step on this stream
-  double Hm[3][3], gr[3], ns = 0.0, ng = 0.0, res_sq = 0.0;
-  if (G2SP) {
-    // models_kitti.py:333-379: r = grd_proj - sat with the L2-normalised features (VGG.py:172-175) and no
-    // further normalisation; the sampled (ground) and streamed (satellite) pyramids carry their own scales
-    const double as_ = a.grd_scale ? (double)a.grd_scale[b] : 1.0, bg_ = a.sat_scale ? (double)a.sat_scale[b] : 1.0;
-    const double f2 = as_ * as_, fsg = as_ * bg_;
-    const double h[6] = {tot[0] * f2, tot[1] * f2, tot[2] * f2, tot[3] * f2, tot[4] * f2, tot[5] * f2};
-    Hm[0][0] = h[0]; Hm[0][1] = Hm[1][0] = h[1]; Hm[0][2] = Hm[2][0] = h[2];
-    Hm[1][1] = h[3]; Hm[1][2] = Hm[2][1] = h[4]; Hm[2][2] = h[5];
-    for (int i = 0; i < 3; ++i) gr[i] = tot[6 + i] * f2 - tot[9 + i] * fsg;
-  } else {
-    if (FULL) { if (a.gg_cache) a.gg_cache[b] = tot[13]; }
-    else tot[13] = a.gg_cache[b];                    // sum g^2 over the unmasked bottom half, from this level's first visit
-
-    // assemble J^T W J, J^T W s, J^T W g from the split sums with the per-sample constant rows of D
-    const double d0x = (GEOM == HA_GEOM_KITTI) ? kp.jux : fp.jux, d0y = (GEOM == HA_GEOM_KITTI) ? kp.juy : fp.juy;
-    const double d1x = (GEOM == HA_GEOM_KITTI) ? kp.jvx : fp.jvx, d1y = (GEOM == HA_GEOM_KITTI) ? kp.jvy : fp.jvy;
-    const double Gaa = tot[0], Gab = tot[1], Gbb = tot[2], Bx = tot[3], By = tot[4], Ctt = tot[5];
-    const double e0x = Gaa * d0x + Gab * d0y, e0y = Gab * d0x + Gbb * d0y;    // sum(G) * D_0
-    const double e1x = Gaa * d1x + Gab * d1y, e1y = Gab * d1x + Gbb * d1y;
-    const double JtJ[6] = {d0x * e0x + d0y * e0y, d0x * e1x + d0y * e1y, d0x * Bx + d0y * By,
-                           d1x * e1x + d1y * e1y, d1x * Bx + d1y * By, Ctt};
-    const double Jts[3] = {d0x * tot[6] + d0y * tot[7], d1x * tot[6] + d1y * tot[7], tot[8]};
-    const double Jtg[3] = {d0x * tot[9] + d0y * tot[10], d1x * tot[9] + d1y * tot[10], tot[11]};
-
-    const double alpha = a.sat_scale ? (double)a.sat_scale[b] : 1.0;
-    const double beta = a.grd_scale ? (double)a.grd_scale[b] : 1.0;
-    ns = fmax(alpha * sqrt(tot[12]), 1e-6);          // models_kitti.py:982-984
-    ng = fmax(beta * sqrt(tot[13]), 1e-6);           // :987-988
-    const double fs = alpha * alpha / (ns * ns), fg = alpha * beta / (ns * ng);
-    Hm[0][0] = JtJ[0] * fs; Hm[0][1] = Hm[1][0] = JtJ[1] * fs; Hm[0][2] = Hm[2][0] = JtJ[2] * fs;
-    Hm[1][1] = JtJ[3] * fs; Hm[1][2] = Hm[2][1] = JtJ[4] * fs; Hm[2][2] = JtJ[5] * fs;
-    for (int i = 0; i < 3; ++i) gr[i] = Jts[i] * fs - Jtg[i] * fg;
-    res_sq = FULL ? alpha * alpha * tot[12] / (ns * ns) + beta * beta * tot[13] / (ng * ng) -
-                        2.0 * alpha * beta * tot[14] / (ns * ng) : 0.0;     // diagnostic, FULL launches only
-  }
-
-  // DOF selection (models_kitti.py:954-957): 3 -> (0,1,2), 2 -> (0,1), 1 -> (2)
-  const int n = a.dof;
-  const int i0 = (n == 1) ? 2 : 0;
-  double Am[3][3], rhs[3], delta[3] = {0, 0, 0};
-  for (int i = 0; i < n; ++i) {
-    for (int j = 0; j < n; ++j) Am[i][j] = Hm[i0 + i][i0 + j];
-    const double lam = (double)a.damping[i];
-    Am[i][i] += a.use_hessian ? lam * Hm[i0 + i][i0 + i] : lam;    // :1005-1012 (column-wise lambda on a diagonal)
-    rhs[i] = gr[i0 + i];
-  }
-  if (n == 1) {
-    delta[0] = -rhs[0] / Am[0][0];
-  } else if (n == 2) {
-    const double det = Am[0][0] * Am[1][1] - Am[0][1] * Am[1][0];
-    delta[0] = -(Am[1][1] * rhs[0] - Am[0][1] * rhs[1]) / det;
-    delta[1] = -(-Am[1][0] * rhs[0] + Am[0][0] * rhs[1]) / det;
-  } else {
-    const double c00 = Am[1][1] * Am[2][2] - Am[1][2] * Am[2][1];
-    const double c01 = Am[1][2] * Am[2][0] - Am[1][0] * Am[2][2];
-    const double c02 = Am[1][0] * Am[2][1] - Am[1][1] * Am[2][0];
-    const double det = Am[0][0] * c00 + Am[0][1] * c01 + Am[0][2] * c02;
-    const double c10 = Am[0][2] * Am[2][1] - Am[0][1] * Am[2][2];
-    const double c11 = Am[0][0] * Am[2][2] - Am[0][2] * Am[2][0];
-    const double c12 = Am[0][1] * Am[2][0] - Am[0][0] * Am[2][1];
-    const double c20 = Am[0][1] * Am[1][2] - Am[0][2] * Am[1][1];
-    const double c21 = Am[0][2] * Am[1][0] - Am[0][0] * Am[1][2];
-    const double c22 = Am[0][0] * Am[1][1] - Am[0][1] * Am[1][0];
-    // inverse = adj / det, adj[i][j] = cofactor[j][i]
-    delta[0] = -(c00 * rhs[0] + c10 * rhs[1] + c20 * rhs[2]) / det;
-    delta[1] = -(c01 * rhs[0] + c11 * rhs[1] + c21 * rhs[2]) / det;
-    delta[2] = -(c02 * rhs[0] + c12 * rhs[1] + c22 * rhs[2]) / det;
-  }
-  float nsu = su, nsv = sv, nth = th;
-  uint32_t st = 0;
-  if (n == 3) {
-    nsu = su + (float)delta[0]; nsv = sv + (float)delta[1]; nth = th + (float)delta[2];
-    // models_kitti.py:1028-1033: shifts outside (-2.5, 2.5) (or NaN) are re-drawn (S2GP models only)
-    if (!G2SP) {
-      if (!(nsu > -2.5f && nsu < 2.5f)) { nsu = a.reset_uv[b]; st |= HA_STATUS_RESET; }
-      if (!(nsv > -2.5f && nsv < 2.5f)) { nsv = a.reset_uv[a.B + b]; st |= HA_STATUS_RESET; }
+    for (int h = 0; h < 2; ++h) {
+      const f32x2 nw = h ? L.nw.hi : L.nw.lo, ne = h ? L.ne.hi : L.ne.lo;
+      const f32x2 sw = h ? L.sw.hi : L.sw.lo, se = h ? L.se.hi : L.se.lo;
+      const f32x2 g = h ? L.g.hi : L.g.lo;
+      const f32x2 dn = sub2(ne, nw), ds = sub2(se, sw);          // east - west on the north / south row
+      const f32x2 top = fma2(dn, wx2, nw), bot = fma2(ds, wx2, sw);   // rows interpolated in x (ex = 1 - wx)
+      const f32x2 db = sub2(bot, top);                           // d/dy  (jacobian.py:192-193)
+      const f32x2 da = fma2(sub2(ds, dn), ny2, dn);              // d/dx = sy dn + ny ds  (:190-191, sy = 1 - ny)
+      const f32x2 s = fma2(db, ny2, top);                        // sy top + ny bot  (:174-186)
+      acc2(p_aa, da, da); acc2(p_ab, da, db); acc2(p_bb, db, db);
+      acc2(p_sa, s, da); acc2(p_sb, s, db); acc2(p_ga, g, da); acc2(p_gb, g, db);
+      acc2(SS, s, s);
+      if (FULL) { acc2(SG, s, g); acc2(GG, g, g); }              // |g|^2 is pose independent: cached after the first visit
     }
-  } else if (n == 2) {
-    nsu = su + (float)delta[0]; nsv = sv + (float)delta[1];
+  };
+  auto finish_pixel = [&]() {
+    if (a.using_weight) {
+      const f32x2 om2 = dup2(om);
+      p_aa = mul2(p_aa, om2); p_ab = mul2(p_ab, om2); p_bb = mul2(p_bb, om2);
+      p_sa = mul2(p_sa, om2); p_sb = mul2(p_sb, om2); p_ga = mul2(p_ga, om2); p_gb = mul2(p_gb, om2);
+    }
+    // d(u,v)/dsu and /dsv are per-sample constants, only d/dtheta = (tx, ty) varies per pixel, so
+    // J^T J splits into sum(G), sum(G t), sum(t^T G t) and the last CTA applies the constant rows.
+    const f32x2 tx2 = dup2(sc.z), ty2 = dup2(sc.w);
+    inc2(A_aa, p_aa); inc2(A_ab, p_ab); inc2(A_bb, p_bb);
+    const f32x2 gx = fma2(p_ab, ty2, mul2(p_aa, tx2)), gy = fma2(p_bb, ty2, mul2(p_ab, tx2));
+    inc2(B_x, gx); inc2(B_y, gy);
+    acc2(C_tt, tx2, gx); acc2(C_tt, ty2, gy);
+    inc2(S_a, p_sa); inc2(S_b, p_sb); acc2(S_t, p_sa, tx2); acc2(S_t, p_sb, ty2);
+    inc2(G_a, p_ga); inc2(G_b, p_gb); acc2(G_t, p_ga, tx2); acc2(G_t, p_gb, ty2);
+    cnt += valid;                                  // every lane of the pixel counts it: divided by LPP below
+    p_aa = p_ab = p_bb = p_sa = p_sb = p_ga = p_gb = 0ull;
+  };
+
+  // addresses of the pixel whose loads are being issued (set by prepare(), used by load_quarter())
+  const float4 *s_n = zeros, *s_s = zeros;
+  int east = 0, q_tap = 0;                         // float4 offsets: to the east tap, between channel quarters of the taps
+  uint32_t g_s = zero_s, g_q = 0;                  // shared address of the pixel's ground vector, bytes between its quarters
+  float4 nsc = sc;                                 // scalars of the pixel whose loads are in flight
+  float nom = 1.f, nvalid = 0.f;
+
+  auto prepare = [&](int t) {                      // per-pixel scalars + addresses of pixel-iteration t
+    const int it = t % IPG;
+    const int gbase = q_begin + (warp + (t / IPG) * kLmWarps) * 32;
+    if (t % CHUNK_IT == 0) wait_chunk(t / CHUNK_IT);             // the chunk this pixel lives in has landed
+    if (it == 0) {                                               // phase A: one lane per pixel, 32 pixels at once
+      __syncwarp();
+      const PixelScalars ps = pixel_scalars<GEOM>(a, kp, fp, gq, tab, conf, gbase + lane, q_end, C4);
+      // taps are read (bit 2) unless the sample point is masked or a corner was clamped (then all weights vanish)
+      const bool taps = ps.valid != 0.f && (ps.ex + ps.wx == 1.f) && (ps.sy + ps.ny == 1.f);
+      const int flags = (ps.east != 0 ? 1 : 0) | (ps.goff >= 0 ? 2 : 0) | (taps ? 4 : 0) | (ps.valid != 0.f ? 8 : 0);
+      ps_s[warp][lane][0] = make_float4(ps.wx, ps.ny, ps.tx, ps.ty);
+      ps_s[warp][lane][1] = make_float4(ps.om, __int_as_float(flags), __int_as_float(ps.off_n), __int_as_float(ps.off_s));
+      __syncwarp();
+    }
+    const int src = it * PPW + sub;
+    nsc = ps_s[warp][src][0];
+    const float4 o = ps_s[warp][src][1];
+    const int flags = __float_as_int(o.y);
+    nom = o.x;
+    nvalid = (flags & 8) ? 1.f : 0.f;
+    const bool taps = (flags & 4) != 0, has_g = (flags & 2) != 0;
+    east = (taps && (flags & 1)) ? C4 : 0;
+    q_tap = taps ? QF4 : 0;
+    s_n = taps ? sat + __float_as_int(o.z) : zeros;              // masked / clamped pixels: taps read a zero vector
+    s_s = taps ? sat + __float_as_int(o.w) : zeros;
+    const int j = t / CHUNK_IT;
+    g_s = has_g ? ring + (j % NSLOT) * SLOT_BYTES + (uint32_t)((t % CHUNK_IT) * PPW + sub) * (C * 4) + cl * 16 : zero_s;
+    g_q = has_g ? C : 0;                                         // masked ground pixels: broadcast zero vector
+  };
+  auto load_quarter = [&](PixelLoads& L, int k) {
+    L.g = ld_ring(g_s + k * g_q);
+    L.nw = ld_cached(s_n + k * q_tap); L.ne = ld_cached(s_n + east + k * q_tap);
+    L.sw = ld_cached(s_s + k * q_tap); L.se = ld_cached(s_s + east + k * q_tap);
+  };
+
+  // Software pipeline at quarter-pixel granularity (ping-pong buffers A / B): the five 128-bit loads of a quarter
+  // are issued two quarters before they are reduced.
+  PixelLoads bufA, bufB;
+  if (T > 0) { prepare(0); load_quarter(bufA, 0); load_quarter(bufB, 1); }
+  for (int t = 0; t < T; ++t) {
+    sc = nsc; om = nom; valid = nvalid;
+    const bool more = t + 1 < T;
+    accumulate(bufA); load_quarter(bufA, 2);
+    accumulate(bufB); load_quarter(bufB, 3);
+    if (more) prepare(t + 1);
+    accumulate(bufA);
+    if (more) load_quarter(bufA, 0);
+    accumulate(bufB);
+    finish_pixel();
+    // the last pixel-iteration of a chunk has been reduced: every lane's reads of the slot have returned (their
+    // values were just consumed), so lane 0 re-arms the slot with the chunk NSLOT ahead
+    if ((t + 1) % CHUNK_IT == 0) {
+      __syncwarp();
+      const int j = t / CHUNK_IT + NSLOT;
+      if (lane == 0 && j < n_chunks) issue_chunk(j);
+    }
+    if (more) load_quarter(bufB, 1);
+  }
+
+  {
+    double v[kLmAcc] = {sum2(A_aa), sum2(A_ab), sum2(A_bb), sum2(B_x), sum2(B_y), sum2(C_tt), sum2(S_a), sum2(S_b),
+                        sum2(S_t), sum2(G_a), sum2(G_b), sum2(G_t), sum2(SS), sum2(GG), sum2(SG), cnt / (float)LPP};
+    lm_reduce_and_solve<GEOM, FULL>(a, b, v, kp, fp, su, sv, th);
+  }
+}
+
+// Kernel selection (HA_LM_VARIANT): 0 = lm_step_kernel (register-staged ground stream; always used for
+// G2SP), k > 0 = lm_step_v4_kernel with a per-warp bulk-copy ring of NSLOT x CHUNK_IT x 2 KB.
+static int lm_variant() {
+  const char* e = getenv("HA_LM_VARIANT");       // looked up per launch (~100 ns) so that one process can A/B the variants
+  const int v = e ? atoi(e) : HA_LM_DEFAULT_VARIANT;
+  return (v < 0 || v > 5) ? HA_LM_DEFAULT_VARIANT : v;
+}
+
+template <int GEOM, int C, bool FULL, int NSLOT, int CHUNK_IT>
+static int launch_v4(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
+  auto kern = lm_step_v4_kernel<GEOM, C, FULL, NSLOT, CHUNK_IT>;
+  constexpr int smem = lm_ring_bytes<NSLOT, CHUNK_IT>();
+  static bool configured = false;            // per instantiation: the attributes belong to the device function
+  if (!configured) {
+    HA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // shared-memory carve-out: exactly what HA_LM_MIN_CTAS resident CTAs need (ring + ~6 KB static + 1 KB reserved
+    // each); the rest of the 228 KB stays L1 for the satellite taps
+    const int want = HA_LM_MIN_CTAS * (smem + 7 * 1024);
+    const int pct = want >= 228 * 1024 ? 100 : (want * 100 + 228 * 1024 - 1) / (228 * 1024);
+    HA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    configured = true;
+  }
+  kern<<<grid, kLmThreads, smem, st>>>(a);
+  return HA_OK;
+}
+
+template <int GEOM, int C, bool FULL>
+static int launch_variant(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
+  if constexpr (GEOM == HA_GEOM_G2SP) {
+    lm_step_kernel<GEOM, C, FULL><<<grid, kLmThreads, 0, st>>>(a);
+    return HA_OK;
   } else {
-    nth = th + (float)delta[0];
-  }
-  if (isnan(nsu) || isnan(nsv) || isnan(nth)) st |= HA_STATUS_NAN_POSE;
-  if (tot[15] == 0.0) st |= HA_STATUS_NO_INRANGE;
-  if (st) atomicOr(a.status, st);
-  a.pose[b * 3 + 0] = nsu; a.pose[b * 3 + 1] = nsv; a.pose[b * 3 + 2] = nth;
-  if (a.traj) {
-    float* tr = a.traj + (size_t)b * a.traj_stride;
-    tr[0] = nsu; tr[1] = nsv; tr[2] = nth;
-  }
-  if (a.stats) {
-    float* s = a.stats + (size_t)b * HA_STATS;
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) s[HA_STAT_H + i * 3 + j] = (float)Hm[i][j];
-    for (int i = 0; i < 3; ++i) s[HA_STAT_GRAD + i] = (float)gr[i];
-    s[HA_STAT_SAT_NORM] = (float)ns; s[HA_STAT_GRD_NORM] = (float)ng; s[HA_STAT_RES_SQ] = (float)res_sq;
-    for (int i = 0; i < 3; ++i) s[HA_STAT_DELTA + i] = (i < n) ? (float)delta[i] : 0.f;
-    s[HA_STAT_N_INRANGE] = (float)tot[15];
-    for (int i = HA_STAT_N_INRANGE + 1; i < HA_STATS; ++i) s[i] = 0.f;
+    switch (lm_variant()) {
+      case 1: return launch_v4<GEOM, C, FULL, 4, 1>(grid, st, a);
+      case 2: return launch_v4<GEOM, C, FULL, 3, 1>(grid, st, a);
+      case 3: return launch_v4<GEOM, C, FULL, 2, 2>(grid, st, a);
+      case 4: return launch_v4<GEOM, C, FULL, 6, 1>(grid, st, a);
+      case 5: return launch_v4<GEOM, C, FULL, 3, 2>(grid, st, a);
+      default: lm_step_kernel<GEOM, C, FULL><<<grid, kLmThreads, 0, st>>>(a); return HA_OK;
+    }
   }
 }
 
 template <int GEOM, bool FULL>
 static int launch_by_channels(int C, dim3 grid, cudaStream_t st, const LmStepArgs& a) {
+  int rc;
   switch (C) {
-    case 256: lm_step_kernel<GEOM, 256, FULL><<<grid, kLmThreads, 0, st>>>(a); break;
-    case 128: lm_step_kernel<GEOM, 128, FULL><<<grid, kLmThreads, 0, st>>>(a); break;
-    case 64: lm_step_kernel<GEOM, 64, FULL><<<grid, kLmThreads, 0, st>>>(a); break;
-    case 32: lm_step_kernel<GEOM, 32, FULL><<<grid, kLmThreads, 0, st>>>(a); break;
-    case 16: lm_step_kernel<GEOM, 16, FULL><<<grid, kLmThreads, 0, st>>>(a); break;
+    case 256: rc = launch_variant<GEOM, 256, FULL>(grid, st, a); break;
+    case 128: rc = launch_variant<GEOM, 128, FULL>(grid, st, a); break;
+    case 64: rc = launch_variant<GEOM, 64, FULL>(grid, st, a); break;
+    case 32: rc = launch_variant<GEOM, 32, FULL>(grid, st, a); break;
+    case 16: rc = launch_variant<GEOM, 16, FULL>(grid, st, a); break;
     default: return HA_EINVAL;
   }
+  if (rc != HA_OK) return rc;
   count_launches(1);
   return check_launch("lm_step_kernel");
 }
