@@ -28,7 +28,7 @@ namespace ha {
 #define HA_LM_MIN_CTAS 4
 #endif
 #ifndef HA_LM_DEFAULT_VARIANT
-#define HA_LM_DEFAULT_VARIANT 1
+#define HA_LM_DEFAULT_VARIANT 4
 #endif
 constexpr int kLmThreads = 128;
 constexpr int kLmWarps = kLmThreads / 32;
@@ -252,7 +252,7 @@ struct PixelScalars {
 
 template <int GEOM>
 __device__ __forceinline__ PixelScalars pixel_scalars(const LmStepArgs& a, const KittiPose& kp, const FordPose& fp,
-                                                      const G2spPose& gp, const float4* tab, const float* conf, int q,
+                                                      const G2spPose& gp, const float4 tab_px, const float* conf, int q,
                                                       int q_end, int c4) {
   PixelScalars r;
   r.ex = r.wx = r.sy = r.ny = 0.f; r.tx = r.ty = 0.f; r.om = 1.f; r.valid = 0.f;
@@ -283,7 +283,7 @@ __device__ __forceinline__ PixelScalars pixel_scalars(const LmStepArgs& a, const
     r.d1x = gp.dv[0] / w - uv1[0] * gp.dv[2] / w2; r.d1y = gp.dv[1] / w - uv1[1] * gp.dv[2] / w2;
     r.tx = dt1[0] / w - uv1[0] * dt1[2] / w2; r.ty = dt1[1] / w - uv1[1] * dt1[2] / w2;
   } else {
-    const float4 p = __ldg(tab + q);
+    const float4 p = tab_px;                                   // ground-plane point (x, y, z, mask) of this pixel
     if (p.w == 0.f) return r;                                  // geometric mask: s, J and g all vanish
     r.goff = q * c4;
     const PixelWarp w = (GEOM == HA_GEOM_KITTI) ? warp_kitti(kp, a, p) : warp_ford(fp, a, p);
@@ -593,7 +593,8 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
     const int gbase = q_begin + (warp + (t / IPG) * kLmWarps) * 32;
     if (it == 0) {                                               // phase A: one lane per pixel, 32 pixels at once
       __syncwarp();
-      const PixelScalars ps = pixel_scalars<GEOM>(a, kp, fp, gq, tab, conf, gbase + lane, q_end, C4);
+      const float4 tab_px = (!G2SP && gbase + lane < q_end) ? __ldg(tab + gbase + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const PixelScalars ps = pixel_scalars<GEOM>(a, kp, fp, gq, tab_px, conf, gbase + lane, q_end, C4);
       if (G2SP) ps_s[warp][lane][G2SP ? 3 : 0] = make_float4(ps.d0x, ps.d0y, ps.d1x, ps.d1y);
       ps_s[warp][lane][0] = make_float4(ps.ex, ps.wx, ps.sy, ps.ny);
       ps_s[warp][lane][1] = make_float4(ps.tx, ps.ty, ps.om, ps.valid);
@@ -643,37 +644,41 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
 // v4 step kernel (S2GP geometries).  What changed against the kernel above and why (B200 measurements):
 //  * HBM latency x bandwidth needs ~40 KB of streamed loads in flight per SM; register-staged loads hold 16 KB
 //    (2 x 512 B per warp), which pinned v3 at 0.4 of the HBM roofline.  Here every warp owns a ring of NSLOT
-//    chunks in shared memory; lane 0 keeps NSLOT-1 chunks of the ground stream in flight with 1-D bulk async copies
-//    (cp.async.bulk -> SASS UBLKCP, completion on a per-slot mbarrier) and re-arms a slot as soon as the warp has
-//    reduced it.  Producer and consumer of a ring are the same warp: no cross-warp synchronisation at all.
+//    2-KB chunks in shared memory; lane 0 keeps NSLOT-1 chunks of the ground stream in flight with 1-D bulk async
+//    copies (cp.async.bulk -> SASS UBLKCP, completion on a per-slot mbarrier) and re-arms a slot as soon as the warp
+//    has reduced it.  Producer and consumer of a ring are the same warp: no cross-warp synchronisation at all.
 //  * The FMA pipe issues one packed FFMA2 per two cycles per SM sub-partition, which capped v3 at ~0.85 of the
 //    roofline even at 100 % pipe utilisation (19 packed ops per channel pair + 19 per pixel and lane).  Here a lane
 //    owns 16 channels of a pixel (the per-pixel work is amortised over twice the channels) and the interpolation
 //    uses wx + ex = 1, ny + sy = 1 (16 ops per pair).  Pixels where that identity fails — a corner clamped at the
 //    last row / column (jacobian.py:147-166: all weights vanish there) — and masked pixels read their taps from a
 //    zero vector instead, which reproduces the reference's zeros exactly.
+//  * ncu showed v3 (and a first cut of this kernel) spending more than half of their issue slots on index
+//    arithmetic.  Phase A therefore leaves finished 64-bit tap addresses in the per-pixel record, all loop state
+//    (ring slot, record pointer, stream position) advances incrementally, and every load uses an immediate offset.
 //  * The satellite taps stay on the L1/L2 path (gathers with heavy reuse between neighbouring pixels).
 extern __shared__ __align__(128) uint8_t lm_dyn_smem[];
 
 constexpr int kLmIterBytes = 2048;   // one warp pixel-iteration streams PPW pixels x C channels x 4 B = 2 KB for every C
+constexpr int kLmRecBytes = 48;      // per-pixel record: (wx, ny, tx, ty) | (&nw, &sw) | (east bytes, has ground, weight, -)
 
-template <int NSLOT, int CHUNK_IT>
-constexpr int lm_ring_bytes() { return kLmWarps * NSLOT * CHUNK_IT * kLmIterBytes + kLmWarps * NSLOT * 8 + 16; }
+template <int NSLOT>
+constexpr int lm_ring_bytes() { return kLmWarps * NSLOT * kLmIterBytes + kLmWarps * NSLOT * 8 + 1024; }
 
-template <int GEOM, int C, bool FULL, int NSLOT, int CHUNK_IT_REQ>
-__global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_v4_kernel(const LmStepArgs a) {
+// Loop-invariant addresses the compiler would otherwise re-derive from %tid / %ctaid inside the loop (it treats them as
+// "cheap to rematerialise" under register pressure; ncu showed ~100 such instructions per iteration): make them opaque.
+#define HA_KEEP32(x) asm volatile("" : "+r"(x))
+#define HA_KEEP64(x) asm volatile("" : "+l"(x))
+
+template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF>
+__global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmStepArgs a) {
   constexpr int LPP = C / 16;                      // lanes per pixel: every lane owns 4 x 4 channels
   constexpr int PPW = 32 / LPP;                    // pixels processed together by one warp
   constexpr int IPG = LPP;                         // pixel-iterations per 32-pixel group
   constexpr int C4 = C / 4;
-  constexpr int QF4 = C / 16;                      // float4s between the four channel quarters of a lane
   static_assert(C % 16 == 0 && LPP >= 1 && LPP <= 32 && PPW * LPP == 32, "channel count");
   static_assert(GEOM != HA_GEOM_G2SP, "G2SP streams only the visible satellite pixels: it stays on lm_step_kernel");
-  constexpr int CHUNK_IT = CHUNK_IT_REQ < IPG ? CHUNK_IT_REQ : IPG;   // a chunk never straddles two 32-pixel groups
-  constexpr int CHUNK_PX = CHUNK_IT * PPW;
-  constexpr int SLOT_BYTES = CHUNK_IT_REQ * kLmIterBytes;             // ring geometry follows the host-side smem size
-  constexpr int CPG = IPG / CHUNK_IT;              // chunks per 32-pixel group
-  static_assert(IPG % CHUNK_IT == 0, "chunk size");
+  static_assert(4 * C <= 1024, "zero vectors cover four channel quarters");
 
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -690,70 +695,65 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_v4_kernel(
   else fp = ford_pose(a, b, su, sv, th);
 
   const size_t px_base = (size_t)b * a.H * a.W + (size_t)(a.H / 2) * a.W;
-  const float4* grd0 = reinterpret_cast<const float4*>(a.grd) + px_base * C4;                   // streamed (bulk copies)
-  const float4* sat = reinterpret_cast<const float4*>(a.sat) + (size_t)b * a.A * a.A * C4 + cl; // gathered
-  const float4* zeros = a.zeros + cl;              // masked / clamped pixels read this zero vector (all quarters at the same address)
+  const float4* grd0 = reinterpret_cast<const float4*>(a.grd) + px_base * C4;              // streamed (bulk copies)
+  const char* sat_b = reinterpret_cast<const char*>(a.sat) + (size_t)b * a.A * a.A * C * 4;  // gathered
   const float4* tab = a.table + (size_t)(a.H / 2) * a.W;
   const float* conf = a.conf ? a.conf + px_base : nullptr;
 
-  // per-warp staging of the per-pixel scalars: phase A writes 32 pixels, phase B reads them back per pixel slot
-  __shared__ __align__(16) float4 ps_s[kLmWarps][32][2];
+  // per-warp pixel records: phase A (one lane per pixel) writes 32 of them, the pixel's channel lanes read them back
+  __shared__ __align__(16) uint8_t ps_s[kLmWarps][32 * kLmRecBytes];
 
-  // bulk-copy ring of this warp: [NSLOT][SLOT_BYTES], then NSLOT mbarriers per warp, then one 16-byte zero vector
+  // dynamic shared memory: [warp][NSLOT][2 KB] rings, [warp][NSLOT] mbarriers, 1 KB of zeros (masked ground pixels)
   const uint32_t dyn = smem_u32(lm_dyn_smem);
-  const uint32_t ring = dyn + warp * (NSLOT * SLOT_BYTES);
-  const uint32_t ring_bar = dyn + kLmWarps * NSLOT * SLOT_BYTES + warp * (NSLOT * 8);
-  const uint32_t zero_s = dyn + kLmWarps * NSLOT * SLOT_BYTES + kLmWarps * NSLOT * 8;
+  const uint32_t ring_w = dyn + warp * (NSLOT * kLmIterBytes);
+  const uint32_t bar_w = dyn + kLmWarps * NSLOT * kLmIterBytes + warp * (NSLOT * 8);
+  const uint32_t zero_s = dyn + kLmWarps * NSLOT * kLmIterBytes + kLmWarps * NSLOT * 8;
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < NSLOT; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ring_bar + s * 8));
+    for (int s = 0; s < NSLOT; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_w + s * 8));
     fence_barrier_init();
   }
-  if (threadIdx.x == 0) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(zero_s), "r"(0) : "memory");
+  asm volatile("st.shared.v2.b32 [%0], {%1, %1};" ::"r"(zero_s + threadIdx.x * 8), "r"(0) : "memory");
   __syncthreads();
+
+  uint32_t ring_lane = ring_w + sub * (C * 4) + cl * 16;           // this lane's slice of slot 0
+  uint32_t zero_lane = zero_s + cl * 16;
+  const uint32_t ps_w = smem_u32(&ps_s[warp][0]);
+  uint32_t ps_lane = ps_w + sub * kLmRecBytes;
+  uint32_t ps_wr = ps_w + lane * kLmRecBytes;                      // the record this lane writes in phase A
+  const uint32_t cl16 = cl * 16;
+  uint32_t ring_bar = ring_w, bar_keep = bar_w;                    // opaque copies used inside the loop
+  uint64_t grd_w = reinterpret_cast<uint64_t>(grd0 + (size_t)(q_begin + warp * 32) * C4);   // first chunk of this warp
+  HA_KEEP32(ring_lane); HA_KEEP32(zero_lane); HA_KEEP32(ps_lane); HA_KEEP32(ps_wr); HA_KEEP32(ring_bar); HA_KEEP32(bar_keep);
+  HA_KEEP64(grd_w);
 
   const int n_groups = (q_end - q_begin + 31) / 32;
   const int my_groups = (n_groups > warp) ? (n_groups - warp + kLmWarps - 1) / kLmWarps : 0;
   const int T = my_groups * IPG;                   // pixel-iterations of this warp
-  const int n_chunks = T / CHUNK_IT;
 
-  // ring producer (lane 0): chunk j = CHUNK_PX consecutive pixels of this warp's pixel stream -> slot j % NSLOT
-  auto chunk_start = [&](int j) { return q_begin + (warp + (j / CPG) * kLmWarps) * 32 + (j % CPG) * CHUNK_PX; };
-  auto issue_chunk = [&](int j) {
-    const int start = chunk_start(j);
-    const int n = min(q_end - start, CHUNK_PX);
-    if (n > 0) {
-      const uint32_t bar = ring_bar + (j % NSLOT) * 8, bytes = (uint32_t)n * (C * 4);
+  // ---- ring producer (lane 0).  Chunk u = pixel-iteration u of this warp; `iss_px` is its first pixel.
+  // `iss_left` = pixels from the chunk's first pixel to q_end (<= 0: nothing to copy), `iss_off` = its byte offset from grd_w.
+  int iss_left = q_end - (q_begin + warp * 32), iss_it = 0, to_issue = T;
+  uint32_t iss_off = 0;
+  auto issue_next = [&](uint32_t slot) {           // arm `slot` with the next chunk of the stream, then advance
+    if (lane == 0 && iss_left > 0) {
+      const uint32_t bar = bar_keep + slot * 8, bytes = (uint32_t)min(iss_left, PPW) * (C * 4);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(ring + (j % NSLOT) * SLOT_BYTES), "l"(grd0 + (size_t)start * C4), "r"(bytes), "r"(bar) : "memory");
+                   ::"r"(ring_bar + slot * kLmIterBytes), "l"(grd_w + iss_off), "r"(bytes), "r"(bar) : "memory");
     }
+    iss_off += kLmIterBytes; iss_left -= PPW; --to_issue;
+    if (++iss_it == IPG) { iss_it = 0; iss_off += (kLmWarps - 1) * 32 * C * 4; iss_left -= (kLmWarps - 1) * 32; }
   };
-  auto wait_chunk = [&](int j) {
-    if (chunk_start(j) < q_end) {
-      const uint32_t bar = ring_bar + (j % NSLOT) * 8, parity = (j / NSLOT) & 1;
-      asm volatile(
-          "{\n"
-          ".reg .pred p;\n"
-          "LM_WAIT:\n"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-          "@p bra LM_DONE;\n"
-          "bra LM_WAIT;\n"
-          "LM_DONE:\n"
-          "}\n" ::"r"(bar), "r"(parity) : "memory");
-    }
-  };
-  if (lane == 0) {
-    for (int j = 0; j < NSLOT && j < n_chunks; ++j) issue_chunk(j);
-  }
+  for (int j = 0; j < NSLOT && to_issue > 0; ++j) issue_next(j);
 
   // running sums over this lane's pixels and channels (two partial sums per register pair)
   f32x2 A_aa = 0, A_ab = 0, A_bb = 0, B_x = 0, B_y = 0, C_tt = 0;
   f32x2 S_a = 0, S_b = 0, S_t = 0, G_a = 0, G_b = 0, G_t = 0, SS = 0, GG = 0, SG = 0;
-  float cnt = 0.f;
+  float cnt = 0.f;                                 // in-range pixels, counted by the phase-A lanes
   f32x2 p_aa = 0, p_ab = 0, p_bb = 0, p_sa = 0, p_sb = 0, p_ga = 0, p_gb = 0;   // per-pixel channel sums
   float4 sc = make_float4(0, 0, 0, 0);             // (wx, ny, tx, ty) of the pixel being reduced
-  float om = 1.f, valid = 0.f;
+  float om = 1.f;
 
   auto accumulate = [&](const PixelLoads& L) {
     const f32x2 wx2 = dup2(sc.x), ny2 = dup2(sc.y);
@@ -788,101 +788,143 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_v4_kernel(
     acc2(C_tt, tx2, gx); acc2(C_tt, ty2, gy);
     inc2(S_a, p_sa); inc2(S_b, p_sb); acc2(S_t, p_sa, tx2); acc2(S_t, p_sb, ty2);
     inc2(G_a, p_ga); inc2(G_b, p_gb); acc2(G_t, p_ga, tx2); acc2(G_t, p_gb, ty2);
-    cnt += valid;                                  // every lane of the pixel counts it: divided by LPP below
     p_aa = p_ab = p_bb = p_sa = p_sb = p_ga = p_gb = 0ull;
   };
 
-  // addresses of the pixel whose loads are being issued (set by prepare(), used by load_quarter())
-  const float4 *s_n = zeros, *s_s = zeros;
-  int east = 0, q_tap = 0;                         // float4 offsets: to the east tap, between channel quarters of the taps
-  uint32_t g_s = zero_s, g_q = 0;                  // shared address of the pixel's ground vector, bytes between its quarters
-  float4 nsc = sc;                                 // scalars of the pixel whose loads are in flight
-  float nom = 1.f, nvalid = 0.f;
+  // ---- consumer state, advanced incrementally by prepare()
+  int nxt_px = q_begin + warp * 32, nxt_it = 0;    // first pixel / position in its group of the NEXT pixel-iteration
+  uint32_t slot = 0, parity = 0;                   // ring slot and mbarrier phase of the next pixel-iteration
+  uint32_t ps_rd = ps_lane;                        // record of the next pixel-iteration
+  uint32_t ps_cur = ps_lane;                       // record of the pixel-iteration whose loads were issued last
+  const char *p_nw = nullptr, *p_ne = nullptr, *p_sw = nullptr, *p_se = nullptr;   // this lane's 16 bytes of the four taps
+  uint32_t g_addr = zero_lane;                     // this lane's 16 bytes of the ground vector (shared memory)
 
-  auto prepare = [&](int t) {                      // per-pixel scalars + addresses of pixel-iteration t
-    const int it = t % IPG;
-    const int gbase = q_begin + (warp + (t / IPG) * kLmWarps) * 32;
-    if (t % CHUNK_IT == 0) wait_chunk(t / CHUNK_IT);             // the chunk this pixel lives in has landed
-    if (it == 0) {                                               // phase A: one lane per pixel, 32 pixels at once
-      __syncwarp();
-      const PixelScalars ps = pixel_scalars<GEOM>(a, kp, fp, gq, tab, conf, gbase + lane, q_end, C4);
-      // taps are read (bit 2) unless the sample point is masked or a corner was clamped (then all weights vanish)
-      const bool taps = ps.valid != 0.f && (ps.ex + ps.wx == 1.f) && (ps.sy + ps.ny == 1.f);
-      const int flags = (ps.east != 0 ? 1 : 0) | (ps.goff >= 0 ? 2 : 0) | (taps ? 4 : 0) | (ps.valid != 0.f ? 8 : 0);
-      ps_s[warp][lane][0] = make_float4(ps.wx, ps.ny, ps.tx, ps.ty);
-      ps_s[warp][lane][1] = make_float4(ps.om, __int_as_float(flags), __int_as_float(ps.off_n), __int_as_float(ps.off_s));
-      __syncwarp();
+  float4 tab_next = make_float4(0.f, 0.f, 0.f, 0.f);   // table entry of this lane's pixel in the group phase A handles next
+  auto load_tab = [&](int px0) { tab_next = (px0 + lane < q_end) ? __ldg(tab + px0 + lane) : make_float4(0.f, 0.f, 0.f, 0.f); };
+  auto phase_a = [&](int px0) {                    // one lane per pixel, 32 pixels [px0, px0 + 32) at once
+    __syncwarp();
+    const PixelScalars ps = pixel_scalars<GEOM>(a, kp, fp, gq, tab_next, conf, px0 + lane, q_end, C4);
+    load_tab(px0 + kLmWarps * 32);                 // table entry for the phase A after this one: its latency is off the path
+    // taps are read unless the sample point is masked or a corner was clamped (then all weights vanish)
+    const bool taps = ps.valid != 0.f && (ps.ex + ps.wx == 1.f) && (ps.sy + ps.ny == 1.f);
+    const char* pn = taps ? sat_b + (size_t)ps.off_n * 16 : reinterpret_cast<const char*>(a.zeros);
+    const char* psw = taps ? sat_b + (size_t)ps.off_s * 16 : reinterpret_cast<const char*>(a.zeros);
+    const uint32_t rec = ps_wr;
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rec), "f"(ps.wx), "f"(ps.ny), "f"(ps.tx), "f"(ps.ty) : "memory");
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(rec + 16), "l"(pn), "l"(psw) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rec + 32), "r"(taps ? ps.east * 16 : 0),
+                 "r"(ps.goff >= 0 ? 1 : 0), "r"(__float_as_int(ps.om)), "r"(0) : "memory");
+    cnt += ps.valid;
+    if (PF != 0 && taps) {
+      // The pixel's two tap rows (nw|ne and sw|se are adjacent texels) are prefetched now: first touches of a satellite
+      // texel miss to DRAM (~1000 cycles), far more than the two-quarter lead of the tap loads themselves.  All but the
+      // first pixel-iteration of the group get at least one iteration of lead.  (Running phase A a whole group ahead
+      // with double-buffered records measured slower: 794 vs 763 us at C = 64, B = 256.)
+      constexpr int kLines = (2 * C * 4 + 127) / 128;
+#pragma unroll
+      for (int k = 0; k < kLines; ++k) {
+        if (PF == 1) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + k * 128));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(psw + k * 128));
+        } else {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + k * 128));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(psw + k * 128));
+        }
+      }
     }
-    const int src = it * PPW + sub;
-    nsc = ps_s[warp][src][0];
-    const float4 o = ps_s[warp][src][1];
-    const int flags = __float_as_int(o.y);
-    nom = o.x;
-    nvalid = (flags & 8) ? 1.f : 0.f;
-    const bool taps = (flags & 4) != 0, has_g = (flags & 2) != 0;
-    east = (taps && (flags & 1)) ? C4 : 0;
-    q_tap = taps ? QF4 : 0;
-    s_n = taps ? sat + __float_as_int(o.z) : zeros;              // masked / clamped pixels: taps read a zero vector
-    s_s = taps ? sat + __float_as_int(o.w) : zeros;
-    const int j = t / CHUNK_IT;
-    g_s = has_g ? ring + (j % NSLOT) * SLOT_BYTES + (uint32_t)((t % CHUNK_IT) * PPW + sub) * (C * 4) + cl * 16 : zero_s;
-    g_q = has_g ? C : 0;                                         // masked ground pixels: broadcast zero vector
+    __syncwarp();
   };
-  auto load_quarter = [&](PixelLoads& L, int k) {
-    L.g = ld_ring(g_s + k * g_q);
-    L.nw = ld_cached(s_n + k * q_tap); L.ne = ld_cached(s_n + east + k * q_tap);
-    L.sw = ld_cached(s_s + k * q_tap); L.se = ld_cached(s_s + east + k * q_tap);
+
+  auto prepare = [&]() {                           // addresses of the next pixel-iteration's loads
+    if (nxt_px < q_end) {                          // its chunk has landed (chunks past the end are never armed)
+      const uint32_t bar = bar_keep + slot * 8;
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "LM_WAIT:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra LM_DONE;\n"
+          "bra LM_WAIT;\n"
+          "LM_DONE:\n"
+          "}\n" ::"r"(bar), "r"(parity) : "memory");
+    }
+    if (nxt_it == 0) {                             // entering a 32-pixel group: phase A
+      phase_a(nxt_px);
+      ps_rd = ps_lane;
+    }
+    uint64_t an, as_;
+    uint32_t east, has_g;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(an), "=l"(as_) : "r"(ps_rd + 16));
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(east), "=r"(has_g) : "r"(ps_rd + 32));
+    p_nw = reinterpret_cast<const char*>(an) + cl16; p_sw = reinterpret_cast<const char*>(as_) + cl16;
+    p_ne = p_nw + east; p_se = p_sw + east;
+    g_addr = has_g ? ring_lane + slot * kLmIterBytes : zero_lane;  // masked ground pixels read zeros
+    ps_cur = ps_rd;
+    // advance to the pixel-iteration after this one
+    ps_rd += PPW * kLmRecBytes; nxt_px += PPW;
+    if (++nxt_it == IPG) { nxt_it = 0; nxt_px += (kLmWarps - 1) * 32; }
+    if (++slot == NSLOT) { slot = 0; parity ^= 1; }
+  };
+  auto load_quarter = [&](PixelLoads& L, int k) {  // k-th channel quarter: immediate offsets k * C bytes
+    L.g = ld_ring(g_addr + k * C);
+    L.nw = ld_cached(reinterpret_cast<const float4*>(p_nw + k * C)); L.ne = ld_cached(reinterpret_cast<const float4*>(p_ne + k * C));
+    L.sw = ld_cached(reinterpret_cast<const float4*>(p_sw + k * C)); L.se = ld_cached(reinterpret_cast<const float4*>(p_se + k * C));
   };
 
   // Software pipeline at quarter-pixel granularity (ping-pong buffers A / B): the five 128-bit loads of a quarter
   // are issued two quarters before they are reduced.
   PixelLoads bufA, bufB;
-  if (T > 0) { prepare(0); load_quarter(bufA, 0); load_quarter(bufB, 1); }
+  uint32_t slot_cur = 0;
+  if (T > 0) {
+    load_tab(nxt_px);
+    prepare(); load_quarter(bufA, 0); load_quarter(bufB, 1);
+  }
   for (int t = 0; t < T; ++t) {
-    sc = nsc; om = nom; valid = nvalid;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w) : "r"(ps_cur));
+    if (a.using_weight) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(om) : "r"(ps_cur + 40));
     const bool more = t + 1 < T;
     accumulate(bufA); load_quarter(bufA, 2);
     accumulate(bufB); load_quarter(bufB, 3);
-    if (more) prepare(t + 1);
+    const uint32_t slot_done = slot_cur;
+    if (more) { slot_cur = slot; prepare(); }
     accumulate(bufA);
     if (more) load_quarter(bufA, 0);
     accumulate(bufB);
     finish_pixel();
-    // the last pixel-iteration of a chunk has been reduced: every lane's reads of the slot have returned (their
-    // values were just consumed), so lane 0 re-arms the slot with the chunk NSLOT ahead
-    if ((t + 1) % CHUNK_IT == 0) {
-      __syncwarp();
-      const int j = t / CHUNK_IT + NSLOT;
-      if (lane == 0 && j < n_chunks) issue_chunk(j);
-    }
+    // this pixel-iteration's chunk has been reduced: every lane's reads of the slot have returned (their values were
+    // just consumed), so lane 0 re-arms the slot with the chunk NSLOT ahead
+    __syncwarp();
+    if (to_issue > 0) issue_next(slot_done);
     if (more) load_quarter(bufB, 1);
   }
 
   {
     double v[kLmAcc] = {sum2(A_aa), sum2(A_ab), sum2(A_bb), sum2(B_x), sum2(B_y), sum2(C_tt), sum2(S_a), sum2(S_b),
-                        sum2(S_t), sum2(G_a), sum2(G_b), sum2(G_t), sum2(SS), sum2(GG), sum2(SG), cnt / (float)LPP};
+                        sum2(S_t), sum2(G_a), sum2(G_b), sum2(G_t), sum2(SS), sum2(GG), sum2(SG), cnt};
     lm_reduce_and_solve<GEOM, FULL>(a, b, v, kp, fp, su, sv, th);
   }
 }
 
 // Kernel selection (HA_LM_VARIANT): 0 = lm_step_kernel (register-staged ground stream; always used for
-// G2SP), k > 0 = lm_step_v4_kernel with a per-warp bulk-copy ring of NSLOT x CHUNK_IT x 2 KB.
+// G2SP), k > 0 = lm_step_v4_kernel with a per-warp bulk-copy ring of NSLOT x 2 KB and MINB resident CTAs per SM (1: 4 slots / 4 CTAs, 2: 6 / 4, 3: 6 / 3, 4: 8 / 3).
 static int lm_variant() {
   const char* e = getenv("HA_LM_VARIANT");       // looked up per launch (~100 ns) so that one process can A/B the variants
   const int v = e ? atoi(e) : HA_LM_DEFAULT_VARIANT;
   return (v < 0 || v > 5) ? HA_LM_DEFAULT_VARIANT : v;
 }
 
-template <int GEOM, int C, bool FULL, int NSLOT, int CHUNK_IT>
+template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF>
 static int launch_v4(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
-  auto kern = lm_step_v4_kernel<GEOM, C, FULL, NSLOT, CHUNK_IT>;
-  constexpr int smem = lm_ring_bytes<NSLOT, CHUNK_IT>();
+  auto kern = lm_step_v4_kernel<GEOM, C, FULL, NSLOT, MINB, PF>;
+  constexpr int smem = lm_ring_bytes<NSLOT>();
   static bool configured = false;            // per instantiation: the attributes belong to the device function
   if (!configured) {
     HA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    // shared-memory carve-out: exactly what HA_LM_MIN_CTAS resident CTAs need (ring + ~6 KB static + 1 KB reserved
-    // each); the rest of the 228 KB stays L1 for the satellite taps
-    const int want = HA_LM_MIN_CTAS * (smem + 7 * 1024);
+    // shared-memory carve-out: exactly what MINB resident CTAs need (ring + static + 1 KB reserved each); the rest of
+    // the 228 KB stays L1 for the satellite taps
+    cudaFuncAttributes fa;
+    HA_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+    const int want = MINB * (smem + (int)fa.sharedSizeBytes + 1024);
     const int pct = want >= 228 * 1024 ? 100 : (want * 100 + 228 * 1024 - 1) / (228 * 1024);
     HA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     configured = true;
@@ -898,11 +940,11 @@ static int launch_variant(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
     return HA_OK;
   } else {
     switch (lm_variant()) {
-      case 1: return launch_v4<GEOM, C, FULL, 4, 1>(grid, st, a);
-      case 2: return launch_v4<GEOM, C, FULL, 3, 1>(grid, st, a);
-      case 3: return launch_v4<GEOM, C, FULL, 2, 2>(grid, st, a);
-      case 4: return launch_v4<GEOM, C, FULL, 6, 1>(grid, st, a);
-      case 5: return launch_v4<GEOM, C, FULL, 3, 2>(grid, st, a);
+      case 1: return launch_v4<GEOM, C, FULL, 6, 3, 0>(grid, st, a);
+      case 2: return launch_v4<GEOM, C, FULL, 6, 3, 1>(grid, st, a);
+      case 3: return launch_v4<GEOM, C, FULL, 6, 3, 2>(grid, st, a);
+      case 4: return launch_v4<GEOM, C, FULL, 4, 3, 2>(grid, st, a);
+      case 5: return launch_v4<GEOM, C, FULL, 4, 3, 1>(grid, st, a);
       default: lm_step_kernel<GEOM, C, FULL><<<grid, kLmThreads, 0, st>>>(a); return HA_OK;
     }
   }
