@@ -283,21 +283,36 @@ def main():
     # ---------------- per-kernel-family timings for the rooflines (same process, CUDA events)
     pk = peaks()
     sat_p, grd_p = net.extract(sat_d, grd_d, False)
+    net.extract(sat_d, grd_d, False)        # untimed: with sat_p / grd_p held, the caching allocator has to grow once more
     vgg_secs = time_region(lambda i: net.extract(sat_d, grd_d, False), K, sync) / K
     # the 15-launch LM loop takes ~1 ms: time it from a CUDA graph so that Python launch overhead (which the
     # full forward hides behind the VGG kernels) does not pollute the kernel's roofline number
-    lm_how = "cuda graph replay"
-    try:
-        net.refine(sat_p, grd_p, reset_uv=draws)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        cap_stream = torch.cuda.Stream(device=dev)
-        with torch.cuda.graph(graph, stream=cap_stream):
-            net.refine(sat_p, grd_p, reset_uv=draws)
-        lm_secs = time_region(lambda i: graph.replay(), K, sync) / K
-    except Exception as e:                                         # pragma: no cover
-        lm_how = "eager loop (graph capture failed: %s)" % type(e).__name__
-        lm_secs = time_region(lambda i: net.refine(sat_p, grd_p, reset_uv=draws), K, sync) / K
+    def time_lm(sat_x, grd_x, draws_x):
+        try:
+            net.refine(sat_x, grd_x, reset_uv=draws_x)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            cap_stream = torch.cuda.Stream(device=dev)
+            with torch.cuda.graph(graph, stream=cap_stream):
+                net.refine(sat_x, grd_x, reset_uv=draws_x)
+            return time_region(lambda i: graph.replay(), K, sync) / K, "cuda graph replay"
+        except Exception as e:                                     # pragma: no cover
+            return (time_region(lambda i: net.refine(sat_x, grd_x, reset_uv=draws_x), K, sync) / K,
+                    "eager loop (graph capture failed: %s)" % type(e).__name__)
+
+    lm_secs, lm_how = time_lm(sat_p, grd_p, draws)
+    # the same loop at the batch the north star quotes the LM roofline on (256 pairs, random features: ~15 GB, so each
+    # launch streams far more than the L2 holds); B = 32 launches last 40-120 us and are dominated by launch/tail effects
+    B_big = 256
+    gen = torch.Generator(device=dev).manual_seed(7)
+    del sat_p, grd_p
+    torch.cuda.empty_cache()
+    sat_big = engine.Pyramid([torch.randn(B_big, 512 >> (3 - l), 512 >> (3 - l), PYR_C[l], device=dev, generator=gen)
+                              for l in range(opt.level)], [None] * opt.level)
+    grd_big = engine.Pyramid([torch.randn(B_big, 256 >> (3 - l), 1024 >> (3 - l), PYR_C[l], device=dev, generator=gen)
+                              for l in range(opt.level)], [None] * opt.level)
+    big_secs, big_how = time_lm(sat_big, grd_big, torch.zeros(n_steps_lm, 2, B_big, device=dev))
+    del sat_big, grd_big
     vgg_flops = VGG_FLOP_PER_PX[opt.level] * 2 * 262144 * B
     mma_mult = {"f16x3": 3, "f16": 1, "fp32": 0}[opt.precision]
     tf = vgg_flops / vgg_secs / 1e12
@@ -312,6 +327,9 @@ def main():
     roof_lm = {"kernel": "lm_step_kernel x %d launches" % n_steps_lm, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
                "unit": "GB/s", "frac": gbs / pk["hbm"], "peak_source": pk["src"], "traffic": None, "ms_per_step": lm_secs * 1e3,
                "bytes_per_pair": lm_bytes_per_pair(opt.level, opt.n_iters), "timed_as": lm_how}
+    gbs_big = lm_bytes_per_pair(opt.level, opt.n_iters) * B_big / big_secs / 1e9
+    roof_lm["at_batch_256"] = {"achieved": gbs_big, "frac": gbs_big / pk["hbm"], "ms_per_step": big_secs * 1e3, "timed_as": big_how,
+                               "data": "random features, KITTI pyramid shapes"}
 
     if rank != 0:
         if world > 1:

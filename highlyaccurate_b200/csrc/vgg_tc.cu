@@ -400,64 +400,109 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 // ------------------------------------------------------------------------------ conv0 + helpers
-// conv0 (3 -> 64, K = 27) is 0.7 % of the FLOPs: CUDA-core fp32 straight from the NCHW image,
-// fused bias + ReLU, writes the hi/lo activation planes conv2 consumes.  Each thread owns 4
-// horizontally adjacent pixels x 16 output channels at a time, so one 128-bit weight load from
-// shared memory feeds 16 FMAs (the 1-pixel version was LDS-issue bound at 25 % of the FMA pipe).
-// (A remap with the four channel chunks of a pixel group on four adjacent threads, so that their stores
-// share 128-byte lines, measured slower: 1.55 ms vs 1.30-1.40 ms at B = 32.)
-constexpr int kC0TW = 64, kC0TH = 16;     // CTA tile: 64 x 16 pixels, 256 threads
+// conv0 (3 -> 64, K = 27) is 0.7 % of the FLOPs but writes the largest activation of the network (2.1 GB of hi/lo
+// planes per branch at B = 32), so it is built around its two real limits:
+//  * FP32 pipe: a lane owns 8 horizontally adjacent pixels x 8 output channels and accumulates with packed FFMA2
+//    (one 128-bit weight broadcast from shared memory feeds 32 FMAs; the scalar-FFMA version ran at half the rate);
+//  * stores: a pixel's output is one contiguous 256-byte record [hi 64 | lo 64]; the eight warps of a CTA (= the eight
+//    channel blocks of the same 256 pixels) park their 16-byte pieces in an XOR-swizzled staging tile and the CTA
+//    writes whole records, 512 contiguous bytes per store instruction (the direct version touched 32 lines per
+//    store and ran at 1.6 TB/s).
+// (A tensor-core variant — im2col channels + 1x1 tcgen05 conv — measured 1.39 ms against 1.30-1.40 ms for the first
+// CUDA-core kernel at B = 32: with one k-block per tile it is bound by the same epilogue.)
+constexpr int kC0TW = 64, kC0TH = 16;     // CTA tile: 64 x 16 pixels, 256 threads, four passes of 64 x 4 pixels
+constexpr int kC0Pitch = kC0TW + 4;       // input row pitch in floats: 272 B keeps every 8-pixel window 16-byte aligned
+constexpr int kC0Smem = 64 * 4 * 256 /*staging*/ + 27 * 64 * 4 + 64 * 4 + 3 * (kC0TH + 2) * kC0Pitch * 4;
+
+typedef unsigned long long c0_f32x2;
+__device__ __forceinline__ c0_f32x2 c0_pack(float lo, float hi) { c0_f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void c0_unpack(c0_f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void c0_fma(c0_f32x2& acc, c0_f32x2 a, c0_f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+
 __global__ void __launch_bounds__(256, 2) conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[9][3][64]*/,
                                                     const float* __restrict__ bias, __half* __restrict__ out, int H, int W) {
-  __shared__ __align__(16) float w_s[27 * 64];
-  __shared__ float b_s[64];
-  __shared__ float in_s[3][kC0TH + 2][kC0TW + 2];
+  extern __shared__ __align__(128) uint8_t c0_smem[];
+  uint8_t* stage = c0_smem;                                                      // [256 pixels][256 B], 16-byte pieces swizzled
+  float* w_s = reinterpret_cast<float*>(c0_smem + 64 * 4 * 256);                 // [27][64]
+  float* b_s = w_s + 27 * 64;                                                    // [64]
+  float* in_s = b_s + 64;                                                        // [3][18][kC0Pitch] halo tile
   const int b = blockIdx.z, tx0 = blockIdx.x * kC0TW, ty0 = blockIdx.y * kC0TH;
   for (int i = threadIdx.x; i < 27 * 64; i += 256) w_s[i] = w[i];
   if (threadIdx.x < 64) b_s[threadIdx.x] = bias[threadIdx.x];
+  // halo tile: in_s[c][yy][xx] = img(c, ty0 + yy - 1, tx0 + xx - 1), zero outside the image (padding = 1)
   for (int i = threadIdx.x; i < 3 * (kC0TH + 2) * (kC0TW + 2); i += 256) {
     const int xx = i % (kC0TW + 2), yy = (i / (kC0TW + 2)) % (kC0TH + 2), c = i / ((kC0TW + 2) * (kC0TH + 2));
     const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
-    in_s[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(((size_t)b * 3 + c) * H + gy) * W + gx] : 0.f;
+    in_s[(c * (kC0TH + 2) + yy) * kC0Pitch + xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(((size_t)b * 3 + c) * H + gy) * W + gx] : 0.f;
   }
   __syncthreads();
-  const int lx = (threadIdx.x & 15) * 4, ly = threadIdx.x >> 4;
-  const int gy = ty0 + ly;
-  if (gy >= H) return;
-  float patch[3][3][6];                    // [channel][row][col]: the 3 x 6 window of 4 adjacent pixels
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int q = 0; q < 6; ++q) patch[c][r][q] = in_s[c][ly + r][lx + q];
+  const int lane = threadIdx.x & 31, cb = threadIdx.x >> 5;      // channel block: channels [8 cb, 8 cb + 8)
+  const int r = lane >> 3, x0 = (lane & 7) * 8;                  // this lane's 8 pixels: row r of the pass, columns [x0, x0 + 8)
+  const uint32_t stage_u = smem_u32(stage);
 #pragma unroll 1
-  for (int n0 = 0; n0 < 64; n0 += 16) {
-    float v[4][16];
+  for (int pass = 0; pass < kC0TH / 4; ++pass) {
+    const int ly = pass * 4 + r;
+    c0_f32x2 acc[8][4];                                          // [pixel][channel pair]
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(b_s + cb * 8), b1 = *reinterpret_cast<const float4*>(b_s + cb * 8 + 4);
+      const c0_f32x2 bp[4] = {c0_pack(b0.x, b0.y), c0_pack(b0.z, b0.w), c0_pack(b1.x, b1.y), c0_pack(b1.z, b1.w)};
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+      for (int p = 0; p < 8; ++p)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[p][j] = b_s[n0 + j];
+        for (int j = 0; j < 4; ++j) acc[p][j] = bp[j];
+    }
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap)
+    for (int c = 0; c < 3; ++c) {
+      float win[3][12];                                          // rows ly-1..ly+1, columns x0-1..x0+8 (+2 unused)
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
+      for (int ky = 0; ky < 3; ++ky) {
+        const float* row = in_s + (c * (kC0TH + 2) + ly + ky) * kC0Pitch + x0;
+        const float4 v0 = *reinterpret_cast<const float4*>(row), v1 = *reinterpret_cast<const float4*>(row + 4);
+        const float2 v2 = *reinterpret_cast<const float2*>(row + 8);
+        win[ky][0] = v0.x; win[ky][1] = v0.y; win[ky][2] = v0.z; win[ky][3] = v0.w;
+        win[ky][4] = v1.x; win[ky][5] = v1.y; win[ky][6] = v1.z; win[ky][7] = v1.w;
+        win[ky][8] = v2.x; win[ky][9] = v2.y;
+      }
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 wv = *reinterpret_cast<const float4*>(&w_s[(tap * 3 + c) * 64 + n0 + j]);
+      for (int tap = 0; tap < 9; ++tap) {
+        const float* wp = w_s + (tap * 3 + c) * 64 + cb * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+        const c0_f32x2 wq[4] = {c0_pack(w0.x, w0.y), c0_pack(w0.z, w0.w), c0_pack(w1.x, w1.y), c0_pack(w1.z, w1.w)};
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const float x = patch[c][tap / 3][p + tap % 3];
-            v[p][j] += x * wv.x; v[p][j + 1] += x * wv.y; v[p][j + 2] += x * wv.z; v[p][j + 3] += x * wv.w;
-          }
+        for (int p = 0; p < 8; ++p) {
+          const float x = win[tap / 3][p + tap % 3];
+          const c0_f32x2 xx = c0_pack(x, x);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) c0_fma(acc[p][j], wq[j], xx);
         }
+      }
+    }
+    // ReLU, hi/lo split, 16-byte pieces into the staging tile: pixel record = [hi 8 pieces | lo 8 pieces], piece index
+    // XOR-ed with (pixel / 8) & 7 so that the 8 lanes of a row hit 8 different bank groups
+    if (pass) __syncthreads();                                   // the previous pass has been written out
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int gx = tx0 + lx + p;
-      if (gx >= W) continue;
+    for (int p = 0; p < 8; ++p) {
+      uint32_t hi[4], lo[4];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[p][j] = fmaxf(v[p][j], 0.f);
-      store_split(out + (((size_t)b * H + gy) * W + gx) * 2 * 64 + n0, 64, v[p], 16);
+      for (int j = 0; j < 4; ++j) {
+        float v0, v1;
+        c0_unpack(acc[p][j], v0, v1);
+        split2(fmaxf(v0, 0.f), fmaxf(v1, 0.f), hi[j], lo[j]);
+      }
+      const int px = r * 64 + x0 + p;
+      const uint32_t rec = stage_u + px * 256 + ((cb ^ ((px >> 3) & 7)) << 4);
+      st_shared_v4(rec, hi[0], hi[1], hi[2], hi[3]);
+      st_shared_v4(rec + 128, lo[0], lo[1], lo[2], lo[3]);
+    }
+    __syncthreads();
+    // write-out: 256 records of 256 B; a warp instruction stores two whole records (512 contiguous bytes)
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int px = (cb * 16 + i) * 2 + (lane >> 4);            // pixel within the pass: row px / 64, column px % 64
+      const int piece = lane & 15;                               // 0-7 hi, 8-15 lo
+      const uint4 d = ld_shared_v4(stage_u + px * 256 + (piece >> 3) * 128 + (((piece & 7) ^ ((px >> 3) & 7)) << 4));
+      const int gy = ty0 + pass * 4 + (px >> 6), gx = tx0 + (px & 63);
+      *reinterpret_cast<uint4*>(out + (((size_t)b * H + gy) * W + gx) * 128 + piece * 8) = d;
     }
   }
 }
@@ -584,9 +629,15 @@ int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, 
   if ((W % (4 * kTileW)) || (H % (4 * kTileH))) return HA_EINVAL;   // tiles must fit down to the 1/4 scale
   int rc;
 #define HA_TRY(x) do { rc = (x); if (rc != HA_OK) return rc; } while (0)
-  // conv0 stays on the CUDA cores: a tensor-core variant (im2col channels + 1x1 tcgen05 conv, n_taps = 1) was
-  // measured at 1.39 ms vs 1.30 ms for this kernel at B = 32 (one k-block per tile: L2->smem and epilogue bound)
-  conv0_kernel<<<dim3((W + kC0TW - 1) / kC0TW, (H + kC0TH - 1) / kC0TH, B), 256, 0, st>>>(
+  // conv0 stays on the CUDA cores (see conv0_kernel); W % 64 == 0 and H % 32 == 0 were checked above
+  {
+    static bool configured = false;
+    if (!configured) {
+      HA_CUDA_TRY(cudaFuncSetAttribute(conv0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC0Smem));
+      configured = true;
+    }
+  }
+  conv0_kernel<<<dim3(W / kC0TW, H / kC0TH, B), 256, kC0Smem, st>>>(
       img, reinterpret_cast<const float*>(packed + L.c[L_CONV0].f32), reinterpret_cast<const float*>(packed + L.c[L_CONV0].bias),
       a1, H, W);
   count_launches(1);
