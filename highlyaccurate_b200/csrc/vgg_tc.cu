@@ -429,11 +429,24 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const float* __restrict__
   const int b = blockIdx.z, tx0 = blockIdx.x * kC0TW, ty0 = blockIdx.y * kC0TH;
   for (int i = threadIdx.x; i < 27 * 64; i += 256) w_s[i] = w[i];
   if (threadIdx.x < 64) b_s[threadIdx.x] = bias[threadIdx.x];
-  // halo tile: in_s[c][yy][xx] = img(c, ty0 + yy - 1, tx0 + xx - 1), zero outside the image (padding = 1)
-  for (int i = threadIdx.x; i < 3 * (kC0TH + 2) * (kC0TW + 2); i += 256) {
-    const int xx = i % (kC0TW + 2), yy = (i / (kC0TW + 2)) % (kC0TH + 2), c = i / ((kC0TW + 2) * (kC0TH + 2));
-    const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
-    in_s[(c * (kC0TH + 2) + yy) * kC0Pitch + xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? img[(((size_t)b * 3 + c) * H + gy) * W + gx] : 0.f;
+  // halo tile: in_s[c][yy][xx] = img(c, ty0 + yy - 1, tx0 + xx - 1), zero outside the image (padding = 1).  All of a
+  // thread's loads are issued before the first store, so their latencies overlap (14 loads per thread).
+  {
+    constexpr int kHalo = 3 * (kC0TH + 2) * (kC0TW + 2), kPer = (kHalo + 255) / 256;
+    float v[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = threadIdx.x + k * 256;
+      const int xx = i % (kC0TW + 2), yy = (i / (kC0TW + 2)) % (kC0TH + 2), c = i / ((kC0TW + 2) * (kC0TH + 2));
+      const int gy = ty0 + yy - 1, gx = tx0 + xx - 1;
+      v[k] = (i < kHalo && gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(img + (((size_t)b * 3 + c) * H + gy) * W + gx) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = threadIdx.x + k * 256;
+      const int xx = i % (kC0TW + 2), yy = (i / (kC0TW + 2)) % (kC0TH + 2), c = i / ((kC0TW + 2) * (kC0TH + 2));
+      if (i < kHalo) in_s[(c * (kC0TH + 2) + yy) * kC0Pitch + xx] = v[k];
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, cb = threadIdx.x >> 5;      // channel block: channels [8 cb, 8 cb + 8)
@@ -495,14 +508,18 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const float* __restrict__
       st_shared_v4(rec + 128, lo[0], lo[1], lo[2], lo[3]);
     }
     __syncthreads();
-    // write-out: 256 records of 256 B; a warp instruction stores two whole records (512 contiguous bytes)
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const int px = (cb * 16 + i) * 2 + (lane >> 4);            // pixel within the pass: row px / 64, column px % 64
-      const int piece = lane & 15;                               // 0-7 hi, 8-15 lo
-      const uint4 d = ld_shared_v4(stage_u + px * 256 + (piece >> 3) * 128 + (((piece & 7) ^ ((px >> 3) & 7)) << 4));
-      const int gy = ty0 + pass * 4 + (px >> 6), gx = tx0 + (px & 63);
-      *reinterpret_cast<uint4*>(out + (((size_t)b * H + gy) * W + gx) * 128 + piece * 8) = d;
+    // write-out: 256 records of 256 B; a warp instruction stores two whole records (512 contiguous bytes).  Warp cb
+    // owns pixels [32 cb, 32 cb + 32) of the pass = half a tile row, so its 16 stores are 512 bytes apart.
+    {
+      const int half_px = lane >> 4, piece = lane & 15;          // piece 0-7: hi, 8-15: lo
+      __half* gp = out + (((size_t)b * H + ty0 + pass * 4 + (cb >> 1)) * W + tx0 + (cb & 1) * 32 + half_px) * 128 + piece * 8;
+      const uint32_t sp = stage_u + (cb * 32 + half_px) * 256 + (piece >> 3) * 128;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int key = (cb * 4 + (i >> 2)) & 7;                 // ((32 cb + 2 i + half_px) >> 3) & 7
+        const uint4 d = ld_shared_v4(sp + i * 512 + (((piece & 7) ^ key) << 4));
+        *reinterpret_cast<uint4*>(gp + i * 256) = d;
+      }
     }
   }
 }

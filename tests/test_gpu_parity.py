@@ -345,3 +345,65 @@ def test_level4_forward_runs():
     out = net(sat, grd, mode="test")
     assert all(torch.isfinite(o).all() for o in out)
     assert net.last_result.traj.shape == (2, 2, 4, 3)
+
+
+# ------------------------------------------------------------------ LM kernel variants, ragged shapes
+def _with_variant(v, fn):
+    old = os.environ.get("HA_LM_VARIANT")
+    os.environ["HA_LM_VARIANT"] = str(v)
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("HA_LM_VARIANT", None)
+        else:
+            os.environ["HA_LM_VARIANT"] = old
+
+
+@pytest.mark.parametrize("name", ["kat4_planted_kitti", "kat4_planted_ford", "kat5_weight"])
+def test_lm_kernel_variants_agree(name):
+    """HA_LM_VARIANT 0 (register-staged stream) and 1-5 (bulk-copy ring kernels) are the same algorithm: every
+    variant meets the trajectory bar against the reference's golden output, and they agree with each other to
+    fp32 summation-order noise."""
+    c = K.build_loop_case(name)
+    net = make_net(c)
+    sat, grd = pyramids(c)
+    want = c["gold"]["traj"][:, -1, -1]
+    got = {}
+    for v in range(6):
+        torch.manual_seed(K.RESET_SEED)
+        res = _with_variant(v, lambda: run_loop(net, c, sat, grd))
+        got[v] = res.pose.cpu().numpy()
+        if name.startswith("kat4"):
+            np.testing.assert_allclose(got[v], want, rtol=1e-4, atol=2e-6, err_msg="variant %d" % v)
+        else:
+            np.testing.assert_allclose(got[v], want, atol=5e-5, err_msg="variant %d" % v)
+    for v in range(1, 6):
+        np.testing.assert_allclose(got[v], got[0], atol=5e-6 if name.startswith("kat4") else 5e-5, err_msg="variant %d vs 0" % v)
+
+
+@pytest.mark.parametrize("C,H,W,A", [(64, 20, 72, 40), (32, 12, 40, 24), (16, 10, 36, 20), (128, 6, 44, 16), (256, 4, 20, 12)])
+def test_lm_step_ragged_shapes_vs_oracle(C, H, W, A):
+    """Pixel counts that are not multiples of 32 / of a CTA's share, every channel count the kernel is instantiated
+    for, satellite maps smaller than the footprint (clamped and out-of-range taps): one step of every kernel variant
+    against the oracle evaluated in fp64."""
+    B = 3
+    g = torch.Generator().manual_seed(C + H)
+    sf = torch.randn(B, C, A, A, generator=g)
+    gf = torch.randn(B, C, H, W, generator=g)
+    k0 = torch.tensor([O._KITTI_K], dtype=torch.float32)
+    xyz, mask = O._lift_to_ground(k0, H, W)
+    a = O.LMArgs()
+    pose = torch.tensor([[0.05, -0.1, 0.3], [-0.2, 0.15, -0.4], [0.0, 0.0, 0.0]])
+    lam = O.resolve_damping(a, None, 3, torch.float64)
+    draws = (torch.zeros(B, 1, dtype=torch.float64), torch.zeros(B, 1, dtype=torch.float64))
+    out = O.lm_one_step("kitti", sf.double(), gf.double(), None, (xyz.double(), mask.double()), pose[:, 0:1].double(),
+                        pose[:, 1:2].double(), pose[:, 2:3].double(), a, lam, draws)
+    want = torch.cat([out[0], out[1], out[2]], dim=-1).numpy()
+    sat = engine.Pyramid.from_nchw([sf.to(DEV)])
+    grd = engine.Pyramid.from_nchw([gf.to(DEV)])
+    tab = torch.cat([xyz, mask[..., None]], dim=-1).contiguous().to(DEV)
+    setup = engine.setup_from_args(K.args_from_lmargs(a), "kitti", 0)
+    for v in range(6):
+        got, _ = _with_variant(v, lambda: engine.lm_step(setup, 0, sat, grd, [tab], [a.damping] * 3, pose, reset_uv=torch.zeros(2, B)))
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-4, atol=2e-5, err_msg="variant %d" % v)
