@@ -19,6 +19,11 @@
 // smem ring of STAGES k-blocks (full/empty mbarriers), two accumulator stages in TMEM
 // (tmem_full/tmem_empty mbarriers) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
+
+#ifndef HA_CONV_HALO_DEFAULT
+#define HA_CONV_HALO_DEFAULT 1
+#endif
 
 #include "vgg_common.cuh"
 
@@ -399,6 +404,253 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 2) { tc_fence_after(); tmem_dealloc_512(tmem_base); }
 }
 
+// ------------------------------------------------------------------------------ halo-tile variant (Cout = 64 layers)
+// ncu on B200: the N = 64 layers (conv2, dec2.1, dec2.3) sat at 52-56 % tensor-pipe activity while moving the same
+// 15.5 TB/s of TMA fill as the N = 128 layers at 91 %: with nine shifted copies of the activation tile per tile they
+// are bound by L2 -> shared-memory bandwidth, not by the tensor pipe.  This variant loads the (16 + 2) x (8 + 2) pixel
+// halo of a 16 x 8 pixel tile ONCE per 64-channel chunk (one TMA box of 18 rows x 10 pixels per plane) and the nine
+// taps are nine shared-memory descriptors into it: start address + (ky * 10 + kx) * 128 B, stride between 8-row
+// groups = one halo row = 1280 B.  The start is no longer 1024-byte aligned; the 128-byte swizzle is a function of
+// the absolute shared-memory address on both the TMA and the UMMA side, so the descriptor's base_offset stays 0
+// (measured: base_offset = kx gives wrong results, 0 passes every parity test).  A-operand fill per tile drops from
+// 288 KB to 74 KB; the weights (16 KB per tap and chunk) stream through their own ring.
+constexpr int kHaloTW = 8, kHaloTH = 16;                 // pixel tile: 16 rows x 8 columns = 128 = UMMA M
+#ifndef HA_HALO_BOX_W
+#define HA_HALO_BOX_W 10
+#endif
+constexpr int kHaloBoxW = HA_HALO_BOX_W, kHaloBoxH = kHaloTH + 2;   // TMA box: 18 rows x 10 pixels
+constexpr int kHaloBoxBytes = kHaloBoxH * kHaloBoxW * 128;                          // what one TMA box delivers (22.5 KB)
+constexpr int kHaloABytes = (kHaloBoxBytes + 1023) / 1024 * 1024;                   // plane slot: 1024-byte aligned for the swizzle
+constexpr int kHaloAStages = 2, kHaloBStages = kHaloBoxW == 10 ? 6 : 3;
+constexpr int kHaloBBytes = 2 * 64 * kBlockK * 2;        // [B_hi | B_lo] of one tap and chunk: 16 KB
+constexpr int kHaloSmemBytes = kHaloAStages * 2 * kHaloABytes + kHaloBStages * kHaloBBytes + 1024 + 256 + 4 * 32 * 128;
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_halo(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((kHaloBoxW * 128) >> 4) << 32; // stride between 8-row groups: one halo row
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bh,
+                       const __grid_constant__ CUtensorMap tmap_bl, const TcConvArgs a) {
+  constexpr int BLOCK_N = 64, CH = 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + kHaloAStages * 2 * kHaloABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kHaloBStages * kHaloBBytes);
+  uint64_t* a_full = bars;                       // [2]  TMA -> MMA (halo tiles)
+  uint64_t* a_empty = a_full + kHaloAStages;     // [2]
+  uint64_t* b_full = a_empty + kHaloAStages;     // [3]  TMA -> MMA (weights of one tap)
+  uint64_t* b_empty = b_full + kHaloBStages;     // [3]
+  uint64_t* tmem_full = b_empty + kHaloBStages;  // [2]  MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* staging = smem_b + kHaloBStages * kHaloBBytes + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_bh); tma_prefetch_desc(&tmap_bl); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kHaloAStages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < kHaloBStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_512(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        int pt = tile;
+        const int x0 = (pt % a.tiles_x) * kHaloTW; pt /= a.tiles_x;
+        const int y0 = (pt % a.tiles_y) * kHaloTH; const int b = pt / a.tiles_y;
+        for (int kc = 0; kc < a.n_kchunks; ++kc) {
+          mbar_wait(a_empty + sa, pa ^ 1);
+          uint8_t* st = smem + sa * 2 * kHaloABytes;
+          mbar_expect_tx(a_full + sa, 2 * kHaloBoxBytes);
+          tma_load_5d(st, &tmap_a, a_full + sa, kc * kBlockK, 0, x0 - 1, y0 - 1, b);
+          tma_load_5d(st + kHaloABytes, &tmap_a, a_full + sa, kc * kBlockK, 1, x0 - 1, y0 - 1, b);
+          if (++sa == kHaloAStages) { sa = 0; pa ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(b_empty + sb, pb ^ 1);
+            uint8_t* sw = smem_b + sb * kHaloBBytes;
+            mbar_expect_tx(b_full + sb, kHaloBBytes);
+            tma_load_3d(sw, &tmap_bh, b_full + sb, kc * kBlockK, 0, tap);
+            tma_load_3d(sw + kHaloBBytes / 2, &tmap_bl, b_full + sb, kc * kBlockK, 0, tap);
+            if (++sb == kHaloBStages) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_f16(BLOCK_N);             // A_lo x B_hi
+    constexpr uint32_t idesc2 = umma_idesc_f16(2 * BLOCK_N);        // A_hi x [B_hi ; B_lo]
+    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0; int t = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++t) {
+      const int as = t & 1; const uint32_t aphase = (t >> 1) & 1;
+      mbar_wait(tmem_empty + as, aphase ^ 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + as * 256, acc1 = acc0 + BLOCK_N;
+      for (int kc = 0; kc < a.n_kchunks; ++kc) {
+        mbar_wait(a_full + sa, pa);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem) + sa * 2 * kHaloABytes, a_lo = a_hi + kHaloABytes;
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(b_full + sb, pb);
+          tc_fence_after();
+          if (lane == 0) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const uint32_t off = (ky * kHaloBoxW + kx) * 128;
+            const uint64_t da = umma_desc_sw128_halo(a_hi + off), dl = umma_desc_sw128_halo(a_lo + off);
+            const uint64_t db = umma_desc_sw128(smem_u32(smem_b) + sb * kHaloBBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              umma_f16(acc0, da + 2 * k, db + 2 * k, idesc2, (kc | tap | k) != 0);
+              umma_f16(acc1, dl + 2 * k, db + 2 * k, idesc, 1);
+            }
+            umma_commit(b_empty + sb);
+            if (tap == 8) {
+              umma_commit(a_empty + sa);
+              if (kc == a.n_kchunks - 1) umma_commit(tmem_full + as);
+            }
+          }
+          __syncwarp();
+          if (++sb == kHaloBStages) { sb = 0; pb ^= 1; }
+        }
+        if (++sa == kHaloAStages) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (tile = 16 rows x 8 columns: TMEM lane m = pixel (m / 8, m % 8)) =====================
+    const int q = warp & 3;                               // TMEM lane quarter = tile rows [4 q, 4 q + 4)
+    const uint32_t stg = smem_u32(staging) + (warp - 4) * (32 * 128);
+    const bool any_pool = a.act_pool != nullptr || a.feat_pooled;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++t) {
+      const int as = t & 1; const uint32_t aphase = (t >> 1) & 1;
+      int pt = tile;
+      const int x0 = (pt % a.tiles_x) * kHaloTW; pt /= a.tiles_x;
+      const int y0 = (pt % a.tiles_y) * kHaloTH; const int b = pt / a.tiles_y;
+      mbar_wait(tmem_full + as, aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_x32(taddr + c0, r0); tmem_ld_x32(taddr + BLOCK_N + c0, r1);
+        tmem_ld_wait();
+        const int n0 = c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+          const float4 bz = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float bb[4] = {bz.x, bz.y, bz.z, bz.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[j + e] = fmaf(__uint_as_float(r1[j + e]), kLoInvScale, __uint_as_float(r0[j + e])) + bb[e];
+        }
+        float pv[32];
+        if (any_pool) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));          // x ^ 1
+            pv[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));                   // y ^ 1
+          }
+        }
+        constexpr int N16 = CH / 4, RPI = 32 / N16;
+        const int rsub = lane / N16, piece = lane % N16;
+        auto stage_f32 = [&](const float (&x)[32]) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < N16; ++j)
+            st_shared_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
+                         __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
+          __syncwarp();
+        };
+        auto stage_f16 = [&](const float (&x)[32]) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < N16 / 2; ++j) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split2(x[8 * j + 2 * e], x[8 * j + 2 * e + 1], hi[e], lo[e]);
+            st_shared_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(stg + lane * 128 + (((j + N16 / 2) ^ (lane & 7)) << 4), lo[0], lo[1], lo[2], lo[3]);
+          }
+          __syncwarp();
+        };
+        // staged row r = lane r of this warp = pixel (4 q + r / 8, r % 8); the 8 pool-window owners are the lanes
+        // with even x and even y: r = 2 (k % 4) + 16 (k / 4), k = 0..7
+        auto row_of = [&](int i, bool owners) { const int k = i * RPI + rsub; return owners ? 2 * (k & 3) + 16 * (k >> 2) : k; };
+        auto write_f32 = [&](float* base, int hh, int ww, bool owners) {
+          const int n_rows = owners ? 8 : 32;
+#pragma unroll 1
+          for (int i = 0; i < (n_rows + RPI - 1) / RPI; ++i) {
+            if (i * RPI + rsub >= n_rows) continue;
+            const int r = row_of(i, owners);
+            const int yy = y0 + q * 4 + (r >> 3), xx = x0 + (r & 7);
+            const size_t px = owners ? ((size_t)b * hh + yy / 2) * ww + xx / 2 : ((size_t)b * hh + yy) * ww + xx;
+            const uint4 d = ld_shared_v4(stg + r * 128 + ((piece ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(base + px * a.cout + n0 + piece * 4) = d;
+          }
+        };
+        auto write_f16 = [&](__half* base, int pitch, int coff, int hh, int ww, int mode, int dy, int dx) {
+          const bool owners = mode == 1;
+          const int n_rows = owners ? 8 : 32;
+          const int plane = piece / (N16 / 2), pc = piece % (N16 / 2);
+#pragma unroll 2
+          for (int i = 0; i < (n_rows + RPI - 1) / RPI; ++i) {
+            if (i * RPI + rsub >= n_rows) continue;
+            const int r = row_of(i, owners);
+            const int yy = y0 + q * 4 + (r >> 3), xx = x0 + (r & 7);
+            size_t px;
+            if (mode == 0) px = ((size_t)b * hh + yy) * ww + xx;
+            else if (mode == 1) px = ((size_t)b * hh + yy / 2) * ww + xx / 2;
+            else px = ((size_t)b * hh + 2 * yy + dy) * ww + 2 * xx + dx;
+            const uint4 d = ld_shared_v4(stg + r * 128 + ((piece ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(base + (px * 2 + plane) * pitch + coff + n0 + pc * 8) = d;
+          }
+        };
+        if (a.feat) {
+          if (a.feat_pooled) { stage_f32(pv); write_f32(a.feat, a.H / 2, a.W / 2, true); }
+          else { stage_f32(v); write_f32(a.feat, a.H, a.W, false); }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { v[j] = fmaxf(v[j], 0.f); if (any_pool) pv[j] = fmaxf(pv[j], 0.f); }
+        if (a.act_full || (a.act_up && !a.feat_pooled)) {
+          stage_f16(v);
+          if (a.act_full) write_f16(a.act_full, a.af_pitch, a.af_coff, a.H, a.W, 0, 0, 0);
+          if (a.act_up && !a.feat_pooled) {
+#pragma unroll 1
+            for (int dd = 0; dd < 4; ++dd) write_f16(a.act_up, a.au_pitch, a.au_coff, 2 * a.H, 2 * a.W, 2, dd >> 1, dd & 1);
+          }
+        }
+        if ((a.act_pool) || (a.act_up && a.feat_pooled)) {
+          stage_f16(pv);
+          if (a.act_pool) write_f16(a.act_pool, a.ap_pitch, a.ap_coff, a.H / 2, a.W / 2, 1, 0, 0);
+          if (a.act_up && a.feat_pooled) write_f16(a.act_up, a.au_pitch, a.au_coff, a.H, a.W, 0, 0, 0);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_512(tmem_base); }
+}
+
 // ------------------------------------------------------------------------------ conv0 + helpers
 // conv0 (3 -> 64, K = 27) is 0.7 % of the FLOPs but writes the largest activation of the network (2.1 GB of hi/lo
 // planes per branch at B = 32), so it is built around its two real limits:
@@ -554,12 +806,13 @@ static EncodeTiledFn encode_fn() {
 }
 
 // activation tensor [B][H][W][2][pitch] (fp16), channel slice [coff, coff + cin): dims (C, plane, W, H, B)
-static int make_act_map(CUtensorMap* m, const __half* base, int pitch, int coff, int cin, int B, int H, int W) {
+static int make_act_map(CUtensorMap* m, const __half* base, int pitch, int coff, int cin, int B, int H, int W,
+                        int box_w = kTileW, int box_h = kTileH) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return HA_ECUDA; }
   cuuint64_t dims[5] = {(cuuint64_t)cin, 2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 4, (cuuint64_t)W * pitch * 4, (cuuint64_t)H * W * pitch * 4};
-  cuuint32_t box[5] = {kBlockK, 1, kTileW, kTileH, 1};
+  cuuint32_t box[5] = {kBlockK, 1, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base + coff), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -583,6 +836,13 @@ static int make_weight_map(CUtensorMap* m, const __half* base, int cin_pad, int 
   return HA_OK;
 }
 
+// HA_CONV_HALO: 0 = nine shifted activation tiles per tile for every layer, 1 = halo-tile kernel for the Cout = 64 layers
+static int halo_variant() {
+  const char* e = getenv("HA_CONV_HALO");
+  const int v = e ? atoi(e) : HA_CONV_HALO_DEFAULT;
+  return (v < 0 || v > 1) ? HA_CONV_HALO_DEFAULT : v;
+}
+
 template <int BLOCK_N, bool SPLIT>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const TcConvArgs& a, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N, SPLIT>;
@@ -601,7 +861,11 @@ int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* pa
   const int block_n = cout >= 128 ? 128 : cout;
   if (block_n != 128 && block_n != 64 && block_n != 32 && block_n != 16) return HA_EINVAL;
   CUtensorMap ta, tbh, tbl;
-  int rc = make_act_map(&ta, in, in_pitch, in_coff, cin, B, H, W);
+  // Cout = 64 layers in f16x3 mode: halo-tile kernel (one activation load per 64-channel chunk instead of nine)
+  const int halo_mode = halo_variant();
+  const bool halo = halo_mode != 0 && split && cout == 64 && n_taps == 9 && (W % kHaloTW) == 0 && (H % kHaloTH) == 0 && (cin % 64) == 0;
+  int rc = halo ? make_act_map(&ta, in, in_pitch, in_coff, cin, B, H, W, kHaloBoxW, kHaloBoxH)
+                : make_act_map(&ta, in, in_pitch, in_coff, cin, B, H, W);
   if (rc != HA_OK) return rc;
   rc = make_weight_map(&tbh, reinterpret_cast<const __half*>(packed + pc.hi), pc.cin_pad, pc.cout_pad, block_n, n_taps);
   if (rc != HA_OK) return rc;
@@ -618,6 +882,15 @@ int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* pa
   a.n_taps = n_taps;
   a.tiles_x = W / kTileW; a.tiles_y = H / kTileH; a.tiles_n = cout / block_n;
   a.n_tiles = a.tiles_x * a.tiles_y * a.tiles_n * B;
+  if (halo) {
+    a.tiles_x = W / kHaloTW; a.tiles_y = H / kHaloTH; a.tiles_n = 1;
+    a.n_tiles = a.tiles_x * a.tiles_y * B;
+    const int grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
+    HA_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemBytes));
+    conv3x3_tc_halo_kernel<<<grid, kTcThreads, kHaloSmemBytes, st>>>(ta, tbh, tbl, a);
+    count_launches(1);
+    return check_launch("conv3x3_tc_halo_kernel");
+  }
 #define HA_TC_CASE(N)                                                              \
   case N: return split ? launch_tc<N, true>(ta, tbh, tbl, a, st) : launch_tc<N, false>(ta, tbh, tbl, a, st);
   switch (block_n) { HA_TC_CASE(128) HA_TC_CASE(64) HA_TC_CASE(32) HA_TC_CASE(16) }
