@@ -736,7 +736,10 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
   int iss_left = q_end - (q_begin + warp * 32), iss_it = 0, to_issue = T;
   uint32_t iss_off = 0;
   auto issue_next = [&](uint32_t slot) {           // arm `slot` with the next chunk of the stream, then advance
-    if (lane == 0 && iss_left > 0) {
+    uint32_t leader = 0;
+    if (iss_left > 0)                              // warp-uniform; the warp is converged here (after __syncwarp)
+      asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(leader));
+    if (leader) {
       const uint32_t bar = bar_keep + slot * 8, bytes = (uint32_t)min(iss_left, PPW) * (C * 4);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
