@@ -318,14 +318,22 @@ def main():
     tf = vgg_flops / vgg_secs / 1e12
     roof = {"kernel": "conv3x3_tc_kernel (VGG16 U-Net, both branches; includes conv0 + L2-norm kernels)",
             "bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
-            "peak_source": pk["src"] + " bf16 sustained", "traffic": None, "ms_per_step": vgg_secs * 1e3,
+            "peak_source": pk["src"] + " bf16 sustained",
+            # DRAM bytes (read + write) of one U-Net branch at B = 32 from profiles/r01c_conv_full.csv (ten tcgen05 conv
+            # launches: 8.61 + 5.97 GB) plus conv0 (0.10 + 2.09 GB), scaled to this step's two branches and batch
+            "traffic": (8.61e9 + 5.97e9 + 2.19e9) * 2 * B / 32 if opt.level == 3 else None,
+            "traffic_note": "bytes per step, ncu dram__bytes_read+write summed over the conv launches (profiles/r01c_conv_full.csv)",
+            "ms_per_step": vgg_secs * 1e3,
             "tensor_pipe_tflops_issued": tf * mma_mult,
             "note": "achieved counts ALGORITHMIC conv FLOPs (272.7 GFLOP/pair); f16x3 issues 3 MMAs per product for fp32-grade "
                     "features, so the tensor pipe executes 3x that"}
     lm_b = lm_bytes_per_pair(opt.level, opt.n_iters) * B
     gbs = lm_b / lm_secs / 1e9
     roof_lm = {"kernel": "lm_step_kernel x %d launches" % n_steps_lm, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
-               "unit": "GB/s", "frac": gbs / pk["hbm"], "peak_source": pk["src"], "traffic": None, "ms_per_step": lm_secs * 1e3,
+               "unit": "GB/s", "frac": gbs / pk["hbm"], "peak_source": pk["src"],
+               # ncu dram__bytes_read+write of the three levels at B = 256 (profiles/r01c_lm_full.csv: 4.51 GB per sweep),
+               # per pair and sweep x n_iters: DRAM traffic equals the algorithmic bytes
+               "traffic": 4.51e9 / 256 * opt.n_iters * B if opt.level == 3 else None, "ms_per_step": lm_secs * 1e3,
                "bytes_per_pair": lm_bytes_per_pair(opt.level, opt.n_iters), "timed_as": lm_how}
     gbs_big = lm_bytes_per_pair(opt.level, opt.n_iters) * B_big / big_secs / 1e9
     roof_lm["at_batch_256"] = {"achieved": gbs_big, "frac": gbs_big / pk["hbm"], "ms_per_step": big_secs * 1e3, "timed_as": big_how,

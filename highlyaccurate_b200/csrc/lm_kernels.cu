@@ -6,10 +6,13 @@
 //   sampler   : jacobian.py:138-205 (4-tap bilinear gather + d/dx, d/dy, chained with duv/dpose)
 //   masking   : models_kitti.py:927-929, :1191-1199 (geometric mask, bottom half only)
 //   LM update : models_kitti.py:939-1041 / models_ford.py:380-466
-// Nothing is materialised: each ground pixel's feature vector is read once (128-bit loads,
-// NHWC), the four satellite taps come through L1/L2, and the per-sample normal equations are
-// reduced in registers -> shuffles -> shared memory -> a deterministic two-stage cross-CTA
-// combine whose last-arriving CTA solves the damped system and updates the pose in place.
+// Nothing is materialised: each ground pixel's feature vector is read once (NHWC; bulk async
+// copies into a per-warp shared-memory ring in lm_step_v4_kernel, 128-bit register loads in
+// lm_step_kernel), the four satellite taps come through L1/L2, and the per-sample normal
+// equations are reduced in registers -> shuffles -> shared memory -> a deterministic two-stage
+// cross-CTA combine whose last-arriving CTA solves the damped system and updates the pose in place.
+// Two kernels share the geometry, the record of per-pixel scalars and the reduce-and-solve tail:
+// lm_step_v4_kernel (S2GP geometries, the default) and lm_step_kernel (G2SP, and HA_LM_VARIANT=0).
 //
 // Algebra: with s_c, a_c = ds_c/dx, b_c = ds_c/dy per channel and the
 // channel-independent 2x3 matrix D_p = d(u,v)/d(pose), the kernel accumulates

@@ -11,6 +11,11 @@
  *
  * Feature layout in HBM: NHWC fp32, i.e. [B][H][W][C] with C contiguous, so that one
  * bilinear tap of one pixel is one contiguous run of 4*C bytes (128-bit loads).
+ *
+ * Kernel selection knobs (environment, read per call; every setting passes the same parity
+ * tests): HA_LM_VARIANT (0 = register-staged LM step kernel, 1-5 = bulk-copy ring kernel,
+ * default 4), HA_CONV_HALO (1 = halo-tile tcgen05 kernel for the Cout = 64 conv layers,
+ * default; 0 = nine shifted TMA boxes for every layer).
  */
 #ifndef HA_B200_H_
 #define HA_B200_H_
