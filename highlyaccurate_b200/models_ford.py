@@ -6,7 +6,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import engine
+from . import compat, engine
 from ._lib import HaError
 from .VGG import VGGUnet
 
@@ -94,6 +94,26 @@ class LM_S2GP_Ford(nn.Module):
                             side_m=float(satmap_sidelength_meters), pose0=pose0, reset_uv=reset_uv, want_stats=want_stats)
         self.last_result = res
         return res
+
+    def project_map_to_grd(self, sat_f, sat_c, R_FL, T_FL, shift_u, shift_v, theta, level, satmap_sidelength_meters,
+                           require_jac=True, depth=None):
+        """models_ford.py:266-378: materialised warp of the satellite features into the front-left camera view; returns
+        (sat_f_trans, sat_c_trans, new_jac [3,B,C,H,W], uv * mask, mask).  Compatibility surface only — forward()
+        fuses this into the LM step kernel and never builds these tensors."""
+        if depth is not None:
+            raise NotImplementedError("estimate_depth is outside the accelerated path")
+        A = sat_f.shape[-1]
+        a = self.args
+        uv, mask, jac = compat.sat_uv_ford(self._tables(sat_f.device)[level].to(sat_f.dtype), R_FL, T_FL, shift_u, shift_v, theta,
+                                           A, a.rotation_range, a.shift_range_lat, a.shift_range_lon,
+                                           float(satmap_sidelength_meters) / A)
+        return compat.project_map_to_grd(uv, mask, jac, sat_f, sat_c, require_jac)
+
+    def LM_update(self, shift_u, shift_v, theta, sat_feat_proj, sat_conf_proj, grd_feat, grd_conf, dfeat_dpose):
+        """models_ford.py:380-466 on materialised tensors (always 3-DOF; compatibility surface)."""
+        lam = compat.resolve_damping_tensor(self.args, self.damping, 3, dfeat_dpose.device)
+        return compat.lm_update_dense(shift_u, shift_v, theta, sat_feat_proj, grd_feat, grd_conf, dfeat_dpose, lam, "full",
+                                      bool(self.using_weight), bool(self.args.use_hessian), redraw=True)
 
     def forward(self, sat_map, grd_img_left, satmap_sidelength_meters, R_FL, T_FL, gt_shift_u=None, gt_shift_v=None,
                 gt_theta=None, mode='train', file_name=None, level_first=0, loop=0):

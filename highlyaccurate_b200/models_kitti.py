@@ -7,7 +7,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import engine
+from . import compat, engine
 from .VGG import VGGUnet
 from .models_ford import loss_func, _TrajectoryOutputs  # noqa: F401  (the reference re-exports loss_func too, :16)
 
@@ -62,6 +62,26 @@ class LM_S2GP(nn.Module):
         return res
 
     # -- reference surface --------------------------------------------------------------------
+    def project_map_to_grd(self, sat_f, sat_c, shift_u, shift_v, heading, level, require_jac=True, gt_depth=None):
+        """models_kitti.py:803-937: materialised warp of the satellite features (and confidence) into the ground view,
+        returns (sat_f_trans, sat_c_trans, new_jac [3,B,C,H,W], uv * mask, mask).  Compatibility surface only — the
+        accelerated forward() fuses this into the LM step kernel and never builds these tensors."""
+        if gt_depth is not None:
+            raise NotImplementedError("use_gt_depth is outside the accelerated path")
+        A = sat_f.shape[-1]
+        a = self.args
+        mpp = engine.kitti_meter_per_pixel() * (engine.SAT_PROCESS_SIDE / A)
+        uv, mask, jac = compat.sat_uv_kitti(self._tables(sat_f.device)[level].to(sat_f.dtype), shift_u, shift_v, heading, A,
+                                            a.rotation_range, a.shift_range_lat, a.shift_range_lon, mpp)
+        return compat.project_map_to_grd(uv, mask, jac, sat_f, sat_c, require_jac)
+
+    def LM_update(self, shift_u, shift_v, theta, sat_feat_proj, sat_conf_proj, grd_feat, grd_conf, dfeat_dpose):
+        """models_kitti.py:939-1041 on materialised tensors (compatibility surface, see project_map_to_grd)."""
+        dof = compat.dof_name(self.args, False)
+        lam = compat.resolve_damping_tensor(self.args, self.damping, {"full": 3, "shift": 2, "rot": 1}[dof], dfeat_dpose.device)
+        return compat.lm_update_dense(shift_u, shift_v, theta, sat_feat_proj, grd_feat, grd_conf, dfeat_dpose, lam, dof,
+                                      bool(self.using_weight), bool(self.args.use_hessian), redraw=True)
+
     def forward(self, sat_map, grd_img_left, gt_shiftu=None, gt_shiftv=None, gt_heading=None, mode='train',
                 file_name=None, gt_depth=None, loop=0, level_first=0):
         """models_kitti.py:1126-1316 (iter-first) / :1318-1492 (level-first)."""
