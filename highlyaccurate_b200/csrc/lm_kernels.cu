@@ -23,6 +23,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace ha {
@@ -927,8 +929,12 @@ template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF, bool WEIGHTED
 static int launch_v4w(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
   auto kern = lm_step_v4_kernel<GEOM, C, FULL, NSLOT, MINB, PF, WEIGHTED, UNR>;
   constexpr int smem = lm_ring_bytes<NSLOT>();
-  static bool configured = false;            // per instantiation: the attributes belong to the device function
-  if (!configured) {
+  // function attributes are per (device function, device): one bit per device ordinal, per instantiation
+  static std::atomic<unsigned long long> configured{0};
+  int dev = 0;
+  HA_CUDA_TRY(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
     HA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // shared-memory carve-out: exactly what MINB resident CTAs need (ring + static + 1 KB reserved each); the rest of
     // the 228 KB stays L1 for the satellite taps
@@ -937,7 +943,7 @@ static int launch_v4w(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
     const int want = MINB * (smem + (int)fa.sharedSizeBytes + 1024);
     const int pct = want >= 228 * 1024 ? 100 : (want * 100 + 228 * 1024 - 1) / (228 * 1024);
     HA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-    configured = true;
+    configured.fetch_or(bit, std::memory_order_release);
   }
   kern<<<grid, kLmThreads, smem, st>>>(a);
   return HA_OK;

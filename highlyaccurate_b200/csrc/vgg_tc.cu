@@ -920,13 +920,8 @@ int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, 
   int rc;
 #define HA_TRY(x) do { rc = (x); if (rc != HA_OK) return rc; } while (0)
   // conv0 stays on the CUDA cores (see conv0_kernel); W % 64 == 0 and H % 32 == 0 were checked above
-  {
-    static bool configured = false;
-    if (!configured) {
-      HA_CUDA_TRY(cudaFuncSetAttribute(conv0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC0Smem));
-      configured = true;
-    }
-  }
+  // (per device and cheap: set on every call, like the tcgen05 kernels' launchers do)
+  HA_CUDA_TRY(cudaFuncSetAttribute(conv0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC0Smem));
   conv0_kernel<<<dim3(W / kC0TW, H / kC0TH, B), 256, kC0Smem, st>>>(
       img, reinterpret_cast<const float*>(packed + L.c[L_CONV0].f32), reinterpret_cast<const float*>(packed + L.c[L_CONV0].bias),
       a1, H, W);
