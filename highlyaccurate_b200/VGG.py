@@ -82,6 +82,28 @@ class VGGUnet(nn.Module):
         confs = [c[:, None] for c in p.confs]
         return feats, confs
 
+    def forward_autograd(self, x):
+        """The same network (VGG.py:121-203) evaluated with torch ops through the parameter containers, so that autograd
+        reaches the weights: used by `forward(mode='train')` of the LM models until the fused backward
+        exists.  Returns the reference's ([L2-normalised features], [confidences]) for level 3 / 4."""
+        F = torch.nn.functional
+        pool = lambda t: F.max_pool2d(t, 2, 2)
+        up = lambda t, like: F.interpolate(t, size=like.shape[-2:], mode="nearest")
+        x1 = F.relu(self.conv0(x))
+        x2 = self.conv2(x1)
+        x4 = F.relu(pool(x2))                                   # the reference's in-place ReLU makes the skip post-ReLU
+        x7 = self.conv7(F.relu(self.conv5(x4)))
+        x9 = F.relu(pool(x7))
+        x15 = pool(self.conv14(F.relu(self.conv12(F.relu(self.conv10(x9))))))
+        x18 = self.conv_dec1(torch.cat([up(x15, x9), x9], dim=1))
+        x21 = self.conv_dec2(torch.cat([up(x18, x4), x4], dim=1))
+        feats = [x15, x18, x21]
+        if self.n_levels() == 4:
+            feats.append(self.conv_dec3(torch.cat([up(x21, x2), x2], dim=1)))
+        heads = [self.conf0, self.conf1, self.conf2, self.conf3]
+        confs = [torch.sigmoid(-heads[i](f)) for i, f in enumerate(feats)]      # VGG.py:160-163
+        return [L2_norm(f) for f in feats], confs
+
 
 def L2_norm(x):
     """VGG.py:511-514."""

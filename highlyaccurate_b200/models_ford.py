@@ -16,9 +16,10 @@ class _TrajectoryOutputs(torch.autograd.Function):
 
     The reference's eval loops call loss.backward() on the outputs "just to release graph"
     (train_kitti.py:60-64, train_ford.py:78-79), so test-mode outputs must require grad and accept a
-    backward; it contributes nothing.  Differentiating the fused LM loop for training is the next
-    scope row: until it lands a train-mode backward fails loudly instead
-    of silently producing zero gradients."""
+    backward; it contributes nothing.  The fused engine has no backward yet:
+    `forward(mode='train')` of the S2GP models therefore takes the differentiable torch path
+    (`train_forward` below) and never reaches this function with train=True; anything else that would
+    fails loudly instead of silently producing zero gradients."""
 
     @staticmethod
     def forward(ctx, anchor, train, *trajs):
@@ -31,6 +32,41 @@ class _TrajectoryOutputs(torch.autograd.Function):
             raise HaError("backward through the fused LM loop is not implemented yet (SURVEY.md section 8 f-1); "
                           "train with the reference model and evaluate with this engine")
         return (None, None) + tuple(None for _ in grads)
+
+
+def train_forward(net, kind, sat_map, grd_img, gt_lat, gt_lon, gt_theta, level_first, coe_theta, ford=None):
+    """`forward(mode='train')` of LM_S2GP / LM_S2GP_Ford until the fused backward exists: the reference's own
+    computation (models_kitti.py:1141-1314 / models_ford.py:652-866) — U-Nets through `VGGUnet.forward_autograd`,
+    then `project_map_to_grd` -> mask -> bottom-half crop -> `LM_update` chained over (iteration, level) without
+    detaching — so that `loss.backward()` reaches both U-Nets and `damping` exactly as in the reference
+    (tests/test_compat_surface.py checks loss and gradients against the reference's autograd).  It runs at the
+    reference's speed: the accelerated engine is the test / eval path.  Returns the reference's 14-tuple."""
+    a = net.args
+    sat_feats, _ = net.SatFeatureNet.forward_autograd(sat_map)
+    grd_feats, grd_confs = net.GrdFeatureNet.forward_autograd(grd_img)
+    B, L = sat_map.shape[0], len(sat_feats)
+    dev = sat_map.device
+    su, sv, th = (torch.zeros(B, 1, device=dev) for _ in range(3))
+    traj = [[None] * L for _ in range(a.N_iters)]
+    order = [(it, lv) for lv in range(L) for it in range(a.N_iters)] if level_first else \
+            [(it, lv) for it in range(a.N_iters) for lv in range(L)]
+    for it, lv in order:
+        if kind == "kitti":
+            sp, _, dj, _, mask = net.project_map_to_grd(sat_feats[lv], None, su, sv, th, lv)
+        else:
+            sp, _, dj, _, mask = net.project_map_to_grd(sat_feats[lv], None, ford["R_FL"], ford["T_FL"], su, sv, th, lv,
+                                                        ford["side_m"])
+        gf = grd_feats[lv] * mask[:, None]                   # models_kitti.py:1191-1199: mask, then the bottom half only
+        gc = grd_confs[lv] * mask[:, None]
+        h2 = gf.shape[-2] // 2
+        su, sv, th = net.LM_update(su, sv, th, sp[:, :, h2:], None, gf[:, :, h2:], gc[:, :, h2:], dj[:, :, :, h2:])
+        traj[it][lv] = torch.cat([su, sv, th], dim=1)
+    t = torch.stack([torch.stack(row, dim=1) for row in traj], dim=1)             # [B, N_iters, L, (su, sv, th)]
+    # KITTI: shift_lats = shift_vs, shift_lons = shift_us (models_kitti.py:1281-1283); Ford: lats = us, lons = vs (:823-825)
+    lats, lons = (t[..., 1], t[..., 0]) if kind == "kitti" else (t[..., 0], t[..., 1])
+    r = loss_func(a.loss_method, None, None, None, lats, lons, t[..., 2], gt_lat, gt_lon, gt_theta, None, None,
+                  a.coe_shift_lat, a.coe_shift_lon, coe_theta, a.coe_L1, a.coe_L2, a.coe_L3, a.coe_L4)
+    return (*r, grd_confs)
 
 
 def loss_func(loss_method, ref_feat_list, pred_feat_dict, gt_feat_dict, shift_lats, shift_lons, thetas,
@@ -118,17 +154,14 @@ class LM_S2GP_Ford(nn.Module):
     def forward(self, sat_map, grd_img_left, satmap_sidelength_meters, R_FL, T_FL, gt_shift_u=None, gt_shift_v=None,
                 gt_theta=None, mode='train', file_name=None, level_first=0, loop=0):
         """models_ford.py:1028-1036 -> forward_iters_level (:652-866) / forward_level_iters (:868-1026)."""
-        want_conf = bool(self.using_weight) or mode == 'train'
+        if mode == 'train':
+            ford = dict(R_FL=R_FL, T_FL=T_FL, side_m=float(satmap_sidelength_meters))
+            return train_forward(self, "ford", sat_map, grd_img_left, gt_shift_u, gt_shift_v, gt_theta, level_first,
+                                 self.args.coe_heading, ford)
+        want_conf = bool(self.using_weight)
         sat, grd = self.extract(sat_map, grd_img_left, want_conf)
         res = self.refine(sat, grd, satmap_sidelength_meters, R_FL, T_FL, level_first)
         traj = res.traj
         # :823-825: shift_lats = shift_us, shift_lons = shift_vs
-        shift_lats, shift_lons, thetas = _TrajectoryOutputs.apply(self.damping, mode == 'train', traj[..., 0],
-                                                                  traj[..., 1], traj[..., 2])
-        if mode == 'train':
-            r = loss_func(self.args.loss_method, None, None, None, shift_lats, shift_lons, thetas,
-                          gt_shift_u, gt_shift_v, gt_theta, None, None,
-                          self.args.coe_shift_lat, self.args.coe_shift_lon, self.args.coe_heading,
-                          self.args.coe_L1, self.args.coe_L2, self.args.coe_L3, self.args.coe_L4)
-            return (*r, [c[:, None] for c in grd.confs])
+        shift_lats, shift_lons, thetas = _TrajectoryOutputs.apply(self.damping, False, traj[..., 0], traj[..., 1], traj[..., 2])
         return shift_lats[:, -1, -1], shift_lons[:, -1, -1], thetas[:, -1, -1]

@@ -9,7 +9,7 @@ import torch.nn as nn
 
 from . import compat, engine
 from .VGG import VGGUnet
-from .models_ford import loss_func, _TrajectoryOutputs  # noqa: F401  (the reference re-exports loss_func too, :16)
+from .models_ford import loss_func, train_forward, _TrajectoryOutputs  # noqa: F401  (the reference re-exports loss_func too, :16)
 
 
 class LM_S2GP(nn.Module):
@@ -85,22 +85,17 @@ class LM_S2GP(nn.Module):
     def forward(self, sat_map, grd_img_left, gt_shiftu=None, gt_shiftv=None, gt_heading=None, mode='train',
                 file_name=None, gt_depth=None, loop=0, level_first=0):
         """models_kitti.py:1126-1316 (iter-first) / :1318-1492 (level-first)."""
-        want_conf = bool(self.using_weight) or mode == 'train'
+        if mode == 'train':
+            coe_heading = 0 if self.args.rotation_range == 0 else self.args.coe_heading      # :1298-1301
+            return train_forward(self, "kitti", sat_map, grd_img_left, gt_shiftv[:, 0], gt_shiftu[:, 0], gt_heading[:, 0],
+                                 level_first, coe_heading)
+        want_conf = bool(self.using_weight)
         sat, grd = self.extract(sat_map, grd_img_left, want_conf)
         res = self.refine(sat, grd, level_first)
         traj = res.traj
         # :1281-1283: shift_lats = shift_vs, shift_lons = shift_us
         shift_lats, shift_lons, thetas = traj[..., 1], traj[..., 0], traj[..., 2]
-        out = _TrajectoryOutputs.apply(self.damping, mode == 'train', shift_lats, shift_lons, thetas)
-        shift_lats, shift_lons, thetas = out
-        if mode == 'train':
-            coe_heading = 0 if self.args.rotation_range == 0 else self.args.coe_heading      # :1298-1301
-            r = loss_func(self.args.loss_method, None, None, None, shift_lats, shift_lons, thetas,
-                          gt_shiftv[:, 0], gt_shiftu[:, 0], gt_heading[:, 0], None, None,
-                          self.args.coe_shift_lat, self.args.coe_shift_lon, coe_heading,
-                          self.args.coe_L1, self.args.coe_L2, self.args.coe_L3, self.args.coe_L4)
-            grd_conf_list = [c[:, None] for c in grd.confs]
-            return (*r, grd_conf_list)
+        shift_lats, shift_lons, thetas = _TrajectoryOutputs.apply(self.damping, False, shift_lats, shift_lons, thetas)
         return shift_lats[:, -1, -1], shift_lons[:, -1, -1], thetas[:, -1, -1]
 
 

@@ -292,6 +292,95 @@ def kat_g2sp(rk, name, make_inputs, **akw):
 FORD_EXT = dict(R=[[0., 0., 1.], [1., 0., 0.], [0., 1., 0.]], T=[1.7, -0.3, -1.5])
 
 
+def kat8_train_gradients(rk):
+    """KAT-8 (groundwork for SURVEY 8 f-1, the backward of the fused loop): the reference's own train-mode loop —
+    project_map_to_grd + LM_update chained WITHOUT detaching (models_kitti.py:1176-1260), loss_func method 0
+    (:1296-1314) — differentiated by autograd w.r.t. both feature pyramids and the trained damping.  Stored: the
+    loss, per-tensor gradient sums / abs-sums and the gradient at 64 seeded positions per tensor."""
+    a = ref_args(N_iters=2, train_damping=1)
+    oa = o_args(a)
+    gt = [[0.3, -0.25, 0.5]]
+    seed, B, A, L = 77, 1, 512, 3
+    sat, grd = O.planted_case("kitti", B, A, L, seed, gt, oa)
+    sat = [s.clone().requires_grad_(True) for s in sat]
+    grd = [g.clone().requires_grad_(True) for g in grd]
+    torch.manual_seed(0)
+    net = rk.LM_S2GP(a)
+    torch.autograd.set_detect_anomaly(False)
+    torch.manual_seed(4242)
+    su = torch.zeros(B, 1); sv = torch.zeros(B, 1); th = torch.zeros(B, 1)
+    us_all, vs_all, th_all = [], [], []
+    for it in range(a.N_iters):
+        us, vs, ths = [], [], []
+        for lv in range(L):
+            sp, _, dj, _, mask = net.project_map_to_grd(sat[lv], None, su, sv, th, lv)
+            gf = grd[lv] * mask[:, None]
+            gc = torch.ones(B, 1, *gf.shape[-2:]) * mask[:, None]
+            h2 = gf.shape[-2] // 2
+            su, sv, th = net.LM_update(su, sv, th, sp[:, :, h2:], gc[:, :, h2:], gf[:, :, h2:], gc[:, :, h2:], dj[:, :, :, h2:])
+            us.append(su[:, 0]); vs.append(sv[:, 0]); ths.append(th[:, 0])
+        us_all.append(torch.stack(us, dim=1)); vs_all.append(torch.stack(vs, dim=1)); th_all.append(torch.stack(ths, dim=1))
+    lats, lons, thetas = torch.stack(vs_all, dim=1), torch.stack(us_all, dim=1), torch.stack(th_all, dim=1)
+    g = torch.tensor(gt)
+    out = rk.loss_func(0, None, None, None, lats, lons, thetas, g[:, 1], g[:, 0], g[:, 2], None, None,
+                       a.coe_shift_lat, a.coe_shift_lon, a.coe_heading, a.coe_L1, a.coe_L2, a.coe_L3, a.coe_L4)
+    loss = out[0]
+    loss.backward()
+    rec = dict(seed=seed, B=B, A=A, L=L, gt=np.array(gt, dtype=np.float32), loss=np.float32(loss.item()),
+               traj=torch.stack([lons, lats, thetas], dim=-1).detach().numpy(), damping_grad=net.damping.grad.numpy(),
+               in_csum=csum(*[t.detach() for t in sat], *[t.detach() for t in grd]))
+    gidx = torch.Generator().manual_seed(99)
+    for name, ts in (("sat", sat), ("grd", grd)):
+        for lv, t in enumerate(ts):
+            gflat = t.grad.reshape(-1)
+            idx = torch.randint(0, gflat.numel(), (64,), generator=gidx)
+            top = torch.topk(gflat.abs(), 32).indices                      # the largest entries carry the signal
+            idx = torch.cat([idx, top])
+            rec["%s%d_idx" % (name, lv)] = idx.numpy()
+            rec["%s%d_val" % (name, lv)] = gflat[idx].numpy()
+            rec["%s%d_sum" % (name, lv)] = np.array([float(gflat.double().sum()), float(gflat.double().abs().sum())])
+    np.savez_compressed(os.path.join(GOLD, "kat8_train_grad.npz"), **rec)
+    print("kat8_train_grad: loss %.6f  |dL/ddamping| %s" % (loss.item(), np.abs(rec["damping_grad"]).ravel()))
+
+
+E2E_TRAIN_PARAMS = ["SatFeatureNet.conv0.weight", "SatFeatureNet.conv_dec2.3.weight", "SatFeatureNet.conv14.bias",
+                    "GrdFeatureNet.conv14.weight", "GrdFeatureNet.conv_dec1.1.weight", "GrdFeatureNet.conv2.bias"]
+
+
+def kat9_train_e2e(rk):
+    """KAT-9: the reference's LM_S2GP.forward(mode='train') end to end (both U-Nets + 1 iteration x 3 levels + loss_func
+    method 0) and its autograd gradients into U-Net weights of both branches: what train_kitti.py:354-365 computes."""
+    a = ref_args(N_iters=1)
+    torch.manual_seed(0)
+    net = rk.LM_S2GP(a)
+    sd = {}
+    sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+    sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+    sd["damping"] = torch.zeros(1, 3)
+    net.load_state_dict(sd)
+    torch.autograd.set_detect_anomaly(False)
+    g = torch.Generator().manual_seed(2022)
+    sat = torch.rand(1, 3, 512, 512, generator=g)
+    grd = torch.rand(1, 3, 256, 1024, generator=g)
+    gt = torch.tensor([[0.3, -0.25, 0.5]])
+    torch.manual_seed(4242)
+    out = net(sat, grd, gt[:, 0:1], gt[:, 1:2], gt[:, 2:3], mode="train")
+    out[0].backward()
+    rec = dict(gt=gt.numpy(), loss=np.float32(out[0].item()), loss_last=out[5].detach().numpy(),
+               lat_last=out[6].detach().numpy(), lon_last=out[7].detach().numpy(), theta_last=out[8].detach().numpy(),
+               loss_decrease=out[1].detach().numpy())
+    gidx = torch.Generator().manual_seed(123)
+    params = dict(net.named_parameters())
+    for k, name in enumerate(E2E_TRAIN_PARAMS):
+        gflat = params[name].grad.reshape(-1)
+        idx = torch.cat([torch.randint(0, gflat.numel(), (32,), generator=gidx), torch.topk(gflat.abs(), min(32, gflat.numel())).indices])
+        rec["p%d_idx" % k] = idx.numpy()
+        rec["p%d_val" % k] = gflat[idx].numpy()
+        rec["p%d_sum" % k] = np.array([float(gflat.double().sum()), float(gflat.double().abs().sum())])
+    np.savez_compressed(os.path.join(GOLD, "kat9_train_e2e.npz"), **rec)
+    print("kat9_train_e2e: loss %.6f, last (lat, lon, theta) errors %s %s %s" % (out[0].item(), rec["lat_last"], rec["lon_last"], rec["theta_last"]))
+
+
 def ford_dict(B, side_m):
     return dict(R_FL=torch.tensor(FORD_EXT["R"])[None].repeat(B, 1, 1),
                 T_FL=torch.tensor(FORD_EXT["T"])[None].repeat(B, 1), side_m=side_m)
@@ -310,6 +399,10 @@ def main():
         kat1_sampler(rj)
     if want("kat2"):
         kat2_geometry(rk, rf)
+    if want("kat8"):
+        kat8_train_gradients(rk)
+    if want("kat9"):
+        kat9_train_e2e(rk)
 
     GT2 = [[0.3, -0.25, 0.5], [-0.2, 0.4, -0.3]]
 

@@ -85,3 +85,81 @@ def test_lm_update_is_differentiable():
     out = net.LM_update(su, sv, th, f, c, grd * mask[:, None], gconf * mask[:, None], jac)
     sum(o.sum() for o in out).backward()
     assert sat.grad is not None and torch.isfinite(sat.grad).all() and float(sat.grad.abs().sum()) > 0
+
+
+def test_train_gradients_match_reference_autograd():
+    """KAT-8: the reference's train-mode loop (project_map_to_grd + LM_update chained without detach, loss_func method 0)
+    differentiated by autograd, stored by oracle/make_golden.py.  The compatibility methods are differentiable closed
+    forms of the same functions, so chaining them must reproduce the loss, the trajectory and the gradients w.r.t. both
+    feature pyramids and the trained damping.  This is the executable specification for the fused backward."""
+    from highlyaccurate_b200.models_kitti import loss_func
+    gold = K.load_golden("kat8_train_grad")
+    a = O.LMArgs(N_iters=2, train_damping=1)
+    B, A, L = int(gold["B"]), int(gold["A"]), int(gold["L"])
+    sat, grd = O.planted_case("kitti", B, A, L, int(gold["seed"]), gold["gt"], a)
+    np.testing.assert_allclose(K.csum(*sat, *grd), gold["in_csum"], rtol=1e-6, err_msg="input regeneration drifted")
+    sat = [s.clone().requires_grad_(True) for s in sat]
+    grd = [g.clone().requires_grad_(True) for g in grd]
+    net = LM_S2GP(K.args_from_lmargs(a))
+    torch.manual_seed(4242)
+    su, sv, th = torch.zeros(B, 1), torch.zeros(B, 1), torch.zeros(B, 1)
+    rows = []
+    for it in range(a.N_iters):
+        row = []
+        for lv in range(L):
+            sp, _, dj, _, mask = net.project_map_to_grd(sat[lv], None, su, sv, th, lv)
+            gf = grd[lv] * mask[:, None]
+            gc = torch.ones(B, 1, *gf.shape[-2:]) * mask[:, None]
+            h2 = gf.shape[-2] // 2
+            su, sv, th = net.LM_update(su, sv, th, sp[:, :, h2:], gc[:, :, h2:], gf[:, :, h2:], gc[:, :, h2:], dj[:, :, :, h2:])
+            row.append(torch.cat([su, sv, th], dim=1))
+        rows.append(torch.stack(row, dim=1))
+    traj = torch.stack(rows, dim=1)                                       # [B, N_iters, L, (su, sv, th)]
+    np.testing.assert_allclose(traj.detach().numpy(), gold["traj"], atol=2e-5, rtol=1e-4)
+    g = torch.from_numpy(gold["gt"])
+    loss = loss_func(0, None, None, None, traj[..., 1], traj[..., 0], traj[..., 2], g[:, 1], g[:, 0], g[:, 2], None, None)[0]
+    np.testing.assert_allclose(float(loss), float(gold["loss"]), rtol=1e-4)
+    loss.backward()
+    np.testing.assert_allclose(net.damping.grad.numpy(), gold["damping_grad"], rtol=2e-3, atol=1e-3)
+    for name, ts in (("sat", sat), ("grd", grd)):
+        for lv, t in enumerate(ts):
+            gflat = t.grad.reshape(-1)
+            want = gold["%s%d_val" % (name, lv)]
+            got = gflat[torch.from_numpy(gold["%s%d_idx" % (name, lv)])].numpy()
+            scale = np.abs(want).max()
+            assert np.abs(got - want).max() <= 5e-3 * scale, "%s level %d: %g of %g" % (name, lv, np.abs(got - want).max(), scale)
+            sums = np.array([float(gflat.double().sum()), float(gflat.double().abs().sum())])
+            np.testing.assert_allclose(sums[1], gold["%s%d_sum" % (name, lv)][1], rtol=5e-3)
+
+
+def test_train_mode_forward_and_gradients_match_reference():
+    """KAT-9: `LM_S2GP.forward(mode='train')` (the differentiable path used until the fused backward exists) against the
+    reference's own forward + autograd on the same seeded weights and images: the 14-tuple's losses and the gradients
+    into U-Net weights of both branches (what train_kitti.py:354-365 consumes)."""
+    from oracle.make_golden import E2E_TRAIN_PARAMS
+    gold = K.load_golden("kat9_train_e2e")
+    net = LM_S2GP(K.ref_args(N_iters=1))
+    sd = {}
+    sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+    sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+    sd["damping"] = torch.zeros(1, 3)
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(2022)
+    sat = torch.rand(1, 3, 512, 512, generator=g)
+    grd = torch.rand(1, 3, 256, 1024, generator=g)
+    gt = torch.from_numpy(gold["gt"])
+    torch.manual_seed(4242)
+    out = net(sat, grd, gt[:, 0:1], gt[:, 1:2], gt[:, 2:3], mode="train")
+    assert len(out) == 14 and len(out[13]) == 3 and out[13][0].shape == (1, 1, 32, 128)
+    np.testing.assert_allclose(float(out[0].detach()), float(gold["loss"]), rtol=1e-5)
+    for i, key in ((5, "loss_last"), (6, "lat_last"), (7, "lon_last"), (8, "theta_last"), (1, "loss_decrease")):
+        np.testing.assert_allclose(out[i].detach().numpy(), gold[key], rtol=1e-4, atol=1e-5)
+    out[0].backward()
+    params = dict(net.named_parameters())
+    for k, name in enumerate(E2E_TRAIN_PARAMS):
+        gflat = params[name].grad.reshape(-1)
+        want = gold["p%d_val" % k]
+        got = gflat[torch.from_numpy(gold["p%d_idx" % k])].numpy()
+        scale = np.abs(want).max()
+        assert np.abs(got - want).max() <= 1e-4 * scale, "%s: %g of %g" % (name, np.abs(got - want).max(), scale)   # measured 2e-6..6e-6
+        np.testing.assert_allclose(float(gflat.double().abs().sum()), gold["p%d_sum" % k][1], rtol=1e-4)
