@@ -407,3 +407,39 @@ def test_lm_step_ragged_shapes_vs_oracle(C, H, W, A):
     for v in range(6):
         got, _ = _with_variant(v, lambda: engine.lm_step(setup, 0, sat, grd, [tab], [a.damping] * 3, pose, reset_uv=torch.zeros(2, B)))
         np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-4, atol=2e-5, err_msg="variant %d" % v)
+
+
+def test_train_mode_on_gpu_matches_reference_gradients():
+    """`forward(mode='train')` on the GPU (differentiable torch path, cuDNN convs with TF32 off) against the reference's
+    CPU forward + autograd (tests/golden/kat9_train_e2e.npz); the eval path of the same module stays on the engine."""
+    from oracle.make_golden import E2E_TRAIN_PARAMS
+    gold = K.load_golden("kat9_train_e2e")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        net = LM_S2GP(K.ref_args(N_iters=1))
+        sd = {}
+        sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+        sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+        sd["damping"] = torch.zeros(1, 3)
+        net.load_state_dict(sd)
+        net = net.to(DEV)
+        g = torch.Generator().manual_seed(2022)
+        sat = torch.rand(1, 3, 512, 512, generator=g).to(DEV)
+        grd = torch.rand(1, 3, 256, 1024, generator=g).to(DEV)
+        gt = torch.from_numpy(gold["gt"]).to(DEV)
+        torch.manual_seed(4242)
+        out = net(sat, grd, gt[:, 0:1], gt[:, 1:2], gt[:, 2:3], mode="train")
+        np.testing.assert_allclose(float(out[0].detach()), float(gold["loss"]), rtol=1e-4)
+        out[0].backward()
+        params = dict(net.named_parameters())
+        for k, name in enumerate(E2E_TRAIN_PARAMS):
+            gflat = params[name].grad.reshape(-1).cpu()
+            want = gold["p%d_val" % k]
+            got = gflat[torch.from_numpy(gold["p%d_idx" % k])].numpy()
+            assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max(), name
+        # the same module still evaluates through the engine
+        lat, lon, th = net(sat, grd, mode="test")
+        assert lat.shape == (1,) and torch.isfinite(lat).all() and torch.isfinite(th).all()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
