@@ -381,6 +381,39 @@ def kat9_train_e2e(rk):
     print("kat9_train_e2e: loss %.6f, last (lat, lon, theta) errors %s %s %s" % (out[0].item(), rec["lat_last"], rec["lon_last"], rec["theta_last"]))
 
 
+def kat9_train_e2e_ford(rf):
+    """KAT-9 for LM_S2GP_Ford.forward(mode='train') (train_ford.py:229-240): losses + autograd gradients."""
+    a = ref_args(N_iters=1)
+    torch.manual_seed(0)
+    net = rf.LM_S2GP_Ford(a)
+    sd = {}
+    sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+    sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+    sd["damping"] = torch.zeros(1, 3)
+    net.load_state_dict(sd)
+    torch.autograd.set_detect_anomaly(False)
+    g = torch.Generator().manual_seed(2023)
+    sat = torch.rand(1, 3, 512, 512, generator=g)
+    grd = torch.rand(1, 3, 256, 1024, generator=g)
+    fd = ford_dict(1, 0.22 * 512)
+    gt = torch.tensor([[0.2, -0.3, 0.4]])
+    torch.manual_seed(4242)
+    out = net(sat, grd, fd["side_m"], fd["R_FL"], fd["T_FL"], gt[:, 0], gt[:, 1], gt[:, 2], mode="train")
+    out[0].backward()
+    rec = dict(gt=gt.numpy(), side_m=np.float32(fd["side_m"]), loss=np.float32(out[0].item()), loss_last=out[5].detach().numpy(),
+               lat_last=out[6].detach().numpy(), lon_last=out[7].detach().numpy(), theta_last=out[8].detach().numpy())
+    gidx = torch.Generator().manual_seed(123)
+    params = dict(net.named_parameters())
+    for k, name in enumerate(E2E_TRAIN_PARAMS):
+        gflat = params[name].grad.reshape(-1)
+        idx = torch.cat([torch.randint(0, gflat.numel(), (32,), generator=gidx), torch.topk(gflat.abs(), min(32, gflat.numel())).indices])
+        rec["p%d_idx" % k] = idx.numpy()
+        rec["p%d_val" % k] = gflat[idx].numpy()
+        rec["p%d_sum" % k] = np.array([float(gflat.double().sum()), float(gflat.double().abs().sum())])
+    np.savez_compressed(os.path.join(GOLD, "kat9_train_e2e_ford.npz"), **rec)
+    print("kat9_train_e2e_ford: loss %.6f" % out[0].item())
+
+
 def ford_dict(B, side_m):
     return dict(R_FL=torch.tensor(FORD_EXT["R"])[None].repeat(B, 1, 1),
                 T_FL=torch.tensor(FORD_EXT["T"])[None].repeat(B, 1), side_m=side_m)
@@ -403,6 +436,7 @@ def main():
         kat8_train_gradients(rk)
     if want("kat9"):
         kat9_train_e2e(rk)
+        kat9_train_e2e_ford(rf)
 
     GT2 = [[0.3, -0.25, 0.5], [-0.2, 0.4, -0.3]]
 

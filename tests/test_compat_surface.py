@@ -163,3 +163,33 @@ def test_train_mode_forward_and_gradients_match_reference():
         scale = np.abs(want).max()
         assert np.abs(got - want).max() <= 1e-4 * scale, "%s: %g of %g" % (name, np.abs(got - want).max(), scale)   # measured 2e-6..6e-6
         np.testing.assert_allclose(float(gflat.double().abs().sum()), gold["p%d_sum" % k][1], rtol=1e-4)
+
+
+def test_ford_train_mode_forward_and_gradients_match_reference():
+    """KAT-9 (Ford): `LM_S2GP_Ford.forward(mode='train')` against the reference's forward + autograd (train_ford.py:229-240)."""
+    from oracle.make_golden import E2E_TRAIN_PARAMS
+    gold = K.load_golden("kat9_train_e2e_ford")
+    net = LM_S2GP_Ford(K.ref_args(N_iters=1))
+    sd = {}
+    sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+    sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+    sd["damping"] = torch.zeros(1, 3)
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(2023)
+    sat = torch.rand(1, 3, 512, 512, generator=g)
+    grd = torch.rand(1, 3, 256, 1024, generator=g)
+    fd = K.ford_dict(1, float(gold["side_m"]))
+    gt = torch.from_numpy(gold["gt"])
+    torch.manual_seed(4242)
+    out = net(sat, grd, fd["side_m"], fd["R_FL"], fd["T_FL"], gt[:, 0], gt[:, 1], gt[:, 2], mode="train")
+    assert len(out) == 14
+    np.testing.assert_allclose(float(out[0].detach()), float(gold["loss"]), rtol=1e-5)
+    for i, key in ((5, "loss_last"), (6, "lat_last"), (7, "lon_last"), (8, "theta_last")):
+        np.testing.assert_allclose(out[i].detach().numpy(), gold[key], rtol=1e-4, atol=1e-5)
+    out[0].backward()
+    params = dict(net.named_parameters())
+    for k, name in enumerate(E2E_TRAIN_PARAMS):
+        gflat = params[name].grad.reshape(-1)
+        want = gold["p%d_val" % k]
+        got = gflat[torch.from_numpy(gold["p%d_idx" % k])].numpy()
+        assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max(), "%s: %g of %g" % (name, np.abs(got - want).max(), np.abs(want).max())
