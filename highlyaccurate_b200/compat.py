@@ -141,6 +141,53 @@ def lm_update_dense(su, sv, th, sat_proj, grd_feat, grd_conf, dfeat, damping: to
     return su_n, sv_n, th_n
 
 
+def cam_uv_g2sp(A: int, su, sv, th, cam_k: torch.Tensor, gh: int, gw: int, ori_h: int, ori_w: int, rot: float, lat: float,
+                lon: float, mpp: float):
+    """models_kitti.py:54-160 (get_warp_sat2real + seq_warp_real2camera): every satellite pixel (row i, column j) is the
+    ground-plane point (X south, 0, Z east) = mpp (i - A//2, 0, j - A//2); it is projected with P = K_l [R(-heading) | T],
+    T = (sv lat, 1.65, -su lon), perspective divide by max(w, 1e-6); quotient-rule Jacobians, zero where w <= 1e-6.
+    Returns uv [B,A,A,2] (ground-image pixel units) and jac [3,B,A,A,2]."""
+    dt, dev = su.dtype, su.device
+    B = su.shape[0]
+    k = cam_k.to(dt).clone()
+    k[:, 0] = cam_k[:, 0].to(dt) * gw / ori_w
+    k[:, 1] = cam_k[:, 1].to(dt) * gh / ori_h
+    kk = rot * math.pi / 180.0
+    h = -(th.reshape(B) * kk)
+    c, s = torch.cos(h), torch.sin(h)
+    z, o = torch.zeros_like(c), torch.ones_like(c)
+    R = torch.stack([c, z, -s, z, o, z, s, z, c], dim=-1).reshape(B, 3, 3)
+    dR = kk * torch.stack([s, z, c, z, z, z, -c, z, s], dim=-1).reshape(B, 3, 3)        # dR/dtheta (heading enters as -theta k)
+    T = torch.stack([sv.reshape(B) * lat, 1.65 * o, -su.reshape(B) * lon], dim=-1)
+    idx = torch.arange(A, device=dev, dtype=dt) - (A // 2)
+    X, Z = (mpp * idx)[:, None].expand(A, A), (mpp * idx)[None, :].expand(A, A)           # rows -> X (south), columns -> Z (east)
+    pts = torch.stack([X, torch.zeros_like(X), Z], dim=-1)                                  # [A,A,3]
+    KR, KT = k @ R, (k @ T[:, :, None])[..., 0]
+    uv1 = torch.einsum("bij,hwj->bhwi", KR, pts) + KT[:, None, None, :]
+    w = uv1[..., 2:3].clamp_min(1e-6)
+    uv = uv1[..., :2] / w
+    vis = (uv1[..., 2:3] > 1e-6).to(dt)
+    e_u = torch.tensor([0.0, 0.0, -lon], dtype=dt, device=dev)
+    e_v = torch.tensor([lat, 0.0, 0.0], dtype=dt, device=dev)
+    d_u = (k @ e_u)[:, None, None, :].expand_as(uv1)                                        # dP/dsu touches only the last column
+    d_v = (k @ e_v)[:, None, None, :].expand_as(uv1)
+    d_t = torch.einsum("bij,hwj->bhwi", k @ dR, pts)
+    quot = lambda d: (d[..., :2] / w - uv1[..., :2] * d[..., 2:3] / (w * w)) * vis
+    return uv, torch.stack([quot(d_u), quot(d_v), quot(d_t)], dim=0)
+
+
+def lm_update_g2sp(su, sv, th, grd_proj, grd_conf_proj, sat_feat, dfeat, damping: torch.Tensor, using_weight: bool):
+    """models_kitti.py:333-379: r = grd_proj - sat with no renormalisation, identity damping, always 3-DOF, no reset."""
+    N, B = dfeat.shape[:2]
+    C = sat_feat.shape[1]
+    J = dfeat.reshape(N, B, -1).permute(1, 0, 2)                                            # [B,3,D]
+    JW = J * grd_conf_proj.expand(-1, C, -1, -1).reshape(B, 1, -1) if using_weight else J
+    r = (grd_proj - sat_feat).reshape(B, -1, 1)
+    eye = torch.eye(N, dtype=J.dtype, device=J.device)[None]
+    delta = -(torch.linalg.inv(JW @ J.transpose(1, 2) + damping * eye) @ (JW @ r))[..., 0]
+    return su + delta[:, 0:1], sv + delta[:, 1:2], th + delta[:, 2:3]
+
+
 def resolve_damping_tensor(args, damping_param: torch.Tensor, n: int, device) -> torch.Tensor:
     """models_kitti.py:960-966: trained 10^(-6 + 11 sigmoid(p)) or the fixed args.damping, shape [1,N]."""
     if getattr(args, "train_damping", 0):

@@ -136,19 +136,56 @@ class LM_G2SP(nn.Module):
         self.last_result = res
         return res
 
+    def project_grd_to_map(self, grd_f, grd_c, shift_u, shift_v, heading, camera_k, satmap_sidelength, ori_grdH, ori_grdW):
+        """models_kitti.py:163-287: materialised warp of the ground features (and confidence) onto the satellite plane;
+        returns (grd_f_trans, grd_c_trans, new_jac [3,B,C,A,A]).  Compatibility surface only (see LM_S2GP)."""
+        A = int(satmap_sidelength)
+        a = self.args
+        mpp = engine.kitti_meter_per_pixel() * (engine.SAT_PROCESS_SIDE / A)
+        uv, jac = compat.cam_uv_g2sp(A, shift_u, shift_v, heading, camera_k, grd_f.shape[-2], grd_f.shape[-1], ori_grdH, ori_grdW,
+                                     a.rotation_range, a.shift_range_lat, a.shift_range_lon, mpp)
+        f, nj = compat.sample_with_jacobian(grd_f, uv, jac)
+        c = compat.sample_with_jacobian(grd_c, uv)[0] if grd_c is not None else None
+        return f, c, nj
+
+    def LM_update(self, shift_u, shift_v, heading, grd_feat_proj, grd_conf_proj, sat_feat, sat_conf, dfeat_dpose):
+        """models_kitti.py:333-379 on materialised tensors (compatibility surface)."""
+        lam = self.damping if getattr(self.args, "train_damping", 0) else \
+            self.args.damping * torch.ones(1, 3, dtype=torch.float32, device=dfeat_dpose.device)
+        return compat.lm_update_g2sp(shift_u, shift_v, heading, grd_feat_proj, grd_conf_proj, sat_feat, dfeat_dpose, lam,
+                                     bool(self.using_weight))
+
+    def _train_forward(self, sat_map, grd_img, cam_k, gt_u, gt_v, gt_h):
+        """`forward(mode='train')` until the fused backward exists: the reference's computation (models_kitti.py:381-499)
+        on the differentiable torch path, so that loss.backward() reaches both U-Nets and `damping`."""
+        a = self.args
+        sat_feats, _ = self.SatFeatureNet.forward_autograd(sat_map)
+        grd_feats, grd_confs = self.GrdFeatureNet.forward_autograd(grd_img)
+        B = sat_map.shape[0]
+        oh, ow = grd_img.shape[-2:]
+        su, sv, th = (torch.zeros(B, 1, device=sat_map.device) for _ in range(3))
+        rows = []
+        for it in range(a.N_iters):
+            row = []
+            for lv, (sf, gf, gc) in enumerate(zip(sat_feats, grd_feats, grd_confs)):
+                gp, gcp, dj = self.project_grd_to_map(gf, gc, su, sv, th, cam_k, sf.shape[-1], oh, ow)
+                su, sv, th = self.LM_update(su, sv, th, gp, gcp, sf, None, dj)
+                row.append(torch.cat([su, sv, th], dim=1))
+            rows.append(torch.stack(row, dim=1))
+        t = torch.stack(rows, dim=1)                                       # [B, N_iters, L, (su, sv, th)]
+        r = loss_func(a.loss_method, None, None, None, t[..., 1], t[..., 0], t[..., 2], gt_v[:, 0], gt_u[:, 0], gt_h[:, 0],
+                      None, None, a.coe_shift_lat, a.coe_shift_lon, a.coe_heading, a.coe_L1, a.coe_L2, a.coe_L3, a.coe_L4)
+        return (*r, grd_confs)
+
     def forward(self, sat_map, grd_img_left, left_camera_k, gt_shift_u=None, gt_shift_v=None, gt_heading=None,
                 mode='train', file_name=None, gt_depth=None):
         """models_kitti.py:381-499."""
-        want_conf = bool(self.using_weight) or mode == 'train'
+        if mode == 'train':
+            return self._train_forward(sat_map, grd_img_left, left_camera_k, gt_shift_u, gt_shift_v, gt_heading)
+        want_conf = bool(self.using_weight)
         sat, grd = self.extract(sat_map, grd_img_left, want_conf)
         res = self.refine(sat, grd, left_camera_k, ori_grd_hw=tuple(grd_img_left.shape[-2:]))
         traj = res.traj
-        shift_lats, shift_lons, thetas = _TrajectoryOutputs.apply(self.damping, mode == 'train', traj[..., 1], traj[..., 0],
+        shift_lats, shift_lons, thetas = _TrajectoryOutputs.apply(self.damping, False, traj[..., 1], traj[..., 0],
                                                                   traj[..., 2])       # :472-474
-        if mode == 'train':
-            r = loss_func(self.args.loss_method, None, None, None, shift_lats, shift_lons, thetas,
-                          gt_shift_v[:, 0], gt_shift_u[:, 0], gt_heading[:, 0], None, None,
-                          self.args.coe_shift_lat, self.args.coe_shift_lon, self.args.coe_heading,
-                          self.args.coe_L1, self.args.coe_L2, self.args.coe_L3, self.args.coe_L4)
-            return (*r, [c[:, None] for c in grd.confs])
         return shift_lats[:, -1, -1], shift_lons[:, -1, -1], thetas[:, -1, -1]

@@ -414,6 +414,42 @@ def kat9_train_e2e_ford(rf):
     print("kat9_train_e2e_ford: loss %.6f" % out[0].item())
 
 
+def kat9_train_e2e_g2sp(rk):
+    """KAT-9 for LM_G2SP.forward(mode='train') (train_kitti.py:363-365) on CPU with Tensor.cuda patched to the identity."""
+    a = ref_args(N_iters=1)
+    g = torch.Generator().manual_seed(2024)
+    sat = torch.rand(1, 3, 512, 512, generator=g)
+    grd = torch.rand(1, 3, 256, 1024, generator=g)
+    cam_k = torch.tensor([O._KITTI_K], dtype=torch.float32)
+    gt = torch.tensor([[0.25, -0.2, 0.35]])
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *x, **k: self
+    try:
+        torch.manual_seed(0)
+        net = rk.LM_G2SP(a)
+        torch.autograd.set_detect_anomaly(False)
+        sd = {}
+        sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+        sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+        sd["damping"] = net.damping.detach().clone()
+        net.load_state_dict(sd)
+        out = net(sat, grd, cam_k, gt[:, 0:1], gt[:, 1:2], gt[:, 2:3], mode="train")
+        out[0].backward()
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    rec = dict(gt=gt.numpy(), cam_k=cam_k.numpy(), loss=np.float32(out[0].item()), loss_last=out[5].detach().numpy(),
+               lat_last=out[6].detach().numpy(), lon_last=out[7].detach().numpy(), theta_last=out[8].detach().numpy())
+    gidx = torch.Generator().manual_seed(123)
+    params = dict(net.named_parameters())
+    for k, name in enumerate(E2E_TRAIN_PARAMS):
+        gflat = params[name].grad.reshape(-1)
+        idx = torch.cat([torch.randint(0, gflat.numel(), (32,), generator=gidx), torch.topk(gflat.abs(), min(32, gflat.numel())).indices])
+        rec["p%d_idx" % k] = idx.numpy()
+        rec["p%d_val" % k] = gflat[idx].numpy()
+    np.savez_compressed(os.path.join(GOLD, "kat9_train_e2e_g2sp.npz"), **rec)
+    print("kat9_train_e2e_g2sp: loss %.6f" % out[0].item())
+
+
 def ford_dict(B, side_m):
     return dict(R_FL=torch.tensor(FORD_EXT["R"])[None].repeat(B, 1, 1),
                 T_FL=torch.tensor(FORD_EXT["T"])[None].repeat(B, 1), side_m=side_m)
@@ -437,6 +473,7 @@ def main():
     if want("kat9"):
         kat9_train_e2e(rk)
         kat9_train_e2e_ford(rf)
+        kat9_train_e2e_g2sp(rk)
 
     GT2 = [[0.3, -0.25, 0.5], [-0.2, 0.4, -0.3]]
 
