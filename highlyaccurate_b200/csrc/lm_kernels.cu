@@ -916,9 +916,10 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
   }
 }
 
-// Kernel selection (HA_LM_VARIANT): 0 = lm_step_kernel (register-staged ground stream; always used for
-// G2SP), k > 0 = lm_step_v4_kernel with a per-warp bulk-copy ring of NSLOT x 2 KB (1: 6 slots, no tap prefetch; 2: 4 slots, taps prefetched to L2; 5: 4 slots, prefetched to L1; 3 / 4 (default): as 5
-// with the pixel loop unrolled by two, 2 % faster), 3 CTAs per SM.
+// Kernel selection (HA_LM_VARIANT): 0 = lm_step_kernel (register-staged ground stream; always used for G2SP);
+// 1-4 (default 4) = lm_step_v4_kernel with a 4-slot x 2 KB ring per warp, tap rows prefetched to L1, 3 CTAs per SM, pixel
+// loop unrolled by two; 5 = the same without the unroll (2 % slower).  Other ring depths (3, 5, 6, 8 slots), L2-only
+// prefetch, no prefetch, 2 and 4 CTAs per SM were measured and dropped.
 static int lm_variant() {
   const char* e = getenv("HA_LM_VARIANT");       // looked up per launch (~100 ns) so that one process can A/B the variants
   const int v = e ? atoi(e) : HA_LM_DEFAULT_VARIANT;
@@ -962,10 +963,8 @@ static int launch_variant(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
     return HA_OK;
   } else {
     switch (lm_variant()) {
-      case 1: return launch_v4<GEOM, C, FULL, 6, 3, 0>(grid, st, a);
-      case 2: return launch_v4<GEOM, C, FULL, 4, 3, 1>(grid, st, a);
       case 5: return launch_v4<GEOM, C, FULL, 4, 3, 2>(grid, st, a);
-      case 3: case 4: return launch_v4<GEOM, C, FULL, 4, 3, 2, 2>(grid, st, a);
+      case 1: case 2: case 3: case 4: return launch_v4<GEOM, C, FULL, 4, 3, 2, 2>(grid, st, a);
       default: lm_step_kernel<GEOM, C, FULL><<<grid, kLmThreads, 0, st>>>(a); return HA_OK;
     }
   }

@@ -13,7 +13,7 @@
  * bilinear tap of one pixel is one contiguous run of 4*C bytes (128-bit loads).
  *
  * Kernel selection knobs (environment, read per call; every setting passes the same parity
- * tests): HA_LM_VARIANT (0 = register-staged LM step kernel, 1-5 = bulk-copy ring kernel,
+ * tests): HA_LM_VARIANT (0 = register-staged LM step kernel, 1-4 = bulk-copy ring kernel, 5 = same without unroll,
  * default 4), HA_CONV_HALO (1 = halo-tile tcgen05 kernel for the Cout = 64 conv layers,
  * default; 0 = nine shifted TMA boxes for every layer).
  */
