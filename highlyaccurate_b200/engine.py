@@ -363,6 +363,7 @@ class VggRunner:
     feature extractor through ha_vgg_forward, chunking the batch to bound the workspace."""
 
     def __init__(self, max_ws_bytes: int = 24 << 30):
+        _lib.lib()                      # fail loudly at construction if libha_b200.so is missing: nothing here degrades to torch
         self.packed = None
         self.key = None
         self.ws = None

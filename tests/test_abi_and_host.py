@@ -113,3 +113,17 @@ def test_loss_func_method0():
     torch.testing.assert_close(out[5], tot[-1])
     torch.testing.assert_close(out[8], e[2][-1])
     assert len(out) == 13 and out[9] is None
+
+
+def test_models_fail_loudly_without_the_library(monkeypatch):
+    """No silent degradation: constructing a model (even for train mode, whose differentiable path is torch ops) needs
+    libha_b200.so, and test-mode forward refuses CPU tensors."""
+    from highlyaccurate_b200.models_kitti import LM_S2GP
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libha_b200.so")
+    with pytest.raises(_lib.HaError):
+        LM_S2GP(K.ref_args())
+    monkeypatch.undo()
+    net = LM_S2GP(K.ref_args())
+    with pytest.raises(_lib.HaError):
+        net(torch.rand(1, 3, 512, 512), torch.rand(1, 3, 256, 1024), mode="test")
