@@ -347,10 +347,10 @@ E2E_TRAIN_PARAMS = ["SatFeatureNet.conv0.weight", "SatFeatureNet.conv_dec2.3.wei
                     "GrdFeatureNet.conv14.weight", "GrdFeatureNet.conv_dec1.1.weight", "GrdFeatureNet.conv2.bias"]
 
 
-def kat9_train_e2e(rk):
-    """KAT-9: the reference's LM_S2GP.forward(mode='train') end to end (both U-Nets + 1 iteration x 3 levels + loss_func
+def kat9_train_e2e(rk, name="kat9_train_e2e", level_first=0, **akw):
+    """KAT-9: the reference's LM_S2GP.forward(mode='train') end to end (both U-Nets + N_iters x 3 levels + loss_func
     method 0) and its autograd gradients into U-Net weights of both branches: what train_kitti.py:354-365 computes."""
-    a = ref_args(N_iters=1)
+    a = ref_args(**dict(dict(N_iters=1), **akw))
     torch.manual_seed(0)
     net = rk.LM_S2GP(a)
     sd = {}
@@ -364,21 +364,21 @@ def kat9_train_e2e(rk):
     grd = torch.rand(1, 3, 256, 1024, generator=g)
     gt = torch.tensor([[0.3, -0.25, 0.5]])
     torch.manual_seed(4242)
-    out = net(sat, grd, gt[:, 0:1], gt[:, 1:2], gt[:, 2:3], mode="train")
+    out = net(sat, grd, gt[:, 0:1], gt[:, 1:2], gt[:, 2:3], mode="train", level_first=level_first)
     out[0].backward()
     rec = dict(gt=gt.numpy(), loss=np.float32(out[0].item()), loss_last=out[5].detach().numpy(),
                lat_last=out[6].detach().numpy(), lon_last=out[7].detach().numpy(), theta_last=out[8].detach().numpy(),
-               loss_decrease=out[1].detach().numpy())
+               loss_decrease=out[1].detach().numpy(), damping_grad=net.damping.grad.numpy() if net.damping.grad is not None else np.zeros(3))
     gidx = torch.Generator().manual_seed(123)
     params = dict(net.named_parameters())
-    for k, name in enumerate(E2E_TRAIN_PARAMS):
-        gflat = params[name].grad.reshape(-1)
+    for k, pname in enumerate(E2E_TRAIN_PARAMS):
+        gflat = params[pname].grad.reshape(-1)
         idx = torch.cat([torch.randint(0, gflat.numel(), (32,), generator=gidx), torch.topk(gflat.abs(), min(32, gflat.numel())).indices])
         rec["p%d_idx" % k] = idx.numpy()
         rec["p%d_val" % k] = gflat[idx].numpy()
         rec["p%d_sum" % k] = np.array([float(gflat.double().sum()), float(gflat.double().abs().sum())])
-    np.savez_compressed(os.path.join(GOLD, "kat9_train_e2e.npz"), **rec)
-    print("kat9_train_e2e: loss %.6f, last (lat, lon, theta) errors %s %s %s" % (out[0].item(), rec["lat_last"], rec["lon_last"], rec["theta_last"]))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+    print("%s: loss %.6f, last (lat, lon, theta) errors %s %s %s" % (name, out[0].item(), rec["lat_last"], rec["lon_last"], rec["theta_last"]))
 
 
 def kat9_train_e2e_ford(rf):
@@ -472,6 +472,7 @@ def main():
         kat8_train_gradients(rk)
     if want("kat9"):
         kat9_train_e2e(rk)
+        kat9_train_e2e(rk, "kat9_train_e2e_weighted_levelfirst", level_first=1, N_iters=2, using_weight=1, train_damping=1)
         kat9_train_e2e_ford(rf)
         kat9_train_e2e_g2sp(rk)
 
