@@ -450,6 +450,30 @@ def kat9_train_e2e_g2sp(rk):
     print("kat9_train_e2e_g2sp: loss %.6f" % out[0].item())
 
 
+def signatures(rk, rf, rv):
+    """Parameter names and defaults of the reference's public surface for the hot path, as a JSON fixture:
+    the drop-in modules must expose the same callables with the same parameters."""
+    import inspect
+    import json
+
+    def sig(f):
+        return [[n, None if p.default is inspect._empty else repr(p.default)] for n, p in inspect.signature(f).parameters.items()]
+
+    out = {}
+    for cls_name, cls in (("LM_S2GP", rk.LM_S2GP), ("LM_G2SP", rk.LM_G2SP), ("LM_S2GP_Ford", rf.LM_S2GP_Ford)):
+        for m in ("__init__", "forward", "LM_update", "project_map_to_grd", "project_grd_to_map"):
+            if hasattr(cls, m):
+                out["%s.%s" % (cls_name, m)] = sig(getattr(cls, m))
+    out["models_kitti.loss_func"] = sig(rk.loss_func)
+    out["models_ford.loss_func"] = sig(rf.loss_func)
+    out["VGGUnet.__init__"] = sig(rv.VGGUnet.__init__)
+    out["VGGUnet.forward"] = sig(rv.VGGUnet.forward)
+    out["L2_norm"] = sig(rv.L2_norm)
+    with open(os.path.join(GOLD, "signatures.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("signatures: %d callables" % len(out))
+
+
 def ford_dict(B, side_m):
     return dict(R_FL=torch.tensor(FORD_EXT["R"])[None].repeat(B, 1, 1),
                 T_FL=torch.tensor(FORD_EXT["T"])[None].repeat(B, 1), side_m=side_m)
@@ -464,6 +488,8 @@ def main():
     rj, rk, rf, rv = import_reference()
     want = lambda k: (not opt.only) or (k in opt.only.split(","))
 
+    if want("signatures"):
+        signatures(rk, rf, rv)
     if want("kat1"):
         kat1_sampler(rj)
     if want("kat2"):

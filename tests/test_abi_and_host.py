@@ -127,3 +127,25 @@ def test_models_fail_loudly_without_the_library(monkeypatch):
     net = LM_S2GP(K.ref_args())
     with pytest.raises(_lib.HaError):
         net(torch.rand(1, 3, 512, 512), torch.rand(1, 3, 256, 1024), mode="test")
+
+
+def test_public_signatures_match_the_reference():
+    """tests/golden/signatures.json holds the parameter names and defaults of the reference's public surface for the hot
+    path (written by oracle/make_golden.py from the unmodified reference): the drop-in modules expose the same callables
+    with the same parameters, in the same order, with the same defaults."""
+    import inspect
+    import json
+    from highlyaccurate_b200 import VGG, models_ford, models_kitti
+    gold = json.load(open(os.path.join(K.GOLDEN, "signatures.json")))
+    mine = {"LM_S2GP": models_kitti.LM_S2GP, "LM_G2SP": models_kitti.LM_G2SP, "LM_S2GP_Ford": models_ford.LM_S2GP_Ford,
+            "VGGUnet": VGG.VGGUnet}
+    for key, want in gold.items():
+        owner, _, attr = key.partition(".")
+        if owner in mine:
+            fn = getattr(mine[owner], attr)
+        elif owner in ("models_kitti", "models_ford"):
+            fn = getattr(models_kitti if owner == "models_kitti" else models_ford, attr)
+        else:
+            fn = getattr(VGG, owner)
+        got = [[n, None if p.default is inspect._empty else repr(p.default)] for n, p in inspect.signature(fn).parameters.items()]
+        assert got == want, "%s: %s != %s" % (key, got, want)
