@@ -65,15 +65,25 @@ class VGGUnet(nn.Module):
             getattr(self, "conv%d" % idx).load_state_dict({"weight": sd["features.%d.weight" % idx],
                                                            "bias": sd["features.%d.bias" % idx]})
 
+    # VGG.py:192-203: level -> (pyramid levels the U-Net has to compute, slice of [x15, x18, x21, x24] that is returned)
+    _LEVELS = {3: (3, slice(0, 3)), 4: (4, slice(0, 4)), -1: (3, slice(0, 1)), 2: (3, slice(1, 3))}
+
     def n_levels(self) -> int:
-        if self.level in (3, 4):
-            return self.level
-        raise NotImplementedError("VGGUnet level %r: only 3 and 4 are on the accelerated path" % (self.level,))
+        """Pyramid levels the U-Net computes (3, or 4 with the full-resolution decoder)."""
+        if self.level in self._LEVELS:
+            return self._LEVELS[self.level][0]
+        raise NotImplementedError("VGGUnet level %r: the reference defines 3, 4, -1 and 2 (VGG.py:192-203)" % (self.level,))
+
+    def level_slice(self) -> slice:
+        self.n_levels()
+        return self._LEVELS[self.level][1]
 
     def pyramid(self, x: torch.Tensor, want_conf: bool = True) -> engine.Pyramid:
-        """Engine-layout output (NHWC raw features + lazy L2 scale + confidences)."""
+        """Engine-layout output (NHWC raw features + lazy L2 scale + confidences) of the levels `level` selects."""
         named = dict(self.named_parameters())
-        return self._runner(named, x, self.n_levels(), want_conf, self.precision)
+        p = self._runner(named, x, self.n_levels(), want_conf, self.precision)
+        sl = self.level_slice()
+        return engine.Pyramid(p.feats[sl], p.scales[sl], p.confs[sl])
 
     def forward(self, x):
         """Reference contract: ([B,C,H,W] L2-normalised features], [B,1,H,W] confidences])."""
@@ -85,7 +95,7 @@ class VGGUnet(nn.Module):
     def forward_autograd(self, x):
         """The same network (VGG.py:121-203) evaluated with torch ops through the parameter containers, so that autograd
         reaches the weights: used by `forward(mode='train')` of the LM models until the fused backward
-        exists.  Returns the reference's ([L2-normalised features], [confidences]) for level 3 / 4."""
+        exists.  Returns the reference's ([L2-normalised features], [confidences]) for `level`."""
         F = torch.nn.functional
         pool = lambda t: F.max_pool2d(t, 2, 2)
         up = lambda t, like: F.interpolate(t, size=like.shape[-2:], mode="nearest")
@@ -102,7 +112,8 @@ class VGGUnet(nn.Module):
             feats.append(self.conv_dec3(torch.cat([up(x21, x2), x2], dim=1)))
         heads = [self.conf0, self.conf1, self.conf2, self.conf3]
         confs = [torch.sigmoid(-heads[i](f)) for i, f in enumerate(feats)]      # VGG.py:160-163
-        return [L2_norm(f) for f in feats], confs
+        sl = self.level_slice()
+        return [L2_norm(f) for f in feats][sl], confs[sl]
 
 
 def L2_norm(x):

@@ -106,7 +106,10 @@ class LM_S2GP_Ford(nn.Module):
         self.GrdFeatureNet = VGGUnet(self.level)
         self.damping = nn.Parameter(torch.zeros(size=(1, 3), dtype=torch.float32, requires_grad=True))   # :38-39
         self.ori_grdH, self.ori_grdW = 256, 1024
-        self._tables_cpu = [engine.ground_table("ford", lv) for lv in range(4)]       # :45-58
+        if self.level == 2:                                                            # :59-65: [x18, x21] with the /4 and /2 grids
+            self._tables_cpu = [engine.ground_table("ford", lv, n_levels=2) for lv in range(2)]
+        else:
+            self._tables_cpu = [engine.ground_table("ford", lv) for lv in range(4)]   # :45-58
         self._tables_dev = {}
         self.last_result = None
 

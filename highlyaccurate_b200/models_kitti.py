@@ -28,6 +28,10 @@ class LM_S2GP(nn.Module):
             raise NotImplementedError("only --Optimizer LM --proj geo is on the accelerated path")
         if getattr(args, "dropout", 0) or getattr(args, "use_gt_depth", 0):
             raise NotImplementedError("dropout / use_gt_depth are outside the accelerated path")
+        if self.level == 2:
+            # models_kitti.py:624-635 indexes xyz_grds 0 -> /8 ... 3 -> /1 whatever `level` is, so the reference's own
+            # level-2 run pairs the /4 features with the /8 grid and fails on shapes (SURVEY.md 8a "level support caveat")
+            raise NotImplementedError("LM_S2GP level 2 is shape-inconsistent in the reference itself; use 3, 4 or -1")
         self.SatFeatureNet = VGGUnet(self.level)
         self.GrdFeatureNet = VGGUnet(self.level)
         if args.rotation_range > 0:                                   # :615-620
@@ -115,6 +119,8 @@ class LM_G2SP(nn.Module):
         self.loss_method = args.loss_method
         if getattr(args, "proj", "geo") != "geo":
             raise NotImplementedError("LM_G2SP: only --proj geo is on the accelerated path (VGGUnet_G2S / 'nn' is out of scope)")
+        if self.level not in (3, 4):
+            raise NotImplementedError("LM_G2SP: levels 3 and 4 are on the accelerated path")
         self.SatFeatureNet = VGGUnet(self.level)
         self.GrdFeatureNet = VGGUnet(self.level)
         self.damping = nn.Parameter(args.damping * torch.ones(size=(1, 3), dtype=torch.float32, requires_grad=True))   # :41

@@ -371,7 +371,10 @@ def kat9_train_e2e(rk, name="kat9_train_e2e", level_first=0, **akw):
                loss_decrease=out[1].detach().numpy(), damping_grad=net.damping.grad.numpy() if net.damping.grad is not None else np.zeros(3))
     gidx = torch.Generator().manual_seed(123)
     params = dict(net.named_parameters())
+    rec["n_conf"] = len(out[13])
     for k, pname in enumerate(E2E_TRAIN_PARAMS):
+        if params[pname].grad is None:
+            continue
         gflat = params[pname].grad.reshape(-1)
         idx = torch.cat([torch.randint(0, gflat.numel(), (32,), generator=gidx), torch.topk(gflat.abs(), min(32, gflat.numel())).indices])
         rec["p%d_idx" % k] = idx.numpy()
@@ -381,9 +384,9 @@ def kat9_train_e2e(rk, name="kat9_train_e2e", level_first=0, **akw):
     print("%s: loss %.6f, last (lat, lon, theta) errors %s %s %s" % (name, out[0].item(), rec["lat_last"], rec["lon_last"], rec["theta_last"]))
 
 
-def kat9_train_e2e_ford(rf):
+def kat9_train_e2e_ford(rf, name="kat9_train_e2e_ford", **akw):
     """KAT-9 for LM_S2GP_Ford.forward(mode='train') (train_ford.py:229-240): losses + autograd gradients."""
-    a = ref_args(N_iters=1)
+    a = ref_args(**dict(dict(N_iters=1), **akw))
     torch.manual_seed(0)
     net = rf.LM_S2GP_Ford(a)
     sd = {}
@@ -404,14 +407,17 @@ def kat9_train_e2e_ford(rf):
                lat_last=out[6].detach().numpy(), lon_last=out[7].detach().numpy(), theta_last=out[8].detach().numpy())
     gidx = torch.Generator().manual_seed(123)
     params = dict(net.named_parameters())
-    for k, name in enumerate(E2E_TRAIN_PARAMS):
-        gflat = params[name].grad.reshape(-1)
+    for k, pname in enumerate(E2E_TRAIN_PARAMS):
+        if params[pname].grad is None:
+            continue
+        gflat = params[pname].grad.reshape(-1)
         idx = torch.cat([torch.randint(0, gflat.numel(), (32,), generator=gidx), torch.topk(gflat.abs(), min(32, gflat.numel())).indices])
         rec["p%d_idx" % k] = idx.numpy()
         rec["p%d_val" % k] = gflat[idx].numpy()
         rec["p%d_sum" % k] = np.array([float(gflat.double().sum()), float(gflat.double().abs().sum())])
-    np.savez_compressed(os.path.join(GOLD, "kat9_train_e2e_ford.npz"), **rec)
-    print("kat9_train_e2e_ford: loss %.6f" % out[0].item())
+    rec["n_conf"] = len(out[13])
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+    print("%s: loss %.6f" % (name, out[0].item()))
 
 
 def kat9_train_e2e_g2sp(rk):
@@ -499,7 +505,9 @@ def main():
     if want("kat9"):
         kat9_train_e2e(rk)
         kat9_train_e2e(rk, "kat9_train_e2e_weighted_levelfirst", level_first=1, N_iters=2, using_weight=1, train_damping=1)
+        kat9_train_e2e(rk, "kat9_train_e2e_level_m1", level=-1, N_iters=2)
         kat9_train_e2e_ford(rf)
+        kat9_train_e2e_ford(rf, "kat9_train_e2e_ford_level2", level=2, N_iters=2)
         kat9_train_e2e_g2sp(rk)
 
     GT2 = [[0.3, -0.25, 0.5], [-0.2, 0.4, -0.3]]

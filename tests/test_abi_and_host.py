@@ -149,3 +149,27 @@ def test_public_signatures_match_the_reference():
             fn = getattr(VGG, owner)
         got = [[n, None if p.default is inspect._empty else repr(p.default)] for n, p in inspect.signature(fn).parameters.items()]
         assert got == want, "%s: %s != %s" % (key, got, want)
+
+
+@pytest.mark.parametrize("level,n_compute,want", [(3, 3, [0, 1, 2]), (4, 4, [0, 1, 2, 3]), (-1, 3, [0]), (2, 3, [1, 2])])
+def test_vggunet_level_selection(level, n_compute, want):
+    """VGG.py:192-203: `level` selects which of [x15, x18, x21, x24] are returned; the engine computes 3 (or 4) pyramid
+    levels and `pyramid()` hands the selected ones on (runner mocked: no GPU needed for the host logic)."""
+    from highlyaccurate_b200.VGG import VGGUnet
+    net = VGGUnet(level)
+    seen = {}
+
+    def fake_runner(named, x, n_levels, want_conf, precision):
+        seen["n"] = n_levels
+        feats = [torch.full((1, 2, 2, 4), float(i)) for i in range(n_levels)]
+        return engine.Pyramid(feats, [torch.full((1,), float(i)) for i in range(n_levels)],
+                              [torch.full((1, 2, 2), float(i)) if want_conf else None for i in range(n_levels)])
+
+    net._runner = fake_runner
+    for want_conf in (True, False):
+        p = net.pyramid(torch.zeros(1, 3, 8, 8), want_conf=want_conf)
+        assert seen["n"] == n_compute
+        assert [int(f[0, 0, 0, 0]) for f in p.feats] == want and [int(s[0]) for s in p.scales] == want
+        assert len(p.confs) == len(want) and all((c is not None) == want_conf for c in p.confs)
+    with pytest.raises(NotImplementedError):
+        VGGUnet(5).n_levels()
