@@ -1,16 +1,18 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: image-pairs/sec through VGG feature extraction + the 5-iteration,
-3-level LM pose refinement (KITTI shapes, BASELINE.json configs[1]).
+"""Benchmark of the hot path: image-pairs/sec through VGG feature extraction + the iterative LM pose
+refinement, on synthetic KITTI- / Ford-shaped pairs (BASELINE.json `configs`).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's engine (one rank per GPU under torchrun)
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+    python bench.py --gpus N --steps K --warmup W              # this repo's engine (one rank per GPU under torchrun)
+    python bench.py --config ford64|kitti1024x8|stress ...     # the other BASELINE configs (default: kitti32 = configs[1])
+    python bench.py --impl reference --steps K --warmup W      # the reference algorithm on the host CPU cores
 
-One "step" = one forward pass (both VGG branches + N_iters x levels LM steps) over one batch of
-synthetic pairs per GPU.  Prints ONE JSON line on rank 0 (see DESIGN.md section "Measurement").
+One "step" = one forward pass (both VGG branches + N_iters x levels LM steps) over one batch of synthetic pairs
+per GPU.  Prints ONE JSON line on rank 0 (see DESIGN.md section "Measurement").
 """
 from __future__ import annotations
 
 import argparse
+import csv
 import json
 import os
 import statistics
@@ -18,6 +20,7 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -27,8 +30,20 @@ import torch  # noqa: E402
 
 METRIC = "image-pairs/sec thru 5-iter LM (KITTI)"
 VGG_FLOP_PER_PX = {3: 520056, 4: 603288}                    # 2*9*Cin*Cout summed over live convs
-SAT_TEXELS_TOUCHED = [372, 1326, 5462, 21880]               # unique sat texels per sample at pose 0
+# unique satellite texels one sample touches at pose 0, per pyramid level
+SAT_TEXELS_TOUCHED = {"kitti": [372, 1326, 5462, 21880], "ford": [326, 1610, 5677, 21193]}
 PYR_C = [256, 128, 64, 16]
+FORD_R = [[0., 0., 1.], [1., 0., 0.], [0., 1., 0.]]          # synthetic extrinsics of SURVEY.md 8c KAT-5
+FORD_T = [1.7, -0.3, -1.5]
+CPU_ARM_PAIRS = 2                                            # pairs per step of the CPU arm (a bounded sample of the batch)
+
+# BASELINE.json `configs`.  batch = pairs per GPU per step.
+CONFIGS = {
+    "kitti32": dict(kind="kitti", batch=32, level=3, n_iters=5, sat=512, baseline="configs[1]: KITTI shapes, batch 32, 3-level pyramid, 5 LM iters, 1xB200"),
+    "ford64": dict(kind="ford", batch=64, level=3, n_iters=5, sat=1280, baseline="configs[2]: Ford-AV shapes (sat 1280x1280), batch 64, 5 LM iters, 1xB200"),
+    "kitti1024x8": dict(kind="kitti", batch=128, level=3, n_iters=5, sat=512, baseline="configs[3]: KITTI shapes, batch 1024 sharded 8xB200 = 128 per GPU, pose all-gather"),
+    "stress": dict(kind="kitti", batch=512, level=4, n_iters=10, sat=512, baseline="configs[4]: 4-level pyramid, 10 LM iters, batch 4096 over 8xB200 = 512 per GPU"),
+}
 
 
 def peaks():
@@ -40,7 +55,6 @@ def peaks():
 
 
 def ref_args(n_iters=5, level=3):
-    import types
     return types.SimpleNamespace(level=level, N_iters=n_iters, using_weight=0, loss_method=0, rotation_range=10.0, proj="geo",
                                  Optimizer="LM", damping=0.1, train_damping=0, shift_range_lat=20.0, shift_range_lon=20.0,
                                  use_hessian=0, dropout=0, use_gt_depth=0, visualize=0, coe_shift_lat=100.0,
@@ -48,14 +62,31 @@ def ref_args(n_iters=5, level=3):
                                  coe_L4=100.0, estimate_depth=0)
 
 
-def lm_bytes_per_pair(n_levels, n_iters):
-    """Algorithmic HBM bytes of the LM loop per pair: ground bottom half read once per
-    step + the unique satellite texels touched, fp32."""
+def lm_bytes_per_pair(n_levels, n_iters, kind="kitti"):
+    """Algorithmic HBM bytes of the LM loop per pair: ground bottom half read once per step + the unique
+    satellite texels touched, fp32."""
     per_sweep = 0
     for l in range(n_levels):
         h, w = 256 >> (3 - l), 1024 >> (3 - l)
-        per_sweep += 4 * PYR_C[l] * ((h // 2) * w + SAT_TEXELS_TOUCHED[l])
+        per_sweep += 4 * PYR_C[l] * ((h // 2) * w + SAT_TEXELS_TOUCHED[kind][l])
     return per_sweep * n_iters
+
+
+def profile_traffic(name, launches=None):
+    """dram__bytes_read + dram__bytes_write (bytes) summed over the launches of a tracked ncu summary under profiles/
+    (written by tools/summarise_profiles.py: one row per metric, one column per launch).  None when the file is absent —
+    the traffic field is then null rather than a constant copied from somewhere."""
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        return None
+    tot, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for row in csv.reader(open(path)):
+        if row and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            vals = [float(v) for v in row[2:] if v != ""]
+            if launches is not None:
+                vals = [vals[i] for i in launches if i < len(vals)]
+            tot += sum(vals) * unit_scale.get(row[1], 1.0)
+    return tot or None
 
 
 class ClockSampler:
@@ -106,9 +137,31 @@ def time_region(fn, steps, sync):
     return e0.elapsed_time(e1) / 1e3
 
 
-def cpu_reference_run(steps, warmup, n_iters=5, level=3, pairs_per_step=1):
-    """The reference algorithm (oracle port, torch CPU, all host threads) on the same workload
-    shape, one bounded sample (pairs_per_step pairs) per step."""
+def workload_config(opt):
+    """Identical in both arms (the driver compares them): names the workload; arm-specific facts live elsewhere."""
+    c = opt.cfg
+    return {"workload": "%s shapes (sat %dx%d, grd 256x1024), batch %d per GPU, %d-level VGG pyramid, %d LM iters"
+                        % ("KITTI" if c["kind"] == "kitti" else "Ford-AV", c["sat"], c["sat"], opt.batch, opt.level, opt.n_iters),
+            "name": opt.config, "baseline_config": c["baseline"], "geometry": c["kind"], "sat_side": c["sat"],
+            "batch_per_gpu": opt.batch, "levels": opt.level, "n_iters": opt.n_iters,
+            "l2": "inputs (%.0f MB of images + GBs of activations per step) exceed the 126 MB L2"
+                  % (opt.batch * (3 * c["sat"] ** 2 + 3 * 256 * 1024) * 4 / 1e6),
+            "cpu_arm_sample": "the CPU (reference) arm times %d pair(s) of this workload per step on the host cores" % CPU_ARM_PAIRS}
+
+
+# ------------------------------------------------------------------------------- the reference algorithm (oracle port)
+def _oracle_forward(O, opt, sd, sat, grd, a):
+    if opt.cfg["kind"] == "kitti":
+        return O.forward_kitti(sd, sat, grd, a)
+    B = sat.shape[0]
+    R = torch.tensor(FORD_R)[None].repeat(B, 1, 1)
+    T = torch.tensor(FORD_T)[None].repeat(B, 1)
+    return O.forward_ford(sd, sat, grd, opt.cfg["sat"] * 0.22, R, T, a)
+
+
+def cpu_reference_run(opt, steps, warmup, pairs_per_step=CPU_ARM_PAIRS):
+    """The reference algorithm (oracle port, torch CPU, all host threads) on the same workload shape, one bounded sample
+    (pairs_per_step pairs) per step."""
     from oracle import oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     sd = {}
@@ -116,43 +169,81 @@ def cpu_reference_run(steps, warmup, n_iters=5, level=3, pairs_per_step=1):
     sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
     sd["damping"] = torch.zeros(1, 3)
     g = torch.Generator().manual_seed(2022)
-    sat = torch.rand(pairs_per_step, 3, 512, 512, generator=g)
+    A = opt.cfg["sat"]
+    sat = torch.rand(pairs_per_step, 3, A, A, generator=g)
     grd = torch.rand(pairs_per_step, 3, 256, 1024, generator=g)
-    a = O.LMArgs(level=level, N_iters=n_iters)
-    ts = []
-    res = None
+    a = O.LMArgs(level=opt.level, N_iters=opt.n_iters)
+    ts, res = [], None
     with torch.no_grad():
         for i in range(warmup + steps):
             torch.manual_seed(999)                      # the reset draws come from the CPU generator: same stream every step
             t0 = time.perf_counter()
-            res = O.forward_kitti(sd, sat, grd, a)
+            res = _oracle_forward(O, opt, sd, sat, grd, a)
             if i >= warmup:
                 ts.append(time.perf_counter() - t0)
     total = sum(ts)
+    # engine convention (su, sv, theta): KITTI lats = sv, lons = su; Ford lats = su, lons = sv
+    traj = torch.stack([res.lons, res.lats, res.thetas] if opt.cfg["kind"] == "kitti" else [res.lats, res.lons, res.thetas], dim=-1)
     return dict(value=pairs_per_step * steps / total, ms_per_step=1e3 * total / steps, cores=torch.get_num_threads(),
-                ref=dict(sd=sd, sat=sat, grd=grd, traj=torch.stack([res.lons, res.lats, res.thetas], dim=-1)),
-                sample="%d synthetic KITTI pair(s) per step x %d steps (+%d warm-up), VGG level %d + %d LM iters, torch %s CPU"
-                       % (pairs_per_step, steps, warmup, level, n_iters, torch.__version__))
+                ref=dict(sd=sd, sat=sat, grd=grd, traj=traj),
+                sample="%d synthetic %s pair(s) per step x %d steps (+%d warm-up), VGG level %d + %d LM iters, torch %s CPU"
+                       % (pairs_per_step, opt.cfg["kind"], steps, warmup, opt.level, opt.n_iters, torch.__version__))
 
 
-def pose_delta_vs_reference(ref, opt, dev):
+def reference_gpu_eager(opt, dev, steps=3):
+    """Informational (BASELINE.md section 2 / SURVEY 8d): the reference's own op sequence — torch eager: cuDNN convolutions,
+    gather-based sampler, materialised [3,B,C,H,W] Jacobians, bmm + inverse — on the SAME B200, with TF32 convolutions off
+    (the fp32 oracle) and on (what `python train_kitti.py` runs by default).  It is the oracle port executed under a CUDA
+    default device; "the existing Blackwell implementation" the engine is compared with.  Never fails the bench."""
+    out = {}
+    try:
+        from oracle import oracle as O
+        B = min(opt.batch, 8)                           # the reference materialises ~1 GB per pair at level 2
+        a = O.LMArgs(level=opt.level, N_iters=opt.n_iters)
+        old_c, old_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        sd = {}
+        sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+        sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+        sd["damping"] = torch.zeros(1, 3)
+        sd = {k: v.to(dev) for k, v in sd.items()}
+        A = opt.cfg["sat"]
+        sat, grd = torch.rand(B, 3, A, A, device=dev), torch.rand(B, 3, 256, 1024, device=dev)
+        with torch.device(dev), torch.no_grad():       # the oracle's tensor factories now create CUDA tensors
+            for name, tf32 in (("tf32_off", False), ("tf32_on", True)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                for _ in range(2):
+                    _oracle_forward(O, opt, sd, sat, grd, a)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    _oracle_forward(O, opt, sd, sat, grd, a)
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / steps
+                out[name] = {"value": B / dt, "unit": "pairs/s", "ms_per_step": 1e3 * dt, "batch": B}
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_c, old_m
+        out["what"] = "oracle port (the reference's eager op sequence) on cuda, wall clock incl. its per-step host syncs"
+    except Exception as e:                                           # pragma: no cover
+        out["error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
+    return out
+
+
+def pose_delta_vs_reference(ref, opt, dev, make_net, fwd):
     """|dpose| of the engine against the reference algorithm (the oracle port just timed as the CPU baseline) on the very
-    same pair, weights and reset-draw stream: the second half of BASELINE.json's metric.  Random-init U-Net features are
+    same pairs, weights and reset-draw stream: the second half of BASELINE.json's metric.  Random-init U-Net features are
     not contractive — the reference's own fp32 and fp64 runs differ by up to 2.6e-4 after 15 steps — so
     the first sweep (before chaos accumulates) is reported next to the final pose.  Never fails the bench."""
     try:
-        from highlyaccurate_b200.models_kitti import LM_S2GP
-        net = LM_S2GP(ref_args(opt.n_iters, opt.level)).to(dev).eval()
+        net = make_net()
         net.load_state_dict(ref["sd"])
-        net.SatFeatureNet.precision = net.GrdFeatureNet.precision = opt.precision
         torch.manual_seed(999)
-        net(ref["sat"].to(dev), ref["grd"].to(dev), mode="test")
+        fwd(net, ref["sat"].to(dev), ref["grd"].to(dev))
         got = net.last_result.traj.float().cpu()                    # [B, N_iters, L, (su, sv, theta)]
-        want = ref["traj"]
-        d = (got - want).abs()
+        d = (got - ref["traj"]).abs()
         return {"final_max_abs": float(d[:, -1, -1].max()), "first_sweep_max_abs": float(d[:, 0].max()), "pairs": int(got.shape[0]),
                 "units": "normalised pose (x shift_range m / rotation_range deg)",
-                "note": "random-init features: the reference's own fp32-vs-fp64 drift is up to 2.6e-4 after 15 steps"}
+                "note": "random-init features: the reference's own fp32-vs-fp64 drift is up to 2.6e-4 after 15 steps; "
+                        "tests/test_gpu_parity.py::test_end_to_end_eight_pairs_vs_reference covers 8 pairs against the reference itself"}
     except Exception as e:                                           # pragma: no cover
         return {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
@@ -161,24 +252,15 @@ def run_reference(opt):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(opt.steps, max(1, min(opt.warmup, 3)), opt.n_iters, opt.level)
+    r = cpu_reference_run(opt, opt.steps, max(1, min(opt.warmup, 3)))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "pairs/s", "n_gpus": opt.gpus, "steps": opt.steps,
             "warmup": opt.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(opt, opt.batch, "host CPU"), vgg_precision="f32 (torch CPU)",
-                           sample="1 pair per step (bounded sample of the batch-%d workload)" % opt.batch),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(opt),
+            "arm": {"device": "host CPU", "vgg_precision": "f32 (torch CPU)", "pairs_per_step": CPU_ARM_PAIRS},
             "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
-
-
-def workload_config(opt, batch, where):
-    return {"workload": "KITTI shapes (sat 512x512, grd 256x1024), batch %d per GPU, %d-level VGG pyramid, %d LM iters"
-                        % (batch, opt.level, opt.n_iters),
-            "batch_per_gpu": batch, "levels": opt.level, "n_iters": opt.n_iters, "device": where,
-            "l2": "inputs (%.0f MB of images + GBs of activations per step) exceed the 126 MB L2" % (batch * 6.29),
-            "vgg_precision": opt.precision}
 
 
 def main():
@@ -187,18 +269,25 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="pairs per GPU per step (BASELINE configs[1]: 32)")
-    ap.add_argument("--n-iters", dest="n_iters", type=int, default=5)
-    ap.add_argument("--level", type=int, default=3)
+    ap.add_argument("--config", default="kitti32", choices=sorted(CONFIGS), help="BASELINE.json workload (default configs[1])")
+    ap.add_argument("--batch", type=int, default=None, help="pairs per GPU per step (overrides the config's)")
+    ap.add_argument("--n-iters", dest="n_iters", type=int, default=None)
+    ap.add_argument("--level", type=int, default=None)
     ap.add_argument("--precision", default=os.environ.get("HA_VGG_PRECISION", "f16x3"), choices=["f16x3", "f16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational rows (reference eager on the GPU, f16 single pass)")
     opt = ap.parse_args()
+    opt.cfg = CONFIGS[opt.config]
+    opt.batch = opt.batch or opt.cfg["batch"]
+    opt.n_iters = opt.n_iters or opt.cfg["n_iters"]
+    opt.level = opt.level or opt.cfg["level"]
     opt.warmup = max(opt.warmup, 3) if opt.impl == "ours" else opt.warmup
     if opt.impl == "reference":
         return run_reference(opt)
 
     from highlyaccurate_b200 import _lib, engine
     from highlyaccurate_b200 import dist as hd
+    from highlyaccurate_b200.models_ford import LM_S2GP_Ford
     from highlyaccurate_b200.models_kitti import LM_S2GP
     import torch.distributed as dist
 
@@ -209,12 +298,33 @@ def main():
     L = _lib.lib()
     _lib.check(L.ha_device_check(local), "ha_device_check")
     B, K, W = opt.batch, opt.steps, opt.warmup
+    kind, A = opt.cfg["kind"], opt.cfg["sat"]
+    comm = hd.PoseComm(rank, world, dev) if world > 1 else None          # ha_comm_* / ha_pose_allgather (C ABI)
 
-    torch.manual_seed(0)
-    net = LM_S2GP(ref_args(opt.n_iters, opt.level)).to(dev).eval()
-    net.SatFeatureNet.precision = net.GrdFeatureNet.precision = opt.precision
+    def make_net(precision=None):
+        torch.manual_seed(0)
+        n = (LM_S2GP if kind == "kitti" else LM_S2GP_Ford)(ref_args(opt.n_iters, opt.level)).to(dev).eval()
+        n.SatFeatureNet.precision = n.GrdFeatureNet.precision = precision or opt.precision
+        return n
+
+    ford_R = torch.tensor(FORD_R, device=dev)[None]
+    ford_T = torch.tensor(FORD_T, device=dev)[None]
+
+    def fwd(n, sat, grd):                     # the call a user of the reference makes
+        if kind == "kitti":
+            return n(sat, grd, mode="test")
+        b = sat.shape[0]
+        return n(sat, grd, A * 0.22, ford_R.expand(b, 3, 3), ford_T.expand(b, 3), mode="test")
+
+    def refine(n, sat, grd, draws_x):
+        if kind == "kitti":
+            return n.refine(sat, grd, reset_uv=draws_x)
+        b = sat.batch
+        return n.refine(sat, grd, A * 0.22, ford_R.expand(b, 3, 3), ford_T.expand(b, 3), reset_uv=draws_x)
+
+    net = make_net()
     g = torch.Generator().manual_seed(1000 + rank)
-    host_sat = [torch.rand(B, 3, 512, 512, generator=g).pin_memory() for _ in range(2)]
+    host_sat = [torch.rand(B, 3, A, A, generator=g).pin_memory() for _ in range(2)]
     host_grd = [torch.rand(B, 3, 256, 1024, generator=g).pin_memory() for _ in range(2)]
     sat_d, grd_d = host_sat[0].to(dev), host_grd[0].to(dev)
     n_steps_lm = opt.n_iters * opt.level
@@ -229,8 +339,8 @@ def main():
 
     def forward_resident(i):
         sat, grd = net.extract(sat_d, grd_d, False)
-        res = net.refine(sat, grd, reset_uv=draws)
-        return hd.gather_poses(res.pose, world)
+        res = refine(net, sat, grd, draws)
+        return hd.gather_poses(res.pose, world, comm)
 
     # ---------------- warm-up + the timed region (inputs resident in HBM)
     for i in range(W):
@@ -239,7 +349,6 @@ def main():
     n0 = L.ha_launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     t_wall0 = time.time()
-    # short runs are repeated so that nvidia-smi gets samples under load, but only K steps are timed per repeat
     secs = time_region(forward_resident, K, sync)
     launches = (L.ha_launch_count() - n0)
     t_wall1 = time.time()
@@ -251,7 +360,7 @@ def main():
         t_end = time.time() + 1.5
         while time.time() < t_end:                             # rank-local work only: no collective in here
             sat_w, grd_w = net.extract(sat_d, grd_d, False)
-            net.refine(sat_w, grd_w, reset_uv=draws)
+            refine(net, sat_w, grd_w, draws)
         torch.cuda.synchronize()
         t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler is not None else None
@@ -282,16 +391,15 @@ def main():
             if i + 1 < n:
                 stage(i + 1)                       # overlap the next batch's H2D with this batch's compute
             torch.cuda.current_stream().wait_event(ready[s])
-            out = net(bufs[s][0], bufs[s][1], mode="test")          # the call a user of the reference makes
+            out = fwd(net, bufs[s][0], bufs[s][1])                   # reads the device status word once (the reference's asserts)
             freed[s].record(torch.cuda.current_stream())
-            poses = hd.gather_poses(torch.stack([o.detach() for o in out], dim=-1), world)
+            poses = hd.gather_poses(torch.stack([o.detach() for o in out], dim=-1), world, comm)
             out_host.copy_(poses, non_blocking=False)                # device -> host read of the result, every step
 
     e2e_loop(2)
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    t0 = time.perf_counter()
     e2e_loop(K)
     e1.record()
     sync()
@@ -301,29 +409,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_secs = float(t.item())
     e2e = {"value": world * B * K / e2e_secs, "unit": "pairs/s",
-           "h2d_bytes_per_step": int(world * B * (3 * 512 * 512 + 3 * 256 * 1024) * 4), "d2h_bytes_per_step": int(world * B * 3 * 4),
-           "how": "pinned host fp32 images -> cudaMemcpyAsync on a copy stream (double buffered) -> LM_S2GP.forward(mode='test') "
-                  "-> poses copied back to host every step"}
+           "h2d_bytes_per_step": int(world * B * (3 * A * A + 3 * 256 * 1024) * 4), "d2h_bytes_per_step": int(world * B * 3 * 4),
+           "how": "pinned host fp32 images -> cudaMemcpyAsync on a copy stream (double buffered) -> %s.forward(mode='test') "
+                  "-> poses copied back to host every step" % type(net).__name__}
+    del bufs
 
-    # ---------------- per-kernel-family timings for the rooflines (same process, CUDA events)
+    # ---------------- per-kernel-family timings for the rooflines (same process, CUDA events on the launching stream)
     pk = peaks()
     sat_p, grd_p = net.extract(sat_d, grd_d, False)
     net.extract(sat_d, grd_d, False)        # untimed: with sat_p / grd_p held, the caching allocator has to grow once more
     vgg_secs = time_region(lambda i: net.extract(sat_d, grd_d, False), K, sync) / K
-    # the 15-launch LM loop takes ~1 ms: time it from a CUDA graph so that Python launch overhead (which the
-    # full forward hides behind the VGG kernels) does not pollute the kernel's roofline number
+
     def time_lm(sat_x, grd_x, draws_x):
-        try:
-            net.refine(sat_x, grd_x, reset_uv=draws_x)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            cap_stream = torch.cuda.Stream(device=dev)
-            with torch.cuda.graph(graph, stream=cap_stream):
-                net.refine(sat_x, grd_x, reset_uv=draws_x)
-            return time_region(lambda i: graph.replay(), K, sync) / K, "cuda graph replay"
-        except Exception as e:                                     # pragma: no cover
-            return (time_region(lambda i: net.refine(sat_x, grd_x, reset_uv=draws_x), K, sync) / K,
-                    "eager loop (graph capture failed: %s)" % type(e).__name__)
+        """The LM loop exactly as the product launches it (ha_lm_run: back-to-back launches on the stream, no graph)."""
+        for _ in range(2):
+            refine(net, sat_x, grd_x, draws_x)
+        return time_region(lambda i: refine(net, sat_x, grd_x, draws_x), max(K, 10), sync) / max(K, 10), "ha_lm_run as shipped (eager launches)"
 
     lm_secs, lm_how = time_lm(sat_p, grd_p, draws)
     # the same loop at the batch the north star quotes the LM roofline on (256 pairs, random features: ~15 GB, so each
@@ -332,57 +433,83 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(7)
     del sat_p, grd_p
     torch.cuda.empty_cache()
-    sat_big = engine.Pyramid([torch.randn(B_big, 512 >> (3 - l), 512 >> (3 - l), PYR_C[l], device=dev, generator=gen)
+    sat_big = engine.Pyramid([torch.randn(B_big, A >> (3 - l), A >> (3 - l), PYR_C[l], device=dev, generator=gen)
                               for l in range(opt.level)], [None] * opt.level)
     grd_big = engine.Pyramid([torch.randn(B_big, 256 >> (3 - l), 1024 >> (3 - l), PYR_C[l], device=dev, generator=gen)
                               for l in range(opt.level)], [None] * opt.level)
     big_secs, big_how = time_lm(sat_big, grd_big, torch.zeros(n_steps_lm, 2, B_big, device=dev))
     del sat_big, grd_big
-    vgg_flops = VGG_FLOP_PER_PX[opt.level] * 2 * 262144 * B
+    torch.cuda.empty_cache()
+    vgg_flops = VGG_FLOP_PER_PX[opt.level] * (A * A + 256 * 1024) * B
     mma_mult = {"f16x3": 3, "f16": 1, "fp32": 0}[opt.precision]
     tf = vgg_flops / vgg_secs / 1e12
-    roof = {"kernel": "conv3x3_tc_kernel (VGG16 U-Net, both branches; includes conv0 + L2-norm kernels)",
+    # DRAM bytes of ONE U-Net branch at B = 32, 512 x 512 (ncu --set full of the conv launches, summarised under profiles/)
+    conv_prof = "r02_conv_full.csv" if os.path.exists(os.path.join(ROOT, "profiles", "r02_conv_full.csv")) else "r01c_conv_full.csv"
+    conv_traffic = profile_traffic(conv_prof)
+    roof = {"kernel": "conv3x3_tc*_kernel (VGG16 U-Net, both branches; includes conv0)",
             "bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"],
             "peak_source": pk["src"] + " bf16 sustained",
-            # DRAM bytes (read + write) of one U-Net branch at B = 32 from profiles/r01c_conv_full.csv (ten tcgen05 conv
-            # launches: 8.61 + 5.97 GB) plus conv0 (0.10 + 2.09 GB), scaled to this step's two branches and batch
-            "traffic": (8.61e9 + 5.97e9 + 2.19e9) * 2 * B / 32 if opt.level == 3 else None,
-            "traffic_note": "bytes per step, ncu dram__bytes_read+write summed over the conv launches (profiles/r01c_conv_full.csv)",
-            "ms_per_step": vgg_secs * 1e3,
-            "tensor_pipe_tflops_issued": tf * mma_mult,
-            "note": "achieved counts ALGORITHMIC conv FLOPs (272.7 GFLOP/pair); f16x3 issues 3 MMAs per product for fp32-grade "
-                    "features, so the tensor pipe executes 3x that"}
-    lm_b = lm_bytes_per_pair(opt.level, opt.n_iters) * B
-    gbs = lm_b / lm_secs / 1e9
-    roof_lm = {"kernel": "lm_step_kernel x %d launches" % n_steps_lm, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
+            "traffic": (conv_traffic * (A * A + 256 * 1024) / 262144 * B / 32) if (conv_traffic and opt.level == 3) else None,
+            "traffic_note": "bytes per step: ncu dram__bytes_read+write summed over the tcgen05 conv launches of one 512x512 "
+                            "branch at B=32 (profiles/%s), scaled by pixels and batch; conv0 is not in that capture" % conv_prof,
+            "ms_per_step": vgg_secs * 1e3, "tensor_pipe_tflops_issued": tf * mma_mult,
+            "note": "achieved counts ALGORITHMIC conv FLOPs (%.1f GFLOP/pair); f16x3 issues 3 MMAs per product for fp32-grade "
+                    "features, so the tensor pipe executes 3x that" % (vgg_flops / B / 1e9)}
+    bpp = lm_bytes_per_pair(opt.level, opt.n_iters, kind)
+    gbs = bpp * B / lm_secs / 1e9
+    lm_prof = "r02_lm_full.csv" if os.path.exists(os.path.join(ROOT, "profiles", "r02_lm_full.csv")) else "r01d_lm_full.csv"
+    lm_traffic = profile_traffic(lm_prof)       # one FULL launch per level at B = 256 = one sweep
+    roof_lm = {"kernel": "lm_step_v4_kernel x %d launches" % n_steps_lm, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
                "unit": "GB/s", "frac": gbs / pk["hbm"], "peak_source": pk["src"],
-               # ncu dram__bytes_read+write of the three levels at B = 256 (profiles/r01c_lm_full.csv: 4.51 GB per sweep),
-               # per pair and sweep x n_iters: DRAM traffic equals the algorithmic bytes
-               "traffic": 4.51e9 / 256 * opt.n_iters * B if opt.level == 3 else None, "ms_per_step": lm_secs * 1e3,
-               "bytes_per_pair": lm_bytes_per_pair(opt.level, opt.n_iters), "timed_as": lm_how}
-    gbs_big = lm_bytes_per_pair(opt.level, opt.n_iters) * B_big / big_secs / 1e9
+               "traffic": (lm_traffic / 256 * opt.n_iters * B) if (lm_traffic and opt.level == 3 and kind == "kitti") else None,
+               "traffic_note": "bytes per step: ncu dram__bytes_read+write of one sweep (3 launches) at B=256 (profiles/%s) "
+                               "per pair x n_iters x batch" % lm_prof,
+               "ms_per_step": lm_secs * 1e3, "bytes_per_pair": bpp, "timed_as": lm_how}
+    gbs_big = bpp * B_big / big_secs / 1e9
     roof_lm["at_batch_256"] = {"achieved": gbs_big, "frac": gbs_big / pk["hbm"], "ms_per_step": big_secs * 1e3, "timed_as": big_how,
-                               "data": "random features, KITTI pyramid shapes"}
+                               "data": "random features, %s pyramid shapes" % kind}
+
+    # ---------------- informational rows (rank 0, one GPU): f16 single pass, the reference's eager ops on this GPU
+    info = {}
+    if rank == 0 and world == 1 and not opt.no_extras:
+        try:
+            net16 = make_net("f16")
+            for _ in range(2):
+                net16.extract(sat_d, grd_d, False)
+            s16 = time_region(lambda i: refine(net16, *net16.extract(sat_d, grd_d, False), draws), max(3, K // 2), sync) / max(3, K // 2)
+            info["engine_f16_single_pass"] = {"value": B / s16, "unit": "pairs/s", "ms_per_step": 1e3 * s16,
+                                              "note": "kind::f16 single MMA per product (11-bit operands: the class of the TF32 convs "
+                                                      "the reference itself runs on a GPU); not the parity configuration"}
+            del net16
+        except Exception as e:                                       # pragma: no cover
+            info["engine_f16_single_pass"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        torch.cuda.empty_cache()
+        info["reference_gpu_eager"] = reference_gpu_eager(opt, dev)
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.barrier()
+            comm.close()
             dist.destroy_process_group()
         return
     cpu, pose_delta = None, None
     if world == 1 and not opt.no_cpu_baseline:
-        r = cpu_reference_run(steps=2, warmup=1, n_iters=opt.n_iters, level=opt.level)
+        r = cpu_reference_run(opt, steps=2, warmup=1)
         cpu = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-        pose_delta = pose_delta_vs_reference(r["ref"], opt, dev)
+        pose_delta = pose_delta_vs_reference(r["ref"], opt, dev, make_net, fwd)
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"f16x3": "f16x3 split on tcgen05 (fp32-grade) + f32 LM", "f16": "f16 tcgen05 + f32 LM", "fp32": "f32"}[opt.precision],
-            "data": "synthetic", "config": workload_config(opt, B, "B200"),
+            "data": "synthetic", "config": workload_config(opt),
+            "arm": {"device": "B200", "vgg_precision": opt.precision,
+                    "collective": "ha_pose_allgather (C ABI, NCCL)" if world > 1 else "none (1 GPU)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_lm": roof_lm,
-            "cpu_baseline": cpu, "pose_delta_vs_ref": pose_delta}
+            "cpu_baseline": cpu, "pose_delta_vs_ref": pose_delta, "informational": info or None}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        comm.close()
         dist.destroy_process_group()
 
 

@@ -50,6 +50,7 @@ class VGGUnet(nn.Module):
         self._load_pretrained_encoder()
         self.precision = os.environ.get("HA_VGG_PRECISION", "f16x3")
         self._runner = engine.VggRunner()
+        self._named = None            # name -> Parameter, built once (Parameter objects are stable across .to() / load_state_dict)
 
     def _load_pretrained_encoder(self):
         """VGG.py:20-29 takes the encoder from torchvision's ImageNet VGG16.  Offline boxes have no
@@ -65,6 +66,13 @@ class VGGUnet(nn.Module):
             getattr(self, "conv%d" % idx).load_state_dict({"weight": sd["features.%d.weight" % idx],
                                                            "bias": sd["features.%d.bias" % idx]})
 
+    def _apply(self, fn, recurse=True):
+        """.to() / .cuda() / .half(): the Parameter objects survive, but drop the cached dict anyway (cheap, and correct
+        under torch.__future__.set_overwrite_module_params_on_conversion)."""
+        out = super()._apply(fn, recurse)
+        self._named = None
+        return out
+
     # VGG.py:192-203: level -> (pyramid levels the U-Net has to compute, slice of [x15, x18, x21, x24] that is returned)
     _LEVELS = {3: (3, slice(0, 3)), 4: (4, slice(0, 4)), -1: (3, slice(0, 1)), 2: (3, slice(1, 3))}
 
@@ -78,10 +86,12 @@ class VGGUnet(nn.Module):
         self.n_levels()
         return self._LEVELS[self.level][1]
 
-    def pyramid(self, x: torch.Tensor, want_conf: bool = True) -> engine.Pyramid:
-        """Engine-layout output (NHWC raw features + lazy L2 scale + confidences) of the levels `level` selects."""
-        named = dict(self.named_parameters())
-        p = self._runner(named, x, self.n_levels(), want_conf, self.precision)
+    def pyramid(self, x: torch.Tensor, want_conf: bool = True, want_scale: bool = True) -> engine.Pyramid:
+        """Engine-layout output (NHWC raw features + lazy L2 scale + confidences) of the levels `level` selects.
+        `want_scale=False` leaves the L2-norm scales out (callers whose LM step renormalises: they cancel)."""
+        if self._named is None:
+            self._named = dict(self.named_parameters())
+        p = self._runner(self._named, x, self.n_levels(), want_conf, self.precision, want_scale)
         sl = self.level_slice()
         return engine.Pyramid(p.feats[sl], p.scales[sl], p.confs[sl])
 

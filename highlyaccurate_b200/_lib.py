@@ -16,14 +16,17 @@ HA_STATS = 24
 HA_VGG_N_CONV = 17
 HA_GEOM_KITTI, HA_GEOM_FORD, HA_GEOM_G2SP = 0, 1, 2
 HA_CONV_FP32_SIMT, HA_CONV_F16X3, HA_CONV_F16 = 0, 1, 2
-HA_STATUS_NO_INRANGE, HA_STATUS_NAN_POSE, HA_STATUS_RESET = 1, 2, 4
+HA_STATUS_NO_INRANGE, HA_STATUS_NAN_POSE, HA_STATUS_RESET, HA_STATUS_SAMPLE_EMPTY = 1, 2, 4, 8
+HA_COMM_ID_BYTES = 128
+HA_ABI_VERSION = 2
 STAT_H, STAT_GRAD, STAT_SAT_NORM, STAT_GRD_NORM, STAT_RES_SQ, STAT_DELTA, STAT_N_INRANGE = 0, 9, 12, 13, 14, 15, 18
 
 # every symbol include/ha_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ["ha_version", "ha_error_string", "ha_last_cuda_error", "ha_device_check", "ha_nchw_to_nhwc",
            "ha_nhwc_to_nchw", "ha_lm_workspace_bytes", "ha_lm_step", "ha_lm_run", "ha_vgg_packed_weight_bytes",
            "ha_vgg_pack_weights", "ha_vgg_workspace_bytes", "ha_vgg_forward", "ha_conv3x3_workspace_bytes",
-           "ha_conv3x3_nhwc", "ha_launch_count"]
+           "ha_conv3x3_nhwc", "ha_launch_count", "ha_comm_unique_id", "ha_comm_init", "ha_comm_destroy",
+           "ha_pose_allgather"]
 
 
 class HaLevel(C.Structure):
@@ -36,7 +39,7 @@ class HaLmParams(C.Structure):
                 ("rotation_range", C.c_float), ("shift_range_lat", C.c_float), ("shift_range_lon", C.c_float),
                 ("damping", C.c_float * 3), ("meter_per_pixel", C.c_float * HA_MAX_LEVELS),
                 ("inv_meter_per_pixel", C.c_float * HA_MAX_LEVELS), ("sat_center", C.c_float * HA_MAX_LEVELS),
-                ("ori_grd_h", C.c_int32), ("ori_grd_w", C.c_int32)]
+                ("ori_grd_h", C.c_int32), ("ori_grd_w", C.c_int32), ("kernel_variant", C.c_int32), ("reserved", C.c_int32)]
 
 
 class HaVggStateDict(C.Structure):
@@ -81,6 +84,12 @@ def lib() -> C.CDLL:
     L.ha_conv3x3_workspace_bytes.restype = sz
     L.ha_conv3x3_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.ha_conv3x3_nhwc.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
+    L.ha_comm_unique_id.argtypes = [vp]
+    L.ha_comm_init.argtypes = [C.POINTER(vp), i32, i32, vp, i32]
+    L.ha_comm_destroy.argtypes = [vp]
+    L.ha_pose_allgather.argtypes = [vp, vp, vp, i32, vp]
+    if L.ha_version() != HA_ABI_VERSION:
+        raise HaError("libha_b200.so has ABI version %d, this package needs %d: rebuild it" % (L.ha_version(), HA_ABI_VERSION))
     for name in EXPORTS:
         f = getattr(L, name)
         if f.restype is C.c_int and name not in ("ha_version",):
@@ -94,6 +103,6 @@ def check(rc: int, what: str) -> None:
         return
     L = lib()
     msg = L.ha_error_string(rc).decode()
-    if rc == -3:
+    if rc in (-3, -5):
         msg += ": " + L.ha_last_cuda_error().decode()
     raise HaError("%s failed: %s" % (what, msg))

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libha_b200.so")
 STAMP = os.path.join(LIB_DIR, "libha_b200.stamp")
-SOURCES = ["api.cu", "lm_kernels.cu", "vgg.cu", "vgg_tc.cu"]
+SOURCES = ["api.cu", "comm.cu", "lm_kernels.cu", "vgg.cu", "vgg_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stdout.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs, "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:
         sys.stdout.write(r.stdout)

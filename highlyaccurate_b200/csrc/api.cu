@@ -14,6 +14,8 @@ void set_cuda_error(cudaError_t e, const char* what) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
+void set_error_text(const char* text) { snprintf(g_cuda_err, sizeof(g_cuda_err), "%s", text); }
+
 // [B][C][HW] <-> [B][HW][C] through a 32x33 shared tile: coalesced on both sides.
 template <bool TO_NHWC>
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
@@ -48,7 +50,7 @@ static int transpose(const float* src, float* dst, int B, int C, int H, int W, v
 
 }  // namespace ha
 
-extern "C" int ha_version(void) { return 1; }
+extern "C" int ha_version(void) { return 2; }
 extern "C" unsigned long long ha_launch_count(void) { return __atomic_load_n(&ha::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" const char* ha_error_string(int code) {
@@ -58,6 +60,7 @@ extern "C" const char* ha_error_string(int code) {
     case HA_ENOSPACE: return "workspace too small";
     case HA_ECUDA: return "CUDA call failed (see ha_last_cuda_error)";
     case HA_EUNSUPPORTED: return "device is not compute capability 10.x (B200, sm_100a)";
+    case HA_ECOMM: return "NCCL unavailable or an NCCL call failed (see ha_last_cuda_error)";
     default: return "unknown error";
   }
 }

@@ -9,6 +9,7 @@
 namespace ha {
 
 void set_cuda_error(cudaError_t e, const char* what);
+void set_error_text(const char* text);   // same thread-local slot as set_cuda_error (ha_last_cuda_error)
 void count_launches(int n);   // statistics only: kernels launched by this library (ha_launch_count)
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -12,7 +12,7 @@
 // equations are reduced in registers -> shuffles -> shared memory -> a deterministic two-stage
 // cross-CTA combine whose last-arriving CTA solves the damped system and updates the pose in place.
 // Two kernels share the geometry, the record of per-pixel scalars and the reduce-and-solve tail:
-// lm_step_v4_kernel (S2GP geometries, the default) and lm_step_kernel (G2SP, and HA_LM_VARIANT=0).
+// lm_step_v4_kernel (S2GP geometries, the default) and lm_step_kernel (G2SP, and HaLmParams.kernel_variant = 1).
 //
 // Algebra: with s_c, a_c = ds_c/dx, b_c = ds_c/dy per channel and the
 // channel-independent 2x3 matrix D_p = d(u,v)/d(pose), the kernel accumulates
@@ -21,7 +21,6 @@
 // and finalises  H = JtJ/ns^2,  grad = Jts/ns^2 - Jtg/(ns*ng)  with ns = max(|s|,1e-6),
 // ng = max(|g|,1e-6)  — identical to normalising s, J and g first (models_kitti.py:982-992).
 #include <math.h>
-#include <stdlib.h>
 
 #include <atomic>
 
@@ -31,9 +30,6 @@ namespace ha {
 
 #ifndef HA_LM_MIN_CTAS
 #define HA_LM_MIN_CTAS 4
-#endif
-#ifndef HA_LM_DEFAULT_VARIANT
-#define HA_LM_DEFAULT_VARIANT 4
 #endif
 constexpr int kLmThreads = 128;
 constexpr int kLmWarps = kLmThreads / 32;
@@ -58,6 +54,7 @@ struct LmStepArgs {
   uint32_t* ticket;        // [B]
   const float4* zeros;     // >= 1 KB of zeros (read in place of masked ground pixels)
   double* gg_cache;        // [B] sum g^2 of this level (written by FULL launches, read by the others) or null
+  unsigned long long* step_word;  // batch-level arrival word of the current step: (samples finished << 32) | samples with an in-range point
   int traj_stride;         // floats between consecutive samples in traj
   int B, A, H, W;
   int px_per_cta;          // bottom-half pixels handled by one CTA
@@ -65,6 +62,7 @@ struct LmStepArgs {
   float rot, lat, lon;     // rotation_range (deg), shift_range_lat / lon (m)
   float mpp, inv_mpp, center;  // satellite metres per pixel, fp32(1/mpp), A/2
   int ori_h, ori_w;        // G2SP: size of the ground IMAGE the camera matrix refers to (models_kitti.py:111-114)
+  int variant;             // HaLmParams.kernel_variant
   float damping[3];
 };
 
@@ -458,7 +456,15 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const i
     nth = th + (float)delta[0];
   }
   if (isnan(nsu) || isnan(nsv) || isnan(nth)) st |= HA_STATUS_NAN_POSE;
-  if (tot[15] == 0.0) st |= HA_STATUS_NO_INRANGE;
+  const bool any_inrange = tot[15] != 0.0;
+  if (!any_inrange) st |= HA_STATUS_SAMPLE_EMPTY;
+  // jacobian.py:172 asserts that SOME sample point of the whole batch is in range: the last sample to finish this step
+  // sees how many samples had one (the word is reset for the next step of the stream)
+  const unsigned long long prev = atomicAdd(a.step_word, (1ull << 32) | (any_inrange ? 1ull : 0ull));
+  if ((unsigned)(prev >> 32) == (unsigned)a.B - 1u) {
+    if ((unsigned)(prev & 0xffffffffull) + (any_inrange ? 1u : 0u) == 0u) st |= HA_STATUS_NO_INRANGE;
+    *a.step_word = 0ull;
+  }
   if (st) atomicOr(a.status, st);
   a.pose[b * 3 + 0] = nsu; a.pose[b * 3 + 1] = nsv; a.pose[b * 3 + 2] = nth;
   if (a.traj) {
@@ -916,16 +922,10 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
   }
 }
 
-// Kernel selection (HA_LM_VARIANT): 0 = lm_step_kernel (register-staged ground stream; always used for G2SP);
-// 1-4 (default 4) = lm_step_v4_kernel with a 4-slot x 2 KB ring per warp, tap rows prefetched to L1, 3 CTAs per SM, pixel
-// loop unrolled by two; 5 = the same without the unroll (2 % slower).  Other ring depths (3, 5, 6, 8 slots), L2-only
-// prefetch, no prefetch, 2 and 4 CTAs per SM were measured and dropped.
-static int lm_variant() {
-  const char* e = getenv("HA_LM_VARIANT");       // looked up per launch (~100 ns) so that one process can A/B the variants
-  const int v = e ? atoi(e) : HA_LM_DEFAULT_VARIANT;
-  return (v < 0 || v > 5) ? HA_LM_DEFAULT_VARIANT : v;
-}
-
+// Kernel selection: HaLmParams.kernel_variant 0 (default) = lm_step_v4_kernel with a 4-slot x 2 KB ring per warp, tap rows
+// prefetched to L1, 3 CTAs per SM, pixel loop unrolled by two; 1 = lm_step_kernel (register-staged ground stream; the
+// validation twin, and always the kernel for G2SP).  Other ring depths (3, 5, 6, 8 slots), L2-only prefetch, no prefetch,
+// 2 and 4 CTAs per SM and the non-unrolled loop were measured and dropped.
 template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF, bool WEIGHTED, int UNR>
 static int launch_v4w(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
   auto kern = lm_step_v4_kernel<GEOM, C, FULL, NSLOT, MINB, PF, WEIGHTED, UNR>;
@@ -962,11 +962,8 @@ static int launch_variant(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
     lm_step_kernel<GEOM, C, FULL><<<grid, kLmThreads, 0, st>>>(a);
     return HA_OK;
   } else {
-    switch (lm_variant()) {
-      case 5: return launch_v4<GEOM, C, FULL, 4, 3, 2>(grid, st, a);
-      case 1: case 2: case 3: case 4: return launch_v4<GEOM, C, FULL, 4, 3, 2, 2>(grid, st, a);
-      default: lm_step_kernel<GEOM, C, FULL><<<grid, kLmThreads, 0, st>>>(a); return HA_OK;
-    }
+    if (a.variant == 1) { lm_step_kernel<GEOM, C, FULL><<<grid, kLmThreads, 0, st>>>(a); return HA_OK; }
+    return launch_v4<GEOM, C, FULL, 4, 3, 2, 2>(grid, st, a);
   }
 }
 
@@ -986,11 +983,28 @@ static int launch_by_channels(int C, dim3 grid, cudaStream_t st, const LmStepArg
   return check_launch("lm_step_kernel");
 }
 
-static size_t lm_ws_bytes(int B) {
-  size_t part = (size_t)B * kLmMaxCtasPerSample * kLmAcc * sizeof(double);
-  size_t tick = ((size_t)B * sizeof(uint32_t) + 255) / 256 * 256;
-  return part + tick + kLmZeroBytes + (size_t)HA_MAX_LEVELS * B * sizeof(double);
+// Workspace layout: [partials B x 256 x 16 fp64][tickets B x u32, padded to 256 B][step word, 256 B][zero vector 2 KB]
+// [|g|^2 cache HA_MAX_LEVELS x B fp64].  Tickets, step word and zero vector are contiguous: one kernel clears them.
+struct LmWs {
+  double* partial; uint32_t* ticket; unsigned long long* step_word; const float4* zeros; double* gg;
+  size_t clear_words;      // u32 words from `ticket` that must be zero when a run starts
+  size_t total;
+};
+static LmWs lm_ws_carve(void* ws, int B) {
+  LmWs w;
+  char* p = reinterpret_cast<char*>(ws);
+  const size_t part = (size_t)B * kLmMaxCtasPerSample * kLmAcc * sizeof(double);
+  const size_t tick = ((size_t)B * sizeof(uint32_t) + 255) / 256 * 256;
+  w.partial = reinterpret_cast<double*>(p);
+  w.ticket = reinterpret_cast<uint32_t*>(p + part);
+  w.step_word = reinterpret_cast<unsigned long long*>(p + part + tick);
+  w.zeros = reinterpret_cast<const float4*>(p + part + tick + 256);
+  w.gg = reinterpret_cast<double*>(p + part + tick + 256 + kLmZeroBytes);
+  w.clear_words = (tick + 256 + kLmZeroBytes) / 4;
+  w.total = part + tick + 256 + kLmZeroBytes + (size_t)HA_MAX_LEVELS * B * sizeof(double);
+  return w;
 }
+static size_t lm_ws_bytes(int B) { return lm_ws_carve(nullptr, B).total; }
 
 // Work split: a CTA takes px_per_cta consecutive bottom-half pixels of one sample, a multiple of
 // 32 * warps so that every warp gets the same number of 32-pixel groups (no barrier skew).  Enough
@@ -1016,6 +1030,7 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   if (level < 0 || level >= HA_MAX_LEVELS) return HA_EINVAL;
   if (sat->C != grd->C || sat->H != sat->W || (grd->H & 1)) return HA_EINVAL;
   if (p->dof < 1 || p->dof > 3) return HA_EINVAL;
+  if (p->kernel_variant < 0 || p->kernel_variant > 1 || p->reserved != 0) return HA_EINVAL;
   if (p->dof == 3 && !reset_uv && !g2sp) return HA_EINVAL;
   if (g2sp && (p->dof != 3 || !extrinsics || p->ori_grd_h <= 0 || p->ori_grd_w <= 0)) return HA_EINVAL;
   if (p->using_weight && !grd_conf) return HA_EINVAL;
@@ -1029,17 +1044,16 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   a.conf = grd_conf; a.table = reinterpret_cast<const float4*>(ground_table); a.extr = extrinsics;
   a.pose = pose; a.reset_uv = reset_uv; a.stats = stats; a.traj = traj_step; a.traj_stride = traj_stride;
   a.status = status;
-  a.partial = reinterpret_cast<double*>(ws);
-  a.ticket = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + (size_t)B * kLmMaxCtasPerSample * kLmAcc * sizeof(double));
-  char* tail = reinterpret_cast<char*>(ws) + lm_ws_bytes(B) - kLmZeroBytes - (size_t)HA_MAX_LEVELS * B * sizeof(double);
-  a.zeros = reinterpret_cast<const float4*>(tail);
-  a.gg_cache = reinterpret_cast<double*>(tail + kLmZeroBytes) + (size_t)level * B;
+  const LmWs w = lm_ws_carve(ws, B);
+  a.partial = w.partial; a.ticket = w.ticket; a.step_word = w.step_word; a.zeros = w.zeros;
+  a.gg_cache = w.gg + (size_t)level * B;
   a.B = B; a.A = sat->H; a.H = grd->H; a.W = grd->W;
   a.dof = p->dof; a.using_weight = p->using_weight; a.use_hessian = p->use_hessian;
   a.rot = p->rotation_range; a.lat = p->shift_range_lat; a.lon = p->shift_range_lon;
   a.mpp = p->meter_per_pixel[level]; a.inv_mpp = p->inv_meter_per_pixel[level]; a.center = p->sat_center[level];
   for (int i = 0; i < 3; ++i) a.damping[i] = p->damping[i];
   a.ori_h = p->ori_grd_h; a.ori_w = p->ori_grd_w;
+  a.variant = p->kernel_variant;
   const int P = g2sp ? sat->H * sat->W : (grd->H - grd->H / 2) * grd->W;
   a.px_per_cta = choose_px_per_cta(B, P);
   dim3 grid((P + a.px_per_cta - 1) / a.px_per_cta, B);
@@ -1051,10 +1065,15 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   return HA_EINVAL;
 }
 
-// clears the tickets [0, n) and the zero vector that follows them (tickets are padded to 256 B)
-__global__ void zero_u32_kernel(uint32_t* p, int n) {
-  const int pad = (n * 4 + 255) / 256 * 64, total = pad + kLmZeroBytes / 4;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) p[i] = 0;
+// start of a run: clears the tickets, the step word and the zero vector (contiguous) and the caller's status word
+__global__ void lm_begin_kernel(uint32_t* p, int n_words, uint32_t* status) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) p[i] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *status = 0;
+}
+static void lm_begin(void* ws, int B, uint32_t* status, cudaStream_t st) {
+  const LmWs w = lm_ws_carve(ws, B);
+  lm_begin_kernel<<<(int)((w.clear_words + 255) / 256), 256, 0, st>>>(w.ticket, (int)w.clear_words, status);
+  count_launches(1);
 }
 
 }  // namespace ha
@@ -1069,12 +1088,9 @@ extern "C" int ha_lm_step(const HaLmParams* p, int level, const HaLevel* sat, co
   const int B = p->batch;
   if (B <= 0) return HA_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // tickets must start at zero: the first use of a fresh workspace zeroes them here (cheap, async)
-  uint32_t* ticket = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) +
-                                                 (size_t)B * ha::kLmMaxCtasPerSample * ha::kLmAcc * sizeof(double));
+  if (!ws || !status) return HA_EINVAL;
   if (ws_bytes < ha::lm_ws_bytes(B)) return HA_ENOSPACE;
-  ha::zero_u32_kernel<<<(B + 255) / 256, 256, 0, st>>>(ticket, B);
-  ha::count_launches(1);
+  ha::lm_begin(ws, B, status, st);        // tickets / step word / zero vector / *status start at zero (cheap, async)
   return ha::lm_step_impl(p, level, sat, grd, grd_conf, ground_table, extrinsics, pose, reset_uv, stats, nullptr, 0,
                           status, ws, ws_bytes, B, /*full=*/true, st);
 }
@@ -1083,15 +1099,12 @@ extern "C" int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel*
                          const float* const* ground_tables, const float* extrinsics, float* pose,
                          const float* reset_uv, float* traj, float* stats, uint32_t* status, void* ws, size_t ws_bytes,
                          void* stream) {
-  if (!p || !sat || !grd || !ground_tables || !pose) return HA_EINVAL;
+  if (!p || !sat || !grd || !ground_tables || !pose || !ws || !status) return HA_EINVAL;
   const int B = p->batch, L = p->n_levels, N = p->n_iters;
   if (B <= 0 || L < 1 || L > HA_MAX_LEVELS || N < 1) return HA_EINVAL;
   if (ws_bytes < ha::lm_ws_bytes(B)) return HA_ENOSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  uint32_t* ticket = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) +
-                                                 (size_t)B * ha::kLmMaxCtasPerSample * ha::kLmAcc * sizeof(double));
-  ha::zero_u32_kernel<<<(B + 255) / 256, 256, 0, st>>>(ticket, B);
-  ha::count_launches(1);
+  ha::lm_begin(ws, B, status, st);
   int k = 0;
   const int outer = p->level_first ? L : N, inner = p->level_first ? N : L;
   for (int o = 0; o < outer; ++o) {

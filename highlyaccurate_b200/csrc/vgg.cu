@@ -157,11 +157,15 @@ __global__ void relu_up2x_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
-// per-sample 1 / max(||x||_2, 1e-12) (VGG.py:511-514, F.normalize): two deterministic stages.
+// per-sample 1 / max(||x||_2, 1e-12) (VGG.py:511-514, F.normalize): two deterministic stages, all pyramid levels of a
+// forward in one launch each (grid.z = level).
 constexpr int kNormChunks = 64;
-__global__ void sumsq_partial_kernel(const float* __restrict__ x, size_t n_per_sample, double* __restrict__ part) {
-  const int b = blockIdx.y;
-  const float4* p = reinterpret_cast<const float4*>(x + (size_t)b * n_per_sample);
+struct NormArgs { const float* x[HA_MAX_LEVELS]; float* scale[HA_MAX_LEVELS]; size_t n_per_sample[HA_MAX_LEVELS]; };
+__global__ void sumsq_partial_kernel(const NormArgs a, int B, double* __restrict__ part) {
+  const int b = blockIdx.y, l = blockIdx.z;
+  if (!a.scale[l]) return;
+  const size_t n_per_sample = a.n_per_sample[l];
+  const float4* p = reinterpret_cast<const float4*>(a.x[l] + (size_t)b * n_per_sample);
   const size_t n4 = n_per_sample / 4;
   const size_t per = (n4 + gridDim.x - 1) / gridDim.x;
   const size_t lo = blockIdx.x * per, hi = min(n4, lo + per);
@@ -177,15 +181,15 @@ __global__ void sumsq_partial_kernel(const float* __restrict__ x, size_t n_per_s
   if (threadIdx.x == 0) {
     double t = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    part[(size_t)b * gridDim.x + blockIdx.x] = t;
+    part[((size_t)l * B + b) * gridDim.x + blockIdx.x] = t;
   }
 }
-__global__ void norm_scale_kernel(const double* __restrict__ part, int chunks, float* __restrict__ scale, int B) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+__global__ void norm_scale_kernel(const NormArgs a, const double* __restrict__ part, int chunks, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y;
+  if (b >= B || !a.scale[l]) return;
   double t = 0;
-  for (int i = 0; i < chunks; ++i) t += part[(size_t)b * chunks + i];
-  scale[b] = (float)(1.0 / fmax(sqrt(t), 1e-12));
+  for (int i = 0; i < chunks; ++i) t += part[((size_t)l * B + b) * chunks + i];
+  a.scale[l][b] = (float)(1.0 / fmax(sqrt(t), 1e-12));
 }
 
 // confidence head (VGG.py:62-81,160-163): sigmoid(-sigmoid(conv3x3_{C->1}(relu(x)))), no bias.
@@ -277,19 +281,29 @@ static int vgg_forward_simt(const char* packed, const PackedLayout& L, const flo
 static int vgg_run(const char* packed, const float* img, int B, int H, int W, int n_levels, int precision,
                    float* const* out_feat, float* const* out_scale, float* const* out_conf, Arena& ar, cudaStream_t st) {
   const PackedLayout L = vgg_packed_layout();
-  double* norm_part = (double*)ar.take((size_t)B * kNormChunks * sizeof(double));
+  double* norm_part = (double*)ar.take((size_t)HA_MAX_LEVELS * B * kNormChunks * sizeof(double));
   int rc;
   if (precision == HA_CONV_FP32_SIMT) rc = vgg_forward_simt(packed, L, img, B, H, W, n_levels, out_feat, ar, st);
   else rc = vgg_forward_tc(packed, L, img, B, H, W, n_levels, precision, out_feat, ar, st);
   if (rc != HA_OK || ar.dry) return rc;
   static const int chans[4] = {256, 128, 64, 16};
+  NormArgs na;
+  bool any_scale = false;
+  for (int l = 0; l < HA_MAX_LEVELS; ++l) {
+    na.x[l] = nullptr; na.scale[l] = nullptr; na.n_per_sample[l] = 0;
+    if (l < n_levels && out_scale && out_scale[l]) {
+      na.x[l] = out_feat[l]; na.scale[l] = out_scale[l];
+      na.n_per_sample[l] = (size_t)(H >> (3 - l)) * (W >> (3 - l)) * chans[l];
+      any_scale = true;
+    }
+  }
+  if (any_scale) {
+    sumsq_partial_kernel<<<dim3(kNormChunks, B, n_levels), 256, 0, st>>>(na, B, norm_part);
+    norm_scale_kernel<<<dim3((B + 127) / 128, n_levels), 128, 0, st>>>(na, norm_part, kNormChunks, B);
+    count_launches(2);
+  }
   for (int l = 0; l < n_levels; ++l) {
     const int h = H >> (3 - l), w = W >> (3 - l), C = chans[l];
-    if (out_scale && out_scale[l]) {
-      sumsq_partial_kernel<<<dim3(kNormChunks, B), 256, 0, st>>>(out_feat[l], (size_t)h * w * C, norm_part);
-      norm_scale_kernel<<<(B + 127) / 128, 128, 0, st>>>(norm_part, kNormChunks, out_scale[l], B);
-      count_launches(2);
-    }
     if (out_conf && out_conf[l]) {
       const size_t n_px = (size_t)B * h * w;
       conf_head_kernel<<<(unsigned)((n_px * 32 + 255) / 256), 256, 0, st>>>(

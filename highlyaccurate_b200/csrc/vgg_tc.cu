@@ -19,11 +19,11 @@
 // smem ring of STAGES k-blocks (full/empty mbarriers), two accumulator stages in TMEM
 // (tmem_full/tmem_empty mbarriers) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
-#include <stdlib.h>
+#include <string.h>
 
-#ifndef HA_CONV_HALO_DEFAULT
-#define HA_CONV_HALO_DEFAULT 1
-#endif
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "vgg_common.cuh"
 
@@ -805,49 +805,83 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled is a pure function of its arguments and costs a few microseconds of host time; a U-Net forward
+// needs 60 of them and the workspace pointers repeat from call to call, so the encoded maps are memoised (bounded).
+struct MapKey {
+  const void* base; unsigned long long d[5], s[4]; unsigned box[5]; int rank;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(&k);
+    size_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey); ++i) h = (h ^ p[i]) * 1099511628211ull;
+    return h;
+  }
+};
+static int encode_cached(CUtensorMap* m, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+                         const cuuint32_t* box, const char* what) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> memo;
+  MapKey k;
+  memset(&k, 0, sizeof(k));
+  k.base = base; k.rank = rank;
+  for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) k.s[i] = strides[i];
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = memo.find(k);
+    if (it != memo.end()) { *m = it->second; return HA_OK; }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return HA_ECUDA; }
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, what); return HA_ECUDA; }
+  std::lock_guard<std::mutex> g(mu);
+  if (memo.size() >= 1024) memo.clear();
+  memo.emplace(k, *m);
+  return HA_OK;
+}
+
 // activation tensor [B][H][W][2][pitch] (fp16), channel slice [coff, coff + cin): dims (C, plane, W, H, B)
 static int make_act_map(CUtensorMap* m, const __half* base, int pitch, int coff, int cin, int B, int H, int W,
                         int box_w = kTileW, int box_h = kTileH) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return HA_ECUDA; }
   cuuint64_t dims[5] = {(cuuint64_t)cin, 2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 4, (cuuint64_t)W * pitch * 4, (cuuint64_t)H * W * pitch * 4};
   cuuint32_t box[5] = {kBlockK, 1, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base + coff), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(activations)"); return HA_ECUDA; }
-  return HA_OK;
+  return encode_cached(m, 5, base + coff, dims, strides, box, "cuTensorMapEncodeTiled(activations)");
 }
 
 // weights [9][cout_pad][cin_pad] fp16: dims (Cin, Cout, tap)
 static int make_weight_map(CUtensorMap* m, const __half* base, int cin_pad, int cout_pad, int block_n, int n_taps) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return HA_ECUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)n_taps};
   cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * cout_pad * 2};
   cuuint32_t box[3] = {kBlockK, (cuuint32_t)block_n, 1};
-  cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(weights)"); return HA_ECUDA; }
-  return HA_OK;
+  return encode_cached(m, 3, base, dims, strides, box, "cuTensorMapEncodeTiled(weights)");
 }
 
-// HA_CONV_HALO: 0 = nine shifted activation tiles per tile for every layer, 1 = halo-tile kernel for the Cout = 64 layers
-static int halo_variant() {
-  const char* e = getenv("HA_CONV_HALO");
-  const int v = e ? atoi(e) : HA_CONV_HALO_DEFAULT;
-  return (v < 0 || v > 1) ? HA_CONV_HALO_DEFAULT : v;
+// cudaFuncSetAttribute once per (kernel instantiation, device): `flag` is that instantiation's bit set of configured devices
+template <typename K>
+static int set_smem_once(K kern, int bytes, std::atomic<unsigned long long>& flag) {
+  int dev = 0;
+  HA_CUDA_TRY(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(flag.load(std::memory_order_acquire) & bit)) {
+    HA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    flag.fetch_or(bit, std::memory_order_release);
+  }
+  return HA_OK;
 }
 
 template <int BLOCK_N, bool SPLIT>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const TcConvArgs& a, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N, SPLIT>;
   auto kern = conv3x3_tc_kernel<BLOCK_N, SPLIT>;
-  HA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  static std::atomic<unsigned long long> configured{0};
+  if (int rc = set_smem_once(kern, Cfg::kSmemBytes, configured)) return rc;
   const int grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
   kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(ta, tbh, tbl, a);
   count_launches(1);
@@ -862,8 +896,7 @@ int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* pa
   if (block_n != 128 && block_n != 64 && block_n != 32 && block_n != 16) return HA_EINVAL;
   CUtensorMap ta, tbh, tbl;
   // Cout = 64 layers in f16x3 mode: halo-tile kernel (one activation load per 64-channel chunk instead of nine)
-  const int halo_mode = halo_variant();
-  const bool halo = halo_mode != 0 && split && cout == 64 && n_taps == 9 && (W % kHaloTW) == 0 && (H % kHaloTH) == 0 && (cin % 64) == 0;
+  const bool halo = split && cout == 64 && n_taps == 9 && (W % kHaloTW) == 0 && (H % kHaloTH) == 0 && (cin % 64) == 0;
   int rc = halo ? make_act_map(&ta, in, in_pitch, in_coff, cin, B, H, W, kHaloBoxW, kHaloBoxH)
                 : make_act_map(&ta, in, in_pitch, in_coff, cin, B, H, W);
   if (rc != HA_OK) return rc;
@@ -886,7 +919,8 @@ int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* pa
     a.tiles_x = W / kHaloTW; a.tiles_y = H / kHaloTH; a.tiles_n = 1;
     a.n_tiles = a.tiles_x * a.tiles_y * B;
     const int grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
-    HA_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemBytes));
+    static std::atomic<unsigned long long> halo_configured{0};
+    if (int rc2 = set_smem_once(conv3x3_tc_halo_kernel, kHaloSmemBytes, halo_configured)) return rc2;
     conv3x3_tc_halo_kernel<<<grid, kTcThreads, kHaloSmemBytes, st>>>(ta, tbh, tbl, a);
     count_launches(1);
     return check_launch("conv3x3_tc_halo_kernel");
@@ -920,8 +954,8 @@ int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, 
   int rc;
 #define HA_TRY(x) do { rc = (x); if (rc != HA_OK) return rc; } while (0)
   // conv0 stays on the CUDA cores (see conv0_kernel); W % 64 == 0 and H % 32 == 0 were checked above
-  // (per device and cheap: set on every call, like the tcgen05 kernels' launchers do)
-  HA_CUDA_TRY(cudaFuncSetAttribute(conv0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC0Smem));
+  static std::atomic<unsigned long long> c0_configured{0};
+  if (int rc0 = set_smem_once(conv0_kernel, kC0Smem, c0_configured)) return rc0;
   conv0_kernel<<<dim3(W / kC0TW, H / kC0TH, B), 256, kC0Smem, st>>>(
       img, reinterpret_cast<const float*>(packed + L.c[L_CONV0].f32), reinterpret_cast<const float*>(packed + L.c[L_CONV0].bias),
       a1, H, W);

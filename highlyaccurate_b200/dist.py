@@ -47,10 +47,53 @@ def shard_reset_draws(draws: torch.Tensor, rank: int, world: int) -> torch.Tenso
     return draws[..., lo:hi].contiguous()
 
 
-def gather_poses(local: torch.Tensor, world: int) -> torch.Tensor:
-    """All-gather the per-rank final poses [b, 3] into [world * b, 3] (equal shards).  This is the
-    only collective of the path; 12 KB at B = 1024, latency bound."""
-    if world == 1 or not dist.is_initialized():
+class PoseComm:
+    """The library's own communicator for the one collective of the path (ha_comm_* / ha_pose_allgather in
+    include/ha_b200.h): NCCL bound by libha_b200.so at run time, no torch types on the data path.  The 128-byte
+    NCCL id travels from rank 0 to the others through the already-initialised torch.distributed group (any
+    out-of-band channel would do); after that torch.distributed is not involved in the gather any more."""
+
+    def __init__(self, rank: int, world: int, device: torch.device):
+        import ctypes as C
+        from . import _lib
+        self._lib, self.rank, self.world, self.device = _lib, rank, world, device
+        L = _lib.lib()
+        ident = (C.c_ubyte * _lib.HA_COMM_ID_BYTES)()
+        if rank == 0:
+            _lib.check(L.ha_comm_unique_id(ident), "ha_comm_unique_id")
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0)
+        ident = (C.c_ubyte * _lib.HA_COMM_ID_BYTES).from_buffer_copy(box[0])
+        handle = C.c_void_p()
+        _lib.check(L.ha_comm_init(C.byref(handle), world, rank, ident, device.index or 0), "ha_comm_init")
+        self.handle = handle
+
+    def allgather(self, local: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """local [b, 3] fp32 (may be the rank's slice of `out`: in place) -> [world * b, 3]."""
+        assert local.is_cuda and local.dtype == torch.float32 and local.is_contiguous() and local.shape[-1] == 3
+        b = local.shape[0]
+        if out is None:
+            out = torch.empty(self.world * b, 3, dtype=torch.float32, device=local.device)
+        st = torch.cuda.current_stream(local.device).cuda_stream
+        self._lib.check(self._lib.lib().ha_pose_allgather(self.handle, local.data_ptr(), out.data_ptr(), b, st),
+                        "ha_pose_allgather")
+        return out
+
+    def close(self):
+        if self.handle is not None:
+            self._lib.lib().ha_comm_destroy(self.handle)
+            self.handle = None
+
+
+def gather_poses(local: torch.Tensor, world: int, comm: "PoseComm | None" = None) -> torch.Tensor:
+    """All-gather the per-rank final poses [b, 3] into [world * b, 3] (equal shards).  This is the only collective of
+    the path; 12 KB at B = 1024, latency bound.  With a PoseComm it goes through the C ABI (ha_pose_allgather);
+    without one (the gloo CPU tests of the host logic) through torch.distributed."""
+    if world == 1:
+        return local
+    if comm is not None:
+        return comm.allgather(local.contiguous())
+    if not dist.is_initialized():
         return local
     out = torch.empty(world * local.shape[0], *local.shape[1:], dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local.contiguous())

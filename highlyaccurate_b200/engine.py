@@ -131,6 +131,7 @@ class LmSetup:
     rotation_range: float
     shift_range_lat: float
     shift_range_lon: float
+    kernel_variant: int = 0    # HaLmParams.kernel_variant: 0 = default kernels, 1 = register-staged validation kernel
 
 
 def dof_of(args, kind: str) -> int:
@@ -205,6 +206,7 @@ def make_params(setup: LmSetup, sat: Pyramid, damping: Sequence[float], side_m: 
     p = HaLmParams()
     p.geometry = {"kitti": _lib.HA_GEOM_KITTI, "ford": _lib.HA_GEOM_FORD, "g2sp": _lib.HA_GEOM_G2SP}[setup.kind]
     p.ori_grd_h, p.ori_grd_w = int(ori_grd_hw[0]), int(ori_grd_hw[1])
+    p.kernel_variant, p.reserved = int(setup.kernel_variant), 0
     p.n_levels, p.n_iters, p.level_first, p.dof = n, setup.n_iters, setup.level_first, setup.dof
     p.using_weight, p.use_hessian, p.batch = setup.using_weight, setup.use_hessian, sat.batch
     p.rotation_range, p.shift_range_lat, p.shift_range_lon = setup.rotation_range, setup.shift_range_lat, setup.shift_range_lon
@@ -228,29 +230,53 @@ def make_params(setup: LmSetup, sat: Pyramid, damping: Sequence[float], side_m: 
 
 
 class LmWorkspace:
-    """Per-device scratch reused across calls (partials + tickets + status word)."""
+    """Scratch of the LM loop (partials, tickets, zero vector, |g|^2 cache), reused across calls."""
 
     def __init__(self):
         self.buf = None
-        self.status = None
 
-    def get(self, B: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    def get(self, B: int, device) -> torch.Tensor:
         need = _lib.lib().ha_lm_workspace_bytes(B)
         if self.buf is None or self.buf.numel() < need or self.buf.device != device:
             self.buf = torch.empty(need, dtype=torch.uint8, device=device)
-        if self.status is None or self.status.device != device:
-            self.status = torch.zeros(1, dtype=torch.int32, device=device)
-        return self.buf, self.status
+        return self.buf
 
 
 _WS = {}
 
 
 def _workspace(device) -> LmWorkspace:
-    key = (device.type, device.index)
+    """One workspace per (device, stream): the C ABI is re-entrant per (device, stream) with caller-owned scratch, so two
+    models (or threads) running on different streams of one device must not share tickets and partials."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     if key not in _WS:
+        if len(_WS) > 64:                       # short-lived streams: do not grow without bound
+            _WS.clear()
         _WS[key] = LmWorkspace()
     return _WS[key]
+
+
+def _new_status(device) -> torch.Tensor:
+    """A status word of its own for every call (ha_lm_run clears it on the stream before OR-ing bits into it), so that
+    results of different calls never alias each other's flags."""
+    return torch.empty(1, dtype=torch.int32, device=device)
+
+
+class LmStatusError(AssertionError):
+    """The reference's `assert torch.sum(mask) > 0` (jacobian.py:172) as seen through the device status word."""
+
+
+def check_status(status: torch.Tensor, where: str = "LM loop") -> int:
+    """Reads a status word (ONE device->host sync; the reference syncs on every step: jacobian.py:172,200,
+    models_kitti.py:1037) and applies the reference's error convention: AssertionError when a step found no satellite
+    sample point in range anywhere in the batch, a printed note for NaN poses.  Returns the bits."""
+    bits = int(status.item())
+    if bits & _lib.HA_STATUS_NO_INRANGE:
+        raise LmStatusError("%s: no sample point of the batch lands inside the satellite map (jacobian.py:172 asserts "
+                            "torch.sum(mask) > 0)" % where)
+    if bits & _lib.HA_STATUS_NAN_POSE:
+        print('theta_new is nan')               # models_kitti.py:1037-1039 prints and carries on
+    return bits
 
 
 @dataclass
@@ -303,7 +329,7 @@ def lm_run(setup: LmSetup, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Te
         else:
             assert tables[i].is_cuda and tables[i].shape[:2] == grd.feats[i].shape[1:3], "ground table / feature shape mismatch"
             tabs[i] = tables[i].data_ptr()
-    ws, status = _workspace(dev).get(B, dev)
+    ws, status = _workspace(dev).get(B, dev), _new_status(dev)
     rc = L.ha_lm_run(C.byref(params), _levels(sat, n), _levels(grd, n), confs, tabs,
                      extrinsics.data_ptr() if extrinsics is not None else None, pose.data_ptr(),
                      reset_uv.data_ptr() if reset_uv is not None else None, traj.data_ptr(),
@@ -334,7 +360,7 @@ def lm_step(setup: LmSetup, level: int, sat: Pyramid, grd: Pyramid, tables: Sequ
         extrinsics = extrinsics.to(dev, torch.float32).contiguous()
     params = make_params(setup, sat, damping, side_m, ori_grd_hw)
     c = grd.confs[level] if (grd.confs and setup.using_weight) else None
-    ws, status = _workspace(dev).get(B, dev)
+    ws, status = _workspace(dev).get(B, dev), _new_status(dev)
     sl, gl = _levels(sat, n), _levels(grd, n)
     rc = L.ha_lm_step(C.byref(params), level, C.byref(sl[level]), C.byref(gl[level]),
                       c.data_ptr() if c is not None else None,
@@ -343,6 +369,7 @@ def lm_step(setup: LmSetup, level: int, sat: Pyramid, grd: Pyramid, tables: Sequ
                       reset_uv.data_ptr() if reset_uv is not None else None, stats.data_ptr(), status.data_ptr(),
                       ws.data_ptr(), ws.numel(), _stream_ptr())
     check(rc, "ha_lm_step")
+    lm_step.last_status = status
     return pose, stats
 
 
@@ -370,7 +397,9 @@ class VggRunner:
         self.max_ws_bytes = max_ws_bytes
 
     def _pack(self, named: dict, device) -> None:
-        key = tuple((n, named[n].data_ptr(), named[n]._version) for n in sorted(named))
+        # `named` is the module's own (cached) name -> Parameter dict: storage address + version counter of every
+        # parameter tell whether a load_state_dict / optimiser step / .to() happened since the weights were packed
+        key = tuple((p.data_ptr(), p._version) for p in named.values())
         if self.packed is not None and key == self.key and self.packed.device == device:
             return
         L = _lib.lib()
@@ -393,7 +422,10 @@ class VggRunner:
         self.key = key
         self._keep = keep
 
-    def __call__(self, named: dict, img: torch.Tensor, n_levels: int, want_conf: bool, precision: str) -> Pyramid:
+    def __call__(self, named: dict, img: torch.Tensor, n_levels: int, want_conf: bool, precision: str,
+                 want_scale: bool = True) -> Pyramid:
+        """`want_scale=False` skips the L2-norm pass (VGG.py:172-175): the S2GP LM step renormalises the sampled and the
+        ground vectors itself (models_kitti.py:982-989), so the per-sample scale cancels there exactly."""
         _require_cuda(img, "image")
         L = _lib.lib()
         dev = img.device
@@ -415,7 +447,7 @@ class VggRunner:
         for l in range(n_levels):
             h, w, ch = H >> (3 - l), W >> (3 - l), PYRAMID_CHANNELS[l]
             feats.append(torch.empty(B, h, w, ch, dtype=torch.float32, device=dev))
-            scales.append(torch.empty(B, dtype=torch.float32, device=dev))
+            scales.append(torch.empty(B, dtype=torch.float32, device=dev) if want_scale else None)
             confs.append(torch.empty(B, h, w, dtype=torch.float32, device=dev) if want_conf else None)
         st = _stream_ptr()
         for b0 in range(0, B, chunk):
@@ -423,7 +455,7 @@ class VggRunner:
             pf, ps, pc = (C.c_void_p * n_levels)(), (C.c_void_p * n_levels)(), (C.c_void_p * n_levels)()
             for l in range(n_levels):
                 pf[l] = feats[l][b0:].data_ptr()
-                ps[l] = scales[l][b0:].data_ptr()
+                ps[l] = scales[l][b0:].data_ptr() if want_scale else None
                 pc[l] = confs[l][b0:].data_ptr() if want_conf else None
             check(L.ha_vgg_forward(self.packed.data_ptr(), img[b0:].data_ptr(), nb, H, W, n_levels, prec, pf, ps, pc,
                                    self.ws.data_ptr(), self.ws.numel(), st), "ha_vgg_forward")

@@ -102,9 +102,13 @@ class LM_S2GP_Ford(nn.Module):
             raise NotImplementedError("estimate_depth is outside the accelerated path")
         if getattr(args, "Optimizer", "LM") != "LM" or getattr(args, "proj", "geo") != "geo":
             raise NotImplementedError("only --Optimizer LM --proj geo is on the accelerated path")
+        if getattr(args, "dropout", 0):
+            # models_ford.py:406-412 subsamples half of the pixels with a numpy permutation when dropout > 0
+            raise NotImplementedError("dropout is outside the accelerated path")
         self.SatFeatureNet = VGGUnet(self.level)
         self.GrdFeatureNet = VGGUnet(self.level)
         self.damping = nn.Parameter(torch.zeros(size=(1, 3), dtype=torch.float32, requires_grad=True))   # :38-39
+        self.check_status = True
         self.ori_grdH, self.ori_grdW = 256, 1024
         if self.level == 2:                                                            # :59-65: [x18, x21] with the /4 and /2 grids
             self._tables_cpu = [engine.ground_table("ford", lv, n_levels=2) for lv in range(2)]
@@ -120,13 +124,15 @@ class LM_S2GP_Ford(nn.Module):
         return self._tables_dev[key]
 
     def extract(self, sat_map, grd_img, want_conf):
-        sat = self.SatFeatureNet.pyramid(sat_map, want_conf=False)
-        grd = self.GrdFeatureNet.pyramid(grd_img, want_conf=want_conf)
+        # the L2 norm of VGG.py:172-175 cancels in LM_update's renormalisation (:420-426): not computed on this path
+        sat = self.SatFeatureNet.pyramid(sat_map, want_conf=False, want_scale=False)
+        grd = self.GrdFeatureNet.pyramid(grd_img, want_conf=want_conf, want_scale=False)
         return sat, grd
 
     def refine(self, sat, grd, satmap_sidelength_meters, R_FL, T_FL, level_first=0, pose0=None, reset_uv=None,
-               want_stats=False) -> engine.LmResult:
+               want_stats=False, kernel_variant=0) -> engine.LmResult:
         setup = engine.setup_from_args(self.args, self.KIND, level_first)
+        setup.kernel_variant = kernel_variant
         lam = engine.resolve_damping(self.args, self.damping, setup.dof)
         ext = engine.ford_extrinsics(R_FL, T_FL)
         res = engine.lm_run(setup, sat, grd, self._tables(sat.feats[0].device), lam, extrinsics=ext,
@@ -159,11 +165,14 @@ class LM_S2GP_Ford(nn.Module):
         """models_ford.py:1028-1036 -> forward_iters_level (:652-866) / forward_level_iters (:868-1026)."""
         if mode == 'train':
             ford = dict(R_FL=R_FL, T_FL=T_FL, side_m=float(satmap_sidelength_meters))
+            coe_heading = 0 if self.args.rotation_range == 0 else self.args.coe_heading        # :843-846, :1000-1003
             return train_forward(self, "ford", sat_map, grd_img_left, gt_shift_u, gt_shift_v, gt_theta, level_first,
-                                 self.args.coe_heading, ford)
+                                 coe_heading, ford)
         want_conf = bool(self.using_weight)
         sat, grd = self.extract(sat_map, grd_img_left, want_conf)
         res = self.refine(sat, grd, satmap_sidelength_meters, R_FL, T_FL, level_first)
+        if self.check_status:                 # the reference's error convention, one host sync per forward (jacobian.py:172)
+            engine.check_status(res.status, "LM_S2GP_Ford.forward")
         traj = res.traj
         # :823-825: shift_lats = shift_us, shift_lons = shift_vs
         shift_lats, shift_lons, thetas = _TrajectoryOutputs.apply(self.damping, False, traj[..., 0], traj[..., 1], traj[..., 2])

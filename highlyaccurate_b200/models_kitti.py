@@ -42,6 +42,10 @@ class LM_S2GP(nn.Module):
         self._tables_dev = {}
         self.meters_per_pixel = [engine.kitti_meter_per_pixel() * (2 ** (3 - lv)) for lv in range(4)]   # :637-640
         self.last_result = None
+        # forward(mode='test') reads the device status word once per call and applies the reference's error convention
+        # (AssertionError of jacobian.py:172, NaN note of :1037); set to False for a fully asynchronous forward and call
+        # engine.check_status(net.last_result.status) when convenient
+        self.check_status = True
 
     # -- helpers ---------------------------------------------------------------------------
     def _tables(self, device):
@@ -51,14 +55,16 @@ class LM_S2GP(nn.Module):
         return self._tables_dev[key]
 
     def extract(self, sat_map, grd_img, want_conf):
-        sat = self.SatFeatureNet.pyramid(sat_map, want_conf=False)
-        grd = self.GrdFeatureNet.pyramid(grd_img, want_conf=want_conf)
+        # the L2 norm of VGG.py:172-175 cancels in LM_update's renormalisation (:982-989): not computed on this path
+        sat = self.SatFeatureNet.pyramid(sat_map, want_conf=False, want_scale=False)
+        grd = self.GrdFeatureNet.pyramid(grd_img, want_conf=want_conf, want_scale=False)
         return sat, grd
 
     def refine(self, sat: engine.Pyramid, grd: engine.Pyramid, level_first=0, pose0=None, reset_uv=None,
-               want_stats=False) -> engine.LmResult:
+               want_stats=False, kernel_variant=0) -> engine.LmResult:
         """The LM loop on already-extracted pyramids (used by forward and by the parity tests)."""
         setup = engine.setup_from_args(self.args, self.KIND, level_first)
+        setup.kernel_variant = kernel_variant
         lam = engine.resolve_damping(self.args, self.damping, setup.dof)
         res = engine.lm_run(setup, sat, grd, self._tables(sat.feats[0].device), lam, pose0=pose0, reset_uv=reset_uv,
                             want_stats=want_stats)
@@ -96,6 +102,8 @@ class LM_S2GP(nn.Module):
         want_conf = bool(self.using_weight)
         sat, grd = self.extract(sat_map, grd_img_left, want_conf)
         res = self.refine(sat, grd, level_first)
+        if self.check_status:
+            engine.check_status(res.status, "LM_S2GP.forward")
         traj = res.traj
         # :1281-1283: shift_lats = shift_vs, shift_lons = shift_us
         shift_lats, shift_lons, thetas = traj[..., 1], traj[..., 0], traj[..., 2]
@@ -126,6 +134,7 @@ class LM_G2SP(nn.Module):
         self.damping = nn.Parameter(args.damping * torch.ones(size=(1, 3), dtype=torch.float32, requires_grad=True))   # :41
         self.meters_per_pixel = [engine.kitti_meter_per_pixel() * (2 ** (3 - lv)) for lv in range(4)]                     # :43-46
         self.last_result = None
+        self.check_status = True
 
     def extract(self, sat_map, grd_img, want_conf):
         sat = self.SatFeatureNet.pyramid(sat_map, want_conf=False)
@@ -191,6 +200,8 @@ class LM_G2SP(nn.Module):
         want_conf = bool(self.using_weight)
         sat, grd = self.extract(sat_map, grd_img_left, want_conf)
         res = self.refine(sat, grd, left_camera_k, ori_grd_hw=tuple(grd_img_left.shape[-2:]))
+        if self.check_status:
+            engine.check_status(res.status, "LM_G2SP.forward")
         traj = res.traj
         shift_lats, shift_lons, thetas = _TrajectoryOutputs.apply(self.damping, False, traj[..., 1], traj[..., 0],
                                                                   traj[..., 2])       # :472-474

@@ -12,10 +12,8 @@
  * Feature layout in HBM: NHWC fp32, i.e. [B][H][W][C] with C contiguous, so that one
  * bilinear tap of one pixel is one contiguous run of 4*C bytes (128-bit loads).
  *
- * Kernel selection knobs (environment, read per call; every setting passes the same parity
- * tests): HA_LM_VARIANT (0 = register-staged LM step kernel, 1-4 = bulk-copy ring kernel, 5 = same without unroll,
- * default 4), HA_CONV_HALO (1 = halo-tile tcgen05 kernel for the Cout = 64 conv layers,
- * default; 0 = nine shifted TMA boxes for every layer).
+ * There are no environment knobs: the one validation switch (HaLmParams.kernel_variant) is an
+ * explicit per-call argument.
  */
 #ifndef HA_B200_H_
 #define HA_B200_H_
@@ -34,7 +32,8 @@ enum {
   HA_EINVAL = -1,      /* bad argument (shape / alignment / unsupported channel count)      */
   HA_ENOSPACE = -2,    /* workspace too small                                              */
   HA_ECUDA = -3,       /* a CUDA runtime / driver call failed (see ha_last_cuda_error)     */
-  HA_EUNSUPPORTED = -4 /* device is not sm_100                                              */
+  HA_EUNSUPPORTED = -4, /* device is not sm_100                                             */
+  HA_ECOMM = -5        /* NCCL missing or an NCCL call failed (see ha_last_cuda_error)      */
 };
 
 /* geometry functors of the satellite->ground warp */
@@ -46,12 +45,17 @@ enum {
                           whole satellite map, LM_update of :333-379 (no renormalisation)     */
 };
 
-/* device status word bits (checked by the host ONCE after the loop, never per step;
- * replaces the reference's per-step host syncs jacobian.py:172,200 / models_kitti.py:1037) */
+/* device status word bits.  ha_lm_run / ha_lm_step CLEAR *status on entry (on the stream) and OR
+ * bits into it; the host reads it ONCE after the loop, never per step (this replaces the
+ * reference's per-step host syncs jacobian.py:172,200 / models_kitti.py:1037). */
 enum {
-  HA_STATUS_NO_INRANGE = 1u, /* some step saw no in-range sample point for some sample     */
-  HA_STATUS_NAN_POSE = 2u,   /* a pose became NaN                                           */
-  HA_STATUS_RESET = 4u       /* an out-of-range shift was re-drawn (models_kitti.py:1030)   */
+  HA_STATUS_NO_INRANGE = 1u, /* some step saw no in-range sample point in the WHOLE batch: the
+                                condition of the reference's `assert torch.sum(mask) > 0`
+                                (jacobian.py:172).  The host mirrors raise AssertionError.     */
+  HA_STATUS_NAN_POSE = 2u,   /* a pose became NaN (the reference prints, models_kitti.py:1037) */
+  HA_STATUS_RESET = 4u,      /* an out-of-range shift was re-drawn (models_kitti.py:1030)      */
+  HA_STATUS_SAMPLE_EMPTY = 8u /* some SAMPLE had no in-range point in some step (its H is 0 and
+                                its pose does not move; the reference carries on silently)     */
 };
 
 /* One pyramid level of one branch. */
@@ -85,10 +89,14 @@ typedef struct {
   float sat_center[HA_MAX_LEVELS];      /* A/2 (KITTI) or A//2 (Ford, G2SP)                  */
   int32_t ori_grd_h, ori_grd_w;         /* G2SP: size of the ground image `left_camera_k` refers to
                                            (models_kitti.py:111-114); ignored otherwise              */
+  int32_t kernel_variant;               /* 0 = default kernels; 1 = register-staged validation kernel for the
+                                           S2GP geometries (same algorithm, other schedule; the parity tests
+                                           hold both to the same bar).  No reference analogue.        */
+  int32_t reserved;                     /* must be 0                                                 */
 } HaLmParams;
 
 /* ---- library ---------------------------------------------------------------------- */
-int ha_version(void);                      /* ABI version, currently 1                     */
+int ha_version(void);                      /* ABI version, currently 2                     */
 const char* ha_error_string(int code);
 const char* ha_last_cuda_error(void);      /* text of the last CUDA failure on this thread  */
 int ha_device_check(int device);           /* HA_OK iff `device` is compute capability 10.x */
@@ -113,7 +121,7 @@ int ha_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, vo
  * reset_uv:  [2][B] uniform(-1,1) draws for this step (models_kitti.py:1028-1029) or NULL
  *            (required iff dof == 3).
  * stats:     NULL or [B][HA_STATS] fp32 diagnostics of this step (see HA_STAT_*).
- * status:    device uint32, OR-ed with HA_STATUS_* bits.
+ * status:    device uint32: cleared on entry, then OR-ed with HA_STATUS_* bits.
  */
 #define HA_STATS 24
 enum { HA_STAT_H = 0 /*9: row-major J~^T W J~*/, HA_STAT_GRAD = 9 /*3: J~^T W r*/, HA_STAT_SAT_NORM = 12,
@@ -161,7 +169,9 @@ size_t ha_vgg_packed_weight_bytes(void);
 int ha_vgg_pack_weights(const HaVggStateDict* sd, void* packed, size_t packed_bytes, void* stream);
 
 /* out_feat[l] : [B][H/2^(3-l)][W/2^(3-l)][C_l] fp32 NHWC, raw (not L2-normalised), C_l =
- * 256,128,64,16; out_scale[l] : [B] = 1/max(||feat||_2, 1e-12) (VGG.py:511-514);
+ * 256,128,64,16; out_scale[l] : [B] = 1/max(||feat||_2, 1e-12) (VGG.py:511-514), or NULL (the
+ * array or an entry) to skip the norm — the S2GP LM step renormalises, so the scale cancels there
+ * (models_kitti.py:982-989) and the S2GP eval path does not ask for it;
  * out_conf[l] : [B][H_l][W_l] fp32 = sigmoid(-sigmoid(conv(relu(feat)))) (VGG.py:160-163)
  * or NULL to skip the confidence heads.  n_levels = 3 (level 3) or 4 (level 4). */
 size_t ha_vgg_workspace_bytes(int B, int H, int W, int n_levels, int precision);
@@ -176,6 +186,24 @@ int ha_vgg_forward(const void* packed_weights, const float* img_nchw, int B, int
 size_t ha_conv3x3_workspace_bytes(int cin, int cout, int B, int H, int W);
 int ha_conv3x3_nhwc(const float* in_nhwc, int cin, const float* w_oihw, const float* bias, float* out_nhwc, int cout,
                     int B, int H, int W, int precision, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- multi-GPU: the ONE collective of the path (the reference has no distributed code) ----
+ * Samples are independent, so ranks own contiguous batch shards and exchange nothing until the
+ * end: one all-gather of the final (shift_u, shift_v, theta) poses.  NCCL (libnccl.so.2) is bound
+ * at run time, from the copy already loaded in the process if there is one (torch's), so a
+ * single-GPU consumer needs no NCCL at all.
+ * ha_comm_unique_id: rank 0 fills `id128_host` (HA_COMM_ID_BYTES bytes, host memory) and ships it
+ *   to the other ranks by any out-of-band means (torch.distributed store, MPI, a file).
+ * ha_comm_init: collective over all ranks; `device` is the CUDA ordinal of this rank.
+ * ha_pose_allgather: local [n_local][3] fp32 -> all [world * n_local][3] fp32, rank-major, on
+ *   `stream`; in place when local == all + rank * n_local * 3 (ha_lm_run can write its final poses
+ *   straight into the gather buffer).
+ */
+#define HA_COMM_ID_BYTES 128
+int ha_comm_unique_id(void* id128_host);
+int ha_comm_init(void** comm, int world, int rank, const void* id128_host, int device);
+int ha_comm_destroy(void* comm);
+int ha_pose_allgather(void* comm, const float* local, float* all, int n_local, void* stream);
 
 #ifdef __cplusplus
 }

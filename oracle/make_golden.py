@@ -508,6 +508,7 @@ def main():
         kat9_train_e2e(rk, "kat9_train_e2e_level_m1", level=-1, N_iters=2)
         kat9_train_e2e_ford(rf)
         kat9_train_e2e_ford(rf, "kat9_train_e2e_ford_level2", level=2, N_iters=2)
+        kat9_train_e2e_ford(rf, "kat9_train_e2e_ford_rot0", rotation_range=0.0)      # coe_heading = 0 (models_ford.py:843-846)
         kat9_train_e2e_g2sp(rk)
 
     GT2 = [[0.3, -0.25, 0.5], [-0.2, 0.4, -0.3]]
@@ -593,6 +594,13 @@ def main():
 
     if want("e2eg2sp"):
         e2e_g2sp(rk)
+    if want("e2ex"):   # round-2 end-to-end goldens: other level selections, config-3 shapes, 8 pairs
+        e2e_more(rk, rf, "e2e_kitti_level_m1", "kitti", 2, 512, seed=2031, level=-1)
+        e2e_more(rk, rf, "e2e_ford_level2", "ford", 2, 512, seed=2032, level=2)
+        e2e_more(rk, rf, "e2e_ford1280", "ford", 2, 1280, seed=2033)
+        e2e_more(rk, rf, "e2e_kitti8", "kitti", 8, 512, seed=2034)
+    if want("b32"):    # config-2 sized planted-pose trajectory (B = 32) from the reference, in chunks
+        planted_b32(rk)
 
     if want("e2e"):    # whole forward through the reference nn.Module (VGG + LM), KITTI + Ford
         sd = {}
@@ -626,6 +634,80 @@ def main():
                                 lats=o.lats.numpy(), lons=o.lons.numpy(), thetas=o.thetas.numpy(),
                                 in_csum=csum(sat, grd))
             print("e2e %s ok (max|d| %.2e) final=%s" % (kind, d, r.tolist()))
+
+
+def e2e_more(rk, rf, name, kind, B, A, seed, **akw):
+    """Whole forward(mode='test') of the UNMODIFIED reference module on B seeded pairs (satellite side A), with the oracle
+    run next to it on the same CPU-RNG state; stores the reference's final poses and the oracle's trajectories."""
+    sd = {}
+    sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+    sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+    sd["damping"] = torch.zeros(1, 3)
+    g = torch.Generator().manual_seed(seed)
+    sat = torch.rand(B, 3, A, A, generator=g)
+    grd = torch.rand(B, 3, 256, 1024, generator=g)
+    a = ref_args(**akw)
+    net = (rk.LM_S2GP if kind == "kitti" else rf.LM_S2GP_Ford)(a)
+    torch.autograd.set_detect_anomaly(False)
+    net.load_state_dict(sd)
+    net.eval()
+    outs, lats, lons, ths = [], [], [], []
+    chunk = 2                                  # bounds the reference's [3,B,C,H,W] Jacobian tensors
+    torch.manual_seed(999)
+    state = torch.get_rng_state()
+    for b0 in range(0, B, chunk):
+        sl = slice(b0, b0 + chunk)
+        with torch.no_grad():
+            torch.set_rng_state(state)         # every chunk sees the draws a 2-pair batch would (no reset fires: checked below)
+            if kind == "kitti":
+                r = net(sat[sl], grd[sl], mode="test")
+                torch.set_rng_state(state)
+                o = O.forward_kitti(sd, sat[sl], grd[sl], o_args(a))
+            else:
+                fd = ford_dict(chunk, A * 0.22)
+                r = net(sat[sl], grd[sl], fd["side_m"], fd["R_FL"], fd["T_FL"], mode="test")
+                torch.set_rng_state(state)
+                o = O.forward_ford(sd, sat[sl], grd[sl], fd["side_m"], fd["R_FL"], fd["T_FL"], o_args(a))
+        outs.append(torch.stack(r, dim=-1))
+        lats.append(o.lats); lons.append(o.lons); ths.append(o.thetas)
+    r = torch.cat(outs)
+    lats, lons, ths = torch.cat(lats), torch.cat(lons), torch.cat(ths)
+    of = torch.stack([lats[:, -1, -1], lons[:, -1, -1], ths[:, -1, -1]], dim=-1)
+    d = close(of, r, 1e-5, name)
+    assert float(torch.stack([lats, lons]).abs().max()) < 2.4, "a reset fired: the chunked RNG replay is not valid for this case"
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), final=r.numpy(), lats=lats.numpy(), lons=lons.numpy(),
+                        thetas=ths.numpy(), in_csum=csum(sat, grd), seed=seed, B=B, A=A)
+    print("%s ok (max|d| %.2e) final[0]=%s" % (name, d, r[0].tolist()))
+
+
+def planted_b32(rk):
+    """BASELINE config-2 size on contractive inputs: 32 planted-pose KITTI pairs through the reference's own
+    project_map_to_grd + LM_update loop (chunks of 4 bound the [3,B,C,H,W] Jacobians) and the float64 oracle."""
+    B, seed = 32, 77
+    a = ref_args()
+    oa = o_args(a)
+    net = rk.LM_S2GP(a)
+    torch.autograd.set_detect_anomaly(False)
+    gen = torch.Generator().manual_seed(5)
+    gt = (torch.rand(B, 3, generator=gen) - 0.5) * 0.8
+    sat, grd = O.planted_case("kitti", B, 512, 3, seed, gt, oa)
+    traj, traj64 = [], []
+    for b0 in range(0, B, 4):
+        s4, g4 = [x[b0:b0 + 4] for x in sat], [x[b0:b0 + 4] for x in grd]
+        c4 = [torch.ones(4, 1, *x.shape[-2:]) for x in g4]
+        torch.manual_seed(4242)
+        with torch.no_grad():
+            t, _ = run_ref_loop(net, "kitti", s4, g4, c4, a)
+        torch.manual_seed(4242)
+        r64 = O.lm_loop("kitti", [x.double() for x in s4], [x.double() for x in g4], [x.double() for x in c4], oa)
+        traj.append(t)
+        traj64.append(torch.stack([r64.lons, r64.lats, r64.thetas], dim=-1))
+        print("  planted_b32 chunk %d: |final - gt| %.2e" % (b0 // 4, float((t[:, -1, -1] - gt[b0:b0 + 4]).abs().max())), flush=True)
+    traj, traj64 = torch.cat(traj), torch.cat(traj64)
+    assert float(traj[..., :2].abs().max()) < 2.4, "a reset fired"
+    np.savez_compressed(os.path.join(GOLD, "kat4_planted_b32.npz"), traj=traj.numpy(), traj64=traj64.numpy(), gt=gt.numpy(),
+                        in_csum=csum(*sat, *grd), seed=seed, B=B)
+    print("kat4_planted_b32 ok: max |final - gt| %.2e" % float((traj[:, -1, -1] - gt).abs().max()))
 
 
 def e2e_g2sp(rk):

@@ -33,15 +33,89 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.EXPORTS) == names
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.ha_version() == 1
+    assert lib.ha_version() == _lib.HA_ABI_VERSION == 2
     assert b"workspace" in lib.ha_error_string(-2)
 
 
+def header_struct_fields(name):
+    """[(field, ctype, count)] of a `typedef struct { ... } name;` in include/ha_b200.h."""
+    src = open(os.path.join(ROOT, "include", "ha_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    body = next(c.split("}")[0] for c in src.split("typedef struct {")[1:] if re.match(r"\s*%s;" % name, c.split("}")[1]))
+    consts = {"HA_MAX_LEVELS": 4, "HA_VGG_N_CONV": 17}
+    out = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        ctype, rest = decl.rsplit(" ", 1)[0], decl.rsplit(" ", 1)[1]
+        if "," in decl:                                   # `int32_t C, H, W` / `int32_t ori_grd_h, ori_grd_w`
+            ctype = decl.split(" ")[0] if not decl.startswith("const") else " ".join(decl.split(" ")[:2])
+            names = decl[len(ctype):].split(",")
+        else:
+            names = [rest]
+        for n in names:
+            n = n.strip()
+            m = re.match(r"(\**)(\w+)(?:\[(\w+)\])?$", n)
+            ptr, ident, cnt = m.group(1), m.group(2), m.group(3)
+            cnt = 1 if cnt is None else int(consts.get(cnt, cnt))
+            out.append((ident, "ptr" if (ptr or "*" in ctype) else ctype.replace("const ", ""), cnt))
+    return out
+
+
+def ctypes_fields(struct):
+    out = []
+    for n, t in struct._fields_:
+        cnt = getattr(t, "_length_", 1)
+        base = getattr(t, "_type_", t) if cnt > 1 else t
+        kind = {ctypes.c_int32: "int32_t", ctypes.c_float: "float", ctypes.c_void_p: "ptr"}[base]
+        out.append((n, kind, cnt))
+    return out
+
+
 def test_struct_layouts_match_header():
-    # sizes implied by include/ha_b200.h (LP64): HaLevel 2 ptr + 3 int32 (+pad), HaLmParams 8 int32 + 18 float
+    """Field for field (name, type, array length, order) against the header, plus the sizes they imply (LP64)."""
+    assert ctypes_fields(_lib.HaLmParams) == header_struct_fields("HaLmParams")
+    assert ctypes_fields(_lib.HaLevel) == header_struct_fields("HaLevel")
+    assert ctypes_fields(_lib.HaVggStateDict) == header_struct_fields("HaVggStateDict")
     assert ctypes.sizeof(_lib.HaLevel) == 32
-    assert ctypes.sizeof(_lib.HaLmParams) == 8 * 4 + (3 + 3 + 4 + 4 + 4) * 4 + 2 * 4
+    assert ctypes.sizeof(_lib.HaLmParams) == 8 * 4 + (3 + 3 + 4 + 4 + 4) * 4 + 4 * 4
     assert ctypes.sizeof(_lib.HaVggStateDict) == 2 * 17 * 8
+
+
+def test_integration_md_stub_matches_the_library():
+    """The ctypes stub INTEGRATION.md tells a maintainer to paste is executed as written (CDLL mocked) and must declare
+    the same structs as highlyaccurate_b200/_lib.py — a stale doc would make the library read past the caller's struct."""
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = next(b for b in re.findall(r"```python\n(.*?)```", md, flags=re.S) if "class HaLmParams" in b)
+    block = "\n".join(l for l in block.splitlines() if not l.startswith(("lib =", "assert lib.")))
+    ns = {}
+    exec(block, ns)
+    for name in ("HaLevel", "HaLmParams"):
+        assert ctypes_fields(ns[name]) == ctypes_fields(getattr(_lib, name)), name
+        assert ctypes.sizeof(ns[name]) == ctypes.sizeof(getattr(_lib, name))
+    assert "ha_version() == %d" % _lib.HA_ABI_VERSION in md
+
+
+def test_status_word_follows_the_reference_error_convention(capsys):
+    """jacobian.py:172 asserts when no sample point of the batch is in range; models_kitti.py:1037 prints on NaN."""
+    assert engine.check_status(torch.tensor([0], dtype=torch.int32)) == 0
+    assert engine.check_status(torch.tensor([_lib.HA_STATUS_RESET | _lib.HA_STATUS_SAMPLE_EMPTY], dtype=torch.int32)) == 12
+    with pytest.raises(AssertionError):
+        engine.check_status(torch.tensor([_lib.HA_STATUS_NO_INRANGE], dtype=torch.int32))
+    engine.check_status(torch.tensor([_lib.HA_STATUS_NAN_POSE], dtype=torch.int32))
+    assert "theta_new is nan" in capsys.readouterr().out
+
+
+def test_out_of_scope_flags_raise_at_construction():
+    """flags outside the accelerated path raise NotImplementedError instead of silently running
+    something else (the Ford model used to accept --dropout)."""
+    for cls in (LM_S2GP, LM_S2GP_Ford):
+        for kw in (dict(dropout=1), dict(Optimizer="SGD"), dict(proj="nn")):
+            with pytest.raises(NotImplementedError):
+                cls(K.ref_args(**kw))
+    with pytest.raises(NotImplementedError):
+        LM_S2GP_Ford(K.ref_args(estimate_depth=1))
 
 
 def test_no_cpu_fallback():
@@ -159,7 +233,7 @@ def test_vggunet_level_selection(level, n_compute, want):
     net = VGGUnet(level)
     seen = {}
 
-    def fake_runner(named, x, n_levels, want_conf, precision):
+    def fake_runner(named, x, n_levels, want_conf, precision, want_scale=True):
         seen["n"] = n_levels
         feats = [torch.full((1, 2, 2, 4), float(i)) for i in range(n_levels)]
         return engine.Pyramid(feats, [torch.full((1,), float(i)) for i in range(n_levels)],

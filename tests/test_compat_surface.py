@@ -178,7 +178,9 @@ def test_train_mode_forward_and_gradients_match_reference(gold_name, kw, level_f
 
 
 @pytest.mark.parametrize("gold_name,kw,gtol", [("kat9_train_e2e_ford", dict(N_iters=1), 1e-4),
-                                               ("kat9_train_e2e_ford_level2", dict(N_iters=2, level=2), 1e-3)])   # models_ford.py:59-65
+                                               ("kat9_train_e2e_ford_level2", dict(N_iters=2, level=2), 1e-3),    # models_ford.py:59-65
+                                               # rotation_range == 0: coe_heading is forced to 0 (models_ford.py:843-846)
+                                               ("kat9_train_e2e_ford_rot0", dict(N_iters=1, rotation_range=0.0), 1e-4)])
 def test_ford_train_mode_forward_and_gradients_match_reference(gold_name, kw, gtol):
     """KAT-9 (Ford): `LM_S2GP_Ford.forward(mode='train')` against the reference's forward + autograd (train_ford.py:229-240),
     at the default level 3 and at level 2 ([x18, x21] with the /4 and /2 ground grids)."""

@@ -41,6 +41,7 @@ def pyramids(c):
 
 
 def run_loop(net, c, sat, grd, **kw):
+    """refine() of the case's model; kw: pose0, reset_uv, want_stats, kernel_variant."""
     if c["kind"] == "ford":
         f = c["ford"]
         return net.refine(sat, grd, f["side_m"], f["R_FL"].to(DEV), f["T_FL"].to(DEV), level_first=c["args"].level_first, **kw)
@@ -290,6 +291,72 @@ def test_end_to_end_g2sp_forward_vs_reference():
     np.testing.assert_allclose(traj[:, 0], ref_traj[:, 0], atol=5e-5)
 
 
+def _e2e_state_dict():
+    sd = {}
+    sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+    sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+    sd["damping"] = torch.zeros(1, 3)
+    return sd
+
+
+# name -> (kind, ctor overrides): whole forward(mode='test') against the UNMODIFIED reference's output
+# (oracle/make_golden.py e2e_more).  Achieved |d| per case is listed in DESIGN.md section 4.
+E2E_MORE = {"e2e_kitti_level_m1": ("kitti", dict(level=-1)),      # VGG.py:192-203: level -1 -> [x15] only
+            "e2e_ford_level2": ("ford", dict(level=2)),            # models_ford.py:59-65: [x18, x21] with the /4, /2 grids
+            "e2e_ford1280": ("ford", {}),                          # BASELINE config-3 shapes: satellite 1280 x 1280
+            "e2e_kitti8": ("kitti", {})}                           # 8 pairs at config-2 shapes
+
+
+@pytest.mark.parametrize("name", list(E2E_MORE))
+def test_end_to_end_more_vs_reference(name):
+    kind, akw = E2E_MORE[name]
+    g = K.load_golden(name)
+    B, A = int(g["B"]), int(g["A"])
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    sat = torch.rand(B, 3, A, A, generator=gen)
+    grd = torch.rand(B, 3, 256, 1024, generator=gen)
+    np.testing.assert_allclose(K.csum(sat, grd), g["in_csum"], rtol=1e-6)
+    net = (LM_S2GP if kind == "kitti" else LM_S2GP_Ford)(K.ref_args(**akw)).to(DEV)
+    net.load_state_dict(_e2e_state_dict())
+    net.eval()
+    torch.manual_seed(999)
+    if kind == "kitti":
+        out = net(sat.to(DEV), grd.to(DEV), mode="test")
+    else:
+        f = K.ford_dict(B, A * 0.22)
+        out = net(sat.to(DEV), grd.to(DEV), f["side_m"], f["R_FL"].to(DEV), f["T_FL"].to(DEV), mode="test")
+    got = torch.stack([o.detach() for o in out], dim=-1).cpu().numpy()
+    traj = net.last_result.traj.cpu().numpy()
+    ref_traj = np.stack([g["lons"], g["lats"], g["thetas"]] if kind == "kitti" else [g["lats"], g["lons"], g["thetas"]], -1)
+    assert traj.shape == ref_traj.shape
+    d_final, d_first = np.abs(got - g["final"]).max(), np.abs(traj[:, 0] - ref_traj[:, 0]).max()
+    print("%s: final max|d| %.2e, first sweep max|d| %.2e" % (name, d_final, d_first))
+    # random-init features are not contractive: the reference's own fp32-vs-fp64 deviation is up to 2.6e-4
+    assert d_final <= 3e-4, d_final
+    assert d_first <= 5e-5, d_first                   # first sweep: before chaos accumulates
+
+
+def test_planted_b32_trajectory_vs_reference():
+    """BASELINE config-2 size (32 KITTI pairs) on contractive inputs: the whole [32, 5, 3, 3] trajectory against the
+    reference's own project_map_to_grd + LM_update loop (tests/golden/kat4_planted_b32.npz) and the float64 truth."""
+    g = K.load_golden("kat4_planted_b32")
+    B = int(g["B"])
+    sat, grd = O.planted_case("kitti", B, 512, 3, int(g["seed"]), g["gt"], O.LMArgs())
+    np.testing.assert_allclose(K.csum(*sat, *grd), g["in_csum"], rtol=1e-6)
+    net = LM_S2GP(K.ref_args()).to(DEV)
+    ps = engine.Pyramid.from_nchw([s.to(DEV) for s in sat])
+    pg = engine.Pyramid.from_nchw([x.to(DEV) for x in grd])
+    res = net.refine(ps, pg, reset_uv=torch.zeros(15, 2, B))
+    assert int(res.status.item()) == 0
+    got, want, truth = res.traj.cpu().numpy(), g["traj"], g["traj64"]
+    fin = np.abs(got[:, -1, -1] - want[:, -1, -1]) / np.maximum(np.abs(want[:, -1, -1]), 1e-2)
+    print("planted B=32: final rel max %.2e, trajectory max|d| vs ref %.2e, vs fp64 %.2e"
+          % (fin.max(), np.abs(got - want).max(), np.abs(got - truth).max()))
+    assert fin.max() < 1e-4                            # the north-star bar on the final pose
+    ok = (np.abs(got - want) <= 1e-4) | (np.abs(got - truth) <= 1.5 * np.abs(want - truth) + 2e-6)
+    assert ok.all(), (np.abs(got - want).max(), np.abs(got - truth).max())
+
+
 def test_full_size_properties():
     """BASELINE config-2 size (B=32, KITTI shapes): planted-pose convergence, determinism, and
     permutation equivariance over the batch — size-independent properties, no oracle run needed."""
@@ -348,44 +415,31 @@ def test_level4_forward_runs():
 
 
 # ------------------------------------------------------------------ LM kernel variants, ragged shapes
-def _with_variant(v, fn):
-    old = os.environ.get("HA_LM_VARIANT")
-    os.environ["HA_LM_VARIANT"] = str(v)
-    try:
-        return fn()
-    finally:
-        if old is None:
-            os.environ.pop("HA_LM_VARIANT", None)
-        else:
-            os.environ["HA_LM_VARIANT"] = old
-
-
 @pytest.mark.parametrize("name", ["kat4_planted_kitti", "kat4_planted_ford", "kat5_weight"])
 def test_lm_kernel_variants_agree(name):
-    """HA_LM_VARIANT 0 (register-staged stream) and 1-5 (bulk-copy ring kernels) are the same algorithm: every
-    variant meets the trajectory bar against the reference's golden output, and they agree with each other to
-    fp32 summation-order noise."""
+    """HaLmParams.kernel_variant 0 (bulk-copy ring kernel, the default) and 1 (register-staged validation kernel) are the
+    same algorithm: both meet the trajectory bar against the reference's golden output, and they agree with each other
+    to fp32 summation-order noise."""
     c = K.build_loop_case(name)
     net = make_net(c)
     sat, grd = pyramids(c)
     want = c["gold"]["traj"][:, -1, -1]
     got = {}
-    for v in range(6):
+    for v in (0, 1):
         torch.manual_seed(K.RESET_SEED)
-        res = _with_variant(v, lambda: run_loop(net, c, sat, grd))
+        res = run_loop(net, c, sat, grd, kernel_variant=v)
         got[v] = res.pose.cpu().numpy()
         if name.startswith("kat4"):
             np.testing.assert_allclose(got[v], want, rtol=1e-4, atol=2e-6, err_msg="variant %d" % v)
         else:
             np.testing.assert_allclose(got[v], want, atol=5e-5, err_msg="variant %d" % v)
-    for v in range(1, 6):
-        np.testing.assert_allclose(got[v], got[0], atol=5e-6 if name.startswith("kat4") else 5e-5, err_msg="variant %d vs 0" % v)
+    np.testing.assert_allclose(got[1], got[0], atol=5e-6 if name.startswith("kat4") else 5e-5)
 
 
 @pytest.mark.parametrize("C,H,W,A", [(64, 20, 72, 40), (32, 12, 40, 24), (16, 10, 36, 20), (128, 6, 44, 16), (256, 4, 20, 12)])
 def test_lm_step_ragged_shapes_vs_oracle(C, H, W, A):
     """Pixel counts that are not multiples of 32 / of a CTA's share, every channel count the kernel is instantiated
-    for, satellite maps smaller than the footprint (clamped and out-of-range taps): one step of every kernel variant
+    for, satellite maps smaller than the footprint (clamped and out-of-range taps): one step of both kernel variants
     against the oracle evaluated in fp64."""
     B = 3
     g = torch.Generator().manual_seed(C + H)
@@ -403,10 +457,46 @@ def test_lm_step_ragged_shapes_vs_oracle(C, H, W, A):
     sat = engine.Pyramid.from_nchw([sf.to(DEV)])
     grd = engine.Pyramid.from_nchw([gf.to(DEV)])
     tab = torch.cat([xyz, mask[..., None]], dim=-1).contiguous().to(DEV)
-    setup = engine.setup_from_args(K.args_from_lmargs(a), "kitti", 0)
-    for v in range(6):
-        got, _ = _with_variant(v, lambda: engine.lm_step(setup, 0, sat, grd, [tab], [a.damping] * 3, pose, reset_uv=torch.zeros(2, B)))
+    for v in (0, 1):
+        setup = engine.setup_from_args(K.args_from_lmargs(a), "kitti", 0)
+        setup.kernel_variant = v
+        got, _ = engine.lm_step(setup, 0, sat, grd, [tab], [a.damping] * 3, pose, reset_uv=torch.zeros(2, B))
         np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-4, atol=2e-5, err_msg="variant %d" % v)
+
+
+def test_status_word_is_per_call_and_raises_like_the_reference():
+    """ADVICE r1 / VERDICT r1: the status word is cleared by every ha_lm_run and owned by its LmResult (no bits leak from
+    an earlier call), and forward() applies the reference's error convention: a batch whose sample points all fall
+    outside the satellite map trips `assert torch.sum(mask) > 0` (jacobian.py:172) -> AssertionError."""
+    c = K.build_loop_case("kat6_reset")
+    net = make_net(c)
+    sat, grd = pyramids(c)
+    pose0 = torch.cat(c["pose0"], dim=1)
+    torch.manual_seed(K.RESET_SEED)
+    r1 = run_loop(net, c, sat, grd, pose0=pose0)
+    assert int(r1.status.item()) & _lib.HA_STATUS_RESET
+    r2 = run_loop(net, c, sat, grd, reset_uv=torch.zeros(c["args"].N_iters * c["L"], 2, c["B"]))     # starts at pose 0: no reset
+    assert int(r2.status.item()) == 0
+    assert int(r1.status.item()) & _lib.HA_STATUS_RESET                     # the earlier result keeps its own word
+    # every ground pixel maps outside a 4 x 4 satellite map placed far away: no in-range point in the whole batch
+    B, C = 2, 16
+    g = torch.Generator().manual_seed(1)
+    sat_small = engine.Pyramid.from_nchw([torch.randn(B, C, 4, 4, generator=g).to(DEV)])
+    grd_small = engine.Pyramid.from_nchw([torch.randn(B, C, 32, 128, generator=g).to(DEV)])
+    setup = engine.setup_from_args(K.ref_args(N_iters=1), "kitti", 0)
+    tabs = [net._tables(torch.device(DEV))[0]]
+    res = engine.lm_run(setup, sat_small, grd_small, tabs, [0.1] * 3, pose0=torch.tensor([[2.4, 2.4, 0.0]] * B),
+                        reset_uv=torch.zeros(1, 2, B))
+    bits = int(res.status.item())
+    assert bits & _lib.HA_STATUS_NO_INRANGE and bits & _lib.HA_STATUS_SAMPLE_EMPTY
+    with pytest.raises(AssertionError):
+        engine.check_status(res.status)
+    # one sample in range, the other not: the reference carries on (its assertion is over the whole batch)
+    res = engine.lm_run(setup, sat_small, grd_small, tabs, [0.1] * 3, pose0=torch.tensor([[2.4, 2.4, 0.0], [0.0, 0.0, 0.0]]),
+                        reset_uv=torch.zeros(1, 2, B))
+    bits = int(res.status.item())
+    assert bits & _lib.HA_STATUS_SAMPLE_EMPTY and not bits & _lib.HA_STATUS_NO_INRANGE
+    assert engine.check_status(res.status) == bits
 
 
 def test_train_mode_on_gpu_matches_reference_gradients():

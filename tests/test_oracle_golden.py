@@ -87,3 +87,29 @@ def test_g2sp_loop_matches_reference(name):
     res = O.lm_loop_g2sp(c["sat"], c["grd"], c["conf"], c["cam_k"], c["args"])
     traj = torch.stack([res.lons, res.lats, res.thetas], dim=-1)
     np.testing.assert_allclose(traj.numpy(), c["gold"]["traj"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("name,kind,akw", [("e2e_kitti_level_m1", "kitti", dict(level=-1)), ("e2e_ford_level2", "ford", dict(level=2))])
+def test_oracle_whole_forward_at_other_level_selections(name, kind, akw):
+    """VGG.py:192-203 level -1 ([x15]) and models_ford.py:59-65 level 2 ([x18, x21] with the /4 and /2 grids): the oracle's
+    whole forward against the unmodified reference's test-mode output (tests/golden, oracle/make_golden.py e2e_more)."""
+    g = K.load_golden(name)
+    B, A = int(g["B"]), int(g["A"])
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    sat = torch.rand(B, 3, A, A, generator=gen)
+    grd = torch.rand(B, 3, 256, 1024, generator=gen)
+    np.testing.assert_allclose(K.csum(sat, grd), g["in_csum"], rtol=1e-6)
+    sd = {}
+    sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+    sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+    sd["damping"] = torch.zeros(1, 3)
+    a = O.LMArgs(**akw)
+    torch.manual_seed(999)
+    with torch.no_grad():
+        if kind == "kitti":
+            o = O.forward_kitti(sd, sat, grd, a)
+        else:
+            f = K.ford_dict(B, A * 0.22)
+            o = O.forward_ford(sd, sat, grd, f["side_m"], f["R_FL"], f["T_FL"], a)
+    got = torch.stack([o.lats[:, -1, -1], o.lons[:, -1, -1], o.thetas[:, -1, -1]], dim=-1).numpy()
+    np.testing.assert_allclose(got, g["final"], rtol=0, atol=1e-5)

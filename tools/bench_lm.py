@@ -2,7 +2,7 @@
 """Micro-benchmark of the fused LM step per pyramid level (random features, B pairs, KITTI shapes).
     python tools/bench_lm.py [B] [reps] [levels] [variants, e.g. 0,1,2]
 Prints per-level time, algorithmic GB/s and fraction of the measured HBM peak for every kernel variant
-(HA_LM_VARIANT, see lm_kernels.cu)."""
+(HaLmParams.kernel_variant: 0 = default ring kernel, 1 = register-staged validation kernel)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -10,7 +10,9 @@ os.environ.setdefault("HA_QUIET", "1")
 import torch
 from highlyaccurate_b200 import engine
 from highlyaccurate_b200.models_kitti import LM_S2GP
-from bench import ref_args, SAT_TEXELS_TOUCHED, PYR_C, peaks
+from bench import ref_args, PYR_C, peaks
+from bench import SAT_TEXELS_TOUCHED as _STT
+SAT_TEXELS_TOUCHED = _STT['kitti']
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
@@ -29,8 +31,8 @@ pk = peaks()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for variant in VARIANTS:
     if variant is not None:
-        os.environ['HA_LM_VARIANT'] = str(variant)
-        print('--- HA_LM_VARIANT=%d  B=%d' % (variant, B))
+        setup.kernel_variant = variant
+        print('--- kernel_variant=%d  B=%d' % (variant, B))
     for lv in range(L):
         for _ in range(3):
             engine.lm_step(setup, lv, sat, grd, tabs, [0.1] * 3, pose, reset_uv=zeros)

@@ -5,8 +5,6 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("HA_QUIET", "1")
-if len(sys.argv) > 2:
-    os.environ["HA_LM_VARIANT"] = sys.argv[2]
 import torch
 from highlyaccurate_b200 import engine
 from highlyaccurate_b200.models_kitti import LM_S2GP
@@ -20,6 +18,8 @@ g = torch.Generator(device=dev).manual_seed(1)
 sat = engine.Pyramid([torch.randn(B, 512 >> (3 - l), 512 >> (3 - l), PYR_C[l], device=dev, generator=g) for l in range(L)], [None] * L)
 grd = engine.Pyramid([torch.randn(B, 256 >> (3 - l), 1024 >> (3 - l), PYR_C[l], device=dev, generator=g) for l in range(L)], [None] * L)
 setup = engine.setup_from_args(net.args, "kitti", 0)
+if len(sys.argv) > 2:
+    setup.kernel_variant = int(sys.argv[2])
 tabs = net._tables(dev)
 pose = (torch.rand(B, 3, device=dev) - 0.5) * 0.4
 zeros = torch.zeros(2, B)
