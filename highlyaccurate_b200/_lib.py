@@ -15,7 +15,7 @@ HA_MAX_LEVELS = 4
 HA_STATS = 24
 HA_VGG_N_CONV = 17
 HA_GEOM_KITTI, HA_GEOM_FORD, HA_GEOM_G2SP = 0, 1, 2
-HA_CONV_FP32_SIMT, HA_CONV_F16X3, HA_CONV_F16 = 0, 1, 2
+HA_CONV_FP32_SIMT, HA_CONV_F16X3, HA_CONV_F16, HA_CONV_F16X3_1CTA = 0, 1, 2, 3
 HA_STATUS_NO_INRANGE, HA_STATUS_NAN_POSE, HA_STATUS_RESET, HA_STATUS_SAMPLE_EMPTY = 1, 2, 4, 8
 HA_COMM_ID_BYTES = 128
 HA_ABI_VERSION = 2

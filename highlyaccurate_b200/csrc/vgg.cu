@@ -340,7 +340,7 @@ extern "C" int ha_vgg_pack_weights(const HaVggStateDict* sd, void* packed, size_
 static bool vgg_shape_ok(int B, int H, int W, int n_levels, int precision) {
   if (B <= 0 || H <= 0 || W <= 0 || (H % 8) || (W % 8)) return false;
   if (n_levels != 3 && n_levels != 4) return false;
-  return precision == HA_CONV_FP32_SIMT || precision == HA_CONV_F16X3 || precision == HA_CONV_F16;
+  return precision == HA_CONV_FP32_SIMT || precision == HA_CONV_F16X3 || precision == HA_CONV_F16 || precision == HA_CONV_F16X3_1CTA;
 }
 
 extern "C" size_t ha_vgg_workspace_bytes(int B, int H, int W, int n_levels, int precision) {

@@ -68,7 +68,7 @@ __global__ void split_act_kernel(const float* __restrict__ in, __half* __restric
 int conv_simt(const float* in, int in_pitch, int in_coff, int cin, const float* w, const float* bias, float* out,
               int out_pitch, int out_coff, int cout, int B, int H, int W, int relu_out, cudaStream_t st);
 int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* packed, const PackedConv& pc, int cout,
-            bool has_bias, const TcOut& o, int B, int H, int W, bool split, cudaStream_t st, int n_taps = 9);
+            bool has_bias, const TcOut& o, int B, int H, int W, bool split, cudaStream_t st, int n_taps = 9, bool pair = true);
 int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, int B, int H, int W, int n_levels,
                    int precision, float* const* out_feat, Arena& ar, cudaStream_t st);
 

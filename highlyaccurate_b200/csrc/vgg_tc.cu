@@ -651,6 +651,381 @@ conv3x3_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   if (warp == 2) { tc_fence_after(); tmem_dealloc_512(tmem_base); }
 }
 
+// ------------------------------------------------------------------------------ CTA-pair halo-tile variant (Cout >= 64)
+// Round-1 ncu (profiles/r01c_conv_full.csv) showed every f16x3 layer bound by UMMA operand reads from shared memory
+// (~69 B/clk per SM whatever the layer): 20 KB per K=16 step on the N = 128 layers (290 cycles against a 192-cycle MMA
+// floor), and the nine-box kernels additionally close to the L2 -> shared-memory fill limit.  This kernel attacks both:
+//  * `tcgen05.mma.cta_group::2`: a pair of CTAs (one thread-block cluster, the two SMs of a TPC) issues ONE M = 256
+//    MMA per step; each CTA supplies its own 128-pixel A tile and only HALF of the B operand, so the weight-side
+//    operand bytes per SM halve: 14 KB per K=16 step instead of 20 (N = 128), 11 instead of 14 (N = 64);
+//  * the halo tile of the kernel above (one 18 x 10-pixel box per 64-channel chunk, nine descriptors into it), so the
+//    activation fill drops 9x and the weights dominate the fill.
+// f16x3 in pair form.  MMA1 = [A_hi(P); A_hi(Q)] x [B_hi | B_lo] (N = 2*BLOCK_N): the pair splits B by columns, so CTA 0
+// holds B_hi and CTA 1 holds B_lo (region `main`, BLOCK_N rows each); accumulator columns [0, BLOCK_N) = hi*hi and
+// [BLOCK_N, 2*BLOCK_N) = hi*lo in BOTH CTAs' TMEM (each for its own pixel tile).  MMA2 = [A_lo(P); A_lo(Q)] x B_hi
+// (N = BLOCK_N) accumulates lo*hi onto the second half; its B operand is split by columns too, so CTA r holds rows
+// [r*BLOCK_N/2, (r+1)*BLOCK_N/2) of B_hi at the same shared-memory offset (region `extra`; CTA 0 loads its half of B_hi a
+// second time, from L2, to keep the two CTAs' layouts identical as the single descriptor requires).
+// Synchronisation: the leader (cluster rank 0) issues every MMA.  TMA loads of the peer complete on the LEADER's full
+// barriers (`cp.async.bulk.tensor...cta_group::2` with the barrier address mapped to rank 0); `tcgen05.commit` with a
+// multicast mask releases shared-memory slots / publishes accumulators in both CTAs; the peer's epilogue warps arrive
+// on the leader's tmem_empty barrier through the cluster address space.
+template <int BLOCK_N>
+struct Halo2Cfg {
+  static constexpr int kBMain = BLOCK_N * kBlockK * 2;            // BLOCK_N rows x 128 B
+  static constexpr int kBExtra = kBMain / 2;
+  static constexpr int kBStage = kBMain + kBExtra;                // 24 KB (N = 128) / 12 KB (N = 64)
+  static constexpr int kAStages = 2;
+  static constexpr int kBStages = BLOCK_N == 128 ? 4 : 9;     // N = 64: nine 12-KB stages = every tap of one 64-channel chunk
+  static constexpr int kSmemBytes = kAStages * 2 * kHaloABytes + kBStages * kBStage + 1024 + 256 + 4 * 32 * 128;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma2_load_5d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                             int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2_512(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2_512(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(addr) : "memory");
+}
+// kind::f16 instruction descriptor for the pair: fp16 x fp16 -> fp32, A and B K-major, M = 256 (128 rows per CTA)
+__host__ __device__ constexpr uint32_t umma2_idesc_f16(int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+// RESIDENT (Cin = 64, N = 64: conv2 and dec2.3): the layer's whole weight set — nine taps x 12 KB per CTA — is loaded
+// into the nine B stages ONCE per CTA and stays there; only the halo tiles stream.  The single-CTA kernels re-read
+// 144 KB of weights from L2 for every 128-pixel tile (9.4 of the 12.9 GB of L2 -> SM traffic of conv2 at B = 32), which
+// held these layers at 51 % tensor-pipe activity; a micro-benchmark (tools/umma_bench.cu) shows the pipe itself
+// sustains the (N = 128, N = 64) instruction pair in 112 cycles against the 188 the streamed kernels achieve.
+template <int BLOCK_N, bool RESIDENT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+conv3x3_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bh,
+                        const __grid_constant__ CUtensorMap tmap_bl, const __grid_constant__ CUtensorMap tmap_bh_half,
+                        const TcConvArgs a) {
+  using Cfg = Halo2Cfg<BLOCK_N>;
+  constexpr int CH = 32, AST = Cfg::kAStages, BST = Cfg::kBStages;
+  constexpr bool TWO = BLOCK_N == 64;            // two MMA-issuing warps, three accumulators per stage (see the issuers)
+  constexpr uint32_t kIssuers = TWO ? 2 : 1;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + AST * 2 * kHaloABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + BST * Cfg::kBStage);
+  uint64_t* a_full = bars;                       // [AST]  TMA (both CTAs) -> leader's MMA warp
+  uint64_t* a_empty = a_full + AST;              // [AST]  MMA commit (multicast) -> both producers
+  uint64_t* b_full = a_empty + AST;              // [BST]
+  uint64_t* b_empty = b_full + BST;              // [BST]
+  uint64_t* tmem_full = b_empty + BST;           // [2]    MMA commit (multicast) -> both epilogues
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]    both epilogues (8 warps) -> leader's MMA warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* staging = smem_b + BST * Cfg::kBStage + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_bh); tma_prefetch_desc(&tmap_bl); tma_prefetch_desc(&tmap_bh_half);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < AST; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, kIssuers); }
+    for (int s = 0; s < BST; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, kIssuers); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, kIssuers); mbar_init(tmem_empty + s, 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2_512(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();                           // the peer's barriers exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // pair-tile u -> (n tile, pixel-tile pair); CTA r of the pair owns pixel tile 2 * pp + r
+  const int n_pairs = a.n_tiles / 2;            // a.n_tiles = pixel tiles * tiles_n, pixel tiles even (host checks)
+  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+  auto decode = [&](int u, int& n_idx, int& x0, int& y0, int& b) {
+    n_idx = u % a.tiles_n;
+    int pt = (u / a.tiles_n) * 2 + (int)rank;
+    x0 = (pt % a.tiles_x) * kHaloTW; pt /= a.tiles_x;
+    y0 = (pt % a.tiles_y) * kHaloTH; b = pt / a.tiles_y;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (one per CTA; completes on the leader's barriers) =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      const CUtensorMap* map_main = leader ? &tmap_bh : &tmap_bl;
+      if (RESIDENT) {                           // one chunk, one N tile: tap t lives in stage t for the whole kernel
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t sw = smem_u32(smem_b) + tap * Cfg::kBStage;
+          const uint32_t bar_b = mapa_rank(smem_u32(b_full + tap), 0);
+          if (leader) mbar_expect_tx(b_full + tap, 2 * Cfg::kBStage);
+          tma2_load_3d(sw, map_main, bar_b, 0, 0, tap);
+          tma2_load_3d(sw + Cfg::kBMain, &tmap_bh_half, bar_b, 0, (int)rank * (BLOCK_N / 2), tap);
+        }
+      }
+      for (int u = pair0; u < n_pairs; u += pair_stride) {
+        int n_idx, x0, y0, b;
+        decode(u, n_idx, x0, y0, b);
+        for (int kc = 0; kc < a.n_kchunks; ++kc) {
+          mbar_wait(a_empty + sa, pa ^ 1);
+          const uint32_t st = smem_u32(smem) + sa * 2 * kHaloABytes;
+          const uint32_t bar_a = mapa_rank(smem_u32(a_full + sa), 0);
+          if (leader) mbar_expect_tx(a_full + sa, 2 * 2 * kHaloBoxBytes);        // both CTAs' halo tiles
+          tma2_load_5d(st, &tmap_a, bar_a, kc * kBlockK, 0, x0 - 1, y0 - 1, b);
+          tma2_load_5d(st + kHaloABytes, &tmap_a, bar_a, kc * kBlockK, 1, x0 - 1, y0 - 1, b);
+          if (++sa == AST) { sa = 0; pa ^= 1; }
+          if (RESIDENT) continue;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(b_empty + sb, pb ^ 1);
+            const uint32_t sw = smem_u32(smem_b) + sb * Cfg::kBStage;
+            const uint32_t bar_b = mapa_rank(smem_u32(b_full + sb), 0);
+            if (leader) mbar_expect_tx(b_full + sb, 2 * Cfg::kBStage);
+            tma2_load_3d(sw, map_main, bar_b, kc * kBlockK, n_idx * BLOCK_N, tap);
+            tma2_load_3d(sw + Cfg::kBMain, &tmap_bh_half, bar_b, kc * kBlockK, n_idx * BLOCK_N + (int)rank * (BLOCK_N / 2), tap);
+            if (++sb == BST) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if ((warp == 1 || (TWO && warp == 3)) && leader) {
+    // ===================== MMA issuers (leader CTA only) =====================
+    // ncu (profiles/r02c): with descriptors built per MMA inside the single-lane region every UTCHMMA cost ~25
+    // instructions (R2UR moves, address arithmetic, the compiler's ELECT loop): the issuing warp needed ~800 cycles per
+    // tap and WAS the critical path — the Cout = 64 layers sat at 49 % tensor-pipe activity with no barrier ever
+    // blocking the issuer, and the N = 128 layers (768 cycles of math per tap) barely hid it.  Now: descriptor fields
+    // are warp-uniform values prepared outside the single-lane region, only the low 32 descriptor bits change per MMA,
+    // the MMAs of a tap go out in one asm block, and for N = 64 (96 cycles of math per K = 16 step) the two MMA streams
+    // are issued by TWO warps: warp 1 issues A_hi x [B_hi | B_lo] into columns [0, 2N), warp 3 issues A_lo x B_hi into
+    // its own columns [2N, 3N) (the epilogue adds the two correction accumulators), so neither stream orders the other.
+    constexpr uint32_t idesc1 = umma2_idesc_f16(2 * BLOCK_N);       // [A_hi; A_hi'] x [B_hi | B_lo]
+    constexpr uint32_t idesc2 = umma2_idesc_f16(BLOCK_N);           // [A_lo; A_lo'] x B_hi
+    constexpr uint32_t kDescHiA = (uint32_t)((kHaloBoxW * 128) >> 4) | (1u << 14) | (2u << 29);   // SBO = one halo row | version 1 | SWIZZLE_128B
+    constexpr uint32_t kDescHiB = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    const bool do1 = warp == 1, do2 = TWO ? warp == 3 : warp == 1;  // which MMA stream(s) this warp issues
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a_field0 = __shfl_sync(0xffffffffu, ((smem_u32(smem) >> 4) & 0x3FFF) | (1u << 16), 0);     // start address | LBO
+    const uint32_t b_field0 = __shfl_sync(0xffffffffu, ((smem_u32(smem_b) >> 4) & 0x3FFF) | (1u << 16), 0);
+    const uint32_t bar_b_empty = __shfl_sync(0xffffffffu, smem_u32(b_empty), 0);
+    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0; int t = 0;
+    for (int u = pair0; u < n_pairs; u += pair_stride, ++t) {
+      const int as = t & 1; const uint32_t aphase = (t >> 1) & 1;
+      mbar_wait(tmem_empty + as, aphase ^ 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_u + as * 256, acc1 = acc0 + (TWO ? 2 * BLOCK_N : BLOCK_N);
+      for (int kc = 0; kc < a.n_kchunks; ++kc) {
+        mbar_wait(a_full + sa, pa);
+        tc_fence_after();
+        const uint32_t a_hi = a_field0 + (uint32_t)(sa * 2 * kHaloABytes >> 4), a_lo = a_hi + (kHaloABytes >> 4);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          if (!RESIDENT || t == 0) {             // resident weights: waited for once, on the first tile
+            mbar_wait(b_full + sb, RESIDENT ? 0u : pb);
+            tc_fence_after();
+          }
+          constexpr int kTapOff[9] = {0, 1, 2, kHaloBoxW, kHaloBoxW + 1, kHaloBoxW + 2, 2 * kHaloBoxW, 2 * kHaloBoxW + 1, 2 * kHaloBoxW + 2};
+          const uint32_t da = a_hi + kTapOff[tap] * (128 >> 4), dl = a_lo + kTapOff[tap] * (128 >> 4);
+          const uint32_t db = b_field0 + (uint32_t)(sb * Cfg::kBStage >> 4), dx = db + (Cfg::kBMain >> 4);
+          const uint32_t first = (kc | tap) != 0 ? 1u : 0u;
+          if (lane == 0) {
+            // the four K = 16 steps of this tap per stream, one asm block each: descriptor high words are constants
+#define HA_MMA4(ACC, DA, DB, HA_, HB_, IDESC, FIRST)                                                                     \
+            asm volatile(                                                                                                \
+                "{\n"                                                                                                    \
+                ".reg .pred p0;\n"                                                                                       \
+                ".reg .b64 da, db;\n"                                                                                    \
+                ".reg .b32 t;\n"                                                                                         \
+                "setp.ne.b32 p0, %5, 0;\n"                                                                               \
+                "mov.b64 da, {%1, %3}; mov.b64 db, {%2, %4};\n"                                                          \
+                "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %6, p0;\n"                                             \
+                "add.u32 t, %1, 2; mov.b64 da, {t, %3}; add.u32 t, %2, 2; mov.b64 db, {t, %4};\n"                        \
+                "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %6, 1;\n"                                              \
+                "add.u32 t, %1, 4; mov.b64 da, {t, %3}; add.u32 t, %2, 4; mov.b64 db, {t, %4};\n"                        \
+                "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %6, 1;\n"                                              \
+                "add.u32 t, %1, 6; mov.b64 da, {t, %3}; add.u32 t, %2, 6; mov.b64 db, {t, %4};\n"                        \
+                "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %6, 1;\n"                                              \
+                "}\n" ::"r"(ACC), "r"(DA), "r"(DB), "n"(HA_), "n"(HB_), "r"(FIRST), "n"(IDESC) : "memory")
+            if (do1) HA_MMA4(acc0, da, db, kDescHiA, kDescHiB, idesc1, first);
+            // one issuer: MMA1's first instruction has zeroed both accumulators; two issuers: the streams are independent
+            if (do2) HA_MMA4(acc1, dl, dx, kDescHiA, kDescHiB, idesc2, TWO ? first : 1u);
+#undef HA_MMA4
+            if (!RESIDENT)
+              asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                           ::"r"(bar_b_empty + sb * 8), "h"((uint16_t)3) : "memory");
+            if (tap == 8) {
+              umma2_commit_mc(a_empty + sa, 3);
+              if (kc == a.n_kchunks - 1) umma2_commit_mc(tmem_full + as, 3);
+            }
+          }
+          __syncwarp();
+          if (++sb == BST) { sb = 0; pb ^= 1; }
+        }
+        if (++sa == AST) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (tile = 16 rows x 8 columns: TMEM lane m = pixel (m / 8, m % 8)) =====================
+    const int q = warp & 3;                               // TMEM lane quarter = tile rows [4 q, 4 q + 4)
+    const uint32_t stg = smem_u32(staging) + (warp - 4) * (32 * 128);
+    const bool any_pool = a.act_pool != nullptr || a.feat_pooled;
+    const uint32_t tmem_empty_leader = mapa_rank(smem_u32(tmem_empty), 0);
+    int t = 0;
+    for (int u = pair0; u < n_pairs; u += pair_stride, ++t) {
+      const int as = t & 1; const uint32_t aphase = (t >> 1) & 1;
+      int n_idx, x0, y0, b;
+      decode(u, n_idx, x0, y0, b);
+      mbar_wait(tmem_full + as, aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_x32(taddr + c0, r0); tmem_ld_x32(taddr + BLOCK_N + c0, r1);
+        tmem_ld_wait();
+        if (TWO) {                               // hi*lo and lo*hi live in separate accumulators: add them first
+          uint32_t r2[32];
+          tmem_ld_x32(taddr + 2 * BLOCK_N + c0, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < CH; ++j) r1[j] = __float_as_uint(__uint_as_float(r1[j]) + __uint_as_float(r2[j]));
+        }
+        const int n0 = n_idx * BLOCK_N + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+          const float4 bz = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float bb[4] = {bz.x, bz.y, bz.z, bz.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[j + e] = fmaf(__uint_as_float(r1[j + e]), kLoInvScale, __uint_as_float(r0[j + e])) + bb[e];
+        }
+        float pv[32];
+        if (any_pool) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));          // x ^ 1
+            pv[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));                   // y ^ 1
+          }
+        }
+        constexpr int N16 = CH / 4, RPI = 32 / N16;
+        const int rsub = lane / N16, piece = lane % N16;
+        auto stage_f32 = [&](const float (&x)[32]) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < N16; ++j)
+            st_shared_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
+                         __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
+          __syncwarp();
+        };
+        auto stage_f16 = [&](const float (&x)[32]) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < N16 / 2; ++j) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split2(x[8 * j + 2 * e], x[8 * j + 2 * e + 1], hi[e], lo[e]);
+            st_shared_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(stg + lane * 128 + (((j + N16 / 2) ^ (lane & 7)) << 4), lo[0], lo[1], lo[2], lo[3]);
+          }
+          __syncwarp();
+        };
+        auto row_of = [&](int i, bool owners) { const int k = i * RPI + rsub; return owners ? 2 * (k & 3) + 16 * (k >> 2) : k; };
+        auto write_f32 = [&](float* base, int hh, int ww, bool owners) {
+          const int n_rows = owners ? 8 : 32;
+#pragma unroll 1
+          for (int i = 0; i < (n_rows + RPI - 1) / RPI; ++i) {
+            if (i * RPI + rsub >= n_rows) continue;
+            const int r = row_of(i, owners);
+            const int yy = y0 + q * 4 + (r >> 3), xx = x0 + (r & 7);
+            const size_t px = owners ? ((size_t)b * hh + yy / 2) * ww + xx / 2 : ((size_t)b * hh + yy) * ww + xx;
+            const uint4 d = ld_shared_v4(stg + r * 128 + ((piece ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(base + px * a.cout + n0 + piece * 4) = d;
+          }
+        };
+        auto write_f16 = [&](__half* base, int pitch, int coff, int hh, int ww, int mode, int dy, int dx) {
+          const bool owners = mode == 1;
+          const int n_rows = owners ? 8 : 32;
+          const int plane = piece / (N16 / 2), pc = piece % (N16 / 2);
+#pragma unroll 2
+          for (int i = 0; i < (n_rows + RPI - 1) / RPI; ++i) {
+            if (i * RPI + rsub >= n_rows) continue;
+            const int r = row_of(i, owners);
+            const int yy = y0 + q * 4 + (r >> 3), xx = x0 + (r & 7);
+            size_t px;
+            if (mode == 0) px = ((size_t)b * hh + yy) * ww + xx;
+            else if (mode == 1) px = ((size_t)b * hh + yy / 2) * ww + xx / 2;
+            else px = ((size_t)b * hh + 2 * yy + dy) * ww + 2 * xx + dx;
+            const uint4 d = ld_shared_v4(stg + r * 128 + ((piece ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(base + (px * 2 + plane) * pitch + coff + n0 + pc * 8) = d;
+          }
+        };
+        if (a.feat) {
+          if (a.feat_pooled) { stage_f32(pv); write_f32(a.feat, a.H / 2, a.W / 2, true); }
+          else { stage_f32(v); write_f32(a.feat, a.H, a.W, false); }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { v[j] = fmaxf(v[j], 0.f); if (any_pool) pv[j] = fmaxf(pv[j], 0.f); }
+        if (a.act_full || (a.act_up && !a.feat_pooled)) {
+          stage_f16(v);
+          if (a.act_full) write_f16(a.act_full, a.af_pitch, a.af_coff, a.H, a.W, 0, 0, 0);
+          if (a.act_up && !a.feat_pooled) {
+#pragma unroll 1
+            for (int dd = 0; dd < 4; ++dd) write_f16(a.act_up, a.au_pitch, a.au_coff, 2 * a.H, 2 * a.W, 2, dd >> 1, dd & 1);
+          }
+        }
+        if ((a.act_pool) || (a.act_up && a.feat_pooled)) {
+          stage_f16(pv);
+          if (a.act_pool) write_f16(a.act_pool, a.ap_pitch, a.ap_coff, a.H / 2, a.W / 2, 1, 0, 0);
+          if (a.act_up && a.feat_pooled) write_f16(a.act_up, a.au_pitch, a.au_coff, a.H, a.W, 0, 0, 0);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {                                     // this accumulator stage is drained in this CTA
+        if (leader) mbar_arrive(tmem_empty + as);
+        else mbar_arrive_cluster(tmem_empty_leader + as * 8);
+      }
+    }
+  }
+  __syncwarp();                                 // lanes of the single-thread roles rejoin their warps: the cluster barrier is .aligned
+  tc_fence_before();
+  cluster_sync_all();                           // no CTA of the pair leaves (or frees TMEM) while the other still computes
+  if (warp == 2) { tc_fence_after(); tmem_dealloc2_512(tmem_base); }
+}
+
 // ------------------------------------------------------------------------------ conv0 + helpers
 // conv0 (3 -> 64, K = 27) is 0.7 % of the FLOPs but writes the largest activation of the network (2.1 GB of hi/lo
 // planes per branch at B = 32), so it is built around its two real limits:
@@ -889,12 +1264,65 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtens
 }
 
 // One 3x3 conv layer on the tensor cores.  in: activation planes (pitch/coff/cin), weights from the packed buffer.
+// CTA-pair launch: 74 clusters of two on a full B200; fewer if the device cannot co-schedule that many pairs.
+template <int BLOCK_N, bool RESIDENT>
+static int launch_halo2(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, const CUtensorMap& tbh_half,
+                        const TcConvArgs& a, cudaStream_t st) {
+  using Cfg = Halo2Cfg<BLOCK_N>;
+  auto kern = conv3x3_tc_halo2_kernel<BLOCK_N, RESIDENT>;
+  static std::atomic<unsigned long long> configured{0};
+  if (int rc = set_smem_once(kern, Cfg::kSmemBytes, configured)) return rc;
+  static std::atomic<int> max_pairs{0};
+  int mp = max_pairs.load(std::memory_order_acquire);
+  if (mp == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = kNumSMs / 2; }
+    mp = n < kNumSMs / 2 ? n : kNumSMs / 2;
+    max_pairs.store(mp, std::memory_order_release);
+  }
+  const int n_pairs = a.n_tiles / 2;
+  const int grid = 2 * (n_pairs < mp ? n_pairs : mp);
+  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(ta, tbh, tbl, tbh_half, a);
+  count_launches(1);
+  return check_launch("conv3x3_tc_halo2_kernel");
+}
+
 int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* packed, const PackedConv& pc, int cout,
-            bool has_bias, const TcOut& o, int B, int H, int W, bool split, cudaStream_t st, int n_taps) {
+            bool has_bias, const TcOut& o, int B, int H, int W, bool split, cudaStream_t st, int n_taps, bool pair) {
   if ((W % kTileW) || (H % kTileH) || (cin % 8) || (in_coff % 8) || (in_pitch % 8)) return HA_EINVAL;
   const int block_n = cout >= 128 ? 128 : cout;
   if (block_n != 128 && block_n != 64 && block_n != 32 && block_n != 16) return HA_EINVAL;
   CUtensorMap ta, tbh, tbl;
+  // Cout >= 64 in f16x3 mode, 16 x 8 pixel tiles in even number: the CTA-pair halo kernel (cta_group::2)
+  if (pair && split && block_n >= 64 && n_taps == 9 && (W % kHaloTW) == 0 && (H % kHaloTH) == 0 && (cin % 64) == 0 &&
+      (((W / kHaloTW) * (H / kHaloTH) * B) % 2) == 0) {
+    CUtensorMap tbh_half;
+    int rc = make_act_map(&ta, in, in_pitch, in_coff, cin, B, H, W, kHaloBoxW, kHaloBoxH);
+    if (rc != HA_OK) return rc;
+    const __half* whi = reinterpret_cast<const __half*>(packed + pc.hi);
+    if ((rc = make_weight_map(&tbh, whi, pc.cin_pad, pc.cout_pad, block_n, n_taps)) != HA_OK) return rc;
+    if ((rc = make_weight_map(&tbl, reinterpret_cast<const __half*>(packed + pc.lo), pc.cin_pad, pc.cout_pad, block_n, n_taps)) != HA_OK) return rc;
+    if ((rc = make_weight_map(&tbh_half, whi, pc.cin_pad, pc.cout_pad, block_n / 2, n_taps)) != HA_OK) return rc;
+    TcConvArgs a;
+    a.bias = has_bias ? reinterpret_cast<const float*>(packed + pc.bias) : nullptr;
+    a.act_full = o.act_full; a.af_pitch = o.af_pitch; a.af_coff = o.af_coff;
+    a.act_pool = o.act_pool; a.ap_pitch = o.ap_pitch; a.ap_coff = o.ap_coff;
+    a.act_up = o.act_up; a.au_pitch = o.au_pitch; a.au_coff = o.au_coff;
+    a.feat = o.feat; a.feat_pooled = o.feat_pooled;
+    a.B = B; a.H = H; a.W = W; a.cout = cout;
+    a.n_kchunks = cin / kBlockK; a.n_taps = 9;
+    a.tiles_x = W / kHaloTW; a.tiles_y = H / kHaloTH; a.tiles_n = cout / block_n;
+    a.n_tiles = a.tiles_x * a.tiles_y * B * a.tiles_n;
+    if (block_n == 128) return launch_halo2<128, false>(ta, tbh, tbl, tbh_half, a, st);
+    return (a.n_kchunks == 1 && a.tiles_n == 1) ? launch_halo2<64, true>(ta, tbh, tbl, tbh_half, a, st)
+                                                : launch_halo2<64, false>(ta, tbh, tbl, tbh_half, a, st);
+  }
   // Cout = 64 layers in f16x3 mode: halo-tile kernel (one activation load per 64-channel chunk instead of nine)
   const bool halo = split && cout == 64 && n_taps == 9 && (W % kHaloTW) == 0 && (H % kHaloTH) == 0 && (cin % 64) == 0;
   int rc = halo ? make_act_map(&ta, in, in_pitch, in_coff, cin, B, H, W, kHaloBoxW, kHaloBoxH)
@@ -935,7 +1363,8 @@ int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* pa
 // Tensor-core schedule of the U-Net; buffer names follow vgg.cu / VGG.py:121-158.
 int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, int B, int H, int W, int n_levels,
                    int precision, float* const* out_feat, Arena& ar, cudaStream_t st) {
-  const bool split = precision == HA_CONV_F16X3;
+  const bool split = precision == HA_CONV_F16X3 || precision == HA_CONV_F16X3_1CTA;
+  const bool pair = precision == HA_CONV_F16X3;
   const size_t px1 = (size_t)B * H * W, px2 = px1 / 4, px4 = px1 / 16;
   auto act = [&](size_t px, int c) { return (__half*)ar.take(px * 2 * c * sizeof(__half)); };
   __half* a1 = act(px1, 64);
@@ -963,7 +1392,7 @@ int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, 
   HA_TRY(check_launch("conv0_kernel"));
   auto conv = [&](int li, const __half* in, int pitch, int coff, const TcOut& o, int h, int w) {
     return conv_tc(in, pitch, coff, kVggConvs[li].cin, packed, L.c[li], kVggConvs[li].cout, kVggConvs[li].has_bias != 0, o,
-                   B, h, w, split, st);
+                   B, h, w, split, st, 9, pair);
   };
   TcOut o;
   o = TcOut(); o.act_pool = cat2; o.ap_pitch = 192; o.ap_coff = 128;                    // x4 = relu(pool(x2))
@@ -1036,12 +1465,13 @@ extern "C" int ha_conv3x3_nhwc(const float* in_nhwc, int cin, const float* w_oih
   if (precision == HA_CONV_FP32_SIMT)
     return ha::conv_simt(in_nhwc, cin, 0, cin, reinterpret_cast<const float*>(base + pc.f32),
                          bias ? reinterpret_cast<const float*>(base + pc.bias) : nullptr, out_nhwc, cout, 0, cout, B, H, W, 0, st);
-  if (precision != HA_CONV_F16X3 && precision != HA_CONV_F16) return HA_EINVAL;
+  if (precision != HA_CONV_F16X3 && precision != HA_CONV_F16 && precision != HA_CONV_F16X3_1CTA) return HA_EINVAL;
   __half* act = reinterpret_cast<__half*>(base + wbytes);
   const size_t n_px = (size_t)B * H * W;
   ha::split_act_kernel<<<ha::kNumSMs * 8, 256, 0, st>>>(in_nhwc, act, cin, n_px);
   ha::count_launches(1);
   ha::TcOut o;
   o.feat = out_nhwc;
-  return ha::conv_tc(act, cin, 0, cin, base, pc, cout, bias != nullptr, o, B, H, W, precision == HA_CONV_F16X3, st);
+  return ha::conv_tc(act, cin, 0, cin, base, pc, cout, bias != nullptr, o, B, H, W, precision != HA_CONV_F16, st, 9,
+                     precision == HA_CONV_F16X3);
 }

@@ -382,7 +382,8 @@ def ford_extrinsics(R_FL: torch.Tensor, T_FL: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------- VGG
 VGG_CONV_NAMES = ["conv0", "conv2", "conv5", "conv7", "conv10", "conv12", "conv14", "conv_dec1.1", "conv_dec1.3",
                   "conv_dec2.1", "conv_dec2.3", "conv_dec3.1", "conv_dec3.3", "conf0.1", "conf1.1", "conf2.1", "conf3.1"]
-PRECISIONS = {"fp32": _lib.HA_CONV_FP32_SIMT, "f16x3": _lib.HA_CONV_F16X3, "f16": _lib.HA_CONV_F16}
+PRECISIONS = {"fp32": _lib.HA_CONV_FP32_SIMT, "f16x3": _lib.HA_CONV_F16X3, "f16": _lib.HA_CONV_F16,
+              "f16x3_1cta": _lib.HA_CONV_F16X3_1CTA}
 
 
 class VggRunner:

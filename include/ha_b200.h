@@ -162,7 +162,9 @@ typedef struct {
 enum {
   HA_CONV_FP32_SIMT = 0,   /* CUDA-core fp32 direct convolution (validation path)            */
   HA_CONV_F16X3 = 1,       /* tcgen05 kind::f16, fp16 hi/lo split, 3 MMAs, fp32-grade result */
-  HA_CONV_F16 = 2          /* tcgen05 kind::f16 single pass (fp16 operands, fp32 accumulate) */
+  HA_CONV_F16 = 2,         /* tcgen05 kind::f16 single pass (fp16 operands, fp32 accumulate) */
+  HA_CONV_F16X3_1CTA = 3   /* HA_CONV_F16X3 on the single-CTA kernels only (cta_group::1): the validation twin of
+                              the CTA-pair (cta_group::2) schedule HA_CONV_F16X3 uses where the shape allows      */
 };
 
 size_t ha_vgg_packed_weight_bytes(void);

@@ -651,7 +651,8 @@ def e2e_more(rk, rf, name, kind, B, A, seed, **akw):
     torch.autograd.set_detect_anomaly(False)
     net.load_state_dict(sd)
     net.eval()
-    outs, lats, lons, ths = [], [], [], []
+    outs, lats, lons, ths, t64 = [], [], [], [], []
+    sd64 = {k: v.double() for k, v in sd.items()}
     chunk = 2                                  # bounds the reference's [3,B,C,H,W] Jacobian tensors
     torch.manual_seed(999)
     state = torch.get_rng_state()
@@ -668,16 +669,25 @@ def e2e_more(rk, rf, name, kind, B, A, seed, **akw):
                 r = net(sat[sl], grd[sl], fd["side_m"], fd["R_FL"], fd["T_FL"], mode="test")
                 torch.set_rng_state(state)
                 o = O.forward_ford(sd, sat[sl], grd[sl], fd["side_m"], fd["R_FL"], fd["T_FL"], o_args(a))
+            # the same algorithm end to end in float64: how far the fp32 reference itself is from the truth on this
+            # (non-contractive, random-weight) input is the noise floor any fp32 implementation is held to
+            torch.set_rng_state(state)
+            if kind == "kitti":
+                o64 = O.forward_kitti(sd64, sat[sl].double(), grd[sl].double(), o_args(a))
+            else:
+                o64 = O.forward_ford(sd64, sat[sl].double(), grd[sl].double(), fd["side_m"], fd["R_FL"].double(), fd["T_FL"].double(), o_args(a))
         outs.append(torch.stack(r, dim=-1))
         lats.append(o.lats); lons.append(o.lons); ths.append(o.thetas)
+        t64.append(torch.stack([o64.lats, o64.lons, o64.thetas], dim=-1))
     r = torch.cat(outs)
     lats, lons, ths = torch.cat(lats), torch.cat(lons), torch.cat(ths)
     of = torch.stack([lats[:, -1, -1], lons[:, -1, -1], ths[:, -1, -1]], dim=-1)
     d = close(of, r, 1e-5, name)
     assert float(torch.stack([lats, lons]).abs().max()) < 2.4, "a reset fired: the chunked RNG replay is not valid for this case"
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), final=r.numpy(), lats=lats.numpy(), lons=lons.numpy(),
-                        thetas=ths.numpy(), in_csum=csum(sat, grd), seed=seed, B=B, A=A)
-    print("%s ok (max|d| %.2e) final[0]=%s" % (name, d, r[0].tolist()))
+                        thetas=ths.numpy(), traj64=torch.cat(t64).numpy(), in_csum=csum(sat, grd), seed=seed, B=B, A=A)
+    n64 = (torch.stack([lats, lons, ths], dim=-1) - torch.cat(t64)).abs().amax(dim=(1, 2, 3))
+    print("%s ok (max|d| %.2e) final[0]=%s; reference fp32 vs fp64 per pair: %s" % (name, d, r[0].tolist(), ["%.1e" % v for v in n64.tolist()]))
 
 
 def planted_b32(rk):

@@ -189,10 +189,14 @@ def test_layout_round_trip():
 
 
 CONV_SHAPES = [(64, 64, 2, 16, 32), (64, 128, 1, 8, 16), (128, 128, 1, 24, 48), (128, 256, 1, 8, 16), (256, 256, 1, 8, 32),
-               (384, 128, 1, 8, 16), (192, 64, 2, 8, 16), (128, 32, 1, 16, 16), (32, 16, 1, 8, 16)]
+               (384, 128, 1, 8, 16), (192, 64, 2, 8, 16), (128, 32, 1, 16, 16), (32, 16, 1, 8, 16),
+               # H % 16 == 0 with an even number of 16 x 8 tiles: the CTA-pair (cta_group::2) halo kernel in f16x3 mode,
+               # N = 64 and N = 128 tiles, one and two N tiles, several K chunks, more pair-tiles than CTA pairs (last one)
+               (64, 128, 1, 32, 32), (128, 128, 2, 16, 16), (128, 256, 1, 32, 16), (256, 256, 1, 16, 32), (384, 128, 1, 16, 32),
+               (192, 64, 1, 32, 16), (64, 64, 3, 96, 128)]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "f16x3", "f16"])
+@pytest.mark.parametrize("precision", ["fp32", "f16x3", "f16x3_1cta", "f16"])
 @pytest.mark.parametrize("cin,cout,B,H,W", CONV_SHAPES)
 def test_single_conv_layer(cin, cout, B, H, W, precision):
     """Every (Cin, Cout) the U-Net uses, through the layer entry point, vs an fp64 torch conv."""
@@ -205,15 +209,15 @@ def test_single_conv_layer(cin, cout, B, H, W, precision):
     err = float((got - want).abs().max() / want.abs().max())
     # f16x3: the split keeps ~22 bits per product, but the tensor pipe's fp32 accumulator truncates, so the
     # error grows with the number of chained MMAs (K = 3456 -> ~5e-6); still fp32-grade, 1000x better than f16
-    tol = {"fp32": 2e-6, "f16x3": 1e-5, "f16": 3e-3}[precision]
+    tol = {"fp32": 2e-6, "f16x3": 1e-5, "f16x3_1cta": 1e-5, "f16": 3e-3}[precision]
     assert err < tol, err
 
 
-VGG_TOL = {"fp32": 2e-5, "f16x3": 5e-5, "f16": 5e-3}
+VGG_TOL = {"fp32": 2e-5, "f16x3": 5e-5, "f16x3_1cta": 5e-5, "f16": 5e-3}
 
 
 def _vgg_precisions():
-    return [p for p in ("fp32", "f16x3", "f16")]
+    return [p for p in ("fp32", "f16x3", "f16x3_1cta", "f16")]
 
 
 @pytest.mark.parametrize("precision", _vgg_precisions())
@@ -329,10 +333,17 @@ def test_end_to_end_more_vs_reference(name):
     traj = net.last_result.traj.cpu().numpy()
     ref_traj = np.stack([g["lons"], g["lats"], g["thetas"]] if kind == "kitti" else [g["lats"], g["lons"], g["thetas"]], -1)
     assert traj.shape == ref_traj.shape
-    d_final, d_first = np.abs(got - g["final"]).max(), np.abs(traj[:, 0] - ref_traj[:, 0]).max()
-    print("%s: final max|d| %.2e, first sweep max|d| %.2e" % (name, d_final, d_first))
-    # random-init features are not contractive: the reference's own fp32-vs-fp64 deviation is up to 2.6e-4
-    assert d_final <= 3e-4, d_final
+    d_first = np.abs(traj[:, 0] - ref_traj[:, 0]).max()
+    # random-init features are not contractive, so the golden carries the same forward in float64: how far the fp32
+    # REFERENCE is from it on each pair (1e-7 ... 4e-4 over these pairs) is the noise floor of that pair.  Per pair the
+    # engine must be within 1e-4 of the reference (the north-star bar) or within twice the reference's own deviation.
+    truth = g["traj64"]                                # [B, N_iters, L, (lat, lon, theta)] in the model's convention
+    ref_mod = np.stack([g["lats"], g["lons"], g["thetas"]], -1)
+    noise = np.abs(ref_mod - truth).reshape(B, -1).max(axis=1)
+    d_pair = np.abs(got - g["final"]).max(axis=1)
+    print("%s: final |d| per pair %s, reference fp32-vs-fp64 per pair %s, first sweep max|d| %.2e"
+          % (name, ["%.1e" % v for v in d_pair], ["%.1e" % v for v in noise], d_first))
+    assert (d_pair <= np.maximum(1e-4, 2.0 * noise)).all(), (d_pair, noise)
     assert d_first <= 5e-5, d_first                   # first sweep: before chaos accumulates
 
 
