@@ -20,13 +20,14 @@ HA_STATUS_NO_INRANGE, HA_STATUS_NAN_POSE, HA_STATUS_RESET, HA_STATUS_SAMPLE_EMPT
 HA_COMM_ID_BYTES = 128
 HA_ABI_VERSION = 2
 STAT_H, STAT_GRAD, STAT_SAT_NORM, STAT_GRD_NORM, STAT_RES_SQ, STAT_DELTA, STAT_N_INRANGE = 0, 9, 12, 13, 14, 15, 18
+STAT_JTG, STAT_RESET_MASK = 19, 22
 
 # every symbol include/ha_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ["ha_version", "ha_error_string", "ha_last_cuda_error", "ha_device_check", "ha_nchw_to_nhwc",
            "ha_nhwc_to_nchw", "ha_lm_workspace_bytes", "ha_lm_step", "ha_lm_run", "ha_vgg_packed_weight_bytes",
            "ha_vgg_pack_weights", "ha_vgg_workspace_bytes", "ha_vgg_forward", "ha_conv3x3_workspace_bytes",
            "ha_conv3x3_nhwc", "ha_launch_count", "ha_comm_unique_id", "ha_comm_init", "ha_comm_destroy",
-           "ha_pose_allgather"]
+           "ha_pose_allgather", "ha_lm_backward_workspace_bytes", "ha_lm_step_backward"]
 
 
 class HaLevel(C.Structure):
@@ -84,6 +85,10 @@ def lib() -> C.CDLL:
     L.ha_conv3x3_workspace_bytes.restype = sz
     L.ha_conv3x3_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.ha_conv3x3_nhwc.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
+    L.ha_lm_backward_workspace_bytes.restype = sz
+    L.ha_lm_backward_workspace_bytes.argtypes = [i32]
+    L.ha_lm_step_backward.argtypes = [C.POINTER(HaLmParams), i32, C.POINTER(HaLevel), C.POINTER(HaLevel), vp, vp, vp, vp, vp,
+                                      vp, vp, vp, vp, vp, sz, vp]
     L.ha_comm_unique_id.argtypes = [vp]
     L.ha_comm_init.argtypes = [C.POINTER(vp), i32, i32, vp, i32]
     L.ha_comm_destroy.argtypes = [vp]

@@ -373,6 +373,61 @@ def lm_step(setup: LmSetup, level: int, sat: Pyramid, grd: Pyramid, tables: Sequ
     return pose, stats
 
 
+class FusedLmLoop(torch.autograd.Function):
+    """The whole LM loop with a native backward (first slice of SURVEY.md section 8 f-1): forward = ha_lm_run with the
+    per-step diagnostics kept, backward = ha_lm_step_backward over the steps in reverse execution order — the adjoint of
+    project_map_to_grd -> jacobian.grid_sample -> LM_update that `loss.backward()` computes in the reference
+    (train_kitti.py:365 through models_kitti.py:1176-1260).  Differentiable inputs: the damping columns `lam` [3] and the
+    L2-normalised NHWC feature pyramids; output: the pose trajectory [B, N_iters, L, 3].  Scope of the slice: S2GP
+    geometries, 3 degrees of freedom, unweighted residuals (`supports()`); everything else keeps the torch path."""
+
+    @staticmethod
+    def supports(setup: LmSetup) -> bool:
+        return setup.kind in ("kitti", "ford") and setup.dof == 3 and not setup.using_weight
+
+    @staticmethod
+    def forward(ctx, setup, tables, extrinsics, side_m, reset_uv, lam, n_levels, *feats):
+        sat = Pyramid([f.detach().contiguous() for f in feats[:n_levels]], [None] * n_levels)
+        grd = Pyramid([f.detach().contiguous() for f in feats[n_levels:]], [None] * n_levels)
+        lam_list = [float(v) for v in lam.detach().reshape(-1).tolist()]
+        res = lm_run(setup, sat, grd, tables, lam_list, extrinsics=extrinsics, side_m=side_m, reset_uv=reset_uv, want_stats=True)
+        ctx.setup, ctx.tables, ctx.extrinsics, ctx.side_m, ctx.lam_list, ctx.n = setup, tables, extrinsics, side_m, lam_list, n_levels
+        ctx.sat, ctx.grd, ctx.res = sat, grd, res
+        ctx.lam_shape = lam.shape
+        return res.traj
+
+    @staticmethod
+    def backward(ctx, gtraj):
+        L = _lib.lib()
+        setup, sat, grd, res, n = ctx.setup, ctx.sat, ctx.grd, ctx.res, ctx.n
+        B = sat.batch
+        dev = sat.feats[0].device
+        gtraj = gtraj.contiguous().float()
+        gsat = [torch.zeros_like(f) for f in sat.feats]
+        ggrd = [torch.zeros_like(f) for f in grd.feats]
+        glam = torch.zeros(B, 3, dtype=torch.float32, device=dev)
+        params = make_params(setup, sat, ctx.lam_list, ctx.side_m)
+        sl, gl = _levels(sat, n), _levels(grd, n)
+        need = L.ha_lm_backward_workspace_bytes(B)
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        ext = ctx.extrinsics.to(dev, torch.float32).contiguous() if ctx.extrinsics is not None else None
+        order = execution_order(setup.n_iters, n, setup.level_first)
+        carry = torch.zeros(B, 3, dtype=torch.float32, device=dev)
+        zero_pose = torch.zeros(B, 3, dtype=torch.float32, device=dev)
+        st = _stream_ptr()
+        for k in range(len(order) - 1, -1, -1):
+            it, lv = order[k]
+            pose_in = zero_pose if k == 0 else res.traj[:, order[k - 1][0], order[k - 1][1]].contiguous()
+            gout = (gtraj[:, it, lv] + carry).contiguous()
+            gin = torch.empty(B, 3, dtype=torch.float32, device=dev)
+            check(L.ha_lm_step_backward(C.byref(params), lv, C.byref(sl[lv]), C.byref(gl[lv]), ctx.tables[lv].data_ptr(),
+                                        ext.data_ptr() if ext is not None else None, pose_in.data_ptr(),
+                                        res.stats[it, lv].data_ptr(), gout.data_ptr(), gin.data_ptr(), gsat[lv].data_ptr(),
+                                        ggrd[lv].data_ptr(), glam.data_ptr(), ws.data_ptr(), need, st), "ha_lm_step_backward")
+            carry = gin
+        return (None, None, None, None, None, glam.sum(dim=0).reshape(ctx.lam_shape), None, *gsat, *ggrd)
+
+
 def ford_extrinsics(R_FL: torch.Tensor, T_FL: torch.Tensor) -> torch.Tensor:
     """[B,3,3] + [B,3] -> [B,12] in the layout ha_lm_* expects."""
     B = R_FL.shape[0]

@@ -34,14 +34,41 @@ class _TrajectoryOutputs(torch.autograd.Function):
         return (None, None) + tuple(None for _ in grads)
 
 
+def train_forward_fused(net, kind, sat_map, grd_img, gt_lat, gt_lon, gt_theta, level_first, coe_theta, ford=None):
+    """`forward(mode='train')` with the native LM backward (engine.FusedLmLoop): the U-Nets run through torch autograd
+    (`VGGUnet.forward_autograd`), the whole LM loop — forward and backward — runs in libha_b200.so, the loss is
+    `loss_func` method 0.  Gradients reach both U-Nets and `damping` exactly as in the reference
+    (tests/test_gpu_parity.py::test_fused_lm_backward_* compare with the reference's autograd, KAT-8 / KAT-9)."""
+    a = net.args
+    sat_feats, _ = net.SatFeatureNet.forward_autograd(sat_map)
+    grd_feats, grd_confs = net.GrdFeatureNet.forward_autograd(grd_img)
+    L = len(sat_feats)
+    dev = sat_map.device
+    setup = engine.setup_from_args(a, kind, level_first)
+    lam = compat.resolve_damping_tensor(a, net.damping, 3, dev).reshape(3)
+    nhwc = [f.permute(0, 2, 3, 1).contiguous() for f in (*sat_feats, *grd_feats)]
+    ext = engine.ford_extrinsics(ford["R_FL"], ford["T_FL"]) if kind == "ford" else None
+    side_m = ford["side_m"] if kind == "ford" else None
+    reset_uv = engine.draw_reset_uv(a.N_iters * L, sat_map.shape[0])          # same CPU-RNG consumption as the reference
+    t = engine.FusedLmLoop.apply(setup, net._tables(dev), ext, side_m, reset_uv, lam, L, *nhwc)
+    lats, lons = (t[..., 1], t[..., 0]) if kind == "kitti" else (t[..., 0], t[..., 1])
+    r = loss_func(a.loss_method, None, None, None, lats, lons, t[..., 2], gt_lat, gt_lon, gt_theta, None, None,
+                  a.coe_shift_lat, a.coe_shift_lon, coe_theta, a.coe_L1, a.coe_L2, a.coe_L3, a.coe_L4)
+    return (*r, grd_confs)
+
+
 def train_forward(net, kind, sat_map, grd_img, gt_lat, gt_lon, gt_theta, level_first, coe_theta, ford=None):
-    """`forward(mode='train')` of LM_S2GP / LM_S2GP_Ford until the fused backward exists: the reference's own
+    """`forward(mode='train')` of LM_S2GP / LM_S2GP_Ford: on CUDA tensors, for the configurations the native LM backward
+    covers (engine.FusedLmLoop.supports: 3 degrees of freedom, unweighted), the fused path above; otherwise the reference's own
     computation (models_kitti.py:1141-1314 / models_ford.py:652-866) — U-Nets through `VGGUnet.forward_autograd`,
     then `project_map_to_grd` -> mask -> bottom-half crop -> `LM_update` chained over (iteration, level) without
     detaching — so that `loss.backward()` reaches both U-Nets and `damping` exactly as in the reference
     (tests/test_compat_surface.py checks loss and gradients against the reference's autograd).  It runs at the
     reference's speed: the accelerated engine is the test / eval path.  Returns the reference's 14-tuple."""
     a = net.args
+    if sat_map.is_cuda and getattr(net, "fused_backward", True) and \
+            engine.FusedLmLoop.supports(engine.setup_from_args(a, kind, level_first)):
+        return train_forward_fused(net, kind, sat_map, grd_img, gt_lat, gt_lon, gt_theta, level_first, coe_theta, ford)
     sat_feats, _ = net.SatFeatureNet.forward_autograd(sat_map)
     grd_feats, grd_confs = net.GrdFeatureNet.forward_autograd(grd_img)
     B, L = sat_map.shape[0], len(sat_feats)

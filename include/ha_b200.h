@@ -125,7 +125,9 @@ int ha_nhwc_to_nchw(const float* src, float* dst, int B, int C, int H, int W, vo
  */
 #define HA_STATS 24
 enum { HA_STAT_H = 0 /*9: row-major J~^T W J~*/, HA_STAT_GRAD = 9 /*3: J~^T W r*/, HA_STAT_SAT_NORM = 12,
-       HA_STAT_GRD_NORM = 13, HA_STAT_RES_SQ = 14, HA_STAT_DELTA = 15 /*3*/, HA_STAT_N_INRANGE = 18 };
+       HA_STAT_GRD_NORM = 13, HA_STAT_RES_SQ = 14, HA_STAT_DELTA = 15 /*3*/, HA_STAT_N_INRANGE = 18,
+       HA_STAT_JTG = 19 /*3: the J~^T W g~ part of GRAD (GRAD = J~^T W s~ - J~^T W g~), kept for the backward pass*/,
+       HA_STAT_RESET_MASK = 22 /*bit 0: shift_u was re-drawn in this step, bit 1: shift_v*/ };
 
 size_t ha_lm_workspace_bytes(int B);
 int ha_lm_step(const HaLmParams* p, int level, const HaLevel* sat, const HaLevel* grd, const float* grd_conf,
@@ -146,6 +148,23 @@ int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel* grd, const
               const float* const* ground_tables, const float* extrinsics, float* pose,
               const float* reset_uv, float* traj, float* stats, uint32_t* status, void* ws, size_t ws_bytes,
               void* stream);
+
+/* ---- backward of ONE fused LM step (training; first slice of SURVEY.md section 8 f-1) -----------------
+ * The adjoint of ha_lm_step for the S2GP geometries with all three degrees of freedom and unweighted residuals
+ * (the defaults of train_kitti.py / train_ford.py): what `loss.backward()` (train_kitti.py:365) computes through
+ * project_map_to_grd -> jacobian.grid_sample -> LM_update of one (iteration, level).  Features must be the
+ * L2-normalised ones (HaLevel.scale == NULL); the U-Net backward stays with the caller.
+ * pose_in:   [B][3] the pose the forward step started from.
+ * stats:     [B][HA_STATS] the forward step's diagnostics (ha_lm_run / ha_lm_step with stats != NULL).
+ * gpose_out: [B][3] adjoint of the step's output pose;  gpose_in: [B][3] adjoint of pose_in (written).
+ * gsat / ggrd: gradients w.r.t. the satellite / ground features of this level, same layout as the features,
+ *            ACCUMULATED into (zero them before the first step of a backward sweep).
+ * glambda:   [B][3] adjoint of the damping columns, accumulated.
+ */
+size_t ha_lm_backward_workspace_bytes(int B);
+int ha_lm_step_backward(const HaLmParams* p, int level, const HaLevel* sat, const HaLevel* grd, const float* ground_table,
+                        const float* extrinsics, const float* pose_in, const float* stats, const float* gpose_out,
+                        float* gpose_in, float* gsat, float* ggrd, float* glambda, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- VGG16 U-Net feature extractor (VGG.py:13-203, estimate_depth off) ----------------- */
 /* Weights, packed by ha_vgg_pack_weights from the reference's state-dict tensors (OIHW fp32,
