@@ -27,7 +27,8 @@ EXPORTS = ["ha_version", "ha_error_string", "ha_last_cuda_error", "ha_device_che
            "ha_nhwc_to_nchw", "ha_lm_workspace_bytes", "ha_lm_step", "ha_lm_run", "ha_vgg_packed_weight_bytes",
            "ha_vgg_pack_weights", "ha_vgg_workspace_bytes", "ha_vgg_forward", "ha_conv3x3_workspace_bytes",
            "ha_conv3x3_nhwc", "ha_launch_count", "ha_comm_unique_id", "ha_comm_init", "ha_comm_destroy",
-           "ha_pose_allgather", "ha_lm_backward_workspace_bytes", "ha_lm_step_backward"]
+           "ha_pose_allgather", "ha_lm_backward_workspace_bytes", "ha_lm_step_backward",
+           "ha_pose_loss", "ha_pose_loss_backward"]
 
 
 class HaLevel(C.Structure):
@@ -89,6 +90,8 @@ def lib() -> C.CDLL:
     L.ha_lm_backward_workspace_bytes.argtypes = [i32]
     L.ha_lm_step_backward.argtypes = [C.POINTER(HaLmParams), i32, C.POINTER(HaLevel), C.POINTER(HaLevel), vp, vp, vp, vp, vp,
                                       vp, vp, vp, vp, vp, sz, vp]
+    L.ha_pose_loss.argtypes = [vp, vp, i32, i32, i32, C.POINTER(C.c_float), vp, vp, vp]
+    L.ha_pose_loss_backward.argtypes = [vp, vp, i32, i32, i32, C.POINTER(C.c_float), vp, vp, vp, vp]
     L.ha_comm_unique_id.argtypes = [vp]
     L.ha_comm_init.argtypes = [C.POINTER(vp), i32, i32, vp, i32]
     L.ha_comm_destroy.argtypes = [vp]

@@ -284,3 +284,65 @@ extern "C" int ha_lm_step_backward(const HaLmParams* p, int level, const HaLevel
   count_launches(2);
   return check_launch("lm_step_backward_kernel");
 }
+
+// ------------------------------------------------------------------------------------ pose loss (loss_func, method 0)
+// models_ford.py:1041-1093 with loss_method 0 (shared by KITTI through models_kitti.py:16): direct supervision of the
+// pose trajectory.  err[n][l][k] = mean_b |traj[b][n][l][k] - gt[b][k]|  (k over the engine's (shift_u, shift_v, theta)),
+// loss = mean_{n,l} sum_k coe[k] err[n][l][k].  One launch forward, one backward; the rest of the reference's 13-tuple
+// (decreases, last-step values) are differences / slices of `err`.
+namespace ha {
+
+__global__ void pose_loss_kernel(const float* __restrict__ traj, const float* __restrict__ gt, int B, int NL, float c0, float c1,
+                                 float c2, float* __restrict__ err, float* __restrict__ loss) {
+  // one warp per (n, l, k); the block's first thread then folds the NL * 3 means into the loss (deterministic order)
+  __shared__ float e_s[HA_MAX_LEVELS * 64 * 3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int item = warp; item < NL * 3; item += nwarps) {
+    const int k = item % 3, nl = item / 3;
+    double acc = 0.0;
+    for (int b = lane; b < B; b += 32) acc += fabs((double)traj[((size_t)b * NL + nl) * 3 + k] - (double)gt[b * 3 + k]);
+    acc = warp_sum(acc);
+    if (lane == 0) { const float m = (float)(acc / B); err[item] = m; e_s[item] = m; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int nl = 0; nl < NL; ++nl) t += (double)c0 * e_s[nl * 3] + (double)c1 * e_s[nl * 3 + 1] + (double)c2 * e_s[nl * 3 + 2];
+    *loss = (float)(t / NL);
+  }
+}
+
+__global__ void pose_loss_backward_kernel(const float* __restrict__ traj, const float* __restrict__ gt, int B, int NL, float c0,
+                                          float c1, float c2, const float* __restrict__ gerr, const float* __restrict__ gloss,
+                                          float* __restrict__ gtraj) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * NL * 3) return;
+  const int k = i % 3, nl = (i / 3) % NL, b = i / (3 * NL);
+  const float d = traj[i] - gt[b * 3 + k];
+  const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);        // torch.abs: zero sub-gradient at 0
+  const float coe = k == 0 ? c0 : (k == 1 ? c1 : c2);
+  const float up = (gerr ? gerr[nl * 3 + k] : 0.f) + (gloss ? gloss[0] * coe / NL : 0.f);
+  gtraj[i] = up * sgn / B;
+}
+
+}  // namespace ha
+
+extern "C" int ha_pose_loss(const float* traj, const float* gt, int B, int n_iters, int n_levels, const float* coe3_host,
+                            float* err, float* loss, void* stream) {
+  if (!traj || !gt || !coe3_host || !err || !loss || B <= 0 || n_iters <= 0 || n_levels <= 0 || n_levels > HA_MAX_LEVELS) return HA_EINVAL;
+  if (n_iters > 64) return HA_EINVAL;
+  ha::pose_loss_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(traj, gt, B, n_iters * n_levels, coe3_host[0],
+                                                                               coe3_host[1], coe3_host[2], err, loss);
+  ha::count_launches(1);
+  return ha::check_launch("pose_loss_kernel");
+}
+
+extern "C" int ha_pose_loss_backward(const float* traj, const float* gt, int B, int n_iters, int n_levels, const float* coe3_host,
+                                     const float* gerr, const float* gloss, float* gtraj, void* stream) {
+  if (!traj || !gt || !coe3_host || !gtraj || B <= 0 || n_iters <= 0 || n_levels <= 0) return HA_EINVAL;
+  const int n = B * n_iters * n_levels * 3;
+  ha::pose_loss_backward_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      traj, gt, B, n_iters * n_levels, coe3_host[0], coe3_host[1], coe3_host[2], gerr, gloss, gtraj);
+  ha::count_launches(1);
+  return ha::check_launch("pose_loss_backward_kernel");
+}

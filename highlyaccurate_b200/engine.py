@@ -428,6 +428,40 @@ class FusedLmLoop(torch.autograd.Function):
         return (None, None, None, None, None, glam.sum(dim=0).reshape(ctx.lam_shape), None, *gsat, *ggrd)
 
 
+class PoseLoss(torch.autograd.Function):
+    """loss_func with loss_method 0 (models_ford.py:1041-1093) as one kernel forward (ha_pose_loss) and one backward
+    (ha_pose_loss_backward).  traj [B, N_iters, L, 3] and gt [B, 3] share a component order; coe = the three loss
+    coefficients in that order.  Returns (loss scalar, err [N_iters, L, 3] = mean_b |traj - gt|)."""
+
+    @staticmethod
+    def forward(ctx, traj, gt, coe):
+        _require_cuda(traj, "trajectory")
+        traj = traj.contiguous().float()
+        gt = gt.to(traj.device, torch.float32).contiguous()
+        B, N, Lv, _ = traj.shape
+        err = torch.empty(N, Lv, 3, dtype=torch.float32, device=traj.device)
+        loss = torch.empty((), dtype=torch.float32, device=traj.device)
+        c = (C.c_float * 3)(*[float(v) for v in coe])
+        check(_lib.lib().ha_pose_loss(traj.data_ptr(), gt.data_ptr(), B, N, Lv, c, err.data_ptr(), loss.data_ptr(), _stream_ptr()),
+              "ha_pose_loss")
+        ctx.save_for_backward(traj, gt)
+        ctx.coe = [float(v) for v in coe]
+        return loss, err
+
+    @staticmethod
+    def backward(ctx, gloss, gerr):
+        traj, gt = ctx.saved_tensors
+        B, N, Lv, _ = traj.shape
+        gtraj = torch.empty_like(traj)
+        c = (C.c_float * 3)(*ctx.coe)
+        gl = gloss.contiguous().float() if gloss is not None else None
+        ge = gerr.contiguous().float() if gerr is not None else None
+        check(_lib.lib().ha_pose_loss_backward(traj.data_ptr(), gt.data_ptr(), B, N, Lv, c, ge.data_ptr() if ge is not None else None,
+                                               gl.data_ptr() if gl is not None else None, gtraj.data_ptr(), _stream_ptr()),
+              "ha_pose_loss_backward")
+        return gtraj, None, None
+
+
 def ford_extrinsics(R_FL: torch.Tensor, T_FL: torch.Tensor) -> torch.Tensor:
     """[B,3,3] + [B,3] -> [B,12] in the layout ha_lm_* expects."""
     B = R_FL.shape[0]

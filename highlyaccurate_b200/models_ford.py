@@ -51,9 +51,16 @@ def train_forward_fused(net, kind, sat_map, grd_img, gt_lat, gt_lon, gt_theta, l
     side_m = ford["side_m"] if kind == "ford" else None
     reset_uv = engine.draw_reset_uv(a.N_iters * L, sat_map.shape[0])          # same CPU-RNG consumption as the reference
     t = engine.FusedLmLoop.apply(setup, net._tables(dev), ext, side_m, reset_uv, lam, L, *nhwc)
-    lats, lons = (t[..., 1], t[..., 0]) if kind == "kitti" else (t[..., 0], t[..., 1])
-    r = loss_func(a.loss_method, None, None, None, lats, lons, t[..., 2], gt_lat, gt_lon, gt_theta, None, None,
-                  a.coe_shift_lat, a.coe_shift_lon, coe_theta, a.coe_L1, a.coe_L2, a.coe_L3, a.coe_L4)
+    if a.loss_method != 0:
+        raise NotImplementedError("loss_method %r is outside the accelerated path" % (a.loss_method,))
+    # the trajectory is already [B, N_iters, L, (su, sv, theta)]: KITTI lat = sv, lon = su (models_kitti.py:1281-1283);
+    # Ford lat = su, lon = sv (models_ford.py:823-825) -> the fused pose loss takes it as is, no re-stacking
+    if kind == "kitti":
+        gt = torch.stack([gt_lon, gt_lat, gt_theta], dim=-1)
+        r = _loss_tuple(t, gt, (a.coe_shift_lon, a.coe_shift_lat, coe_theta), (1, 0, 2))
+    else:
+        gt = torch.stack([gt_lat, gt_lon, gt_theta], dim=-1)
+        r = _loss_tuple(t, gt, (a.coe_shift_lat, a.coe_shift_lon, coe_theta), (0, 1, 2))
     return (*r, grd_confs)
 
 
@@ -104,11 +111,27 @@ def loss_func(loss_method, ref_feat_list, pred_feat_dict, gt_feat_dict, shift_la
     materialised warped features the fused engine never builds and are out of scope."""
     if loss_method != 0:
         raise NotImplementedError("loss_method %r is outside the accelerated path" % (loss_method,))
+    if shift_lats.is_cuda:
+        # one kernel forward, one backward (engine.PoseLoss -> ha_pose_loss); the stack is the only torch op left
+        traj = torch.stack([shift_lats, shift_lons, thetas], dim=-1)
+        gt = torch.stack([gt_shift_lat, gt_shift_lon, gt_theta], dim=-1)
+        return _loss_tuple(traj, gt, (coe_shift_lat, coe_shift_lon, coe_theta), (0, 1, 2))
     err = [torch.abs(t - g[:, None, None]).mean(dim=0)
            for t, g in ((shift_lats, gt_shift_lat), (shift_lons, gt_shift_lon), (thetas, gt_theta))]   # [N_iters, Level] each
     lat_e, lon_e, th_e = err
     total = coe_shift_lat * lat_e + coe_shift_lon * lon_e + coe_theta * th_e
     return (total.mean(), total[0] - total[-1], lat_e[0] - lat_e[-1], lon_e[0] - lon_e[-1], th_e[0] - th_e[-1],
+            total[-1], lat_e[-1], lon_e[-1], th_e[-1], None, None, None, None)
+
+
+def _loss_tuple(traj, gt, coe, order):
+    """The reference's 13-tuple from the fused pose-loss kernel.  traj [B, N_iters, L, 3] / gt [B, 3] / coe share one
+    component order; `order` = positions of (lat, lon, theta) in it."""
+    loss, err = engine.PoseLoss.apply(traj, gt, coe)
+    ilat, ilon, ith = order
+    lat_e, lon_e, th_e = err[..., ilat], err[..., ilon], err[..., ith]
+    total = coe[ilat] * lat_e + coe[ilon] * lon_e + coe[ith] * th_e
+    return (loss, total[0] - total[-1], lat_e[0] - lat_e[-1], lon_e[0] - lon_e[-1], th_e[0] - th_e[-1],
             total[-1], lat_e[-1], lon_e[-1], th_e[-1], None, None, None, None)
 
 

@@ -166,6 +166,17 @@ int ha_lm_step_backward(const HaLmParams* p, int level, const HaLevel* sat, cons
                         const float* extrinsics, const float* pose_in, const float* stats, const float* gpose_out,
                         float* gpose_in, float* gsat, float* ggrd, float* glambda, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- pose loss: loss_func with loss_method 0 (models_ford.py:1041-1093; KITTI imports it, models_kitti.py:16) ----
+ * traj: [B][n_iters][n_levels][3] device (shift_u, shift_v, theta);  gt: [B][3] device, same component order.
+ * coe3_host: HOST array of the three loss coefficients in that order.
+ * err:  [n_iters][n_levels][3] device = mean_b |traj - gt|;  loss: device scalar = mean_{n,l} sum_k coe[k] err[n][l][k].
+ * The rest of the reference's 13-tuple (decreases, last-iteration values) are differences / slices of `err`.
+ * Backward: gtraj = (gerr[n][l][k] + gloss coe[k] / (n_iters n_levels)) sign(traj - gt) / B; gerr / gloss may be NULL. */
+int ha_pose_loss(const float* traj, const float* gt, int B, int n_iters, int n_levels, const float* coe3_host, float* err,
+                 float* loss, void* stream);
+int ha_pose_loss_backward(const float* traj, const float* gt, int B, int n_iters, int n_levels, const float* coe3_host,
+                          const float* gerr, const float* gloss, float* gtraj, void* stream);
+
 /* ---- VGG16 U-Net feature extractor (VGG.py:13-203, estimate_depth off) ----------------- */
 /* Weights, packed by ha_vgg_pack_weights from the reference's state-dict tensors (OIHW fp32,
  * DEVICE pointers). */

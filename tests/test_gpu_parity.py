@@ -549,6 +549,26 @@ def test_fused_lm_backward_matches_reference_autograd():
             np.testing.assert_allclose(float(gflat.double().abs().sum()), gold["%s%d_sum" % (name, lv)][1], rtol=5e-3)
 
 
+def test_fused_pose_loss_matches_torch():
+    """loss_func method 0 as one kernel (ha_pose_loss / ha_pose_loss_backward) against the reference's tensor expression
+    (models_ford.py:1074-1093) — the 13-tuple and the gradient w.r.t. the trajectories."""
+    from highlyaccurate_b200.models_ford import loss_func
+    g = torch.Generator().manual_seed(3)
+    lat, lon, th = (torch.randn(5, 4, 3, generator=g) for _ in range(3))
+    gl, go, gt = (torch.randn(5, generator=g) for _ in range(3))
+    ref_in = [t.clone().requires_grad_(True) for t in (lat, lon, th)]
+    dev_in = [t.clone().to(DEV).requires_grad_(True) for t in (lat, lon, th)]
+    ref = loss_func(0, None, None, None, *ref_in, gl, go, gt, None, None, 100, 50, 25)              # CPU tensors: torch expression
+    out = loss_func(0, None, None, None, *dev_in, gl.to(DEV), go.to(DEV), gt.to(DEV), None, None, 100, 50, 25)
+    assert len(out) == 13 and all(o is None for o in out[9:])
+    for r, o in zip(ref[:9], out[:9]):
+        torch.testing.assert_close(o.cpu(), r, rtol=1e-5, atol=1e-6)
+    (ref[0] + ref[5].sum()).backward()
+    (out[0] + out[5].sum()).backward()
+    for r, o in zip(ref_in, dev_in):
+        torch.testing.assert_close(o.grad.cpu(), r.grad, rtol=1e-5, atol=1e-7)
+
+
 def test_fused_lm_backward_ford_train_mode():
     """`LM_S2GP_Ford.forward(mode='train')` on the GPU = torch U-Nets + the native LM loop forward/backward, against the
     reference's CPU forward + autograd (KAT-9 Ford): loss, last-step errors and weight gradients."""
