@@ -676,7 +676,7 @@ struct Halo2Cfg {
   static constexpr int kBExtra = kBMain / 2;
   static constexpr int kBStage = kBMain + kBExtra;                // 24 KB (N = 128) / 12 KB (N = 64)
   static constexpr int kAStages = 2;
-  static constexpr int kBStages = BLOCK_N == 128 ? 4 : 9;     // N = 64: nine 12-KB stages = every tap of one 64-channel chunk
+  static constexpr int kBStages = BLOCK_N == 128 ? 4 : 9;     // N <= 64: nine stages = every tap of one 64-channel chunk
   static constexpr int kSmemBytes = kAStages * 2 * kHaloABytes + kBStages * kBStage + 1024 + 256 + 4 * 32 * 128;
 };
 
@@ -741,7 +741,7 @@ conv3x3_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                         const TcConvArgs a) {
   using Cfg = Halo2Cfg<BLOCK_N>;
   constexpr int CH = 32, AST = Cfg::kAStages, BST = Cfg::kBStages;
-  constexpr bool TWO = BLOCK_N == 64;            // two MMA-issuing warps, three accumulators per stage (see the issuers)
+  constexpr bool TWO = BLOCK_N <= 64;            // two MMA-issuing warps, three accumulators per stage (see the issuers)
   constexpr uint32_t kIssuers = TWO ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1299,8 +1299,8 @@ int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* pa
   const int block_n = cout >= 128 ? 128 : cout;
   if (block_n != 128 && block_n != 64 && block_n != 32 && block_n != 16) return HA_EINVAL;
   CUtensorMap ta, tbh, tbl;
-  // Cout >= 64 in f16x3 mode, 16 x 8 pixel tiles in even number: the CTA-pair halo kernel (cta_group::2)
-  if (pair && split && block_n >= 64 && n_taps == 9 && (W % kHaloTW) == 0 && (H % kHaloTH) == 0 && (cin % 64) == 0 &&
+  // Cout >= 32 in f16x3 mode, 16 x 8 pixel tiles in even number: the CTA-pair halo kernel (cta_group::2)
+  if (pair && split && block_n >= 32 && n_taps == 9 && (W % kHaloTW) == 0 && (H % kHaloTH) == 0 && (cin % 64) == 0 &&
       (((W / kHaloTW) * (H / kHaloTH) * B) % 2) == 0) {
     CUtensorMap tbh_half;
     int rc = make_act_map(&ta, in, in_pitch, in_coff, cin, B, H, W, kHaloBoxW, kHaloBoxH);
@@ -1320,6 +1320,7 @@ int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* pa
     a.tiles_x = W / kHaloTW; a.tiles_y = H / kHaloTH; a.tiles_n = cout / block_n;
     a.n_tiles = a.tiles_x * a.tiles_y * B * a.tiles_n;
     if (block_n == 128) return launch_halo2<128, false>(ta, tbh, tbl, tbh_half, a, st);
+    if (block_n == 32) return launch_halo2<32, false>(ta, tbh, tbl, tbh_half, a, st);
     return (a.n_kchunks == 1 && a.tiles_n == 1) ? launch_halo2<64, true>(ta, tbh, tbl, tbh_half, a, st)
                                                 : launch_halo2<64, false>(ta, tbh, tbl, tbh_half, a, st);
   }

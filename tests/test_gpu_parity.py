@@ -193,7 +193,7 @@ CONV_SHAPES = [(64, 64, 2, 16, 32), (64, 128, 1, 8, 16), (128, 128, 1, 24, 48), 
                # H % 16 == 0 with an even number of 16 x 8 tiles: the CTA-pair (cta_group::2) halo kernel in f16x3 mode,
                # N = 64 and N = 128 tiles, one and two N tiles, several K chunks, more pair-tiles than CTA pairs (last one)
                (64, 128, 1, 32, 32), (128, 128, 2, 16, 16), (128, 256, 1, 32, 16), (256, 256, 1, 16, 32), (384, 128, 1, 16, 32),
-               (192, 64, 1, 32, 16), (64, 64, 3, 96, 128)]
+               (192, 64, 1, 32, 16), (64, 64, 3, 96, 128), (128, 32, 2, 32, 32)]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "f16x3", "f16x3_1cta", "f16"])

@@ -6,9 +6,16 @@
 #   bench [config]    bench.py (default kitti32)            launches   ncu launch list of a short bench run
 #   ncu_conv          ncu --set full of the tcgen05 convs   ncu_lm     ncu --set full of the LM step (B=256)
 #   lm_ab             tools/bench_lm.py at B=256 and B=32   sanitize   compute-sanitizer memcheck on smoke()
+#   ncu_lm_stress / ncu_conv_stress   BASELINE config 5 captures    convab     per-layer CTA-pair vs single-CTA conv table
 TAG=$1; shift
 OUT=gpurun_out
-mkdir -p $OUT
+REP=/tmp/ha_ncu          # raw .ncu-rep files stay on the box (gpurun copies back at most 64 MiB): their raw pages come back as CSV
+mkdir -p $OUT $REP
+export_rep() {           # export_rep <name>: raw metrics page (+ SASS source page of the first launch) of $REP/<name>.ncu-rep
+  ncu -i $REP/$1.ncu-rep --page raw --csv > $OUT/$1_raw.csv 2>/dev/null
+  ncu -i $REP/$1.ncu-rep --page source --csv --print-source sass --launch-skip ${2:-0} --launch-count 1 > $OUT/$1_sass.csv 2>/dev/null
+  ls -la $REP/$1.ncu-rep $OUT/$1_raw.csv | cut -c20-120
+}
 summarise_bench() {
 python - "$1" <<'PY'
 import json, sys
@@ -41,13 +48,26 @@ while [ $# -gt 0 ]; do
         python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $OUT/launches_$TAG.log 2>&1
       tail -1 $OUT/launches_$TAG.log | cut -c1-200 ;;
     ncu_conv)
-      timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc -s 40 -c 10 -f -o $OUT/conv_$TAG \
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc -s 40 -c 10 -f -o $REP/conv_$TAG \
         python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > $OUT/conv_$TAG.log 2>&1
-      tail -1 $OUT/conv_$TAG.log | cut -c1-200 ;;
+      export_rep conv_$TAG 2 ;;
     ncu_lm)
-      timeout 400 ncu --set full --clock-control none --import-source on -k regex:lm_step -s 3 -c 3 -f -o $OUT/lm_$TAG \
+      timeout 400 ncu --set full --clock-control none --import-source on -k regex:lm_step -s 3 -c 3 -f -o $REP/lm_$TAG \
         python tools/ncu_lm.py 256 > $OUT/lm_$TAG.log 2>&1
-      tail -1 $OUT/lm_$TAG.log | cut -c1-200 ;;
+      export_rep lm_$TAG 2 ;;
+    ncu_lm_stress)   # BASELINE config 5: 4-level pyramid, 512 pairs per GPU
+      timeout 600 ncu --set full --clock-control none -k regex:lm_step -s 4 -c 4 -f -o $REP/lmstress_$TAG \
+        python tools/ncu_lm.py 512 0 4 > $OUT/lmstress_$TAG.log 2>&1
+      export_rep lmstress_$TAG 3 ;;
+    ncu_conv_stress) # the level-4 U-Net (adds conv_dec3) at a batch ncu can replay: tensor-pipe metrics per conv launch
+      timeout 900 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_elapsed.max,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_tensor.sum \
+        --clock-control none -k regex:conv -s 52 -c 26 --csv --log-file $OUT/convstress_$TAG.csv \
+        python bench.py --config stress --batch 32 --steps 1 --warmup 3 --no-cpu-baseline --no-extras > $OUT/convstress_$TAG.log 2>&1
+      tail -1 $OUT/convstress_$TAG.log | cut -c1-200 ;;
+    convab)
+      timeout 400 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_elapsed.max,lts__t_bytes.sum \
+        --clock-control none -k regex:conv3x3 --csv --log-file $OUT/convab_$TAG.csv python tools/bench_conv.py 32 1 > $OUT/convab_$TAG.log 2>&1
+      python tools/convab_report.py $OUT/convab_$TAG.csv ;;
     lm_ab)
       timeout 400 python tools/bench_lm.py 256 10 3 0,1 > $OUT/bench_lm_b256_$TAG.log 2>&1
       timeout 400 python tools/bench_lm.py 32 20 3 0 > $OUT/bench_lm_b32_$TAG.log 2>&1

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Launch the fused LM step once per pyramid level (after one warm-up sweep) for an ncu capture:
-    ncu --set full --import-source on -k regex:lm_step -s 3 -c 3 -o out python tools/ncu_lm.py [B] [variant]"""
+    ncu --set full --import-source on -k regex:lm_step -s L -c L -o out python tools/ncu_lm.py [B] [variant] [levels]
+(levels = 3: BASELINE config 2 pyramid; 4: config 5, adds the C = 16 full-resolution level)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,7 +12,7 @@ from highlyaccurate_b200.models_kitti import LM_S2GP
 from bench import ref_args, PYR_C
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-L = 3
+L = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dev = torch.device("cuda:0")
 net = LM_S2GP(ref_args(5, L)).to(dev)
 g = torch.Generator(device=dev).manual_seed(1)

@@ -44,11 +44,15 @@ if os.path.exists(f):
             o.write("| `%s` | %d | %.1f | %.1f%% | %.1f |\n" % (k[:70], len(v), sum(v), 100 * sum(v) / tot, sum(v) / len(v)))
     print("wrote launches summary")
 
-for kind in ("conv", "lm"):
+for kind in ("conv", "lm", "lmstress"):
     rep = os.path.join(G, "%s_%s.ncu-rep" % (kind, tag))
-    if not os.path.exists(rep):
+    raw = os.path.join(G, "%s_%s_raw.csv" % (kind, tag))       # exported on the GPU box by tools/gpu_session.sh
+    if os.path.exists(raw):
+        out = open(raw).read()
+    elif os.path.exists(rep):
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    else:
         continue
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = [hdr.index(k) for k in KEEP if k in hdr]
