@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libha_b200.so")
 STAMP = os.path.join(LIB_DIR, "libha_b200.stamp")
 SOURCES = ["api.cu", "comm.cu", "lm_backward.cu", "lm_kernels.cu", "vgg.cu", "vgg_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("HA_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -422,7 +422,7 @@ constexpr int lm_ring_bytes() { return kLmWarps * NSLOT * kLmIterBytes + kLmWarp
 #define HA_KEEP32(x) asm volatile("" : "+r"(x))
 #define HA_KEEP64(x) asm volatile("" : "+l"(x))
 
-template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF, bool WEIGHTED, int UNR = 1>
+template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF, bool WEIGHTED, int UNR = 1, bool SCAL = false>
 __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmStepArgs a) {
   constexpr int LPP = C / 16;                      // lanes per pixel: every lane owns 4 x 4 channels
   constexpr int PPW = 32 / LPP;                    // pixels processed together by one warp
@@ -509,6 +509,7 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
   f32x2 p_aa = 0, p_ab = 0, p_bb = 0, p_sa = 0, p_sb = 0, p_ga = 0, p_gb = 0;   // per-pixel channel sums
   float4 sc = make_float4(0, 0, 0, 0);             // (wx, ny, tx, ty) of the pixel being reduced
   float om = 1.f;
+  float rs[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // SCAL: the twelve pose sums as scalars
 
   auto accumulate = [&](const PixelLoads& L) {
     const f32x2 wx2 = dup2(sc.x), ny2 = dup2(sc.y);
@@ -536,6 +537,18 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
     }
     // d(u,v)/dsu and /dsv are per-sample constants, only d/dtheta = (tx, ty) varies per pixel, so
     // J^T J splits into sum(G), sum(G t), sum(t^T G t) and the last CTA applies the constant rows.
+    if (SCAL) {
+      // the channel-pair halves are added first and the per-pixel fold runs on scalars: 26 one-cycle operations instead of
+      // 19 packed ones (two FMA-pipe cycles each), and the twelve running sums take 12 registers instead of 24
+      const float aa = sum2(p_aa), ab = sum2(p_ab), bb = sum2(p_bb), sa = sum2(p_sa), sb = sum2(p_sb), ga = sum2(p_ga), gb = sum2(p_gb);
+      const float tx = sc.z, ty = sc.w;
+      const float gx = fmaf(ab, ty, aa * tx), gy = fmaf(bb, ty, ab * tx);
+      rs[0] += aa; rs[1] += ab; rs[2] += bb; rs[3] += gx; rs[4] += gy; rs[5] = fmaf(ty, gy, fmaf(tx, gx, rs[5]));
+      rs[6] += sa; rs[7] += sb; rs[8] = fmaf(sb, ty, fmaf(sa, tx, rs[8]));
+      rs[9] += ga; rs[10] += gb; rs[11] = fmaf(gb, ty, fmaf(ga, tx, rs[11]));
+      p_aa = p_ab = p_bb = p_sa = p_sb = p_ga = p_gb = 0ull;
+      return;
+    }
     const f32x2 tx2 = dup2(sc.z), ty2 = dup2(sc.w);
     inc2(A_aa, p_aa); inc2(A_ab, p_ab); inc2(A_bb, p_bb);
     const f32x2 gx = fma2(p_ab, ty2, mul2(p_aa, tx2)), gy = fma2(p_bb, ty2, mul2(p_ab, tx2));
@@ -659,6 +672,10 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
   {
     double v[kLmAcc] = {sum2(A_aa), sum2(A_ab), sum2(A_bb), sum2(B_x), sum2(B_y), sum2(C_tt), sum2(S_a), sum2(S_b),
                         sum2(S_t), sum2(G_a), sum2(G_b), sum2(G_t), sum2(SS), sum2(GG), sum2(SG), cnt};
+    if (SCAL) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) v[i] = rs[i];
+    }
     lm_reduce_and_solve<GEOM, FULL>(a, b, v, kp, fp, su, sv, th);
   }
 }
@@ -667,9 +684,9 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
 // prefetched to L1, 3 CTAs per SM, pixel loop unrolled by two; 1 = lm_step_kernel (register-staged ground stream; the
 // validation twin, and always the kernel for G2SP).  Other ring depths (3, 5, 6, 8 slots), L2-only prefetch, no prefetch,
 // 2 and 4 CTAs per SM and the non-unrolled loop were measured and dropped.
-template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF, bool WEIGHTED, int UNR>
+template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF, bool WEIGHTED, int UNR, bool SCAL = false>
 static int launch_v4w(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
-  auto kern = lm_step_v4_kernel<GEOM, C, FULL, NSLOT, MINB, PF, WEIGHTED, UNR>;
+  auto kern = lm_step_v4_kernel<GEOM, C, FULL, NSLOT, MINB, PF, WEIGHTED, UNR, SCAL>;
   constexpr int smem = lm_ring_bytes<NSLOT>();
   // function attributes are per (device function, device): one bit per device ordinal, per instantiation
   static std::atomic<unsigned long long> configured{0};
@@ -691,10 +708,10 @@ static int launch_v4w(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
   return HA_OK;
 }
 
-template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF, int UNR = 1>
+template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF, int UNR = 1, bool SCAL = false>
 static int launch_v4(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
-  return a.using_weight ? launch_v4w<GEOM, C, FULL, NSLOT, MINB, PF, true, UNR>(grid, st, a)
-                        : launch_v4w<GEOM, C, FULL, NSLOT, MINB, PF, false, UNR>(grid, st, a);
+  return a.using_weight ? launch_v4w<GEOM, C, FULL, NSLOT, MINB, PF, true, UNR, SCAL>(grid, st, a)
+                        : launch_v4w<GEOM, C, FULL, NSLOT, MINB, PF, false, UNR, SCAL>(grid, st, a);
 }
 
 template <int GEOM, int C, bool FULL>
@@ -704,7 +721,12 @@ static int launch_variant(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
     return HA_OK;
   } else {
     if (a.variant == 1) { lm_step_kernel<GEOM, C, FULL><<<grid, kLmThreads, 0, st>>>(a); return HA_OK; }
-    return launch_v4<GEOM, C, FULL, 4, 3, 2, 2>(grid, st, a);
+#ifdef HA_LM_DEV_VARIANTS      // A/B builds only (tools/bench_lm.py); measured at B = 256 on B200, per level 0 / 1 / 2 in us:
+    if (a.variant == 2) return launch_v4<GEOM, C, FULL, 4, 3, 2, 2, false>(grid, st, a);  // packed per-pixel fold: 256 / 414 / 759
+    if (a.variant == 3) return launch_v4<GEOM, C, FULL, 4, 4, 2, 2, true>(grid, st, a);   // 4 CTAs/SM, 128 regs, spills: 265 / 415 / 756
+    if (a.variant == 4) return launch_v4<GEOM, C, FULL, 3, 4, 2, 2, true>(grid, st, a);   // same with a 3-slot ring: 253 / 403 / 739
+#endif
+    return launch_v4<GEOM, C, FULL, 4, 3, 2, 2, true>(grid, st, a);                       // scalar per-pixel fold: 252 / 407 / 748
   }
 }
 
@@ -771,7 +793,11 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   if (level < 0 || level >= HA_MAX_LEVELS) return HA_EINVAL;
   if (sat->C != grd->C || sat->H != sat->W || (grd->H & 1)) return HA_EINVAL;
   if (p->dof < 1 || p->dof > 3) return HA_EINVAL;
+#ifdef HA_LM_DEV_VARIANTS
+  if (p->kernel_variant < 0 || p->kernel_variant > 4 || p->reserved != 0) return HA_EINVAL;
+#else
   if (p->kernel_variant < 0 || p->kernel_variant > 1 || p->reserved != 0) return HA_EINVAL;
+#endif
   if (p->dof == 3 && !reset_uv && !g2sp) return HA_EINVAL;
   if (g2sp && (p->dof != 3 || !extrinsics || p->ori_grd_h <= 0 || p->ori_grd_w <= 0)) return HA_EINVAL;
   if (p->using_weight && !grd_conf) return HA_EINVAL;

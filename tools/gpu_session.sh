@@ -13,7 +13,9 @@ REP=/tmp/ha_ncu          # raw .ncu-rep files stay on the box (gpurun copies bac
 mkdir -p $OUT $REP
 export_rep() {           # export_rep <name>: raw metrics page (+ SASS source page of the first launch) of $REP/<name>.ncu-rep
   ncu -i $REP/$1.ncu-rep --page raw --csv > $OUT/$1_raw.csv 2>/dev/null
-  ncu -i $REP/$1.ncu-rep --page source --csv --print-source sass --launch-skip ${2:-0} --launch-count 1 > $OUT/$1_sass.csv 2>/dev/null
+  for k in ${2:-0}; do   # SASS source page (per-instruction samples / executed counts) of the listed launches
+    ncu -i $REP/$1.ncu-rep --page source --csv --print-source sass --launch-skip $k --launch-count 1 2>/dev/null | awk 'NR==1||!/^"Kernel Name"/||!s++' > $OUT/$1_sass$k.csv
+  done
   ls -la $REP/$1.ncu-rep $OUT/$1_raw.csv | cut -c20-120
 }
 summarise_bench() {
@@ -50,7 +52,7 @@ while [ $# -gt 0 ]; do
     ncu_conv)
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc -s 40 -c 10 -f -o $REP/conv_$TAG \
         python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > $OUT/conv_$TAG.log 2>&1
-      export_rep conv_$TAG 2 ;;
+      export_rep conv_$TAG "0 7 8" ;;
     ncu_lm)
       timeout 400 ncu --set full --clock-control none --import-source on -k regex:lm_step -s 3 -c 3 -f -o $REP/lm_$TAG \
         python tools/ncu_lm.py 256 > $OUT/lm_$TAG.log 2>&1
