@@ -15,10 +15,11 @@ HA_MAX_LEVELS = 4
 HA_STATS = 24
 HA_VGG_N_CONV = 17
 HA_GEOM_KITTI, HA_GEOM_FORD, HA_GEOM_G2SP = 0, 1, 2
+HA_OPT_LM, HA_OPT_SGD, HA_OPT_ADAM, HA_OPT_GN = 0, 1, 2, 3
 HA_CONV_FP32_SIMT, HA_CONV_F16X3, HA_CONV_F16, HA_CONV_F16X3_1CTA = 0, 1, 2, 3
 HA_STATUS_NO_INRANGE, HA_STATUS_NAN_POSE, HA_STATUS_RESET, HA_STATUS_SAMPLE_EMPTY = 1, 2, 4, 8
 HA_COMM_ID_BYTES = 128
-HA_ABI_VERSION = 2
+HA_ABI_VERSION = 3
 STAT_H, STAT_GRAD, STAT_SAT_NORM, STAT_GRD_NORM, STAT_RES_SQ, STAT_DELTA, STAT_N_INRANGE = 0, 9, 12, 13, 14, 15, 18
 STAT_JTG, STAT_RESET_MASK = 19, 22
 
@@ -41,7 +42,9 @@ class HaLmParams(C.Structure):
                 ("rotation_range", C.c_float), ("shift_range_lat", C.c_float), ("shift_range_lon", C.c_float),
                 ("damping", C.c_float * 3), ("meter_per_pixel", C.c_float * HA_MAX_LEVELS),
                 ("inv_meter_per_pixel", C.c_float * HA_MAX_LEVELS), ("sat_center", C.c_float * HA_MAX_LEVELS),
-                ("ori_grd_h", C.c_int32), ("ori_grd_w", C.c_int32), ("kernel_variant", C.c_int32), ("reserved", C.c_int32)]
+                ("ori_grd_h", C.c_int32), ("ori_grd_w", C.c_int32), ("kernel_variant", C.c_int32), ("optimizer", C.c_int32),
+                ("full_height", C.c_int32), ("adam_level_mult", C.c_int32), ("adam_iter", C.c_int32), ("adam_beta1", C.c_float),
+                ("adam_beta2", C.c_float), ("reserved", C.c_int32)]
 
 
 class HaVggStateDict(C.Structure):

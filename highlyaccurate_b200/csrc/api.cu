@@ -50,7 +50,7 @@ static int transpose(const float* src, float* dst, int B, int C, int H, int W, v
 
 }  // namespace ha
 
-extern "C" int ha_version(void) { return 2; }
+extern "C" int ha_version(void) { return 3; }
 extern "C" unsigned long long ha_launch_count(void) { return __atomic_load_n(&ha::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" const char* ha_error_string(int code) {

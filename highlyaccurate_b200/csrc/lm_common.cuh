@@ -46,6 +46,11 @@ struct LmStepArgs {
   int ori_h, ori_w;        // G2SP: size of the ground IMAGE the camera matrix refers to (models_kitti.py:111-114)
   int variant;             // HaLmParams.kernel_variant
   float damping[3];
+  int row0;                // first ground row of the residual: H/2 (proj 'geo', models_kitti.py:1194-1199) or 0 (other proj)
+  int optimizer;           // HA_OPT_*
+  int adam_t;              // HA_OPT_ADAM: t of this step (iter * args.level + level, models_kitti.py:1241)
+  float adam_b1, adam_b2;  // HA_OPT_ADAM: args.beta1 / args.beta2
+  float* adam_mv;          // HA_OPT_ADAM: [B][6] first / second moments, carried between the steps of a run
 };
 
 // Per-sample constants of the warp, evaluated in the reference's fp32 operation order.

@@ -137,9 +137,21 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const i
 
     const double alpha = a.sat_scale ? (double)a.sat_scale[b] : 1.0;
     const double beta = a.grd_scale ? (double)a.grd_scale[b] : 1.0;
-    ns = fmax(alpha * sqrt(tot[12]), 1e-6);          // models_kitti.py:982-984
-    ng = fmax(beta * sqrt(tot[13]), 1e-6);           // :987-988
-    const double fs = alpha * alpha / (ns * ns), fg = alpha * beta / (ns * ng);
+    double fs, fg;
+    if (a.optimizer == HA_OPT_SGD || a.optimizer == HA_OPT_ADAM) {
+      // SGD_update / ADAM_update (models_kitti.py:1056-1124): r = s - g on the L2-normalised features as they are
+      // (no renormalisation), gradient = sum 2 r J over the whole residual
+      ns = alpha * sqrt(tot[12]); ng = beta * sqrt(tot[13]);
+      fs = 2.0 * alpha * alpha; fg = 2.0 * alpha * beta;
+    } else if (a.optimizer == HA_OPT_GN) {
+      // GN_update (models_ford.py:549-566): s / ||s|| without the 1e-6 clamp, g taken as it is
+      ns = alpha * sqrt(tot[12]); ng = beta * sqrt(tot[13]);
+      fs = alpha * alpha / (ns * ns); fg = alpha * beta / ns;
+    } else {
+      ns = fmax(alpha * sqrt(tot[12]), 1e-6);          // models_kitti.py:982-984
+      ng = fmax(beta * sqrt(tot[13]), 1e-6);           // :987-988
+      fs = alpha * alpha / (ns * ns); fg = alpha * beta / (ns * ng);
+    }
     Hm[0][0] = JtJ[0] * fs; Hm[0][1] = Hm[1][0] = JtJ[1] * fs; Hm[0][2] = Hm[2][0] = JtJ[2] * fs;
     Hm[1][1] = JtJ[3] * fs; Hm[1][2] = Hm[2][1] = JtJ[4] * fs; Hm[2][2] = JtJ[5] * fs;
     for (int i = 0; i < 3; ++i) { gr[i] = Jts[i] * fs - Jtg[i] * fg; jtg_f[i] = Jtg[i] * fg; }
@@ -150,14 +162,35 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const i
   // DOF selection (models_kitti.py:954-957): 3 -> (0,1,2), 2 -> (0,1), 1 -> (2)
   const int n = a.dof;
   const int i0 = (n == 1) ? 2 : 0;
+  const bool first_order = !G2SP && (a.optimizer == HA_OPT_SGD || a.optimizer == HA_OPT_ADAM);
   double Am[3][3], rhs[3], delta[3] = {0, 0, 0};
   for (int i = 0; i < n; ++i) {
     for (int j = 0; j < n; ++j) Am[i][j] = Hm[i0 + i][i0 + j];
-    const double lam = (double)a.damping[i];
-    Am[i][i] += a.use_hessian ? lam * Hm[i0 + i][i0 + i] : lam;    // :1005-1012 (column-wise lambda on a diagonal)
+    const double lam = (!G2SP && a.optimizer == HA_OPT_GN) ? 0.0 : (double)a.damping[i];   // GN: inverse(Hessian), models_ford.py:577
+    Am[i][i] += (a.use_hessian && a.optimizer != HA_OPT_GN) ? lam * Hm[i0 + i][i0 + i] : lam;    // :1005-1012 (column-wise lambda on a diagonal)
     rhs[i] = gr[i0 + i];
   }
-  if (n == 1) {
+  float nsu = su, nsv = sv, nth = th;
+  uint32_t st = 0;
+  if (first_order) {
+    // pose -= 0.01 * step, all three components whatever the ranges, no reset (models_kitti.py:1080-1083, :1119-1123);
+    // fp32 arithmetic in the reference's order (python-double hyper-parameters become fp32 scalars)
+    float stepv[3] = {(float)gr[0], (float)gr[1], (float)gr[2]};
+    if (a.optimizer == HA_OPT_ADAM) {
+      float* mv = a.adam_mv + (size_t)b * 6;
+      const double b1 = (double)a.adam_b1, b2 = (double)a.adam_b2;
+      const float c1 = (float)(1.0 - pow(b1, (double)(a.adam_t + 1))), c2 = (float)(1.0 - pow(b2, (double)(a.adam_t + 1)));
+      for (int i = 0; i < 3; ++i) {
+        const float m0 = a.adam_t == 0 ? 0.f : mv[i], v0 = a.adam_t == 0 ? 0.f : mv[3 + i];      // :1242-1244
+        const float m = __fadd_rn(__fmul_rn((float)b1, m0), __fmul_rn((float)(1.0 - b1), stepv[i]));
+        const float v = __fadd_rn(__fmul_rn((float)b2, v0), __fmul_rn((float)(1.0 - b2), __fmul_rn(stepv[i], stepv[i])));
+        mv[i] = m; mv[3 + i] = v;
+        stepv[i] = __fdiv_rn(__fdiv_rn(m, c1), __fadd_rn(sqrtf(__fdiv_rn(v, c2)), 1e-8f));
+      }
+    }
+    for (int i = 0; i < 3; ++i) delta[i] = -(double)__fmul_rn(0.01f, stepv[i]);
+    nsu = __fadd_rn(su, (float)delta[0]); nsv = __fadd_rn(sv, (float)delta[1]); nth = __fadd_rn(th, (float)delta[2]);
+  } else if (n == 1) {
     delta[0] = -rhs[0] / Am[0][0];
   } else if (n == 2) {
     const double det = Am[0][0] * Am[1][1] - Am[0][1] * Am[1][0];
@@ -179,9 +212,9 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const i
     delta[1] = -(c01 * rhs[0] + c11 * rhs[1] + c21 * rhs[2]) / det;
     delta[2] = -(c02 * rhs[0] + c12 * rhs[1] + c22 * rhs[2]) / det;
   }
-  float nsu = su, nsv = sv, nth = th;
-  uint32_t st = 0;
-  if (n == 3) {
+  if (first_order) {
+    // pose already updated above
+  } else if (n == 3) {
     nsu = su + (float)delta[0]; nsv = sv + (float)delta[1]; nth = th + (float)delta[2];
     // models_kitti.py:1028-1033: shifts outside (-2.5, 2.5) (or NaN) are re-drawn (S2GP models only)
     if (!G2SP) {
@@ -215,7 +248,7 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const i
       for (int j = 0; j < 3; ++j) s[HA_STAT_H + i * 3 + j] = (float)Hm[i][j];
     for (int i = 0; i < 3; ++i) s[HA_STAT_GRAD + i] = (float)gr[i];
     s[HA_STAT_SAT_NORM] = (float)ns; s[HA_STAT_GRD_NORM] = (float)ng; s[HA_STAT_RES_SQ] = (float)res_sq;
-    for (int i = 0; i < 3; ++i) s[HA_STAT_DELTA + i] = (i < n) ? (float)delta[i] : 0.f;
+    for (int i = 0; i < 3; ++i) s[HA_STAT_DELTA + i] = (i < n || first_order) ? (float)delta[i] : 0.f;
     s[HA_STAT_N_INRANGE] = (float)tot[15];
     // saved for the backward pass (ha_lm_step_backward): the J~^T W g~ part of grad and which shifts were re-drawn
     for (int i = 0; i < 3; ++i) s[HA_STAT_JTG + i] = G2SP ? 0.f : (float)jtg_f[i];
@@ -239,7 +272,7 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
   // S2GP: the residual lives on the bottom half of the ground image (models_kitti.py:1195-1199), the ground
   // features are streamed and the satellite map is gathered.  G2SP: the residual lives on the whole satellite
   // map (:333-379), the satellite features are streamed and the ground features are gathered.
-  const int P = G2SP ? a.A * a.A : (a.H - a.H / 2) * a.W;
+  const int P = G2SP ? a.A * a.A : (a.H - a.row0) * a.W;
   const int q_begin = blockIdx.x * a.px_per_cta;
   const int q_end = min(P, q_begin + a.px_per_cta);
 
@@ -252,13 +285,13 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
   else gq = g2sp_pose(a, b, su, sv, th);
 
   // first streamed pixel of sample b, in pixels of the streamed tensor
-  const size_t px_base = G2SP ? (size_t)b * a.A * a.A : (size_t)b * a.H * a.W + (size_t)(a.H / 2) * a.W;
+  const size_t px_base = G2SP ? (size_t)b * a.A * a.A : (size_t)b * a.H * a.W + (size_t)a.row0 * a.W;
   // half 0 = channels [4*cl, 4*cl+4), half 1 = channels [C/2 + 4*cl, ...): each half of a pixel is one
   // contiguous 16*LPP-byte run across the pixel's lanes
   const float4* grd = reinterpret_cast<const float4*>(G2SP ? a.sat : a.grd) + px_base * C4 + cl;              // streamed
   const float4* sat = reinterpret_cast<const float4*>(G2SP ? a.grd : a.sat) +
                       (G2SP ? (size_t)b * a.H * a.W : (size_t)b * a.A * a.A) * C4 + cl;                        // gathered
-  const float4* tab = G2SP ? nullptr : a.table + (size_t)(a.H / 2) * a.W;
+  const float4* tab = G2SP ? nullptr : a.table + (size_t)a.row0 * a.W;
   const float* conf = a.conf ? (G2SP ? a.conf + (size_t)b * a.H * a.W : a.conf + px_base) : nullptr;
 
   // per-warp staging of the per-pixel scalars: phase A writes 32 pixels, phase B broadcasts them
@@ -435,7 +468,7 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPP, cl = lane % LPP;     // pixel slot within the warp, channel lane
-  const int P = (a.H - a.H / 2) * a.W;             // the residual lives on the bottom half (models_kitti.py:1195-1199)
+  const int P = (a.H - a.row0) * a.W;              // the residual lives on the bottom half (models_kitti.py:1195-1199; row0 = H/2)
   const int q_begin = blockIdx.x * a.px_per_cta;
   const int q_end = min(P, q_begin + a.px_per_cta);
 
@@ -446,10 +479,10 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
   if (GEOM == HA_GEOM_KITTI) kp = kitti_pose(a, su, sv, th);
   else fp = ford_pose(a, b, su, sv, th);
 
-  const size_t px_base = (size_t)b * a.H * a.W + (size_t)(a.H / 2) * a.W;
+  const size_t px_base = (size_t)b * a.H * a.W + (size_t)a.row0 * a.W;
   const float4* grd0 = reinterpret_cast<const float4*>(a.grd) + px_base * C4;              // streamed (bulk copies)
   const char* sat_b = reinterpret_cast<const char*>(a.sat) + (size_t)b * a.A * a.A * C * 4;  // gathered
-  const float4* tab = a.table + (size_t)(a.H / 2) * a.W;
+  const float4* tab = a.table + (size_t)a.row0 * a.W;
   const float* conf = a.conf ? a.conf + px_base : nullptr;
 
   // per-warp pixel records: phase A (one lane per pixel) writes 32 of them, the pixel's channel lanes read them back
@@ -747,9 +780,9 @@ static int launch_by_channels(int C, dim3 grid, cudaStream_t st, const LmStepArg
 }
 
 // Workspace layout: [partials B x 256 x 16 fp64][tickets B x u32, padded to 256 B][step word, 256 B][zero vector 2 KB]
-// [|g|^2 cache HA_MAX_LEVELS x B fp64].  Tickets, step word and zero vector are contiguous: one kernel clears them.
+// [|g|^2 cache HA_MAX_LEVELS x B fp64][Adam moments B x 6 fp32].  Tickets, step word and zero vector are contiguous: one kernel clears them.
 struct LmWs {
-  double* partial; uint32_t* ticket; unsigned long long* step_word; const float4* zeros; double* gg;
+  double* partial; uint32_t* ticket; unsigned long long* step_word; const float4* zeros; double* gg; float* adam_mv;
   size_t clear_words;      // u32 words from `ticket` that must be zero when a run starts
   size_t total;
 };
@@ -764,7 +797,9 @@ static LmWs lm_ws_carve(void* ws, int B) {
   w.zeros = reinterpret_cast<const float4*>(p + part + tick + 256);
   w.gg = reinterpret_cast<double*>(p + part + tick + 256 + kLmZeroBytes);
   w.clear_words = (tick + 256 + kLmZeroBytes) / 4;
-  w.total = part + tick + 256 + kLmZeroBytes + (size_t)HA_MAX_LEVELS * B * sizeof(double);
+  const size_t gg = (size_t)HA_MAX_LEVELS * B * sizeof(double);
+  w.adam_mv = reinterpret_cast<float*>(p + part + tick + 256 + kLmZeroBytes + gg);     // [B][6], HA_OPT_ADAM only
+  w.total = part + tick + 256 + kLmZeroBytes + gg + (size_t)B * 6 * sizeof(float);
   return w;
 }
 static size_t lm_ws_bytes(int B) { return lm_ws_carve(nullptr, B).total; }
@@ -787,7 +822,7 @@ static int choose_px_per_cta(int B, int P) {
 static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, const HaLevel* grd, const float* grd_conf,
                         const float* ground_table, const float* extrinsics, float* pose, const float* reset_uv,
                         float* stats, float* traj_step, int traj_stride, uint32_t* status, void* ws, size_t ws_bytes,
-                        int B, bool full, cudaStream_t st) {
+                        int B, bool full, int iter, cudaStream_t st) {
   const bool g2sp = p && p->geometry == HA_GEOM_G2SP;
   if (!p || !sat || !grd || !pose || !status || !ws || (!ground_table && !g2sp)) return HA_EINVAL;
   if (level < 0 || level >= HA_MAX_LEVELS) return HA_EINVAL;
@@ -798,7 +833,15 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
 #else
   if (p->kernel_variant < 0 || p->kernel_variant > 1 || p->reserved != 0) return HA_EINVAL;
 #endif
-  if (p->dof == 3 && !reset_uv && !g2sp) return HA_EINVAL;
+  if (p->optimizer < HA_OPT_LM || p->optimizer > HA_OPT_GN || (p->full_height != 0 && p->full_height != 1)) return HA_EINVAL;
+  const bool first_order = p->optimizer == HA_OPT_SGD || p->optimizer == HA_OPT_ADAM;
+  // the ablation update rules exist for the models that define them: SGD / ADAM in LM_S2GP, GN in LM_S2GP_Ford; they
+  // work on the L2-normalised features (SGD / ADAM: both branches, GN: the ground branch): HaLevel.scale must carry the
+  // U-Net's 1 / ||x|| there (NULL = the data is already normalised)
+  if (p->optimizer != HA_OPT_LM && g2sp) return HA_EINVAL;
+  if (first_order && (p->using_weight || p->dof != 3)) return HA_EINVAL;
+  if (p->optimizer == HA_OPT_GN && p->dof != 3) return HA_EINVAL;
+  if (p->dof == 3 && !reset_uv && !g2sp && !first_order) return HA_EINVAL;
   if (g2sp && (p->dof != 3 || !extrinsics || p->ori_grd_h <= 0 || p->ori_grd_w <= 0)) return HA_EINVAL;
   if (p->using_weight && !grd_conf) return HA_EINVAL;
   if (p->geometry == HA_GEOM_FORD && !extrinsics) return HA_EINVAL;
@@ -821,7 +864,12 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   for (int i = 0; i < 3; ++i) a.damping[i] = p->damping[i];
   a.ori_h = p->ori_grd_h; a.ori_w = p->ori_grd_w;
   a.variant = p->kernel_variant;
-  const int P = g2sp ? sat->H * sat->W : (grd->H - grd->H / 2) * grd->W;
+  a.row0 = p->full_height ? 0 : grd->H / 2;
+  a.optimizer = p->optimizer;
+  a.adam_t = iter * p->adam_level_mult + level;
+  a.adam_b1 = p->adam_beta1; a.adam_b2 = p->adam_beta2;
+  a.adam_mv = w.adam_mv;
+  const int P = g2sp ? sat->H * sat->W : (grd->H - a.row0) * grd->W;
   a.px_per_cta = choose_px_per_cta(B, P);
   dim3 grid((P + a.px_per_cta - 1) / a.px_per_cta, B);
   if (p->geometry == HA_GEOM_KITTI)
@@ -859,7 +907,7 @@ extern "C" int ha_lm_step(const HaLmParams* p, int level, const HaLevel* sat, co
   if (ws_bytes < ha::lm_ws_bytes(B)) return HA_ENOSPACE;
   ha::lm_begin(ws, B, status, st);        // tickets / step word / zero vector / *status start at zero (cheap, async)
   return ha::lm_step_impl(p, level, sat, grd, grd_conf, ground_table, extrinsics, pose, reset_uv, stats, nullptr, 0,
-                          status, ws, ws_bytes, B, /*full=*/true, st);
+                          status, ws, ws_bytes, B, /*full=*/true, p->adam_iter, st);
 }
 
 extern "C" int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel* grd, const float* const* grd_conf,
@@ -877,13 +925,13 @@ extern "C" int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel*
   for (int o = 0; o < outer; ++o) {
     for (int i = 0; i < inner; ++i, ++k) {
       const int it = p->level_first ? i : o, lv = p->level_first ? o : i;
-      const float* ruv = (p->dof == 3 && reset_uv) ? reset_uv + (size_t)k * 2 * B : nullptr;
+      const float* ruv = (p->dof == 3 && reset_uv) ? reset_uv + (size_t)k * 2 * B : nullptr;   // SGD / ADAM draw nothing: reset_uv NULL
       float* tr = traj ? traj + ((size_t)it * L + lv) * 3 : nullptr;
       float* stp = stats ? stats + ((size_t)it * L + lv) * B * HA_STATS : nullptr;
       // the first visit of a level also reduces |g|^2 (pose independent) and caches it; later visits skip it
       const bool full = (it == 0) || stats != nullptr;
       int rc = ha::lm_step_impl(p, lv, sat + lv, grd + lv, grd_conf ? grd_conf[lv] : nullptr, ground_tables[lv],
-                                extrinsics, pose, ruv, stp, tr, N * L * 3, status, ws, ws_bytes, B, full, st);
+                                extrinsics, pose, ruv, stp, tr, N * L * 3, status, ws, ws_bytes, B, full, it, st);
       if (rc != HA_OK) return rc;
     }
   }

@@ -40,10 +40,26 @@ def _stream_ptr() -> int:
 
 
 # ------------------------------------------------------------------------------- ground tables
-def ground_table(kind: str, level: int, n_levels: int = 3) -> torch.Tensor:
+def polar_ground_table(level: int) -> torch.Tensor:
+    """The ground table of every `proj` other than 'geo' (models_kitti.py:684-698 / models_ford.py:156-170,
+    grd_img2cam_polar): image column -> bearing over a 45 degree fan, image row -> range up to 30 m, every pixel valid.
+    [H, W, 4] fp32 = (x, y, z, 1), same arithmetic as the reference so the values are identical."""
+    gh, gw = 256 / (2 ** (3 - level)), 1024 / (2 ** (3 - level))
+    vv, uu = torch.meshgrid(torch.arange(0, gh, dtype=torch.float32), torch.arange(0, gw, dtype=torch.float32), indexing="ij")
+    bearing = uu / gw * np.pi / 4
+    rng = (1 - vv / gh) * 30
+    z = rng * torch.cos(np.pi / 4 - bearing)
+    x = -rng * torch.sin(np.pi / 4 - bearing)
+    y = CAMERA_HEIGHT * torch.ones_like(z)
+    return torch.stack([x, y, z, torch.ones_like(z)], dim=-1).contiguous()
+
+
+def ground_table(kind: str, level: int, n_levels: int = 3, proj: str = "geo") -> torch.Tensor:
     """Ground-plane lift of every ground-image pixel at a pyramid level, in the camera frame:
     [H, W, 4] fp32 = (x, y, z, mask).  Init-time CPU work, same arithmetic as
     models_kitti.py:655-682 (grd_img2cam) / models_ford.py:110-155 so the values are identical."""
+    if proj != "geo":
+        return polar_ground_table(level)
     if kind == "kitti":
         top = 3
         k0 = torch.tensor([KITTI_K], dtype=torch.float32)
@@ -132,6 +148,11 @@ class LmSetup:
     shift_range_lat: float
     shift_range_lon: float
     kernel_variant: int = 0    # HaLmParams.kernel_variant: 0 = default kernels, 1 = register-staged validation kernel
+    optimizer: str = "LM"      # args.Optimizer: 'LM' | 'SGD' | 'ADAM' (LM_S2GP) | 'GN' (LM_S2GP_Ford)
+    full_height: int = 0       # 1: residual over the whole ground image (args.proj != 'geo', models_kitti.py:1200-1205)
+    adam_level_mult: int = 0   # args.level: the reference's Adam step count is iter * args.level + level (:1241)
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
 
 
 def dof_of(args, kind: str) -> int:
@@ -146,10 +167,16 @@ def dof_of(args, kind: str) -> int:
 
 
 def setup_from_args(args, kind: str, level_first: int = 0) -> LmSetup:
-    return LmSetup(kind=kind, n_iters=int(args.N_iters), level_first=int(level_first), dof=dof_of(args, kind),
-                   using_weight=int(bool(args.using_weight)), use_hessian=int(bool(getattr(args, "use_hessian", 0))),
+    opt = getattr(args, "Optimizer", "LM")
+    first_order = opt in ("SGD", "ADAM")                 # SGD_update / ADAM_update ignore the confidence weights and the DOF switch
+    return LmSetup(kind=kind, n_iters=int(args.N_iters), level_first=int(level_first), dof=3 if first_order else dof_of(args, kind),
+                   using_weight=0 if first_order else int(bool(args.using_weight)),
+                   use_hessian=int(bool(getattr(args, "use_hessian", 0))),
                    rotation_range=float(args.rotation_range), shift_range_lat=float(args.shift_range_lat),
-                   shift_range_lon=float(args.shift_range_lon))
+                   shift_range_lon=float(args.shift_range_lon), optimizer=opt,
+                   full_height=int(kind != "g2sp" and getattr(args, "proj", "geo") != "geo"),
+                   adam_level_mult=int(args.level), adam_beta1=float(getattr(args, "beta1", 0.9)),
+                   adam_beta2=float(getattr(args, "beta2", 0.999)))
 
 
 def resolve_damping(args, damping_param: Optional[torch.Tensor], dof: int, kind: str = "kitti") -> List[float]:
@@ -207,6 +234,9 @@ def make_params(setup: LmSetup, sat: Pyramid, damping: Sequence[float], side_m: 
     p.geometry = {"kitti": _lib.HA_GEOM_KITTI, "ford": _lib.HA_GEOM_FORD, "g2sp": _lib.HA_GEOM_G2SP}[setup.kind]
     p.ori_grd_h, p.ori_grd_w = int(ori_grd_hw[0]), int(ori_grd_hw[1])
     p.kernel_variant, p.reserved = int(setup.kernel_variant), 0
+    p.optimizer = OPTIMIZERS[setup.optimizer]
+    p.full_height, p.adam_level_mult, p.adam_iter = int(setup.full_height), int(setup.adam_level_mult), 0
+    p.adam_beta1, p.adam_beta2 = setup.adam_beta1, setup.adam_beta2
     p.n_levels, p.n_iters, p.level_first, p.dof = n, setup.n_iters, setup.level_first, setup.dof
     p.using_weight, p.use_hessian, p.batch = setup.using_weight, setup.use_hessian, sat.batch
     p.rotation_range, p.shift_range_lat, p.shift_range_lon = setup.rotation_range, setup.shift_range_lat, setup.shift_range_lon
@@ -227,6 +257,15 @@ def make_params(setup: LmSetup, sat: Pyramid, damping: Sequence[float], side_m: 
         p.inv_meter_per_pixel[lv] = 1.0 / mpp
         p.sat_center[lv] = center
     return p
+
+
+OPTIMIZERS = {"LM": _lib.HA_OPT_LM, "SGD": _lib.HA_OPT_SGD, "ADAM": _lib.HA_OPT_ADAM, "GN": _lib.HA_OPT_GN}
+
+
+def draws_reset(setup: LmSetup) -> bool:
+    """Whether a step consumes the two [B,1] CPU-RNG draws: the 3-DOF LM / GN updates of the S2GP models do
+    (models_kitti.py:1028-1029, models_ford.py:453-454, :583-584); SGD / ADAM and LM_G2SP never draw."""
+    return setup.dof == 3 and setup.kind != "g2sp" and setup.optimizer in ("LM", "GN")
 
 
 class LmWorkspace:
@@ -302,7 +341,7 @@ def lm_run(setup: LmSetup, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Te
     traj = torch.empty(B, setup.n_iters, n, 3, dtype=torch.float32, device=dev)
     stats = torch.empty(setup.n_iters, n, B, _lib.HA_STATS, dtype=torch.float32, device=dev) if want_stats else None
     n_steps = setup.n_iters * n
-    if setup.dof == 3 and setup.kind != "g2sp":       # LM_G2SP has no out-of-range reset, hence no RNG draws
+    if draws_reset(setup):                            # LM_G2SP / SGD / ADAM have no out-of-range reset, hence no RNG draws
         if reset_uv is None:
             reset_uv = draw_reset_uv(n_steps, B)
         reset_uv = reset_uv.to(dev, torch.float32, non_blocking=True).contiguous()
@@ -342,15 +381,16 @@ def lm_run(setup: LmSetup, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Te
 def lm_step(setup: LmSetup, level: int, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Tensor],
             damping: Sequence[float], pose: torch.Tensor, extrinsics: Optional[torch.Tensor] = None,
             side_m: Optional[float] = None, reset_uv: Optional[torch.Tensor] = None,
-            ori_grd_hw: Tuple[int, int] = (256, 1024)):
-    """One fused LM step at `level` from `pose` [B,3]; returns (new_pose [B,3], stats [B,HA_STATS])."""
+            ori_grd_hw: Tuple[int, int] = (256, 1024), adam_iter: int = 0):
+    """One fused LM step at `level` from `pose` [B,3]; returns (new_pose [B,3], stats [B,HA_STATS]).
+    `adam_iter`: iteration index of the step (Optimizer 'ADAM' only: its moments persist in the stream's workspace)."""
     L = _lib.lib()
     n = len(sat.feats)
     B = sat.batch
     dev = sat.feats[0].device
     pose = pose.to(dev, torch.float32).clone().contiguous()
     stats = torch.empty(B, _lib.HA_STATS, dtype=torch.float32, device=dev)
-    if setup.dof == 3 and setup.kind != "g2sp":
+    if draws_reset(setup):
         if reset_uv is None:
             reset_uv = draw_reset_uv(1, B)[0]
         reset_uv = reset_uv.to(dev, torch.float32).contiguous()
@@ -359,6 +399,7 @@ def lm_step(setup: LmSetup, level: int, sat: Pyramid, grd: Pyramid, tables: Sequ
     if extrinsics is not None:
         extrinsics = extrinsics.to(dev, torch.float32).contiguous()
     params = make_params(setup, sat, damping, side_m, ori_grd_hw)
+    params.adam_iter = int(adam_iter)
     c = grd.confs[level] if (grd.confs and setup.using_weight) else None
     ws, status = _workspace(dev).get(B, dev), _new_status(dev)
     sl, gl = _levels(sat, n), _levels(grd, n)
@@ -383,7 +424,8 @@ class FusedLmLoop(torch.autograd.Function):
 
     @staticmethod
     def supports(setup: LmSetup) -> bool:
-        return setup.kind in ("kitti", "ford") and setup.dof == 3 and not setup.using_weight
+        return setup.kind in ("kitti", "ford") and setup.dof == 3 and not setup.using_weight and \
+            setup.optimizer == "LM" and not setup.full_height
 
     @staticmethod
     def forward(ctx, setup, tables, extrinsics, side_m, reset_uv, lam, n_levels, *feats):

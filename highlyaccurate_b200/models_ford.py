@@ -150,8 +150,12 @@ class LM_S2GP_Ford(nn.Module):
         self.estimate_depth = getattr(args, "estimate_depth", 0)
         if self.estimate_depth:
             raise NotImplementedError("estimate_depth is outside the accelerated path")
-        if getattr(args, "Optimizer", "LM") != "LM" or getattr(args, "proj", "geo") != "geo":
-            raise NotImplementedError("only --Optimizer LM --proj geo is on the accelerated path")
+        self.optimizer = getattr(args, "Optimizer", "LM")
+        self.proj = getattr(args, "proj", "geo")
+        if self.optimizer not in ("LM", "GN"):
+            # models_ford.py:609-628 SGD_update indexes its [B,3] gradient with three subscripts and :600-607 NN_update adds
+            # a [B] row to a [B,1] column: neither runs in the reference itself; GN (:534-598) does
+            raise NotImplementedError("--Optimizer %s: LM and GN are on the accelerated path" % self.optimizer)
         if getattr(args, "dropout", 0):
             # models_ford.py:406-412 subsamples half of the pixels with a numpy permutation when dropout > 0
             raise NotImplementedError("dropout is outside the accelerated path")
@@ -162,8 +166,8 @@ class LM_S2GP_Ford(nn.Module):
         self.ori_grdH, self.ori_grdW = 256, 1024
         if self.level == 2:                                                            # :59-65: [x18, x21] with the /4 and /2 grids
             self._tables_cpu = [engine.ground_table("ford", lv, n_levels=2) for lv in range(2)]
-        else:
-            self._tables_cpu = [engine.ground_table("ford", lv) for lv in range(4)]   # :45-58
+        else:                                                                          # :45-58, polar fan (:156-170) unless 'geo'
+            self._tables_cpu = [engine.ground_table("ford", lv, proj=self.proj) for lv in range(4)]
         self._tables_dev = {}
         self.last_result = None
 
@@ -174,9 +178,11 @@ class LM_S2GP_Ford(nn.Module):
         return self._tables_dev[key]
 
     def extract(self, sat_map, grd_img, want_conf):
-        # the L2 norm of VGG.py:172-175 cancels in LM_update's renormalisation (:420-426): not computed on this path
-        sat = self.SatFeatureNet.pyramid(sat_map, want_conf=False, want_scale=False)
-        grd = self.GrdFeatureNet.pyramid(grd_img, want_conf=want_conf, want_scale=False)
+        # the L2 norm of VGG.py:172-175 cancels in LM_update's renormalisation (:420-426): not computed on that path;
+        # GN_update (:549-566) keeps the ground features as normalised by the U-Net
+        scale = self.optimizer != "LM"
+        sat = self.SatFeatureNet.pyramid(sat_map, want_conf=False, want_scale=scale)
+        grd = self.GrdFeatureNet.pyramid(grd_img, want_conf=want_conf, want_scale=scale)
         return sat, grd
 
     def refine(self, sat, grd, satmap_sidelength_meters, R_FL, T_FL, level_first=0, pose0=None, reset_uv=None,
@@ -213,7 +219,11 @@ class LM_S2GP_Ford(nn.Module):
     def forward(self, sat_map, grd_img_left, satmap_sidelength_meters, R_FL, T_FL, gt_shift_u=None, gt_shift_v=None,
                 gt_theta=None, mode='train', file_name=None, level_first=0, loop=0):
         """models_ford.py:1028-1036 -> forward_iters_level (:652-866) / forward_level_iters (:868-1026)."""
+        if self.optimizer == "GN" and level_first:
+            raise NotImplementedError("forward_level_iters has no GN branch (models_ford.py:933-955)")
         if mode == 'train':
+            if self.optimizer != "LM" or self.proj != "geo":
+                raise NotImplementedError("train mode covers --Optimizer LM --proj geo; the ablation flags run in test mode")
             ford = dict(R_FL=R_FL, T_FL=T_FL, side_m=float(satmap_sidelength_meters))
             coe_heading = 0 if self.args.rotation_range == 0 else self.args.coe_heading        # :843-846, :1000-1003
             return train_forward(self, "ford", sat_map, grd_img_left, gt_shift_u, gt_shift_v, gt_theta, level_first,

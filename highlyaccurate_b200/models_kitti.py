@@ -24,8 +24,12 @@ class LM_S2GP(nn.Module):
         self.N_iters = args.N_iters
         self.using_weight = args.using_weight
         self.loss_method = args.loss_method
-        if getattr(args, "Optimizer", "LM") != "LM" or getattr(args, "proj", "geo") != "geo":
-            raise NotImplementedError("only --Optimizer LM --proj geo is on the accelerated path")
+        self.optimizer = getattr(args, "Optimizer", "LM")
+        self.proj = getattr(args, "proj", "geo")
+        if self.optimizer not in ("LM", "SGD", "ADAM"):
+            # :1233 'NN' (RNNs.NNrefine on the materialised residual) is not on the accelerated path; anything else
+            # leaves the reference's own loop without an update (:1207-1254)
+            raise NotImplementedError("--Optimizer %s: LM, SGD and ADAM are on the accelerated path" % self.optimizer)
         if getattr(args, "dropout", 0) or getattr(args, "use_gt_depth", 0):
             raise NotImplementedError("dropout / use_gt_depth are outside the accelerated path")
         if self.level == 2:
@@ -38,7 +42,8 @@ class LM_S2GP(nn.Module):
             self.damping = nn.Parameter(torch.zeros(size=(1, 3), dtype=torch.float32, requires_grad=True))
         else:
             self.damping = nn.Parameter(torch.zeros(size=(), dtype=torch.float32, requires_grad=True))
-        self._tables_cpu = [engine.ground_table("kitti", lv) for lv in range(4)]   # :622-635
+        # :622-635: the ground-plane lift for proj 'geo', the polar fan of grd_img2cam_polar (:684-698) for any other value
+        self._tables_cpu = [engine.ground_table("kitti", lv, proj=self.proj) for lv in range(4)]
         self._tables_dev = {}
         self.meters_per_pixel = [engine.kitti_meter_per_pixel() * (2 ** (3 - lv)) for lv in range(4)]   # :637-640
         self.last_result = None
@@ -55,9 +60,11 @@ class LM_S2GP(nn.Module):
         return self._tables_dev[key]
 
     def extract(self, sat_map, grd_img, want_conf):
-        # the L2 norm of VGG.py:172-175 cancels in LM_update's renormalisation (:982-989): not computed on this path
-        sat = self.SatFeatureNet.pyramid(sat_map, want_conf=False, want_scale=False)
-        grd = self.GrdFeatureNet.pyramid(grd_img, want_conf=want_conf, want_scale=False)
+        # the L2 norm of VGG.py:172-175 cancels in LM_update's renormalisation (:982-989): not computed on that path;
+        # SGD_update / ADAM_update (:1056-1124) take the normalised features as they are
+        scale = self.optimizer != "LM"
+        sat = self.SatFeatureNet.pyramid(sat_map, want_conf=False, want_scale=scale)
+        grd = self.GrdFeatureNet.pyramid(grd_img, want_conf=want_conf, want_scale=scale)
         return sat, grd
 
     def refine(self, sat: engine.Pyramid, grd: engine.Pyramid, level_first=0, pose0=None, reset_uv=None,
@@ -96,10 +103,12 @@ class LM_S2GP(nn.Module):
                 file_name=None, gt_depth=None, loop=0, level_first=0):
         """models_kitti.py:1126-1316 (iter-first) / :1318-1492 (level-first)."""
         if mode == 'train':
+            if self.optimizer != "LM" or self.proj != "geo":
+                raise NotImplementedError("train mode covers --Optimizer LM --proj geo; the ablation flags run in test mode")
             coe_heading = 0 if self.args.rotation_range == 0 else self.args.coe_heading      # :1298-1301
             return train_forward(self, "kitti", sat_map, grd_img_left, gt_shiftv[:, 0], gt_shiftu[:, 0], gt_heading[:, 0],
                                  level_first, coe_heading)
-        want_conf = bool(self.using_weight)
+        want_conf = bool(self.using_weight) and self.optimizer == "LM"
         sat, grd = self.extract(sat_map, grd_img_left, want_conf)
         res = self.refine(sat, grd, level_first)
         if self.check_status:

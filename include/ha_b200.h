@@ -45,6 +45,17 @@ enum {
                           whole satellite map, LM_update of :333-379 (no renormalisation)     */
 };
 
+/* update rule applied by a step to the reduced sums (args.Optimizer; the default everywhere is LM) */
+enum {
+  HA_OPT_LM = 0,    /* models_kitti.py:939-1041 / models_ford.py:380-466 / G2SP :333-379                          */
+  HA_OPT_SGD = 1,   /* LM_S2GP.SGD_update (models_kitti.py:1056-1084): pose -= 0.01 * J^T (2 r), r = s - g with the
+                       L2-normalised features (HaLevel.scale = the U-Net's 1/||x||, or NULL for data that is already
+                       normalised), all three components, dof = 3, unweighted, no reset draws                  */
+  HA_OPT_ADAM = 2,  /* LM_S2GP.ADAM_update (:1086-1124): the same gradient through Adam moments kept in the workspace */
+  HA_OPT_GN = 3     /* LM_S2GP_Ford.GN_update (models_ford.py:534-598): s / ||s|| (no clamp), g as is, undamped
+                       inverse of J^T W J, reset draws as in LM                                                 */
+};
+
 /* device status word bits.  ha_lm_run / ha_lm_step CLEAR *status on entry (on the stream) and OR
  * bits into it; the host reads it ONCE after the loop, never per step (this replaces the
  * reference's per-step host syncs jacobian.py:172,200 / models_kitti.py:1037). */
@@ -92,11 +103,20 @@ typedef struct {
   int32_t kernel_variant;               /* 0 = default kernels; 1 = register-staged validation kernel for the
                                            S2GP geometries (same algorithm, other schedule; the parity tests
                                            hold both to the same bar).  No reference analogue.        */
+  int32_t optimizer;                    /* HA_OPT_*: the update rule of a step (args.Optimizer)       */
+  int32_t full_height;                  /* 0: residual over the bottom half of the ground image (args.proj == 'geo',
+                                           models_kitti.py:1194-1199); 1: over the whole image (any other proj:
+                                           the polar ground table of models_kitti.py:684-698, :1200-1205)        */
+  int32_t adam_level_mult;              /* HA_OPT_ADAM: t = iter * adam_level_mult + level (the reference multiplies
+                                           by args.level, models_kitti.py:1241)                                  */
+  int32_t adam_iter;                    /* HA_OPT_ADAM with ha_lm_step: the iteration index of this step (ha_lm_run
+                                           counts for itself); the moments live in the caller's workspace         */
+  float adam_beta1, adam_beta2;         /* HA_OPT_ADAM: args.beta1 / args.beta2 (train_kitti.py:480-481)         */
   int32_t reserved;                     /* must be 0                                                 */
 } HaLmParams;
 
 /* ---- library ---------------------------------------------------------------------- */
-int ha_version(void);                      /* ABI version, currently 2                     */
+int ha_version(void);                      /* ABI version, currently 3                     */
 const char* ha_error_string(int code);
 const char* ha_last_cuda_error(void);      /* text of the last CUDA failure on this thread  */
 int ha_device_check(int device);           /* HA_OK iff `device` is compute capability 10.x */

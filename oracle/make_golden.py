@@ -46,7 +46,8 @@ def ref_args(**kw):
     d = dict(level=3, N_iters=5, using_weight=0, loss_method=0, rotation_range=10.0, proj="geo", Optimizer="LM",
              damping=0.1, train_damping=0, shift_range_lat=20.0, shift_range_lon=20.0, use_hessian=0, dropout=0,
              use_gt_depth=0, visualize=0, coe_shift_lat=100.0, coe_shift_lon=100.0, coe_heading=100.0,
-             coe_L1=100.0, coe_L2=100.0, coe_L3=100.0, coe_L4=100.0, estimate_depth=0, level_first=0)
+             coe_L1=100.0, coe_L2=100.0, coe_L3=100.0, coe_L4=100.0, estimate_depth=0, level_first=0,
+             beta1=0.9, beta2=0.999)
     d.update(kw)
     return types.SimpleNamespace(**d)
 
@@ -55,7 +56,8 @@ def o_args(a) -> O.LMArgs:
     return O.LMArgs(level=a.level, N_iters=a.N_iters, using_weight=a.using_weight, damping=a.damping,
                     train_damping=a.train_damping, rotation_range=a.rotation_range,
                     shift_range_lat=a.shift_range_lat, shift_range_lon=a.shift_range_lon,
-                    use_hessian=a.use_hessian, level_first=a.level_first)
+                    use_hessian=a.use_hessian, level_first=a.level_first, Optimizer=a.Optimizer, proj=a.proj,
+                    beta1=a.beta1, beta2=a.beta2)
 
 
 def csum(*ts) -> np.ndarray:
@@ -157,10 +159,20 @@ def run_ref_loop(net, kind, sat, grd, conf, a, ford=None, pose0=None):
                                                            ford["side_m"], require_jac=True)
         gf = grd[lv] * mask[:, None]
         gc = conf[lv] * mask[:, None]
-        h2 = gf.shape[-2] // 2
+        h2 = gf.shape[-2] // 2 if a.proj == "geo" else 0            # models_kitti.py:1194-1205
         pin[:, it, lv] = torch.cat([su, sv, th], dim=1)
-        su, sv, th = net.LM_update(su, sv, th, sp[:, :, h2:], gc[:, :, h2:], gf[:, :, h2:], gc[:, :, h2:],
-                                   dj[:, :, :, h2:])
+        step_in = (su, sv, th, sp[:, :, h2:], gc[:, :, h2:], gf[:, :, h2:], gc[:, :, h2:], dj[:, :, :, h2:])
+        if a.Optimizer == "LM":
+            su, sv, th = net.LM_update(*step_in)
+        elif a.Optimizer == "SGD":                                   # :1214-1232
+            su, sv, th = net.SGD_update(*step_in)
+        elif a.Optimizer == "ADAM":                                  # :1240-1253
+            t = it * a.level + lv
+            if t == 0:
+                adam_m, adam_v = 0, 0
+            su, sv, th, adam_m, adam_v = net.ADAM_update(*step_in, adam_m, adam_v, t)
+        elif a.Optimizer == "GN":                                    # models_ford.py:775-781
+            su, sv, th = net.GN_update(*step_in)
         su, sv, th = su.detach(), sv.detach(), th.detach()
         traj[:, it, lv] = torch.cat([su, sv, th], dim=1)
     return traj, pin
@@ -190,7 +202,9 @@ def fp64_truth(kind, sat, grd, conf, oa, damp, ford, pose0, r_pin):
     else:
         traj64 = torch.stack([res.lats, res.lons, res.thetas], dim=-1)
     L, B = len(sat), sat[0].shape[0]
-    nd = O.n_dof(kind, oa)
+    if oa.Optimizer == "ADAM":          # the Adam moments make a step depend on the whole history: no per-step restart
+        return dict(traj64=traj64.numpy())
+    nd = O.n_dof(kind, oa) if oa.Optimizer in ("LM", "GN") else 3
     lam = O.resolve_damping(oa, None if damp is None else damp.double(), nd, torch.float64)
     step = torch.zeros(B, oa.N_iters, L, 3, dtype=torch.float64)
     hess = torch.zeros(oa.N_iters, L, B, nd, nd, dtype=torch.float64)
@@ -200,7 +214,7 @@ def fp64_truth(kind, sat, grd, conf, oa, damp, ford, pose0, r_pin):
     for it in range(oa.N_iters):
         for lv in range(L):
             pin = r_pin[:, it, lv].double()
-            tab = O.kitti_ground_table(lv) if kind == "kitti" else O.ford_ground_table(lv, L)
+            tab = tuple(t.double() for t in O.ground_table(kind, lv, L, oa.proj))
             su, sv, th, st = O.lm_one_step(kind, s64[lv], g64[lv], c64[lv], tab, pin[:, 0:1], pin[:, 1:2], pin[:, 2:3],
                                            oa, lam, zero, f64)
             step[:, it, lv] = torch.cat([su, sv, th], dim=1)
@@ -519,11 +533,11 @@ def main():
             return sat, grd, conf, None, dict(seed=seed, B=B, A=A, L=L)
         return f
 
-    def planted_inputs(kind, seed, gt, A=512, L=3, side_m=None):
+    def planted_inputs(kind, seed, gt, A=512, L=3, side_m=None, l2=False):
         def f(oa):
             B = len(gt)
             fd = ford_dict(B, side_m) if kind == "ford" else None
-            sat, grd = O.planted_case(kind, B, A, L, seed, gt, oa, fd)
+            sat, grd = O.planted_case(kind, B, A, L, seed, gt, oa, fd, l2=l2)
             conf = [torch.ones(B, 1, *g.shape[-2:]) for g in grd]
             return sat, grd, conf, fd, dict(seed=seed, B=B, A=A, L=L, gt=np.array(gt, dtype=np.float32),
                                             side_m=np.float32(side_m or 0))
@@ -548,6 +562,18 @@ def main():
                  N_iters=3)
         kat_loop(rk, rf, "kat5_anisotropic", "kitti", planted_inputs("kitti", 59, GT2), shift_range_lat=20.0,
                  shift_range_lon=12.0, rotation_range=15.0)
+    if want("kat10"):  # optimiser ablations and the polar ground table (non-default flags)
+        kat_loop(rk, rf, "kat10_sgd", "kitti", planted_inputs("kitti", 101, GT2, l2=True), Optimizer="SGD", N_iters=3)
+        kat_loop(rk, rf, "kat10_adam", "kitti", planted_inputs("kitti", 102, GT2, l2=True), Optimizer="ADAM", N_iters=3)
+        kat_loop(rk, rf, "kat10_adam_level4", "kitti", planted_inputs("kitti", 103, GT2[:1], L=4, l2=True), Optimizer="ADAM",
+                 level=4, N_iters=2)
+        # GN_update ends in `if torch.isnan(theta_new):` (models_ford.py:594), which only evaluates for a batch of one
+        kat_loop(rk, rf, "kat10_gn_ford", "ford", planted_inputs("ford", 104, GT2[:1], A=512, side_m=512 * 0.22, l2=True),
+                 Optimizer="GN", N_iters=3)
+        kat_loop(rk, rf, "kat10_polar_kitti", "kitti", planted_inputs("kitti", 105, GT2), proj="polar", N_iters=3)
+        kat_loop(rk, rf, "kat10_polar_ford", "ford", planted_inputs("ford", 106, GT2, A=512, side_m=512 * 0.22), proj="nn",
+                 N_iters=2)
+        kat_loop(rk, rf, "kat10_polar_sgd", "kitti", rand_inputs(107), proj="polar", Optimizer="SGD", N_iters=2)
     if want("kat6"):   # forced out-of-range reset (models_kitti.py:1028-1033): start outside (-2.5, 2.5)
         p0 = torch.tensor([[3.0, 0.1, 0.2], [0.1, -2.8, -0.1]])
         kat_loop(rk, rf, "kat6_reset", "kitti", rand_inputs(61), N_iters=2,

@@ -57,6 +57,10 @@ class LMArgs:
     shift_range_lon: float = 20.0
     use_hessian: int = 0
     level_first: int = 0
+    Optimizer: str = "LM"          # 'LM' | 'SGD' | 'ADAM' (LM_S2GP) | 'GN' (LM_S2GP_Ford)
+    proj: str = "geo"              # anything else: polar ground table, residual over the whole ground image
+    beta1: float = 0.9             # train_kitti.py:480-481
+    beta2: float = 0.999
 
 
 # ----------------------------------------------------------------------------- ground tables
@@ -99,6 +103,24 @@ def ford_ground_table(level: int, n_levels: int = 3) -> Tuple[torch.Tensor, torc
     k0[0, 1] = kfl[0, 1] / 860 * 256
     k0[0, 2] = kfl[0, 2]
     return _lift_to_ground(k0, gh, gw)
+
+
+def polar_ground_table(level: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """models_kitti.py:684-698 / models_ford.py:156-170 (grd_img2cam_polar), used for every proj != 'geo'."""
+    gh, gw = 256 / (2 ** (3 - level)), 1024 / (2 ** (3 - level))
+    v, u = torch.meshgrid(torch.arange(0, gh, dtype=torch.float32), torch.arange(0, gw, dtype=torch.float32), indexing="ij")
+    theta = u / gw * np.pi / 4
+    radius = (1 - v / gh) * 30
+    z = radius * torch.cos(np.pi / 4 - theta)
+    x = -radius * torch.sin(np.pi / 4 - theta)
+    y = CAMERA_HEIGHT * torch.ones_like(z)
+    return torch.stack([x, y, z], dim=-1).contiguous(), torch.ones_like(z)
+
+
+def ground_table(kind: str, level: int, n_levels: int, proj: str = "geo"):
+    if proj != "geo":
+        return polar_ground_table(level)
+    return kitti_ground_table(level) if kind == "kitti" else ford_ground_table(level, n_levels)
 
 
 # ----------------------------------------------------------------------------- geometry
@@ -274,6 +296,58 @@ def lm_update(su, sv, th, sat_proj, grd_feat, grd_conf, dfeat, args: LMArgs, dam
     return su_n, sv_n, th_n, stats
 
 
+def pose_gradient(sat_proj, grd_feat, dfeat):
+    """The l2-loss gradient both first-order updates use (models_kitti.py:1072-1078, :1106-1112): sum 2 (s - g) J."""
+    r = sat_proj - grd_feat
+    return torch.sum((2 * r)[None, ...] * dfeat, dim=[2, 3, 4]).transpose(0, 1)       # [B, 3]
+
+
+def sgd_update(su, sv, th, sat_proj, grd_feat, dfeat):
+    """LM_S2GP.SGD_update, models_kitti.py:1056-1084: all three components, step 0.01, no reset, no RNG draw."""
+    d = pose_gradient(sat_proj, grd_feat, dfeat)
+    zero = torch.zeros(d.shape[0], dtype=d.dtype)
+    return su - 0.01 * d[:, 0:1], sv - 0.01 * d[:, 1:2], th - 0.01 * d[:, 2:3], StepStats(
+        torch.zeros(d.shape[0], 3, 3, dtype=d.dtype), d, zero, zero, zero, -0.01 * d)
+
+
+def adam_update(su, sv, th, sat_proj, grd_feat, dfeat, m, v, t, args: LMArgs):
+    """LM_S2GP.ADAM_update, models_kitti.py:1086-1124."""
+    d = pose_gradient(sat_proj, grd_feat, dfeat)
+    m = args.beta1 * m + (1 - args.beta1) * d
+    v = args.beta2 * v + (1 - args.beta2) * (d * d)
+    m_hat = m / (1 - args.beta1 ** (t + 1))
+    v_hat = v / (1 - args.beta2 ** (t + 1))
+    step = m_hat / (v_hat ** 0.5 + 1e-8)
+    zero = torch.zeros(d.shape[0], dtype=d.dtype)
+    st = StepStats(torch.zeros(d.shape[0], 3, 3, dtype=d.dtype), d, zero, zero, zero, -0.01 * step)
+    return su - 0.01 * step[:, 0:1], sv - 0.01 * step[:, 1:2], th - 0.01 * step[:, 2:3], m, v, st
+
+
+def gn_update(su, sv, th, sat_proj, grd_feat, grd_conf, dfeat, args: LMArgs, rand_uv):
+    """LM_S2GP_Ford.GN_update, models_ford.py:534-598: s / ||s|| (no clamp), g as it is, inverse of the undamped
+    J^T W J, the LM update's reset rule and RNG draws."""
+    N, B, C, H, W = dfeat.shape
+    sn = torch.norm(sat_proj.reshape(B, -1), p=2, dim=-1)
+    s = sat_proj / sn[:, None, None, None]
+    dfeat = dfeat / sn[None, :, None, None, None]
+    r = s - grd_feat
+    if args.using_weight:
+        w = grd_conf.repeat(1, C, 1, 1).reshape(B, C * H * W)
+    else:
+        w = torch.ones([B, C * H * W], dtype=s.dtype)
+    J = dfeat.flatten(start_dim=2).permute(1, 2, 0)
+    JtW = J.transpose(1, 2) * w.unsqueeze(1)
+    Hm = JtW @ J
+    grad = JtW @ r.reshape(B, -1, 1)
+    delta = -torch.inverse(Hm) @ JtW @ r.reshape(B, C * H * W, 1)
+    su_n, sv_n, th_n = su + delta[:, 0:1, 0], sv + delta[:, 1:2, 0], th + delta[:, 2:3, 0]
+    ru, rv = rand_uv
+    su_n = torch.where((su_n > -2.5) & (su_n < 2.5), su_n, ru.to(su_n.dtype))
+    sv_n = torch.where((sv_n > -2.5) & (sv_n < 2.5), sv_n, rv.to(sv_n.dtype))
+    gn = torch.norm(grd_feat.reshape(B, -1), p=2, dim=-1)
+    return su_n, sv_n, th_n, StepStats(Hm, grad[:, :, 0], sn, gn, torch.sum(r.reshape(B, -1) ** 2, dim=-1), delta[:, :, 0])
+
+
 def resolve_damping(args: LMArgs, damping_param: Optional[torch.Tensor], n_dof: int, dtype=torch.float32):
     """models_kitti.py:958-966: trained lambda = 10^(-6 + 11*sigmoid(p)), else args.damping."""
     if args.train_damping:
@@ -288,9 +362,11 @@ def draw_reset(B: int):
     return u, v
 
 
-def lm_one_step(kind: str, sf, gf, gc, tab, su, sv, th, args: LMArgs, lam, draws, ford: Optional[dict] = None):
+def lm_one_step(kind: str, sf, gf, gc, tab, su, sv, th, args: LMArgs, lam, draws, ford: Optional[dict] = None,
+                adam: Optional[dict] = None):
     """One (iteration, level) body of the reference's forward loop: project_map_to_grd ->
-    masking / bottom-half crop -> LM_update (models_kitti.py:1187-1260 / models_ford.py:700-800)."""
+    masking / bottom-half crop (proj 'geo' only) -> the update of args.Optimizer
+    (models_kitti.py:1187-1260 / models_ford.py:700-800).  `adam` = dict(m, v, t), updated in place."""
     B = sf.shape[0]
     dt = sf.dtype
     A = sf.shape[-1]
@@ -305,9 +381,16 @@ def lm_one_step(kind: str, sf, gf, gc, tab, su, sv, th, args: LMArgs, lam, draws
     dj = dj * mask[None, :, None]                               # :929
     gfm = gf * mask[:, None]                                    # :1191
     gcm = (gc * mask[:, None]) if gc is not None else torch.ones(B, 1, *gf.shape[-2:], dtype=dt) * mask[:, None]
-    h2 = gf.shape[-2] // 2                                      # :1195-1199 bottom half only
-    return lm_update(su, sv, th, sp[:, :, h2:], gfm[:, :, h2:], gcm[:, :, h2:], dj[:, :, :, h2:],
-                     args, lam, draws, always_3dof=(kind == "ford"))
+    h2 = gf.shape[-2] // 2 if args.proj == "geo" else 0         # :1194-1205 bottom half only for the ground-plane lift
+    sp, gfm, gcm, dj = sp[:, :, h2:], gfm[:, :, h2:], gcm[:, :, h2:], dj[:, :, :, h2:]
+    if args.Optimizer == "SGD":
+        return sgd_update(su, sv, th, sp, gfm, dj)
+    if args.Optimizer == "ADAM":
+        su, sv, th, adam["m"], adam["v"], st = adam_update(su, sv, th, sp, gfm, dj, adam["m"], adam["v"], adam["t"], args)
+        return su, sv, th, st
+    if args.Optimizer == "GN":
+        return gn_update(su, sv, th, sp, gfm, gcm, dj, args, draws)
+    return lm_update(su, sv, th, sp, gfm, gcm, dj, args, lam, draws, always_3dof=(kind == "ford"))
 
 
 def n_dof(kind: str, args: LMArgs) -> int:
@@ -354,9 +437,11 @@ def lm_loop(kind: str, sat_feats: Sequence[torch.Tensor], grd_feats: Sequence[to
     else:
         ndof = 2 if args.rotation_range == 0 else 1
     lam = resolve_damping(args, damping_param, ndof, dt)
+    draws_rng = ndof == 3 and args.Optimizer in ("LM", "GN")     # SGD_update / ADAM_update draw nothing
+    adam = dict(m=0, v=0, t=0)
     tabs = []
     for lv in range(L):
-        tabs.append(kitti_ground_table(lv) if kind == "kitti" else ford_ground_table(lv, L))
+        tabs.append(tuple(t.to(dt) for t in ground_table(kind, lv, L, args.proj)))
     rec_u = torch.zeros(B, args.N_iters, L, dtype=dt)
     rec_v = torch.zeros(B, args.N_iters, L, dtype=dt)
     rec_t = torch.zeros(B, args.N_iters, L, dtype=dt)
@@ -364,11 +449,14 @@ def lm_loop(kind: str, sat_feats: Sequence[torch.Tensor], grd_feats: Sequence[to
     pin = [[None] * L for _ in range(args.N_iters)]
     for k, (it, lv) in enumerate(_step_order(args.N_iters, L, args.level_first)):
         draws = None
-        if ndof == 3:
+        if draws_rng:
             draws = reset_draws[k] if reset_draws is not None else draw_reset(B)
         pin[it][lv] = (su.clone(), sv.clone(), th.clone())
+        adam["t"] = it * args.level + lv                          # models_kitti.py:1241 (it multiplies by args.level)
+        if adam["t"] == 0:
+            adam["m"], adam["v"] = 0, 0                           # :1242-1244
         su, sv, th, st = lm_one_step(kind, sat_feats[lv], grd_feats[lv], grd_confs[lv], tabs[lv], su, sv, th, args, lam,
-                                     draws, ford)
+                                     draws, ford, adam)
         stats[it][lv] = st
         rec_u[:, it, lv], rec_v[:, it, lv], rec_t[:, it, lv] = su[:, 0], sv[:, 0], th[:, 0]
     if kind == "kitti":      # models_kitti.py:1281-1283: lats = shift_v, lons = shift_u
@@ -580,23 +668,27 @@ def smooth_pyramid(B: int, A: int, n_levels: int, seed: int, dtype=torch.float32
     return out
 
 
-def planted_case(kind: str, B: int, A: int, n_levels: int, seed: int, gt, args: LMArgs, ford: Optional[dict] = None):
+def planted_case(kind: str, B: int, A: int, n_levels: int, seed: int, gt, args: LMArgs, ford: Optional[dict] = None,
+                 l2: bool = False):
     """KAT-4: ground features are the satellite features warped at a planted pose `gt`
-    ([B,3] = su,sv,th), so the LM loop contracts onto gt."""
+    ([B,3] = su,sv,th), so the LM loop contracts onto gt.  `l2`: both pyramids L2-normalised per sample like the
+    U-Net outputs (VGG.py:172-175) — the first-order updates take the features as they are."""
     sat = smooth_pyramid(B, A, n_levels, seed)
+    if l2:
+        sat = [l2_norm(x) for x in sat]
     gt = torch.as_tensor(gt, dtype=torch.float32).reshape(B, 3)
     su, sv, th = gt[:, 0:1], gt[:, 1:2], gt[:, 2:3]
     grd = []
     for lv in range(n_levels):
+        tab = ground_table(kind, lv, n_levels, args.proj)
         if kind == "kitti":
-            tab = kitti_ground_table(lv)
             uv, mask, *_ = kitti_sat_uv(tab[0], tab[1], su, sv, th, sat[lv].shape[-1], args, want_jac=False)
         else:
-            tab = ford_ground_table(lv, n_levels)
             uv, mask, *_ = ford_sat_uv(tab[0], tab[1], ford["R_FL"], ford["T_FL"], su, sv, th, sat[lv].shape[-1],
                                        ford["side_m"], args, want_jac=False)
         f, _ = bilinear_sample(sat[lv], uv)
-        grd.append((f * mask[:, None]).contiguous())
+        f = (f * mask[:, None]).contiguous()
+        grd.append(l2_norm(f) if l2 else f)
     return sat, grd
 
 

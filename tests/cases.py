@@ -29,10 +29,20 @@ LOOP_CASES = {
     "kat5_ford1280": ("ford", "planted", dict(N_iters=3), {}),
     "kat5_anisotropic": ("kitti", "planted", dict(shift_range_lat=20.0, shift_range_lon=12.0, rotation_range=15.0), {}),
     "kat6_reset": ("kitti", "rand", dict(N_iters=2), dict(pose0_from_golden=True)),
+    # the optimiser ablations (models_kitti.py:1056-1124, models_ford.py:534-598) and the polar ground
+    # table of every proj != 'geo' (models_kitti.py:684-698); "planted_l2" = planted pose on L2-normalised pyramids
+    "kat10_sgd": ("kitti", "planted_l2", dict(Optimizer="SGD", N_iters=3), {}),
+    "kat10_adam": ("kitti", "planted_l2", dict(Optimizer="ADAM", N_iters=3), {}),
+    "kat10_adam_level4": ("kitti", "planted_l2", dict(Optimizer="ADAM", level=4, N_iters=2), {}),
+    "kat10_gn_ford": ("ford", "planted_l2", dict(Optimizer="GN", N_iters=3), {}),
+    "kat10_polar_kitti": ("kitti", "planted", dict(proj="polar", N_iters=3), {}),
+    "kat10_polar_ford": ("ford", "planted", dict(proj="nn", N_iters=2), {}),
+    "kat10_polar_sgd": ("kitti", "rand", dict(proj="polar", Optimizer="SGD", N_iters=2), {}),
 }
 # the cases cheap enough for the CPU suite (the rest are exercised by the gpu parity tests)
 CPU_LOOP_CASES = ["kat3_random_kitti", "kat4_planted_kitti", "kat4_planted_ford", "kat5_weight", "kat5_shiftonly",
-                  "kat5_rotonly", "kat5_level4", "kat6_reset"]
+                  "kat5_rotonly", "kat5_level4", "kat6_reset", "kat10_sgd", "kat10_adam_level4", "kat10_gn_ford",
+                  "kat10_polar_ford"]
 
 
 def csum(*ts) -> np.ndarray:
@@ -60,7 +70,7 @@ def build_loop_case(name):
     else:
         gt = gold["gt"]
         ford = ford_dict(B, float(gold["side_m"])) if kind == "ford" else None
-        sat, grd = O.planted_case(kind, B, A, L, seed, gt, args, ford)
+        sat, grd = O.planted_case(kind, B, A, L, seed, gt, args, ford, l2=(fam == "planted_l2"))
         conf = [torch.ones(B, 1, *g.shape[-2:]) for g in grd]
     np.testing.assert_allclose(csum(*sat, *grd), gold["in_csum"], rtol=1e-6, err_msg="input regeneration drifted")
     pose0 = None
@@ -80,7 +90,7 @@ def ref_args(**kw):
     d = dict(level=3, N_iters=5, using_weight=0, loss_method=0, rotation_range=10.0, proj="geo", Optimizer="LM",
              damping=0.1, train_damping=0, shift_range_lat=20.0, shift_range_lon=20.0, use_hessian=0, dropout=0,
              use_gt_depth=0, visualize=0, coe_shift_lat=100.0, coe_shift_lon=100.0, coe_heading=100.0,
-             coe_L1=100.0, coe_L2=100.0, coe_L3=100.0, coe_L4=100.0, estimate_depth=0)
+             coe_L1=100.0, coe_L2=100.0, coe_L3=100.0, coe_L4=100.0, estimate_depth=0, beta1=0.9, beta2=0.999)
     d.update(kw)
     return types.SimpleNamespace(**d)
 
@@ -88,7 +98,8 @@ def ref_args(**kw):
 def args_from_lmargs(a: "O.LMArgs"):
     return ref_args(level=a.level, N_iters=a.N_iters, using_weight=a.using_weight, damping=a.damping,
                     train_damping=a.train_damping, rotation_range=a.rotation_range, shift_range_lat=a.shift_range_lat,
-                    shift_range_lon=a.shift_range_lon, use_hessian=a.use_hessian)
+                    shift_range_lon=a.shift_range_lon, use_hessian=a.use_hessian, Optimizer=a.Optimizer, proj=a.proj,
+                    beta1=a.beta1, beta2=a.beta2)
 
 
 G2SP_CASES = {"g2sp_planted": ("planted", dict(N_iters=3)), "g2sp_random": ("rand", dict(N_iters=2)),

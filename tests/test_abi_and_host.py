@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.EXPORTS) == names
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.ha_version() == _lib.HA_ABI_VERSION == 2
+    assert lib.ha_version() == _lib.HA_ABI_VERSION == 3
     assert b"workspace" in lib.ha_error_string(-2)
 
 
@@ -79,7 +79,7 @@ def test_struct_layouts_match_header():
     assert ctypes_fields(_lib.HaLevel) == header_struct_fields("HaLevel")
     assert ctypes_fields(_lib.HaVggStateDict) == header_struct_fields("HaVggStateDict")
     assert ctypes.sizeof(_lib.HaLevel) == 32
-    assert ctypes.sizeof(_lib.HaLmParams) == 8 * 4 + (3 + 3 + 4 + 4 + 4) * 4 + 4 * 4
+    assert ctypes.sizeof(_lib.HaLmParams) == 8 * 4 + (3 + 3 + 4 + 4 + 4) * 4 + 4 * 4 + 6 * 4
     assert ctypes.sizeof(_lib.HaVggStateDict) == 2 * 17 * 8
 
 
@@ -111,11 +111,36 @@ def test_out_of_scope_flags_raise_at_construction():
     """flags outside the accelerated path raise NotImplementedError instead of silently running
     something else (the Ford model used to accept --dropout)."""
     for cls in (LM_S2GP, LM_S2GP_Ford):
-        for kw in (dict(dropout=1), dict(Optimizer="SGD"), dict(proj="nn")):
+        for kw in (dict(dropout=1), dict(Optimizer="NN"), dict(Optimizer="RMSprop")):
             with pytest.raises(NotImplementedError):
                 cls(K.ref_args(**kw))
     with pytest.raises(NotImplementedError):
         LM_S2GP_Ford(K.ref_args(estimate_depth=1))
+    # the reference's own Ford SGD_update / ADAM branch cannot run (models_ford.py:609-628 indexes a 2-D tensor with three
+    # subscripts; there is no ADAM_update): refused; KITTI has no GN
+    for kw in (dict(Optimizer="SGD"), dict(Optimizer="ADAM")):
+        with pytest.raises(NotImplementedError):
+            LM_S2GP_Ford(K.ref_args(**kw))
+    with pytest.raises(NotImplementedError):
+        LM_S2GP(K.ref_args(Optimizer="GN"))
+
+
+def test_ablation_flags_map_to_the_engine_setup():
+    """--Optimizer SGD / ADAM (LM_S2GP), GN (LM_S2GP_Ford) and any --proj other than 'geo' (polar ground
+    table, whole ground image) are accepted and reach the kernel as HaLmParams fields."""
+    net = LM_S2GP(K.ref_args(Optimizer="ADAM", proj="polar", level=4, rotation_range=0.0, using_weight=1, beta1=0.8))
+    st = engine.setup_from_args(net.args, "kitti", 0)
+    assert (st.optimizer, st.full_height, st.adam_level_mult, st.dof, st.using_weight, st.adam_beta1) == ("ADAM", 1, 4, 3, 0, 0.8)
+    assert not engine.draws_reset(st)                                  # ADAM_update draws nothing from the CPU generator
+    np.testing.assert_array_equal(net._tables_cpu[1][..., :3].numpy(), O.polar_ground_table(1)[0].numpy())
+    assert float(net._tables_cpu[1][..., 3].min()) == 1.0
+    f = LM_S2GP_Ford(K.ref_args(Optimizer="GN", proj="nn"))
+    st = engine.setup_from_args(f.args, "ford", 0)
+    assert (st.optimizer, st.full_height, st.dof) == ("GN", 1, 3) and engine.draws_reset(st)
+    p = engine.make_params(st, engine.Pyramid([torch.zeros(1, 64, 64, 256)], [None]), [0.1] * 3, 112.64)
+    assert (p.optimizer, p.full_height) == (_lib.HA_OPT_GN, 1)
+    st = engine.setup_from_args(K.ref_args(), "kitti", 0)
+    assert (st.optimizer, st.full_height) == ("LM", 0) and engine.draws_reset(st)
 
 
 def test_no_cpu_fallback():

@@ -121,6 +121,38 @@ def test_lm_per_step_vs_reference(name):
             assert near(st[:, 15:15 + n], g["delta"][it, lv], g["delta64"][it, lv], 2e-6)
 
 
+@pytest.mark.parametrize("name", ["kat10_sgd", "kat10_gn_ford", "kat10_polar_kitti", "kat10_polar_ford", "kat10_polar_sgd"])
+def test_ablation_step_vs_reference(name):
+    """SURVEY.md 8 f-3 (SGD_update, GN_update, the polar ground table): every step restarted from the REFERENCE's pose
+    state; the new pose against the reference's and against the float64 run of the same step."""
+    c = K.build_loop_case(name)
+    net = make_net(c)
+    sat, grd = pyramids(c)
+    g, a = c["gold"], c["args"]
+    ra = K.args_from_lmargs(a)
+    setup = engine.setup_from_args(ra, c["kind"], a.level_first)
+    lam = engine.resolve_damping(ra, net.damping, setup.dof)
+    tabs = net._tables(torch.device(DEV))
+    ext, side = None, None
+    if c["kind"] == "ford":
+        ext = engine.ford_extrinsics(c["ford"]["R_FL"], c["ford"]["T_FL"]).to(DEV)
+        side = c["ford"]["side_m"]
+    zeros = torch.zeros(2, c["B"])
+    worst = 0.0
+    for it in range(a.N_iters):
+        for lv in range(c["L"]):
+            pin = torch.from_numpy(g["pose_in"][:, it, lv])
+            pose, st = engine.lm_step(setup, lv, sat, grd, tabs, lam, pin, ext, side, reset_uv=zeros)
+            pose = pose.cpu().numpy()
+            want, truth = g["traj"][:, it, lv], g["step64"][:, it, lv]
+            noise = np.abs(want - truth)
+            ok = (np.abs(pose - want) <= 2e-6 + 1e-4 * np.abs(want)) | (np.abs(pose - truth) <= 1.5 * noise + 1e-6)
+            assert ok.all(), "%s it%d lv%d: %g vs ref, %g vs fp64" % (name, it, lv, np.abs(pose - want).max(),
+                                                                     np.abs(pose - truth).max())
+            worst = max(worst, float(np.abs(pose - want).max()))
+    print("%s: per-step max|d| vs reference %.2e" % (name, worst))
+
+
 @pytest.mark.parametrize("name", list(K.G2SP_CASES))
 def test_g2sp_vs_reference(name):
     """LM_G2SP (ground -> satellite plane): whole trajectory and every step restarted from the

@@ -64,7 +64,7 @@ def test_lm_loop_matches_reference(name):
     else:
         traj = torch.stack([res.lats, res.lons, res.thetas], dim=-1)
     np.testing.assert_allclose(traj.numpy(), c["gold"]["traj"], rtol=0, atol=2e-6)
-    if "gt" in c["gold"].files and name not in ("kat5_ford1280",):
+    if "gt" in c["gold"].files and name not in ("kat5_ford1280",) and (not name.startswith("kat10") or name == "kat10_gn_ford"):
         # planted pose: the reference itself converges onto gt (contractive input)
         np.testing.assert_allclose(c["gold"]["traj"][:, -1, -1], c["gold"]["gt"], atol=5e-5)
 
