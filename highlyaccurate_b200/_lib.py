@@ -29,7 +29,8 @@ EXPORTS = ["ha_version", "ha_error_string", "ha_last_cuda_error", "ha_device_che
            "ha_vgg_pack_weights", "ha_vgg_workspace_bytes", "ha_vgg_forward", "ha_conv3x3_workspace_bytes",
            "ha_conv3x3_nhwc", "ha_launch_count", "ha_comm_unique_id", "ha_comm_init", "ha_comm_destroy",
            "ha_pose_allgather", "ha_lm_backward_workspace_bytes", "ha_lm_step_backward",
-           "ha_pose_loss", "ha_pose_loss_backward"]
+           "ha_pose_loss", "ha_pose_loss_backward", "ha_img_affine_u8", "ha_img_resize_workspace_bytes",
+           "ha_img_resize_to_tensor"]
 
 
 class HaLevel(C.Structure):
@@ -95,6 +96,10 @@ def lib() -> C.CDLL:
                                       vp, vp, vp, vp, vp, sz, vp]
     L.ha_pose_loss.argtypes = [vp, vp, i32, i32, i32, C.POINTER(C.c_float), vp, vp, vp]
     L.ha_pose_loss_backward.argtypes = [vp, vp, i32, i32, i32, C.POINTER(C.c_float), vp, vp, vp, vp]
+    L.ha_img_affine_u8.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, vp]
+    L.ha_img_resize_workspace_bytes.restype = sz
+    L.ha_img_resize_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.ha_img_resize_to_tensor.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, sz, vp]
     L.ha_comm_unique_id.argtypes = [vp]
     L.ha_comm_init.argtypes = [C.POINTER(vp), i32, i32, vp, i32]
     L.ha_comm_destroy.argtypes = [vp]

@@ -239,6 +239,29 @@ size_t ha_conv3x3_workspace_bytes(int cin, int cout, int B, int H, int W);
 int ha_conv3x3_nhwc(const float* in_nhwc, int cin, const float* w_oihw, const float* bias, float* out_nhwc, int cout,
                     int B, int H, int W, int precision, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- input pipeline on the device --------------------------------------------------------
+ * Replaces the per-sample PIL / torchvision preparation of dataLoader/KITTI_dataset.py:128-157, :256-288 and
+ * dataLoader/Ford_dataset.py:178-209, stage by stage and bit for bit (Pillow's libImaging arithmetic; every stage
+ * rounds to uint8, so the stages stay separate launches).  Images are uint8 RGB, [B][H][W][3] packed
+ * (src_pixel_bytes = 3, what PNG decoders deliver) or [B][H][W][4] RGBX (src_pixel_bytes = 4, what these functions write).
+ *
+ * ha_img_affine_u8: Image.transform(size, Image.AFFINE, data, resample) of a batch, one 6-vector per image.
+ *   coef:     DEVICE [B][6] float64 = PIL's `data` (destination pixel centre -> source point), as Image.rotate builds
+ *             it (round(cos, 15), ...) or (1, 0, tx, 0, 1, ty) for the shifts.
+ *   resample: 0 = NEAREST (Image.rotate's default: 16.16 fixed point, Geometry.c affine_fixed), 2 = BILINEAR
+ *             (float64, clamped neighbours, truncation; Geometry.c bilinear_filter32RGB); zero fill outside.
+ *   dst_rgbx: [B][H][W][4] uint8, or NULL when dst_chw is given.
+ *   dst_chw:  NULL, or [B][3][crop_side][crop_side] fp32: TF.center_crop(crop_side) + ToTensor (x / 255) of the
+ *             result, written directly (KITTI_dataset.py:150-155, Ford_dataset.py:206-207).
+ * ha_img_resize_to_tensor: transforms.Resize([out_h, out_w]) (PIL's antialiased bilinear resample, Resample.c 8bpc:
+ *   horizontal then vertical pass in 22-bit fixed point) + ToTensor: [B][H][W] uint8 -> [B][3][out_h][out_w] fp32
+ *   (grdimage_transform, KITTI_dataset.py:299-302, Ford_dataset.py:151-154).  Equal sizes = ToTensor alone. */
+int ha_img_affine_u8(const uint8_t* src, int src_pixel_bytes, uint8_t* dst_rgbx, float* dst_chw, int crop_side, int B, int H,
+                     int W, const double* coef, int resample, void* stream);
+size_t ha_img_resize_workspace_bytes(int B, int H, int W, int out_h, int out_w);
+int ha_img_resize_to_tensor(const uint8_t* src, int src_pixel_bytes, int B, int H, int W, int out_h, int out_w, float* dst_chw,
+                            void* ws, size_t ws_bytes, void* stream);
+
 /* ---- multi-GPU: the ONE collective of the path (the reference has no distributed code) ----
  * Samples are independent, so ranks own contiguous batch shards and exchange nothing until the
  * end: one all-gather of the final (shift_u, shift_v, theta) poses.  NCCL (libnccl.so.2) is bound
