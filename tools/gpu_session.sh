@@ -7,6 +7,7 @@
 #   ncu_conv          ncu --set full of the tcgen05 convs   ncu_lm     ncu --set full of the LM step (B=256)
 #   lm_ab             tools/bench_lm.py at B=256 and B=32   sanitize   compute-sanitizer memcheck on smoke()
 #   ncu_lm_stress / ncu_conv_stress   BASELINE config 5 captures    convab     per-layer CTA-pair vs single-CTA conv table
+#   pipeline          input pipeline (f-4) bench + launch list
 TAG=$1; shift
 OUT=gpurun_out
 REP=/tmp/ha_ncu          # raw .ncu-rep files stay on the box (gpurun copies back at most 64 MiB): their raw pages come back as CSV
@@ -76,6 +77,12 @@ while [ $# -gt 0 ]; do
       timeout 400 python tools/bench_lm.py 256 10 3 0,1 > $OUT/bench_lm_b256_$TAG.log 2>&1
       timeout 400 python tools/bench_lm.py 32 20 3 0 > $OUT/bench_lm_b32_$TAG.log 2>&1
       grep -h "variant\|level\|whole" $OUT/bench_lm_b256_$TAG.log $OUT/bench_lm_b32_$TAG.log | cut -c1-200 ;;
+    pipeline)        # input pipeline on the GPU vs PIL on the host, plus its ncu launch list
+      timeout 300 python tools/bench_input_pipeline.py 32 20 8 > $OUT/pipeline_$TAG.json 2> $OUT/pipeline_$TAG.err
+      cat $OUT/pipeline_$TAG.json | cut -c1-900
+      timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:img_ -s 24 -c 8 --csv \
+        --log-file $OUT/pipeline_launches_$TAG.csv python tools/bench_input_pipeline.py 32 2 1 > /dev/null 2>&1
+      grep -v "^==" $OUT/pipeline_launches_$TAG.csv | cut -d, -f5,12- | head -30 ;;
     sanitize)
       timeout 600 compute-sanitizer --tool memcheck python __graft_entry__.py smoke > $OUT/memcheck_smoke_$TAG.log 2>&1
       tail -3 $OUT/memcheck_smoke_$TAG.log ;;
