@@ -50,6 +50,7 @@ class VGGUnet(nn.Module):
         self._load_pretrained_encoder()
         self.precision = os.environ.get("HA_VGG_PRECISION", "f16x3")
         self._runner = engine.VggRunner()
+        self.native_train = True      # train mode: U-Net backward in libha_b200.so (engine.VggTrain); False = torch autograd / cuDNN
         self._named = None            # name -> Parameter, built once (Parameter objects are stable across .to() / load_state_dict)
 
     def _load_pretrained_encoder(self):
@@ -101,6 +102,27 @@ class VGGUnet(nn.Module):
         feats = [p.nchw(l, normalised=True) for l in range(len(p.feats))]
         confs = [c[:, None] for c in p.confs]
         return feats, confs
+
+    def forward_train(self, x):
+        """Train-mode features with the NATIVE backward (engine.VggTrain: tcgen05 forward keeping its activations, tcgen05
+        data / weight gradients) where it applies — CUDA, three computed levels, f16x3 — else `forward_autograd`.
+        Returns ([L2-normalised NHWC features], [confidences [B,1,H,W]]) for `level`."""
+        if not (self.native_train and engine.VggTrain.supports(x, self.n_levels(), self.precision)):
+            feats, confs = self.forward_autograd(x)
+            return [f.permute(0, 2, 3, 1).contiguous() for f in feats], confs
+        if self._named is None:
+            self._named = dict(self.named_parameters())
+        names = engine.VGG_CONV_NAMES
+        params = [self._named[n + ".weight"] for n in names[:engine.N_FEATURE_CONVS]] + \
+                 [self._named[n + ".bias"] for n in names[:engine.N_BIASED_CONVS]]
+        out = engine.VggTrain.apply(self._runner, self._named, x, *params)
+        raw, confs = out[:3], out[3:]
+        feats = []
+        for f in raw:                                                  # VGG.py:172-175 / :511-514, on the NHWC tensor
+            nrm = f.reshape(f.shape[0], -1).norm(p=2, dim=-1).clamp_min(1e-12)
+            feats.append(f / nrm[:, None, None, None])
+        sl = self.level_slice()
+        return feats[sl], [c[:, None] for c in confs][sl]
 
     def forward_autograd(self, x):
         """The same network (VGG.py:121-203) evaluated with torch ops through the parameter containers, so that autograd

@@ -30,7 +30,9 @@ EXPORTS = ["ha_version", "ha_error_string", "ha_last_cuda_error", "ha_device_che
            "ha_conv3x3_nhwc", "ha_launch_count", "ha_comm_unique_id", "ha_comm_init", "ha_comm_destroy",
            "ha_pose_allgather", "ha_lm_backward_workspace_bytes", "ha_lm_step_backward",
            "ha_pose_loss", "ha_pose_loss_backward", "ha_img_affine_u8", "ha_img_resize_workspace_bytes",
-           "ha_img_resize_to_tensor"]
+           "ha_img_resize_to_tensor", "ha_vgg_train_workspace_bytes", "ha_vgg_forward_train",
+           "ha_vgg_backward_workspace_bytes", "ha_vgg_backward", "ha_conv3x3_backward_workspace_bytes",
+           "ha_conv3x3_backward_nhwc"]
 
 
 class HaLevel(C.Structure):
@@ -87,6 +89,16 @@ def lib() -> C.CDLL:
     L.ha_vgg_workspace_bytes.restype = sz
     L.ha_vgg_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.ha_vgg_forward.argtypes = [vp, vp, i32, i32, i32, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, sz, vp]
+    L.ha_vgg_train_workspace_bytes.restype = sz
+    L.ha_vgg_train_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    L.ha_vgg_forward_train.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, sz, vp]
+    L.ha_vgg_backward_workspace_bytes.restype = sz
+    L.ha_vgg_backward_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    L.ha_vgg_backward.argtypes = [C.POINTER(HaVggStateDict), vp, i32, i32, i32, i32, vp, C.POINTER(vp), C.POINTER(HaVggStateDict),
+                                  vp, sz, vp]
+    L.ha_conv3x3_backward_workspace_bytes.restype = sz
+    L.ha_conv3x3_backward_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.ha_conv3x3_backward_nhwc.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
     L.ha_conv3x3_workspace_bytes.restype = sz
     L.ha_conv3x3_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.ha_conv3x3_nhwc.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]

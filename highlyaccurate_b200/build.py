@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libha_b200.so")
 STAMP = os.path.join(LIB_DIR, "libha_b200.stamp")
-SOURCES = ["api.cu", "comm.cu", "imgproc.cu", "lm_backward.cu", "lm_kernels.cu", "vgg.cu", "vgg_tc.cu"]
+SOURCES = ["api.cu", "comm.cu", "imgproc.cu", "lm_backward.cu", "lm_kernels.cu", "vgg.cu", "vgg_backward.cu", "vgg_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("HA_NVCC_EXTRA", "").split()
 

@@ -279,12 +279,13 @@ static int vgg_forward_simt(const char* packed, const PackedLayout& L, const flo
 }
 
 static int vgg_run(const char* packed, const float* img, int B, int H, int W, int n_levels, int precision,
-                   float* const* out_feat, float* const* out_scale, float* const* out_conf, Arena& ar, cudaStream_t st) {
+                   float* const* out_feat, float* const* out_scale, float* const* out_conf, Arena& ar, cudaStream_t st,
+                   TcSaved* saved = nullptr) {
   const PackedLayout L = vgg_packed_layout();
   double* norm_part = (double*)ar.take((size_t)HA_MAX_LEVELS * B * kNormChunks * sizeof(double));
   int rc;
   if (precision == HA_CONV_FP32_SIMT) rc = vgg_forward_simt(packed, L, img, B, H, W, n_levels, out_feat, ar, st);
-  else rc = vgg_forward_tc(packed, L, img, B, H, W, n_levels, precision, out_feat, ar, st);
+  else rc = vgg_forward_tc(packed, L, img, B, H, W, n_levels, precision, out_feat, ar, st, saved);
   if (rc != HA_OK || ar.dry) return rc;
   static const int chans[4] = {256, 128, 64, 16};
   NormArgs na;
@@ -312,6 +313,13 @@ static int vgg_run(const char* packed, const float* img, int B, int H, int W, in
     }
   }
   return check_launch("vgg_run");
+}
+
+// where a train-mode forward (ha_vgg_forward_train) left the activations in its workspace
+TcSaved vgg_train_saved(char* ws, int B, int H, int W, int n_levels) {
+  Arena ar{ws, 0, ~(size_t)0, false};
+  ar.take((size_t)HA_MAX_LEVELS * B * kNormChunks * sizeof(double));
+  return vgg_tc_carve(ar, B, H, W, n_levels, true);
 }
 
 }  // namespace ha
@@ -360,4 +368,26 @@ extern "C" int ha_vgg_forward(const void* packed_weights, const float* img_nchw,
   ha::Arena ar{reinterpret_cast<char*>(ws), 0, ws_bytes, false};
   return ha::vgg_run(reinterpret_cast<const char*>(packed_weights), img_nchw, B, H, W, n_levels, precision, out_feat,
                      out_scale, out_conf, ar, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- train-mode forward: the same tcgen05 schedule, keeping what the backward pass needs (vgg_backward.cu)
+extern "C" size_t ha_vgg_train_workspace_bytes(int B, int H, int W, int n_levels) {
+  if (!vgg_shape_ok(B, H, W, n_levels, HA_CONV_F16X3)) return 0;
+  ha::Arena ar{nullptr, 0, 0, true};
+  ha::TcSaved sv;
+  ha::vgg_run(nullptr, nullptr, B, H, W, n_levels, HA_CONV_F16X3, nullptr, nullptr, nullptr, ar, nullptr, &sv);
+  return ha::align_up(ar.off, 256);
+}
+
+extern "C" int ha_vgg_forward_train(const void* packed_weights, const float* img_nchw, int B, int H, int W, int n_levels,
+                                    float* const* out_feat, float* const* out_scale, float* const* out_conf, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  if (!packed_weights || !img_nchw || !out_feat || !ws) return HA_EINVAL;
+  if (!vgg_shape_ok(B, H, W, n_levels, HA_CONV_F16X3)) return HA_EINVAL;
+  for (int l = 0; l < n_levels; ++l)
+    if (!out_feat[l]) return HA_EINVAL;
+  ha::Arena ar{reinterpret_cast<char*>(ws), 0, ws_bytes, false};
+  ha::TcSaved sv;
+  return ha::vgg_run(reinterpret_cast<const char*>(packed_weights), img_nchw, B, H, W, n_levels, HA_CONV_F16X3, out_feat,
+                     out_scale, out_conf, ar, reinterpret_cast<cudaStream_t>(stream), &sv);
 }

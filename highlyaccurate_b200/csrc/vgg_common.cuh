@@ -69,8 +69,16 @@ int conv_simt(const float* in, int in_pitch, int in_coff, int cin, const float* 
               int out_pitch, int out_coff, int cout, int B, int H, int W, int relu_out, cudaStream_t st);
 int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* packed, const PackedConv& pc, int cout,
             bool has_bias, const TcOut& o, int B, int H, int W, bool split, cudaStream_t st, int n_taps = 9, bool pair = true);
+// Activations the backward pass needs, where vgg_forward_tc laid them out in the caller's workspace (train mode)
+struct TcSaved {
+  __half *a1, *cat3, *cat2, *a5, *cat1, *a10, *a12, *d1, *d2, *d3;   // post-ReLU inputs of the convolutions, hi/lo planes
+  float *x2, *x7, *x14;        // raw conv outputs in front of the three max-pools (the argmax of the unpooling), fp32 NHWC
+};
+TcSaved vgg_tc_carve(Arena& ar, int B, int H, int W, int n_levels, bool train);
+TcSaved vgg_train_saved(char* ws, int B, int H, int W, int n_levels);
+// `saved` != nullptr = train mode: conv2 / conv7 / conv14 also keep their raw outputs and x15 is pooled by a kernel of its own
 int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, int B, int H, int W, int n_levels,
-                   int precision, float* const* out_feat, Arena& ar, cudaStream_t st);
+                   int precision, float* const* out_feat, Arena& ar, cudaStream_t st, TcSaved* saved = nullptr);
 
 constexpr float kLoScale = 2048.f;          // 2^11
 constexpr float kLoInvScale = 1.f / 2048.f;

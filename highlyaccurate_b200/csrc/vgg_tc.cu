@@ -25,82 +25,10 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "tc_ptx.cuh"
 #include "vgg_common.cuh"
 
 namespace ha {
-
-// ------------------------------------------------------------------------------ PTX wrappers (mbarrier helpers live in common.cuh)
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc_512(uint32_t* slot) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_512(uint32_t addr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(addr) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], kind::f16, issued by ONE thread for the CTA
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// arrive on an mbarrier when all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address  [0,14)
-  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major) [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B  [32,46)
-  d |= (uint64_t)1 << 46;                        // descriptor version 1 (sm_100)      [46,48)
-  d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B           [61,64)
-  return d;
-}
-// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, A and B K-major, M = 128
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
 
 // ------------------------------------------------------------------------------ the kernel
 constexpr int kTileW = 16, kTileH = 8, kBlockM = kTileW * kTileH;   // 128 pixels = UMMA M
@@ -1163,6 +1091,39 @@ __global__ void split_act_kernel(const float* __restrict__ in, __half* __restric
   }
 }
 
+// train mode: x15 = maxpool2x2(x14) as the fp32 feature, and relu(x15) replicated 2x2 into the first 256 channels of cat1
+// (what conv14's epilogue does in one go on the eval path).  One thread per pooled pixel and 8 channels.
+__global__ void pool_x15_kernel(const float* __restrict__ x14, float* __restrict__ x15, __half* __restrict__ cat1, int B, int h, int w) {
+  const size_t total = (size_t)B * (h / 2) * (w / 2) * 32;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 32) * 8;
+    size_t p = i / 32;
+    const int x = (int)(p % (w / 2)); p /= (w / 2);
+    const int y = (int)(p % (h / 2)); const size_t b = p / (h / 2);
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float* s = x14 + ((b * h + 2 * y + (k >> 1)) * w + 2 * x + (k & 1)) * 256 + c;
+      const float4 v0 = *reinterpret_cast<const float4*>(s), v1 = *reinterpret_cast<const float4*>(s + 4);
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m[e] = k == 0 ? v[e] : fmaxf(m[e], v[e]);
+    }
+    float* d = x15 + ((b * (h / 2) + y) * (w / 2) + x) * 256 + c;
+    *reinterpret_cast<float4*>(d) = make_float4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(m[4], m[5], m[6], m[7]);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split2(fmaxf(m[2 * e], 0.f), fmaxf(m[2 * e + 1], 0.f), hi[e], lo[e]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __half* o = cat1 + ((b * h + 2 * y + (k >> 1)) * w + 2 * x + (k & 1)) * (2 * 384) + c;
+      *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(o + 384) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1194,8 +1155,8 @@ struct MapKeyHash {
     return h;
   }
 };
-static int encode_cached(CUtensorMap* m, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
-                         const cuuint32_t* box, const char* what) {
+int encode_cached(CUtensorMap* m, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box, const char* what) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> memo;
   MapKey k;
@@ -1361,23 +1322,41 @@ int conv_tc(const __half* in, int in_pitch, int in_coff, int cin, const char* pa
   return HA_EINVAL;
 }
 
+// Workspace layout of the tensor-core schedule (one sequential carve-up, shared with the backward pass, which finds the
+// saved activations of a train-mode forward by repeating it on the same base pointer)
+TcSaved vgg_tc_carve(Arena& ar, int B, int H, int W, int n_levels, bool train) {
+  const size_t px1 = (size_t)B * H * W, px2 = px1 / 4, px4 = px1 / 16;
+  auto act = [&](size_t px, int c) { return (__half*)ar.take(px * 2 * c * sizeof(__half)); };
+  TcSaved s{};
+  s.a1 = act(px1, 64);
+  s.cat3 = n_levels == 4 ? act(px1, 128) : nullptr;
+  s.cat2 = act(px2, 192);
+  s.a5 = act(px2, 128);
+  s.cat1 = act(px4, 384);
+  s.a10 = act(px4, 256);
+  s.a12 = act(px4, 256);
+  s.d1 = act(px4, 128);
+  s.d2 = act(px2, 64);
+  s.d3 = n_levels == 4 ? act(px1, 32) : nullptr;
+  if (train) {
+    s.x2 = (float*)ar.take(px1 * 64 * sizeof(float));
+    s.x7 = (float*)ar.take(px2 * 128 * sizeof(float));
+    s.x14 = (float*)ar.take(px4 * 256 * sizeof(float));
+  }
+  return s;
+}
+
 // Tensor-core schedule of the U-Net; buffer names follow vgg.cu / VGG.py:121-158.
 int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, int B, int H, int W, int n_levels,
-                   int precision, float* const* out_feat, Arena& ar, cudaStream_t st) {
+                   int precision, float* const* out_feat, Arena& ar, cudaStream_t st, TcSaved* saved) {
   const bool split = precision == HA_CONV_F16X3 || precision == HA_CONV_F16X3_1CTA;
   const bool pair = precision == HA_CONV_F16X3;
   const size_t px1 = (size_t)B * H * W, px2 = px1 / 4, px4 = px1 / 16;
-  auto act = [&](size_t px, int c) { return (__half*)ar.take(px * 2 * c * sizeof(__half)); };
-  __half* a1 = act(px1, 64);
-  __half* cat3 = n_levels == 4 ? act(px1, 128) : nullptr;
-  __half* cat2 = act(px2, 192);
-  __half* a5 = act(px2, 128);
-  __half* cat1 = act(px4, 384);
-  __half* a10 = act(px4, 256);
-  __half* a12 = act(px4, 256);
-  __half* d1 = act(px4, 128);
-  __half* d2 = act(px2, 64);
-  __half* d3 = n_levels == 4 ? act(px1, 32) : nullptr;
+  const TcSaved sv = vgg_tc_carve(ar, B, H, W, n_levels, saved != nullptr);
+  __half *a1 = sv.a1, *cat3 = sv.cat3, *cat2 = sv.cat2, *a5 = sv.a5, *cat1 = sv.cat1, *a10 = sv.a10, *a12 = sv.a12;
+  __half *d1 = sv.d1, *d2 = sv.d2, *d3 = sv.d3;
+  float *x2 = sv.x2, *x7 = sv.x7, *x14 = sv.x14;
+  if (saved) *saved = sv;
   if (ar.dry) return HA_OK;
   if (ar.off > ar.cap) return HA_ENOSPACE;
   if ((W % (4 * kTileW)) || (H % (4 * kTileH))) return HA_EINVAL;   // tiles must fit down to the 1/4 scale
@@ -1398,17 +1377,28 @@ int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, 
   TcOut o;
   o = TcOut(); o.act_pool = cat2; o.ap_pitch = 192; o.ap_coff = 128;                    // x4 = relu(pool(x2))
   if (n_levels == 4) { o.act_full = cat3; o.af_pitch = 128; o.af_coff = 64; }           // relu(x2) skip for dec3
+  if (saved) o.feat = x2;
   HA_TRY(conv(L_CONV2, a1, 64, 0, o, H, W));
   o = TcOut(); o.act_full = a5; o.af_pitch = 128;
   HA_TRY(conv(L_CONV5, cat2, 192, 128, o, H / 2, W / 2));
   o = TcOut(); o.act_pool = cat1; o.ap_pitch = 384; o.ap_coff = 256;                    // x9 = relu(pool(x7))
+  if (saved) o.feat = x7;
   HA_TRY(conv(L_CONV7, a5, 128, 0, o, H / 2, W / 2));
   o = TcOut(); o.act_full = a10; o.af_pitch = 256;
   HA_TRY(conv(L_CONV10, cat1, 384, 256, o, H / 4, W / 4));
   o = TcOut(); o.act_full = a12; o.af_pitch = 256;
   HA_TRY(conv(L_CONV12, a10, 256, 0, o, H / 4, W / 4));
-  o = TcOut(); o.feat = out_feat[0]; o.feat_pooled = 1; o.act_up = cat1; o.au_pitch = 384; o.au_coff = 0;   // x15
-  HA_TRY(conv(L_CONV14, a12, 256, 0, o, H / 4, W / 4));
+  if (saved) {                                                                          // x14 kept; x15 and its upsample by a kernel
+    o = TcOut(); o.feat = x14;
+    HA_TRY(conv(L_CONV14, a12, 256, 0, o, H / 4, W / 4));
+    const size_t n = px4 / 4 * 32;
+    pool_x15_kernel<<<(unsigned)((n + 255) / 256 < (size_t)kNumSMs * 16 ? (n + 255) / 256 : (size_t)kNumSMs * 16), 256, 0, st>>>(
+        x14, out_feat[0], cat1, B, H / 4, W / 4);
+    count_launches(1);
+  } else {
+    o = TcOut(); o.feat = out_feat[0]; o.feat_pooled = 1; o.act_up = cat1; o.au_pitch = 384; o.au_coff = 0;   // x15
+    HA_TRY(conv(L_CONV14, a12, 256, 0, o, H / 4, W / 4));
+  }
   o = TcOut(); o.act_full = d1; o.af_pitch = 128;
   HA_TRY(conv(L_DEC1A, cat1, 384, 0, o, H / 4, W / 4));
   o = TcOut(); o.feat = out_feat[1]; o.act_up = cat2; o.au_pitch = 192; o.au_coff = 0;                      // x18

@@ -594,6 +594,75 @@ class VggRunner:
         return Pyramid(feats, scales, confs)
 
 
+N_FEATURE_CONVS = 13            # conv0 ... conv_dec3.3: the convolutions the pyramid features depend on
+N_BIASED_CONVS = 7              # the VGG16 encoder convolutions carry a bias (VGG.py:23-29)
+
+
+class VggTrain(torch.autograd.Function):
+    """The U-Net with a native backward (second slice): forward = ha_vgg_forward_train (the tcgen05
+    schedule of the eval path, keeping the activations in its workspace), backward = ha_vgg_backward (data gradients on the
+    same tcgen05 convolution kernels with flipped weights, weight gradients on a tcgen05 split-K GEMM over the pixels).
+    apply(runner, named, img, *params) with params = the 13 feature-conv weights then the 7 encoder biases (autograd inputs);
+    returns the three raw NHWC feature maps x15 / x18 / x21 (VGG.py:141,147,152); the caller L2-normalises and slices."""
+
+    @staticmethod
+    def supports(img: torch.Tensor, n_levels: int, precision: str) -> bool:
+        return img.is_cuda and n_levels == 3 and precision == "f16x3" and img.shape[-1] % 64 == 0 and img.shape[-2] % 32 == 0
+
+    @staticmethod
+    def forward(ctx, runner, named, img, *params):
+        L = _lib.lib()
+        dev = img.device
+        img = img.float().contiguous()
+        B, _, H, W = img.shape
+        runner._pack(named, dev)
+        need = L.ha_vgg_train_workspace_bytes(B, H, W, 3)
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)          # owned by this call's graph until backward
+        feats = [torch.empty(B, H >> (3 - l), W >> (3 - l), PYRAMID_CHANNELS[l], dtype=torch.float32, device=dev) for l in range(3)]
+        confs = [torch.empty(B, H >> (3 - l), W >> (3 - l), dtype=torch.float32, device=dev) for l in range(3)]
+        pf, pc = (C.c_void_p * 3)(*[f.data_ptr() for f in feats]), (C.c_void_p * 3)(*[c.data_ptr() for c in confs])
+        check(L.ha_vgg_forward_train(runner.packed.data_ptr(), img.data_ptr(), B, H, W, 3, pf, None, pc, ws.data_ptr(), need,
+                                     _stream_ptr()), "ha_vgg_forward_train")
+        ctx.ws, ctx.img, ctx.named, ctx.shape = ws, img, named, (B, H, W)
+        ctx.confs = confs
+        ctx.mark_non_differentiable(*confs)
+        return (*feats, *confs)
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2, *_gconf):
+        L = _lib.lib()
+        B, H, W = ctx.shape
+        dev = ctx.img.device
+        named = ctx.named
+        gs = []
+        for l, g in enumerate((g0, g1, g2)):
+            shape = (B, H >> (3 - l), W >> (3 - l), PYRAMID_CHANNELS[l])
+            gs.append(torch.zeros(shape, dtype=torch.float32, device=dev) if g is None else g.float().contiguous())
+        sd, gd = HaVggStateDict(), HaVggStateDict()
+        keep, gw, gb = [], [], []
+        for i, n in enumerate(VGG_CONV_NAMES):
+            wt = named[n + ".weight"].detach().float().contiguous()
+            keep.append(wt)
+            sd.weight[i] = wt.data_ptr()
+            if i < N_FEATURE_CONVS and i < 11:                      # conv_dec3 only exists at level 4 (not on this path)
+                g = torch.empty_like(wt)
+                gw.append(g)
+                gd.weight[i] = g.data_ptr()
+            elif i < N_FEATURE_CONVS:
+                gw.append(None)
+            if i < N_BIASED_CONVS:
+                g = torch.empty(wt.shape[0], dtype=torch.float32, device=dev)
+                gb.append(g)
+                gd.bias[i] = g.data_ptr()
+        need = L.ha_vgg_backward_workspace_bytes(B, H, W, 3)
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        pg = (C.c_void_p * 3)(*[g.data_ptr() for g in gs])
+        check(L.ha_vgg_backward(C.byref(sd), ctx.img.data_ptr(), B, H, W, 3, ctx.ws.data_ptr(), pg, C.byref(gd), ws.data_ptr(), need,
+                                _stream_ptr()), "ha_vgg_backward")
+        ctx.ws = None
+        return (None, None, None, *gw, *gb)
+
+
 def conv3x3(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: str) -> torch.Tensor:
     """One 3x3/pad-1 convolution through ha_conv3x3_nhwc: fp32 NHWC in -> fp32 NHWC out (bias, no activation)."""
     _require_cuda(x_nhwc, "conv3x3 input")
@@ -609,3 +678,25 @@ def conv3x3(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
     check(L.ha_conv3x3_nhwc(x.data_ptr(), cin, w.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(), cout,
                             B, H, W, PRECISIONS[precision], ws.data_ptr(), need, _stream_ptr()), "ha_conv3x3_nhwc")
     return out
+
+
+def conv3x3_backward(x_nhwc: torch.Tensor, weight: torch.Tensor, dy_nhwc: torch.Tensor, want_dx: bool = True):
+    """Backward of one 3x3 / pad-1 convolution through ha_conv3x3_backward_nhwc (tcgen05 data and weight gradients):
+    returns (dx NHWC or None, dw OIHW, db)."""
+    _require_cuda(x_nhwc, "conv3x3_backward input")
+    L = _lib.lib()
+    x = x_nhwc.float().contiguous()
+    dy = dy_nhwc.float().contiguous()
+    w = weight.detach().float().contiguous().to(x.device)
+    B, H, W, cin = x.shape
+    cout = w.shape[0]
+    dx = torch.empty_like(x) if want_dx else None
+    dw = torch.empty_like(w)
+    db = torch.empty(cout, dtype=torch.float32, device=x.device)
+    need = L.ha_conv3x3_backward_workspace_bytes(cin, cout, B, H, W)
+    if need == 0:
+        raise _lib.HaError("unsupported conv3x3_backward shape")
+    ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+    check(L.ha_conv3x3_backward_nhwc(x.data_ptr(), cin, w.data_ptr(), dy.data_ptr(), cout, B, H, W, dx.data_ptr() if want_dx else None,
+                                     dw.data_ptr(), db.data_ptr(), ws.data_ptr(), need, _stream_ptr()), "ha_conv3x3_backward_nhwc")
+    return dx, dw, db

@@ -40,13 +40,13 @@ def train_forward_fused(net, kind, sat_map, grd_img, gt_lat, gt_lon, gt_theta, l
     `loss_func` method 0.  Gradients reach both U-Nets and `damping` exactly as in the reference
     (tests/test_gpu_parity.py::test_fused_lm_backward_* compare with the reference's autograd, KAT-8 / KAT-9)."""
     a = net.args
-    sat_feats, _ = net.SatFeatureNet.forward_autograd(sat_map)
-    grd_feats, grd_confs = net.GrdFeatureNet.forward_autograd(grd_img)
+    sat_feats, _ = net.SatFeatureNet.forward_train(sat_map)            # NHWC, L2-normalised; native U-Net backward where it applies
+    grd_feats, grd_confs = net.GrdFeatureNet.forward_train(grd_img)
     L = len(sat_feats)
     dev = sat_map.device
     setup = engine.setup_from_args(a, kind, level_first)
     lam = compat.resolve_damping_tensor(a, net.damping, 3, dev).reshape(3)
-    nhwc = [f.permute(0, 2, 3, 1).contiguous() for f in (*sat_feats, *grd_feats)]
+    nhwc = [f.contiguous() for f in (*sat_feats, *grd_feats)]
     ext = engine.ford_extrinsics(ford["R_FL"], ford["T_FL"]) if kind == "ford" else None
     side_m = ford["side_m"] if kind == "ford" else None
     reset_uv = engine.draw_reset_uv(a.N_iters * L, sat_map.shape[0])          # same CPU-RNG consumption as the reference

@@ -231,6 +231,25 @@ int ha_vgg_forward(const void* packed_weights, const float* img_nchw, int B, int
                    int precision, float* const* out_feat, float* const* out_scale, float* const* out_conf,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* ---- training: the same U-Net, keeping what its backward pass needs, and that backward pass ----------
+ * Replaces what torch autograd does for VGGUnet.forward under `loss.backward()` (train_kitti.py:365, VGG.py:121-203).
+ * ha_vgg_forward_train = ha_vgg_forward in HA_CONV_F16X3 precision whose workspace afterwards holds the post-ReLU input of
+ *   every convolution (fp16 hi / lo planes) and the raw conv outputs in front of the three max-pools; keep `ws` untouched
+ *   until ha_vgg_backward has run.
+ * ha_vgg_backward: g_feat[l] = gradient w.r.t. out_feat[l] of the forward (fp32 NHWC, all n_levels required, zeros where a
+ *   level is unused) -> grads->weight[i] ([Cout][Cin][3][3] fp32, torch layout) and grads->bias[i] ([Cout]) for the 13
+ *   feature convolutions (entries may be NULL to skip; the confidence heads are not differentiated: they only matter with
+ *   using_weight, which keeps the torch path).  sd = the raw OIHW weights (device), img_nchw = the forward's input.
+ *   Data gradients run on the forward's tcgen05 convolution kernels with flipped weights, weight gradients on a tcgen05
+ *   split-K GEMM over the pixels (csrc/vgg_backward.cu).  n_levels = 3 (level 3 / -1 / 2 models); W % 64 == 0, H % 32 == 0. */
+size_t ha_vgg_train_workspace_bytes(int B, int H, int W, int n_levels);
+int ha_vgg_forward_train(const void* packed_weights, const float* img_nchw, int B, int H, int W, int n_levels,
+                         float* const* out_feat, float* const* out_scale, float* const* out_conf, void* ws, size_t ws_bytes,
+                         void* stream);
+size_t ha_vgg_backward_workspace_bytes(int B, int H, int W, int n_levels);
+int ha_vgg_backward(const HaVggStateDict* sd, const float* img_nchw, int B, int H, int W, int n_levels, void* fwd_ws,
+                    const float* const* g_feat, const HaVggStateDict* grads, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- one 3x3 / pad 1 / stride 1 convolution layer (the building block of ha_vgg_forward) ----
  * Replaces a single nn.Conv2d call of VGG.py:123-155.  fp32 NHWC in ([B][H][W][cin]) and out
  * ([B][H][W][cout], bias added, no activation); weights in torch OIHW layout, device pointers.
@@ -238,6 +257,13 @@ int ha_vgg_forward(const void* packed_weights, const float* img_nchw, int B, int
 size_t ha_conv3x3_workspace_bytes(int cin, int cout, int B, int H, int W);
 int ha_conv3x3_nhwc(const float* in_nhwc, int cin, const float* w_oihw, const float* bias, float* out_nhwc, int cout,
                     int B, int H, int W, int precision, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- backward of one 3x3 / pad 1 convolution layer (the twin of ha_conv3x3_nhwc; building blocks of ha_vgg_backward) ----
+ * x [B][H][W][cin], dy [B][H][W][cout] fp32 NHWC, w OIHW -> dx [B][H][W][cin] (or NULL), dw [cout][cin][3][3] (or NULL),
+ * db [cout] (or NULL).  f16x3 precision on tcgen05 (fp32-grade).  cin, cout multiples of 64 (dx: cin in {64, 128, 256}). */
+size_t ha_conv3x3_backward_workspace_bytes(int cin, int cout, int B, int H, int W);
+int ha_conv3x3_backward_nhwc(const float* x_nhwc, int cin, const float* w_oihw, const float* dy_nhwc, int cout, int B, int H, int W,
+                             float* dx_nhwc, float* dw_oihw, float* db, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- input pipeline on the device --------------------------------------------------------
  * Replaces the per-sample PIL / torchvision preparation of dataLoader/KITTI_dataset.py:128-157, :256-288 and

@@ -629,15 +629,21 @@ def test_fused_lm_backward_ford_train_mode():
             gflat = params[name].grad.reshape(-1).cpu()
             want = gold["p%d_val" % k]
             got = gflat[torch.from_numpy(gold["p%d_idx" % k])].numpy()
-            assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max(), (name, np.abs(got - want).max(), np.abs(want).max())
+            assert np.abs(got - want).max() <= 5e-3 * np.abs(want).max(), (name, np.abs(got - want).max(), np.abs(want).max())   # native U-Net backward: see test_train_mode_on_gpu_matches_reference_gradients
     finally:
         torch.backends.cudnn.allow_tf32 = old
 
 
-def test_train_mode_on_gpu_matches_reference_gradients():
-    """`forward(mode='train')` on the GPU (U-Nets through torch / cuDNN with TF32 off, LM loop forward AND backward in
-    libha_b200.so: engine.FusedLmLoop) against the reference's CPU forward + autograd
-    (tests/golden/kat9_train_e2e.npz); the eval path of the same module stays on the engine."""
+@pytest.mark.parametrize("unet_backward", ["native", "torch"])
+def test_train_mode_on_gpu_matches_reference_gradients(unet_backward):
+    """`forward(mode='train')` on the GPU — LM loop forward AND backward in libha_b200.so (engine.FusedLmLoop), U-Nets either
+    fully native (engine.VggTrain: tcgen05 forward, data and weight gradients) or through torch / cuDNN with TF32 off —
+    against the reference's CPU forward + autograd (tests/golden/kat9_train_e2e.npz); the eval path of the same module
+    stays on the engine.  Weight gradients of a random-weight U-Net are discontinuous in the activations (ReLU masks,
+    max-pool routing): cuDNN fp32 itself sits ~2e-3 of the largest entry from float64 autograd
+    (test_vgg_native_backward_vs_torch_autograd), so the two fp32 paths are held to 2e-3 (torch) / 5e-3 (native: its
+    f16x3 forward differs from the CPU forward by 5e-6 instead of 1e-7, i.e. more mask flips); the exactness of the native
+    schedule is test_vgg_native_backward_exact_on_integer_network."""
     from oracle.make_golden import E2E_TRAIN_PARAMS
     gold = K.load_golden("kat9_train_e2e")
     old = torch.backends.cudnn.allow_tf32
@@ -650,6 +656,8 @@ def test_train_mode_on_gpu_matches_reference_gradients():
         sd["damping"] = torch.zeros(1, 3)
         net.load_state_dict(sd)
         net = net.to(DEV)
+        net.SatFeatureNet.native_train = net.GrdFeatureNet.native_train = unet_backward == "native"
+        tol = 5e-3 if unet_backward == "native" else 2e-3
         g = torch.Generator().manual_seed(2022)
         sat = torch.rand(1, 3, 512, 512, generator=g).to(DEV)
         grd = torch.rand(1, 3, 256, 1024, generator=g).to(DEV)
@@ -659,13 +667,156 @@ def test_train_mode_on_gpu_matches_reference_gradients():
         np.testing.assert_allclose(float(out[0].detach()), float(gold["loss"]), rtol=1e-4)
         out[0].backward()
         params = dict(net.named_parameters())
+        worst = 0.0
         for k, name in enumerate(E2E_TRAIN_PARAMS):
             gflat = params[name].grad.reshape(-1).cpu()
             want = gold["p%d_val" % k]
             got = gflat[torch.from_numpy(gold["p%d_idx" % k])].numpy()
-            assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max(), name
+            err = np.abs(got - want).max() / np.abs(want).max()
+            worst = max(worst, float(err))
+            assert err <= tol, (name, err)
+        print("train mode (%s U-Net backward): worst max|d|/max|g| vs the reference's autograd %.2e" % (unet_backward, worst))
         # the same module still evaluates through the engine
         lat, lon, th = net(sat, grd, mode="test")
         assert lat.shape == (1,) and torch.isfinite(lat).all() and torch.isfinite(th).all()
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 128), (1, 256, 1024), (3, 128, 128)])
+def test_vgg_native_backward_vs_torch_autograd(shape):
+    """SURVEY 8 f-1, second slice: the U-Net backward in libha_b200.so (engine.VggTrain: tcgen05 forward keeping its
+    activations, data gradients on the forward's tcgen05 conv kernels with flipped weights, weight gradients on the
+    tcgen05 split-K GEMM) against torch autograd through the same module's torch-op forward (cuDNN, TF32 off): features and
+    the gradients of all 11 weights and 7 biases for a random linear functional of the L2-normalised pyramid."""
+    from highlyaccurate_b200.VGG import VGGUnet
+    B, H, W = shape
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        net = VGGUnet(3)
+        net.load_state_dict(O.vgg_state_dict(123))
+        net = net.to(DEV)
+        g = torch.Generator().manual_seed(B * 1000 + H)
+        x = torch.rand(B, 3, H, W, generator=g).to(DEV)
+        assert engine.VggTrain.supports(x, 3, net.precision)
+        probes = [torch.randn(B, H >> (3 - l), W >> (3 - l), c, generator=g).to(DEV) for l, c in enumerate((256, 128, 64))]
+        feats, confs = net.forward_train(x)
+        loss = sum((f * p).sum() for f, p in zip(feats, probes))
+        loss.backward()
+        got = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+        net.zero_grad()
+        # the same functional in float64 (torch autograd): the truth both fp32 paths deviate from
+        import copy
+        net64 = copy.deepcopy(net).double()
+        f64, _ = net64.forward_autograd(x.double())
+        sum((f.permute(0, 2, 3, 1) * p.double()).sum() for f, p in zip(f64, probes)).backward()
+        truth = {n: p.grad for n, p in net64.named_parameters() if p.grad is not None}
+        rf, rc = net.forward_autograd(x)
+        loss_ref = sum((f.permute(0, 2, 3, 1) * p).sum() for f, p in zip(rf, probes))
+        loss_ref.backward()
+        for l in range(3):
+            torch.testing.assert_close(feats[l], rf[l].permute(0, 2, 3, 1), rtol=0, atol=2e-5 * float(rf[l].abs().max()))
+            torch.testing.assert_close(confs[l], rc[l], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(float(loss.detach()), float(loss_ref.detach()), rtol=1e-4)
+        worst, bad, TOL = 0.0, False, 1e-2
+        for n, p in net.named_parameters():
+            if n.startswith(("conf", "conv_dec3")):
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0 or n.startswith("conf")
+                continue
+            want = p.grad
+            assert n in got, n
+            t = truth[n]
+            err = float((got[n].double() - t).abs().max() / t.abs().max())
+            err32 = float((want.double() - t).abs().max() / t.abs().max())
+            print("  %-22s vs fp64 autograd: native max|d|/max|g| %.2e   torch fp32 (cuDNN) %.2e" % (n, err, err32))
+            worst = max(worst, err)
+            # ReLU masks and max-pool routing make the gradient discontinuous in the activations: torch's own fp32 path
+            # (cuDNN) sits ~2e-3 from the float64 truth on these random-weight networks; the native path is held to the
+            # same class (its building blocks alone are fp32-grade: test_single_conv_layer_backward)
+            bad = bad or err > max(4 * err32, TOL)
+        print("vgg native backward %s: worst max|d|/max|g| over the parameters %.2e" % (shape, worst))
+        assert not bad
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("cin,cout,B,H,W", [(64, 64, 2, 32, 64), (128, 128, 1, 64, 64), (256, 256, 2, 16, 32), (64, 128, 3, 32, 32),
+                                            (256, 128, 1, 32, 64), (192, 64, 1, 32, 64), (384, 128, 2, 16, 16)])
+def test_single_conv_layer_backward(cin, cout, B, H, W):
+    """ha_conv3x3_backward_nhwc (tcgen05 data gradient with flipped weights, tcgen05 split-K weight gradient, bias
+    gradient) against torch's conv2d autograd in float64; gradients spanning many orders of magnitude (the power-of-two
+    rescale) are part of the case.  fp32-grade: 2e-5 of the largest entry."""
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(B, cin, H, W, generator=g).relu()
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (1.0 / (3 * cin ** 0.5))
+    dy = torch.randn(B, cout, H, W, generator=g) * torch.logspace(-9, -3, cout)[None, :, None, None]
+    x64, w64 = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    y = torch.nn.functional.conv2d(x64, w64, padding=1)
+    y.backward(dy.double())
+    want_dx = cin in (64, 128, 256)
+    dx, dw, db = engine.conv3x3_backward(x.permute(0, 2, 3, 1).contiguous().to(DEV), w.to(DEV),
+                                         dy.permute(0, 2, 3, 1).contiguous().to(DEV), want_dx=want_dx)
+    def rel(a, b):
+        return float((a.double().cpu() - b).abs().max() / b.abs().max())
+    e_w, e_b = rel(dw, w64.grad), rel(db, dy.double().sum(dim=(0, 2, 3)))
+    e_x = rel(dx.permute(0, 3, 1, 2), x64.grad) if want_dx else 0.0
+    print("conv backward %d->%d: dW %.2e  db %.2e  dx %.2e (max|d| / max|g|)" % (cin, cout, e_w, e_b, e_x))
+    assert e_w < 2e-5 and e_b < 2e-5 and e_x < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 128), (1, 128, 256)])
+def test_vgg_native_backward_exact_on_integer_network(shape):
+    """The whole backward schedule (ReLU masks, max-pool routing incl. ties, upsample sums, concat splits, the two-part
+    data gradients of the decoders) without the discontinuity noise of the test above: sparse ternary weights, integer
+    biases / image / probes make every activation an exactly representable integer, so the native forward equals the float64
+    forward bit for bit, masks and argmax agree, and the gradients must agree to fp32 rounding."""
+    from highlyaccurate_b200.VGG import VGGUnet
+    F = torch.nn.functional
+    B, H, W = shape
+    g = torch.Generator().manual_seed(H + 17)
+    net = VGGUnet(3)
+    sd = net.state_dict()
+    for k, v in sd.items():
+        if k.endswith("weight"):
+            fan = v.shape[1] * 9
+            keep = (torch.rand(v.shape, generator=g) < 4.0 / fan).float()
+            sd[k] = keep * torch.where(torch.rand(v.shape, generator=g) < 0.6, 1.0, -1.0)
+        else:
+            sd[k] = torch.randint(-1, 2, v.shape, generator=g).float()
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    x = torch.randint(0, 4, (B, 3, H, W), generator=g).float().to(DEV)
+    probes = [torch.randint(-2, 3, (B, H >> (3 - l), W >> (3 - l), c), generator=g).float().to(DEV) for l, c in enumerate((256, 128, 64))]
+    if net._named is None:
+        net._named = dict(net.named_parameters())
+    names = engine.VGG_CONV_NAMES
+    params = [net._named[n + ".weight"] for n in names[:engine.N_FEATURE_CONVS]] + [net._named[n + ".bias"] for n in names[:engine.N_BIASED_CONVS]]
+    out = engine.VggTrain.apply(net._runner, net._named, x, *params)
+    sum((f * p).sum() for f, p in zip(out[:3], probes)).backward()
+    got = {n: p.grad.double().cpu() for n, p in net.named_parameters() if p.grad is not None}
+    # float64 reference of VGG.py:121-152 (raw features)
+    w = {k: v.detach().double().cpu().requires_grad_(True) for k, v in net.state_dict().items()}
+    conv = lambda t, n: F.conv2d(t, w[n + ".weight"], w.get(n + ".bias"), padding=1)
+    pool = lambda t: F.max_pool2d(t, 2, 2)
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")
+    x1 = F.relu(conv(x.double().cpu(), "conv0"))
+    x4 = F.relu(pool(conv(x1, "conv2")))
+    x9 = F.relu(pool(conv(F.relu(conv(x4, "conv5")), "conv7")))
+    x15 = pool(conv(F.relu(conv(F.relu(conv(x9, "conv10")), "conv12")), "conv14"))
+    x18 = conv(F.relu(conv(F.relu(torch.cat([up(x15), x9], 1)), "conv_dec1.1")), "conv_dec1.3")
+    x21 = conv(F.relu(conv(F.relu(torch.cat([up(x18), x4], 1)), "conv_dec2.1")), "conv_dec2.3")
+    ref = [x15, x18, x21]
+    for f, r in zip(out[:3], ref):
+        assert float(r.abs().max()) < 2 ** 22 and float(r.abs().max()) > 0
+        np.testing.assert_array_equal(f.detach().cpu().double().numpy(), r.permute(0, 2, 3, 1).detach().numpy())   # exact forward
+    sum((r.permute(0, 2, 3, 1) * p.double().cpu()).sum() for r, p in zip(ref, probes)).backward()
+    worst = 0.0
+    for n in got:
+        t = w[n].grad
+        assert float(t.abs().max()) > 0, n                          # every parameter receives gradient: the check is not vacuous
+        err = float((got[n] - t).abs().max() / t.abs().max().clamp_min(1e-30))
+        worst = max(worst, err)
+        assert err < 2e-6, "%s: max|d| / max|g| = %g (max|g| %g)" % (n, err, float(t.abs().max()))
+    assert len(got) == 18
+    print("integer network %s: features exact, worst gradient max|d|/max|g| %.2e" % (shape, worst))
