@@ -44,27 +44,40 @@ __device__ __forceinline__ float grad_scale(unsigned bits, float* inv) {
 
 __global__ void absmax_kernel(const float* __restrict__ g, size_t n, unsigned* __restrict__ bits) {
   float m = 0.f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float v = fabsf(g[i]);
-    if (v > m && v < INFINITY) m = v;
+  const float4* g4 = reinterpret_cast<const float4*>(g);      // n is a multiple of 4 (channel counts are multiples of 16)
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = g4[i];
+    const float a = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    if (a > m && a < INFINITY) m = a;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(bits, __float_as_uint(m));
 }
 
-// fp32 NHWC gradient -> scaled hi / lo activation planes [P][2][C] (the format conv_tc reads)
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((v0 - hf.x) * kLoScale, (v1 - hf.y) * kLoScale);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// fp32 NHWC gradient -> scaled hi / lo activation planes [P][2][C] (the format conv_tc reads); four channels per thread
 __global__ void split_scaled_kernel(const float* __restrict__ g, const unsigned* __restrict__ bits, __half* __restrict__ out, int C,
                                     size_t n_px) {
   float inv;
   const float s = grad_scale(*bits, &inv);
-  const size_t total = n_px * C;
+  const int C4 = C / 4;
+  const size_t total = n_px * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t p = i / C; const int c = (int)(i % C);
-    const float v = g[i] * s;
-    const __half h = __float2half_rn(v);
-    out[p * 2 * C + c] = h;
-    out[p * 2 * C + C + c] = __float2half_rn((v - __half2float(h)) * kLoScale);
+    const size_t p = i / C4; const int c = (int)(i % C4) * 4;
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    uint32_t h0, l0, h1, l1;
+    split_pair(v.x * s, v.y * s, h0, l0);
+    split_pair(v.z * s, v.w * s, h1, l1);
+    *reinterpret_cast<uint2*>(out + p * 2 * C + c) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(out + p * 2 * C + C + c) = make_uint2(l0, l1);
   }
 }
 
@@ -79,35 +92,46 @@ __global__ void colsum_kernel(const float* __restrict__ g, size_t n_px, int C, f
 }
 
 // hi / lo activation planes [B][H][W][2][pitch] (channels [coff, coff + C)) -> K-major planes [shift][2][Cpad][Ppad] over the
-// padded pixel index p = (b (H + 2) + y + 1)(W + 8) + x + 1; padding and the channel rows >= C are zero.  Copy `shift`
-// (blockIdx.z / 2) holds the pixel p + shift - 1 at position p when n_shifts == 3 (the kx taps), the pixel p itself otherwise.
-// grid (Ppad / 64, Cpad / 32, 2 * n_shifts), 256 threads.
+// padded pixel index p = (b (H + 2) + y + 1)(W + 8) + x + 1; padding and the channel rows >= C are zero.  NSH == 3: copy s
+// holds the pixel p + s - 1 at position p (the kx taps of the weight gradient); NSH == 1: the pixel itself.
+// One CTA moves a 64-channel x 64-pixel tile (+ one pixel either side) through shared memory: 16-byte loads along the
+// channels, 16-byte stores along the pixels, every source byte read once for all three copies.
+// grid (Ppad / 64, Cpad / 64, 2 planes), 256 threads.
 constexpr int kRowPad = 8;
+constexpr int kTrPitch = 67;      // odd: channel rows 8 apart land in different banks
+template <int NSH>
 __global__ void __launch_bounds__(256) transpose_pad_kernel(const __half* __restrict__ src, int pitch, int coff, int C, int B, int H,
                                                             int W, __half* __restrict__ dst, int Cpad, size_t Ppad) {
-  __shared__ __half tile[64][34];
-  const int plane = blockIdx.z & 1, c0 = blockIdx.y * 32;
-  const long long shift = gridDim.z == 6 ? (long long)(blockIdx.z >> 1) - 1 : 0;
+  __shared__ __half tile[64 * kTrPitch];           // [channel][pixel p0 - 1 .. p0 + 64]
+  const int plane = blockIdx.z, c0 = blockIdx.y * 64;
   const size_t p0 = (size_t)blockIdx.x * 64;
   const int Wp = W + kRowPad, Hp = H + 2;
-  {
-    const int cl = threadIdx.x & 31;
-    for (int r = threadIdx.x >> 5; r < 64; r += 8) {
-      const long long ps = (long long)(p0 + r) + shift;
-      const size_t p = ps < 0 ? (size_t)B * Hp * Wp : (size_t)ps;       // before the first pixel: zero
-      const int xx = (int)(p % Wp); size_t t = p / Wp;
+  for (int item = threadIdx.x; item < 66 * 8; item += 256) {
+    const int r = item >> 3, j = item & 7;         // tile pixel row (p0 - 1 + r), 8-channel chunk
+    const long long ps = (long long)p0 - 1 + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (ps >= 0 && c0 + 8 * j < C) {
+      const size_t p = (size_t)ps;
+      const int xx = (int)(p % Wp); const size_t t = p / Wp;
       const int yy = (int)(t % Hp); const size_t b = t / Hp;
-      __half v = __float2half_rn(0.f);
-      if (b < (size_t)B && xx >= 1 && xx <= W && yy >= 1 && yy <= H && c0 + cl < C)
-        v = src[(((b * H + yy - 1) * W + xx - 1) * 2 + plane) * pitch + coff + c0 + cl];
-      tile[r][cl] = v;
+      if (b < (size_t)B && xx >= 1 && xx <= W && yy >= 1 && yy <= H)
+        v = *reinterpret_cast<const uint4*>(src + (((b * H + yy - 1) * W + xx - 1) * 2 + plane) * pitch + coff + c0 + 8 * j);
     }
+    const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) tile[(8 * j + e) * kTrPitch + r] = h[e];
   }
   __syncthreads();
-  {
-    const int pl = threadIdx.x & 63;
-    for (int c = threadIdx.x >> 6; c < 32; c += 4)
-      dst[((size_t)blockIdx.z * Cpad + c0 + c) * Ppad + p0 + pl] = tile[pl][c];
+#pragma unroll
+  for (int s = 0; s < NSH; ++s) {
+    const int first = NSH == 3 ? s : 1;             // tile column of output pixel 0: p0 + (s - 1) -> column s
+    for (int item = threadIdx.x; item < 64 * 8; item += 256) {
+      const int c = item >> 3, g = item & 7;
+      __align__(16) __half o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = tile[c * kTrPitch + 8 * g + k + first];
+      *reinterpret_cast<uint4*>(dst + ((size_t)(s * 2 + plane) * Cpad + c0 + c) * Ppad + p0 + 8 * g) = *reinterpret_cast<const uint4*>(o);
+    }
   }
 }
 
@@ -132,16 +156,26 @@ __global__ void image_pad_kernel(const float* __restrict__ img, int B, int H, in
   }
 }
 
-// out = add + R / s * [act > 0]      (R: data gradient of a convolution whose dy was scaled by s; act: the saved post-ReLU input)
+// out = add + R / s * [act > 0]      (R: data gradient of a convolution whose dy was scaled by s; act: the saved post-ReLU input);
+// four channels per thread
 __global__ void post_mask_kernel(const float* __restrict__ R, const unsigned* __restrict__ bits, const __half* __restrict__ act, int pitch,
                                  int coff, const float* __restrict__ add, float* __restrict__ out, int C, size_t n_px) {
   float inv;
   grad_scale(*bits, &inv);
-  const size_t total = n_px * C;
+  const int C4 = C / 4;
+  const size_t total = n_px * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t p = i / C; const int c = (int)(i % C);
-    const bool on = !act || __half2float(act[p * 2 * pitch + coff + c]) > 0.f;
-    out[i] = (add ? add[i] : 0.f) + (on ? R[i] * inv : 0.f);
+    const size_t p = i / C4; const int c = (int)(i % C4) * 4;
+    const float4 r = reinterpret_cast<const float4*>(R)[i];
+    float4 o = add ? reinterpret_cast<const float4*>(add)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    bool on[4] = {true, true, true, true};
+    if (act) {
+      const uint2 a = *reinterpret_cast<const uint2*>(act + p * 2 * pitch + coff + c);
+      const __half2 a0 = *reinterpret_cast<const __half2*>(&a.x), a1 = *reinterpret_cast<const __half2*>(&a.y);
+      on[0] = __low2float(a0) > 0.f; on[1] = __high2float(a0) > 0.f; on[2] = __low2float(a1) > 0.f; on[3] = __high2float(a1) > 0.f;
+    }
+    o.x += on[0] ? r.x * inv : 0.f; o.y += on[1] ? r.y * inv : 0.f; o.z += on[2] ? r.z * inv : 0.f; o.w += on[3] ? r.w * inv : 0.f;
+    reinterpret_cast<float4*>(out)[i] = o;
   }
 }
 
@@ -216,7 +250,7 @@ struct WgArgs {
   const unsigned* gbits;   // abs-max bits of dy (its scale)
   int cout, cin;
   int Wp;                  // padded row pitch W + 8 (a multiple of 8 pixels: TMA boxes start on 16-byte boundaries)
-  int n_kblocks, kb_per_split, n_splits, n_ci_chunks;
+  int n_kblocks, kb_per_split, n_splits, n_ci_chunks, n_co_tiles;
 };
 
 template <int N>
@@ -233,11 +267,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTAs that run at the same time share a pixel range (split is the slowest index), so the operand tiles they all read
+  // come from L2 once instead of from HBM once per (ky, channel chunk)
   int bid = blockIdx.x;
-  const int split = bid % a.n_splits; bid /= a.n_splits;
   const int ky = bid % 3; bid /= 3;
-  const int cic = bid % a.n_ci_chunks;
-  const int cot = bid / a.n_ci_chunks;
+  const int cic = bid % a.n_ci_chunks; bid /= a.n_ci_chunks;
+  const int cot = bid % a.n_co_tiles;
+  const int split = bid / a.n_co_tiles;
   const int kb0 = split * a.kb_per_split;
   const int kb1 = min(a.n_kblocks, kb0 + a.kb_per_split);
 
@@ -362,6 +398,7 @@ static int launch_wgrad(const __half* gT, int cout_pad, const __half* xT, int ci
   WgArgs a = a0;
   a.n_kblocks = (int)(Ppad / 64);
   a.n_ci_chunks = cin_pad / N;
+  a.n_co_tiles = cout_pad / 128;
   const int units = (cout_pad / 128) * a.n_ci_chunks * 3;
   int splits = (2 * kNumSMs + units - 1) / units;               // about two waves of CTAs
   if (splits > a.n_kblocks) splits = a.n_kblocks;
@@ -432,10 +469,10 @@ struct BwdOps {
     unsigned* bits = w.bits + (layer_no++);
     const size_t n_px = (size_t)B * h * wd;
     absmax_kernel<<<ew_grid(n_px * C / 4), 256, 0, st>>>(gy, n_px * C, bits);
-    split_scaled_kernel<<<ew_grid(n_px * C), 256, 0, st>>>(gy, bits, w.hs, C, n_px);
+    split_scaled_kernel<<<ew_grid(n_px * C / 4), 256, 0, st>>>(gy, bits, w.hs, C, n_px);
     const int cpad = (int)align_up(C, 128);
     const size_t Pp = padded_pixels(B, h, wd);
-    transpose_pad_kernel<<<dim3((unsigned)(Pp / 64), cpad / 32, 2), 256, 0, st>>>(w.hs, C, 0, C, B, h, wd, w.gT, cpad, Pp);
+    transpose_pad_kernel<1><<<dim3((unsigned)(Pp / 64), cpad / 64, 2), 256, 0, st>>>(w.hs, C, 0, C, B, h, wd, w.gT, cpad, Pp);
     count_launches(3);
     if (db) {
       zero_f32_kernel<<<1, 256, 0, st>>>(db, C);
@@ -451,7 +488,7 @@ struct BwdOps {
     if (!dw) return HA_OK;
     const int cin_pad = (int)align_up(cin, 64), cout_pad = (int)align_up(cout, 128);
     const size_t Pp = padded_pixels(B, h, wd);
-    transpose_pad_kernel<<<dim3((unsigned)(Pp / 64), cin_pad / 32, 6), 256, 0, st>>>(x, pitch, coff, cin, B, h, wd, w.xT, cin_pad, Pp);
+    transpose_pad_kernel<3><<<dim3((unsigned)(Pp / 64), cin_pad / 64, 2), 256, 0, st>>>(x, pitch, coff, cin, B, h, wd, w.xT, cin_pad, Pp);
     zero_f32_kernel<<<ew_grid((size_t)cout * cin * 9), 256, 0, st>>>(dw, (size_t)cout * cin * 9);
     count_launches(2);
     WgArgs a{};
@@ -509,7 +546,7 @@ extern "C" int ha_vgg_backward(const HaVggStateDict* sd, const float* img_nchw, 
   };
   auto mask = [&](const float* R, const unsigned* bits, const __half* act, int pitch, int coff, const float* add, float* out, int C,
                   size_t n_px) {
-    post_mask_kernel<<<ew_grid(n_px * C), 256, 0, st>>>(R, bits, act, pitch, coff, add, out, C, n_px);
+    post_mask_kernel<<<ew_grid(n_px * C / 4), 256, 0, st>>>(R, bits, act, pitch, coff, add, out, C, n_px);
     count_launches(1);
   };
   auto sumpool = [&](const float* R, const unsigned* bits, const __half* cat, int pitch, int coff, const float* base, float* out, int C,
@@ -622,7 +659,7 @@ extern "C" int ha_conv3x3_backward_nhwc(const float* x_nhwc, int cin, const floa
   if (dx_nhwc) {
     if (cin != 64 && cin != 128 && cin != 256) return HA_EINVAL;   // other widths (the concat inputs) are split by ha_vgg_backward's schedule
     if ((rc = ops.dgrad(w_oihw, cin, cout, 0, cin, H, W, w.buf[0])) != HA_OK) return rc;
-    post_mask_kernel<<<ew_grid(n_px * cin), 256, 0, st>>>(w.buf[0], bits, nullptr, 0, 0, nullptr, dx_nhwc, cin, n_px);
+    post_mask_kernel<<<ew_grid(n_px * cin / 4), 256, 0, st>>>(w.buf[0], bits, nullptr, 0, 0, nullptr, dx_nhwc, cin, n_px);
     count_launches(1);
   }
   return check_launch("ha_conv3x3_backward_nhwc");

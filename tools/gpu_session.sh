@@ -83,6 +83,11 @@ while [ $# -gt 0 ]; do
       timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:img_ -s 24 -c 8 --csv \
         --log-file $OUT/pipeline_launches_$TAG.csv python tools/bench_input_pipeline.py 32 2 1 > /dev/null 2>&1
       grep -v "^==" $OUT/pipeline_launches_$TAG.csv | cut -d, -f5,12- | head -30 ;;
+    train)           # native train step vs the torch / cuDNN U-Net path; launch list of one native step
+      timeout 400 python tools/bench_train.py 3 5 > $OUT/train_$TAG.json 2> $OUT/train_$TAG.err; cat $OUT/train_$TAG.json | cut -c1-1200
+      timeout 400 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum \
+        --clock-control none -c 3000 --csv --log-file $OUT/train_launches_$TAG.csv python tools/bench_train.py 3 1 native > /dev/null 2>&1
+      python tools/train_launch_report.py $OUT/train_launches_$TAG.csv > $OUT/train_launches_$TAG.md; head -45 $OUT/train_launches_$TAG.md ;;
     sanitize)
       timeout 600 compute-sanitizer --tool memcheck python __graft_entry__.py smoke > $OUT/memcheck_smoke_$TAG.log 2>&1
       tail -3 $OUT/memcheck_smoke_$TAG.log ;;
