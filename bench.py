@@ -248,6 +248,55 @@ def pose_delta_vs_reference(ref, opt, dev, make_net, fwd):
         return {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
 
+def train_step_rows(dev, B=3, reps=3):
+    """SURVEY 8 f-1 (informational): forward(mode='train') + loss.backward() at the reference's training batch size
+    (train_kitti.py:453), fully native (tcgen05 U-Net forward / data / weight gradients + fused LM loop forward / backward)
+    vs the same module with its U-Nets on torch autograd / cuDNN fp32."""
+    from highlyaccurate_b200.models_kitti import LM_S2GP
+    out = {"batch": B, "what": "LM_S2GP forward(mode='train') + backward, level 3, 5 LM iterations"}
+    try:
+        net = LM_S2GP(ref_args()).to(dev)
+        g = torch.Generator().manual_seed(1)
+        sat, grd = torch.rand(B, 3, 512, 512, generator=g).to(dev), torch.rand(B, 3, 256, 1024, generator=g).to(dev)
+        gt = (torch.rand(B, 3, generator=g) * 2 - 1).to(dev)
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        for name, native in (("native", True), ("unet_on_torch_cudnn_fp32", False)):
+            net.SatFeatureNet.native_train = net.GrdFeatureNet.native_train = native
+
+            def step(_i=0):
+                net.zero_grad(set_to_none=True)
+                net(sat, grd, gt[:, 0:1], gt[:, 1:2], gt[:, 2:3], mode="train")[0].backward()
+            step(); step()
+            secs = time_region(step, reps, torch.cuda.synchronize) / reps
+            out[name] = {"ms_per_step": 1e3 * secs, "pairs_per_s": B / secs}
+        torch.backends.cudnn.allow_tf32 = old
+    except Exception as e:                                           # pragma: no cover
+        out["error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
+    return out
+
+
+def input_pipeline_row(dev, B):
+    """SURVEY 8 f-4 (informational): the datasets' sample preparation (KITTI_dataset.py:256-288, :299-302) on the GPU from
+    decoded uint8 images in pinned host memory (H2D inside the timed region), bit-identical to PIL (tests/test_imgproc.py)."""
+    from highlyaccurate_b200 import input_pipeline as P
+    try:
+        g = torch.Generator().manual_seed(5)
+        sat = torch.randint(0, 256, (B, 512, 512, 3), dtype=torch.uint8, generator=g).pin_memory()
+        grd = torch.randint(0, 256, (B, 375, 1242, 3), dtype=torch.uint8, generator=g).pin_memory()
+        hd, gx, gy, th = ((torch.rand(B, generator=g) * 2 - 1).tolist() for _ in range(4))
+
+        def prep(_i=0):
+            s = P.kitti_satellite_batch(sat.to(dev, non_blocking=True), hd, gx, gy, th)
+            return s, P.ground_batch(grd.to(dev, non_blocking=True))
+        prep(); prep()
+        secs = time_region(prep, 5, torch.cuda.synchronize) / 5
+        return {"batch": B, "ms_per_batch": 1e3 * secs, "pairs_per_s": B / secs, "h2d_bytes_per_pair": 512 * 512 * 3 + 375 * 1242 * 3,
+                "what": "4 affine stages + crop + ToTensor (satellite), antialiased resize + ToTensor (ground), pinned uint8 in"}
+    except Exception as e:                                           # pragma: no cover
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
 def run_reference(opt):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -486,6 +535,10 @@ def main():
         torch.cuda.empty_cache()
         info["reference_gpu_eager"] = reference_gpu_eager(opt, dev)
         torch.cuda.empty_cache()
+        if kind == "kitti" and opt.level == 3:
+            info["train_step"] = train_step_rows(dev)
+            info["input_pipeline"] = input_pipeline_row(dev, min(B, 32))
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
