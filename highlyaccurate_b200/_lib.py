@@ -32,7 +32,7 @@ EXPORTS = ["ha_version", "ha_error_string", "ha_last_cuda_error", "ha_device_che
            "ha_pose_loss", "ha_pose_loss_backward", "ha_img_affine_u8", "ha_img_resize_workspace_bytes",
            "ha_img_resize_to_tensor", "ha_vgg_train_workspace_bytes", "ha_vgg_forward_train",
            "ha_vgg_backward_workspace_bytes", "ha_vgg_backward", "ha_conv3x3_backward_workspace_bytes",
-           "ha_conv3x3_backward_nhwc"]
+           "ha_conv3x3_backward_nhwc", "ha_lm_residual", "ha_nn_pose_update"]
 
 
 class HaLevel(C.Structure):
@@ -84,6 +84,8 @@ def lib() -> C.CDLL:
                              vp, vp, vp, sz, vp]
     L.ha_lm_run.argtypes = [C.POINTER(HaLmParams), C.POINTER(HaLevel), C.POINTER(HaLevel), C.POINTER(vp),
                             C.POINTER(vp), vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.ha_lm_residual.argtypes = [C.POINTER(HaLmParams), i32, C.POINTER(HaLevel), C.POINTER(HaLevel), vp, vp, vp, i32, vp, vp]
+    L.ha_nn_pose_update.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     L.ha_vgg_packed_weight_bytes.restype = sz
     L.ha_vgg_pack_weights.argtypes = [C.POINTER(HaVggStateDict), vp, sz, vp]
     L.ha_vgg_workspace_bytes.restype = sz

@@ -891,9 +891,116 @@ static void lm_begin(void* ws, int B, uint32_t* status, cudaStream_t st) {
   count_launches(1);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Optimizer 'NN' (LM_S2GP.NN_update, models_kitti.py:1043-1054; RNNs.NNrefine): the learned update works on the
+// MATERIALISED residual, so this one ablation writes it out: out[b][q][c] = relu(s_c(uv(q, pose)) - g_c) over the
+// residual pixels (the leading ReLU of NNrefine.linear_k is applied here), s = the satellite features warped with the
+// same sampler as the LM step, both sides L2-normalised (HaLevel.scale) and masked like models_kitti.py:927,1191.
+// One warp per pixel, lanes across channel quads.
+template <int GEOM>
+__global__ void __launch_bounds__(256) lm_residual_kernel(const LmStepArgs a, float* __restrict__ out, int C, int relu) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int P = (a.H - a.row0) * a.W;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= P) return;
+  const float su = a.pose[b * 3 + 0], sv = a.pose[b * 3 + 1], th = a.pose[b * 3 + 2];
+  KittiPose kp;
+  FordPose fp;
+  G2spPose gq;
+  if (GEOM == HA_GEOM_KITTI) kp = kitti_pose(a, su, sv, th);
+  else fp = ford_pose(a, b, su, sv, th);
+  const int C4 = C / 4;
+  const float4* tab = a.table + (size_t)a.row0 * a.W;
+  const PixelScalars ps = pixel_scalars<GEOM>(a, kp, fp, gq, tab[q], nullptr, q, P, C4);
+  const float4* sat = reinterpret_cast<const float4*>(a.sat) + (size_t)b * a.A * a.A * C4;
+  const float4* grd = reinterpret_cast<const float4*>(a.grd) + ((size_t)b * a.H * a.W + (size_t)a.row0 * a.W) * C4;
+  const float alpha = a.sat_scale ? a.sat_scale[b] : 1.f, beta = a.grd_scale ? a.grd_scale[b] : 1.f;
+  float4* o = reinterpret_cast<float4*>(out) + ((size_t)b * P + q) * C4;
+  for (int c = lane; c < C4; c += 32) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ps.valid != 0.f) {
+      const float4 nw = sat[ps.off_n + c], ne = sat[ps.off_n + ps.east + c], sw = sat[ps.off_s + c], se = sat[ps.off_s + ps.east + c];
+      // jacobian.py:174-186: out = sum of the four taps times their (clamped-corner) weights
+      const float wnw = ps.ex * ps.sy, wne = ps.wx * ps.sy, wsw = ps.ex * ps.ny, wse = ps.wx * ps.ny;
+      s.x = nw.x * wnw + ne.x * wne + sw.x * wsw + se.x * wse; s.y = nw.y * wnw + ne.y * wne + sw.y * wsw + se.y * wse;
+      s.z = nw.z * wnw + ne.z * wne + sw.z * wsw + se.z * wse; s.w = nw.w * wnw + ne.w * wne + sw.w * wsw + se.w * wse;
+    }
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ps.goff >= 0) g = grd[ps.goff + c];
+    float4 r = make_float4(alpha * s.x - beta * g.x, alpha * s.y - beta * g.y, alpha * s.z - beta * g.z, alpha * s.w - beta * g.w);
+    if (relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+    o[c] = r;
+  }
+}
+
+// NNrefine tail (RNNs.py:118-126) + NN_update (models_kitti.py:1045-1053): x = mean over the pixels of the 64-channel conv
+// output, y = tanh(W1 relu(W0 relu(x) + b0) + b1), pose += y (all three components, no reset).  One CTA per sample.
+__global__ void __launch_bounds__(256) nn_pose_update_kernel(const float* __restrict__ x, int P, const float* __restrict__ w0,
+                                                             const float* __restrict__ b0, const float* __restrict__ w1,
+                                                             const float* __restrict__ b1, float* __restrict__ pose,
+                                                             float* __restrict__ traj, int traj_stride, uint32_t* status) {
+  __shared__ double part[4][64];
+  __shared__ float mean[64], hid[16];
+  const int b = blockIdx.x, c = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const float* xb = x + (size_t)b * P * 64;
+  double acc = 0.0;
+  for (int p = slice; p < P; p += 4) acc += (double)xb[(size_t)p * 64 + c];
+  part[slice][c] = acc;
+  __syncthreads();
+  if (threadIdx.x < 64) mean[c] = fmaxf((float)((part[0][c] + part[1][c] + part[2][c] + part[3][c]) / (double)P), 0.f);   // mapping[0]: ReLU
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float h = b0[threadIdx.x];
+    for (int k = 0; k < 64; ++k) h += w0[threadIdx.x * 64 + k] * mean[k];
+    hid[threadIdx.x] = fmaxf(h, 0.f);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float y = b1[threadIdx.x];
+    for (int k = 0; k < 16; ++k) y += w1[threadIdx.x * 16 + k] * hid[k];
+    const float np = pose[b * 3 + threadIdx.x] + tanhf(y);
+    pose[b * 3 + threadIdx.x] = np;
+    if (traj) traj[(size_t)b * traj_stride + threadIdx.x] = np;
+    if (np != np) atomicOr(status, HA_STATUS_NAN_POSE);
+  }
+}
+
 }  // namespace ha
 
 // ------------------------------------------------------------------------------------ C ABI
+extern "C" int ha_lm_residual(const HaLmParams* p, int level, const HaLevel* sat, const HaLevel* grd, const float* ground_table,
+                              const float* extrinsics, const float* pose, int relu, float* out, void* stream) {
+  using namespace ha;
+  if (!p || !sat || !grd || !ground_table || !pose || !out || level < 0 || level >= HA_MAX_LEVELS) return HA_EINVAL;
+  if (p->geometry != HA_GEOM_KITTI && p->geometry != HA_GEOM_FORD) return HA_EINVAL;
+  if (sat->C != grd->C || (grd->C % 4) || sat->H != sat->W || (grd->H & 1) || p->batch <= 0) return HA_EINVAL;
+  if (p->geometry == HA_GEOM_FORD && !extrinsics) return HA_EINVAL;
+  LmStepArgs a{};
+  a.sat = sat->data; a.grd = grd->data; a.sat_scale = sat->scale; a.grd_scale = grd->scale;
+  a.table = reinterpret_cast<const float4*>(ground_table); a.extr = extrinsics; a.pose = const_cast<float*>(pose);
+  a.B = p->batch; a.A = sat->H; a.H = grd->H; a.W = grd->W; a.grd_C = grd->C;
+  a.rot = p->rotation_range; a.lat = p->shift_range_lat; a.lon = p->shift_range_lon;
+  a.mpp = p->meter_per_pixel[level]; a.inv_mpp = p->inv_meter_per_pixel[level]; a.center = p->sat_center[level];
+  a.row0 = p->full_height ? 0 : grd->H / 2;
+  const int P = (grd->H - a.row0) * grd->W;
+  const dim3 grid((P + 7) / 8, p->batch);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p->geometry == HA_GEOM_KITTI) lm_residual_kernel<HA_GEOM_KITTI><<<grid, 256, 0, st>>>(a, out, grd->C, relu);
+  else lm_residual_kernel<HA_GEOM_FORD><<<grid, 256, 0, st>>>(a, out, grd->C, relu);
+  count_launches(1);
+  return check_launch("lm_residual_kernel");
+}
+
+extern "C" int ha_nn_pose_update(const float* x, int B, int n_px, const float* w0, const float* b0, const float* w1, const float* b1,
+                                 float* pose, float* traj_step, int traj_stride, uint32_t* status, void* stream) {
+  if (!x || !w0 || !b0 || !w1 || !b1 || !pose || !status || B <= 0 || n_px <= 0) return HA_EINVAL;
+  ha::nn_pose_update_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n_px, w0, b0, w1, b1, pose, traj_step, traj_stride,
+                                                                                   status);
+  ha::count_launches(1);
+  return ha::check_launch("nn_pose_update_kernel");
+}
+
 extern "C" size_t ha_lm_workspace_bytes(int B) { return B > 0 ? ha::lm_ws_bytes(B) : 0; }
 
 extern "C" int ha_lm_step(const HaLmParams* p, int level, const HaLevel* sat, const HaLevel* grd, const float* grd_conf,

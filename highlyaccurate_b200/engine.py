@@ -168,7 +168,7 @@ def dof_of(args, kind: str) -> int:
 
 def setup_from_args(args, kind: str, level_first: int = 0) -> LmSetup:
     opt = getattr(args, "Optimizer", "LM")
-    first_order = opt in ("SGD", "ADAM")                 # SGD_update / ADAM_update ignore the confidence weights and the DOF switch
+    first_order = opt in ("SGD", "ADAM", "NN")           # SGD_update / ADAM_update / NN_update ignore the confidence weights and the DOF switch
     return LmSetup(kind=kind, n_iters=int(args.N_iters), level_first=int(level_first), dof=3 if first_order else dof_of(args, kind),
                    using_weight=0 if first_order else int(bool(args.using_weight)),
                    use_hessian=int(bool(getattr(args, "use_hessian", 0))),
@@ -259,7 +259,8 @@ def make_params(setup: LmSetup, sat: Pyramid, damping: Sequence[float], side_m: 
     return p
 
 
-OPTIMIZERS = {"LM": _lib.HA_OPT_LM, "SGD": _lib.HA_OPT_SGD, "ADAM": _lib.HA_OPT_ADAM, "GN": _lib.HA_OPT_GN}
+OPTIMIZERS = {"LM": _lib.HA_OPT_LM, "SGD": _lib.HA_OPT_SGD, "ADAM": _lib.HA_OPT_ADAM, "GN": _lib.HA_OPT_GN,
+              "NN": _lib.HA_OPT_LM}      # 'NN' never reaches the step kernel (engine.nn_run): the field is unused there
 
 
 def draws_reset(setup: LmSetup) -> bool:
@@ -700,3 +701,38 @@ def conv3x3_backward(x_nhwc: torch.Tensor, weight: torch.Tensor, dy_nhwc: torch.
     check(L.ha_conv3x3_backward_nhwc(x.data_ptr(), cin, w.data_ptr(), dy.data_ptr(), cout, B, H, W, dx.data_ptr() if want_dx else None,
                                      dw.data_ptr(), db.data_ptr(), ws.data_ptr(), need, _stream_ptr()), "ha_conv3x3_backward_nhwc")
     return dx, dw, db
+
+
+def nn_run(setup: LmSetup, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Tensor], nn_params: dict, precision: str = "f16x3",
+           extrinsics: Optional[torch.Tensor] = None, side_m: Optional[float] = None, pose0: Optional[torch.Tensor] = None) -> LmResult:
+    """The refinement loop with Optimizer 'NN' (models_kitti.py:1233-1239, NN_update :1043-1054, RNNs.NNrefine): per step
+    ha_lm_residual (materialised relu(sat_proj - grd)) -> ha_conv3x3_nhwc (linear_k: Conv2d(C, 64) + bias on tcgen05) ->
+    ha_nn_pose_update (mean, 64-16-3 mapping, tanh, pose += delta).  `nn_params`: the NNrefine state dict
+    ('linear{k}.1.weight/bias' for C = 256 / 128 / 64 / 16, 'mapping.1.*', 'mapping.3.*') as CUDA tensors."""
+    L = _lib.lib()
+    n = len(sat.feats)
+    B = sat.batch
+    dev = sat.feats[0].device
+    _require_cuda(sat.feats[0], "satellite features")
+    pose = torch.zeros(B, 3, dtype=torch.float32, device=dev) if pose0 is None else pose0.to(dev, torch.float32).clone()
+    traj = torch.empty(B, setup.n_iters, n, 3, dtype=torch.float32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    params = make_params(setup, sat, [0.0] * 3, side_m)
+    sl, gl = _levels(sat, n), _levels(grd, n)
+    ext = extrinsics.to(dev, torch.float32).contiguous() if extrinsics is not None else None
+    head = {256: "linear0", 128: "linear1", 64: "linear2", 16: "linear3"}            # RNNs.py:118-125: chosen by channel count
+    w0, b0 = nn_params["mapping.1.weight"].float().contiguous(), nn_params["mapping.1.bias"].float().contiguous()
+    w1, b1 = nn_params["mapping.3.weight"].float().contiguous(), nn_params["mapping.3.bias"].float().contiguous()
+    st = _stream_ptr()
+    for it, lv in execution_order(setup.n_iters, n, setup.level_first):
+        g = grd.feats[lv]
+        rows = g.shape[1] if setup.full_height else g.shape[1] - g.shape[1] // 2
+        res = torch.empty(B, rows, g.shape[2], g.shape[3], dtype=torch.float32, device=dev)
+        check(L.ha_lm_residual(C.byref(params), lv, C.byref(sl[lv]), C.byref(gl[lv]), tables[lv].data_ptr(),
+                               ext.data_ptr() if ext is not None else None, pose.data_ptr(), 1, res.data_ptr(), st), "ha_lm_residual")
+        k = head[g.shape[3]]
+        x = conv3x3(res, nn_params[k + ".1.weight"], nn_params[k + ".1.bias"], precision)
+        step = traj[:, it, lv]
+        check(L.ha_nn_pose_update(x.data_ptr(), B, rows * g.shape[2], w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(),
+                                  pose.data_ptr(), step.data_ptr(), setup.n_iters * n * 3, status.data_ptr(), st), "ha_nn_pose_update")
+    return LmResult(traj, pose, None, status)

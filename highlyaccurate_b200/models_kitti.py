@@ -12,6 +12,18 @@ from .VGG import VGGUnet
 from .models_ford import loss_func, train_forward, _TrajectoryOutputs  # noqa: F401  (the reference re-exports loss_func too, :16)
 
 
+class NNrefine(nn.Module):
+    """RNNs.py:98-126: parameter container with the reference's names (`NNrefine.linear{0..3}.1.*`, `NNrefine.mapping.{1,3}.*`
+    in the model's state dict); the computation runs in engine.nn_run."""
+
+    def __init__(self):
+        super().__init__()
+        for i, c in enumerate((256, 128, 64, 16)):
+            setattr(self, "linear%d" % i, nn.Sequential(nn.ReLU(inplace=True),
+                                                        nn.Conv2d(c, 64, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1))))
+        self.mapping = nn.Sequential(nn.ReLU(inplace=True), nn.Linear(64, 16), nn.ReLU(inplace=True), nn.Linear(16, 3), nn.Tanh())
+
+
 class LM_S2GP(nn.Module):
     """models_kitti.py:598.  forward(sat_map, grd_img_left, ..., mode='test') -> (lat, lon, theta)."""
 
@@ -26,10 +38,9 @@ class LM_S2GP(nn.Module):
         self.loss_method = args.loss_method
         self.optimizer = getattr(args, "Optimizer", "LM")
         self.proj = getattr(args, "proj", "geo")
-        if self.optimizer not in ("LM", "SGD", "ADAM"):
-            # :1233 'NN' (RNNs.NNrefine on the materialised residual) is not on the accelerated path; anything else
-            # leaves the reference's own loop without an update (:1207-1254)
-            raise NotImplementedError("--Optimizer %s: LM, SGD and ADAM are on the accelerated path" % self.optimizer)
+        if self.optimizer not in ("LM", "SGD", "ADAM", "NN"):
+            # anything else leaves the reference's own loop without an update (:1207-1254)
+            raise NotImplementedError("--Optimizer %s: LM, SGD, ADAM and NN are on the accelerated path" % self.optimizer)
         if getattr(args, "dropout", 0) or getattr(args, "use_gt_depth", 0):
             raise NotImplementedError("dropout / use_gt_depth are outside the accelerated path")
         if self.level == 2:
@@ -46,6 +57,8 @@ class LM_S2GP(nn.Module):
         self._tables_cpu = [engine.ground_table("kitti", lv, proj=self.proj) for lv in range(4)]
         self._tables_dev = {}
         self.meters_per_pixel = [engine.kitti_meter_per_pixel() * (2 ** (3 - lv)) for lv in range(4)]   # :637-640
+        if self.optimizer == "NN":                                   # :648-649
+            self.NNrefine = NNrefine()
         self.last_result = None
         # forward(mode='test') reads the device status word once per call and applies the reference's error convention
         # (AssertionError of jacobian.py:172, NaN note of :1037); set to False for a fully asynchronous forward and call
@@ -72,6 +85,12 @@ class LM_S2GP(nn.Module):
         """The LM loop on already-extracted pyramids (used by forward and by the parity tests)."""
         setup = engine.setup_from_args(self.args, self.KIND, level_first)
         setup.kernel_variant = kernel_variant
+        if self.optimizer == "NN":
+            nn_params = {k: v.detach() for k, v in self.NNrefine.state_dict().items()}
+            res = engine.nn_run(setup, sat, grd, self._tables(sat.feats[0].device), nn_params, self.SatFeatureNet.precision,
+                                pose0=pose0)
+            self.last_result = res
+            return res
         lam = engine.resolve_damping(self.args, self.damping, setup.dof)
         res = engine.lm_run(setup, sat, grd, self._tables(sat.feats[0].device), lam, pose0=pose0, reset_uv=reset_uv,
                             want_stats=want_stats)

@@ -169,6 +169,19 @@ int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel* grd, const
               const float* reset_uv, float* traj, float* stats, uint32_t* status, void* ws, size_t ws_bytes,
               void* stream);
 
+/* ---- Optimizer 'NN' (LM_S2GP.NN_update, models_kitti.py:1043-1054 + RNNs.NNrefine, RNNs.py:98-126): the one ablation that
+ * needs the MATERIALISED residual.  A step = ha_lm_residual (relu = 1: the leading ReLU of NNrefine.linear_k) ->
+ * ha_conv3x3_nhwc (linear_k's Conv2d(C, 64) with bias) -> ha_nn_pose_update (spatial mean, the 64-16-3 mapping with its
+ * ReLUs and Tanh, pose += delta for all three components, no reset, no RNG draw).
+ * ha_lm_residual: out [B][n_px][C] fp32 = (relu of) sat_proj - grd over the residual pixels (the bottom half of the ground
+ *   image, or all of it with full_height), features scaled by HaLevel.scale, masks as in models_kitti.py:927,1191.
+ * ha_nn_pose_update: x [B][n_px][64] fp32; w0 [16][64], b0 [16], w1 [3][16], b1 [3] (torch Linear layouts, device);
+ *   pose [B][3] updated in place; traj_step = &traj[0][it][lv][0] (or NULL), traj_stride floats between samples. */
+int ha_lm_residual(const HaLmParams* p, int level, const HaLevel* sat, const HaLevel* grd, const float* ground_table,
+                   const float* extrinsics, const float* pose, int relu, float* out, void* stream);
+int ha_nn_pose_update(const float* x, int B, int n_px, const float* w0, const float* b0, const float* w1, const float* b1, float* pose,
+                      float* traj_step, int traj_stride, uint32_t* status, void* stream);
+
 /* ---- backward of ONE fused LM step (training; first slice of SURVEY.md section 8 f-1) -----------------
  * The adjoint of ha_lm_step for the S2GP geometries with all three degrees of freedom and unweighted residuals
  * (the defaults of train_kitti.py / train_ford.py): what `loss.backward()` (train_kitti.py:365) computes through

@@ -173,6 +173,8 @@ def run_ref_loop(net, kind, sat, grd, conf, a, ford=None, pose0=None):
             su, sv, th, adam_m, adam_v = net.ADAM_update(*step_in, adam_m, adam_v, t)
         elif a.Optimizer == "GN":                                    # models_ford.py:775-781
             su, sv, th = net.GN_update(*step_in)
+        elif a.Optimizer == "NN":                                    # :1233-1239
+            su, sv, th = net.NN_update(*step_in)
         su, sv, th = su.detach(), sv.detach(), th.detach()
         traj[:, it, lv] = torch.cat([su, sv, th], dim=1)
     return traj, pin
@@ -187,7 +189,7 @@ def stats_arrays(res: O.LoopResult, n_iters, L):
     return out
 
 
-def fp64_truth(kind, sat, grd, conf, oa, damp, ford, pose0, r_pin):
+def fp64_truth(kind, sat, grd, conf, oa, damp, ford, pose0, r_pin, nn_sd=None):
     """The same algorithm in float64 = the truth the fp32 reference itself deviates from
     (SURVEY 8c noise floor).  traj64: whole loop with the same draws; step64/hess64/grad64/delta64:
     every step restarted from the REFERENCE's fp32 pose state."""
@@ -196,7 +198,8 @@ def fp64_truth(kind, sat, grd, conf, oa, damp, ford, pose0, r_pin):
     f64 = None if ford is None else dict(R_FL=ford["R_FL"].double(), T_FL=ford["T_FL"].double(), side_m=ford["side_m"])
     p64 = None if pose0 is None else tuple(p.double() for p in pose0)
     torch.manual_seed(4242)
-    res = O.lm_loop(kind, s64, g64, c64, oa, None if damp is None else damp.double(), None, f64, p64)
+    nn64 = None if nn_sd is None else {k: v.double() for k, v in nn_sd.items()}
+    res = O.lm_loop(kind, s64, g64, c64, oa, None if damp is None else damp.double(), None, f64, p64, nn_sd=nn64)
     if kind == "kitti":
         traj64 = torch.stack([res.lons, res.lats, res.thetas], dim=-1)
     else:
@@ -216,7 +219,7 @@ def fp64_truth(kind, sat, grd, conf, oa, damp, ford, pose0, r_pin):
             pin = r_pin[:, it, lv].double()
             tab = tuple(t.double() for t in O.ground_table(kind, lv, L, oa.proj))
             su, sv, th, st = O.lm_one_step(kind, s64[lv], g64[lv], c64[lv], tab, pin[:, 0:1], pin[:, 1:2], pin[:, 2:3],
-                                           oa, lam, zero, f64)
+                                           oa, lam, zero, f64, dict(m=0, v=0, t=0, nn=nn64))
             step[:, it, lv] = torch.cat([su, sv, th], dim=1)
             hess[it, lv], grad[it, lv], delta[it, lv] = st.hessian, st.grad, st.delta
     return dict(traj64=traj64.numpy(), step64=step.numpy(), hess64=hess.numpy(), grad64=grad.numpy(),
@@ -234,11 +237,15 @@ def kat_loop(rk, rf, name, kind, make_inputs, tol=2e-6, pose0=None, **akw):
     damp = None
     if a.train_damping:
         damp = net.damping.detach().clone()
+    nn_sd = None
+    if a.Optimizer == "NN":                                # seeded NNrefine weights (RNNs.py:98-116) loaded into the reference
+        nn_sd = O.nnrefine_state_dict(int(meta["seed"]) + 1000)
+        net.NNrefine.load_state_dict(nn_sd)
     torch.manual_seed(4242)
     with torch.no_grad():
         r_traj, r_pin = run_ref_loop(net, kind, sat, grd, conf, a, ford, pose0)
     torch.manual_seed(4242)
-    res = O.lm_loop(kind, sat, grd, conf, oa, damp, None, ford, pose0)
+    res = O.lm_loop(kind, sat, grd, conf, oa, damp, None, ford, pose0, nn_sd=nn_sd)
     # reference loop records (su,sv,th); oracle LoopResult is (lat,lon,theta) in the model's convention
     if kind == "kitti":
         o_traj = torch.stack([res.lons, res.lats, res.thetas], dim=-1)
@@ -246,7 +253,7 @@ def kat_loop(rk, rf, name, kind, make_inputs, tol=2e-6, pose0=None, **akw):
         o_traj = torch.stack([res.lats, res.lons, res.thetas], dim=-1)
     d = close(o_traj, r_traj, tol, name + " trajectory")
     out = dict(traj=r_traj.numpy(), pose_in=r_pin.numpy(), in_csum=csum(*sat, *grd), **stats_arrays(res, a.N_iters, len(sat)))
-    out.update(fp64_truth(kind, sat, grd, conf, oa, damp, ford, pose0, r_pin))
+    out.update(fp64_truth(kind, sat, grd, conf, oa, damp, ford, pose0, r_pin, nn_sd))
     out.update(meta)
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
     print("%s ok  (oracle vs reference max|d| = %.2e; final pose sample0 = %s)" % (name, d, r_traj[0, -1, -1].tolist()))
@@ -574,6 +581,10 @@ def main():
         kat_loop(rk, rf, "kat10_polar_ford", "ford", planted_inputs("ford", 106, GT2, A=512, side_m=512 * 0.22), proj="nn",
                  N_iters=2)
         kat_loop(rk, rf, "kat10_polar_sgd", "kitti", rand_inputs(107), proj="polar", Optimizer="SGD", N_iters=2)
+    if want("kat10nn"):
+        kat_loop(rk, rf, "kat10_nn", "kitti", planted_inputs("kitti", 108, GT2, l2=True), Optimizer="NN", N_iters=2, tol=5e-6)
+        kat_loop(rk, rf, "kat10_nn_level4_polar", "kitti", planted_inputs("kitti", 109, GT2[:1], L=4, l2=True), Optimizer="NN", level=4,
+                 proj="polar", N_iters=1, tol=5e-6)
     if want("kat6"):   # forced out-of-range reset (models_kitti.py:1028-1033): start outside (-2.5, 2.5)
         p0 = torch.tensor([[3.0, 0.1, 0.2], [0.1, -2.8, -0.1]])
         kat_loop(rk, rf, "kat6_reset", "kitti", rand_inputs(61), N_iters=2,

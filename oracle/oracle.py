@@ -348,6 +348,32 @@ def gn_update(su, sv, th, sat_proj, grd_feat, grd_conf, dfeat, args: LMArgs, ran
     return su_n, sv_n, th_n, StepStats(Hm, grad[:, :, 0], sn, gn, torch.sum(r.reshape(B, -1) ** 2, dim=-1), delta[:, :, 0])
 
 
+def nnrefine_state_dict(seed: int, dtype=torch.float32) -> dict:
+    """Seeded weights with the shapes of RNNs.NNrefine (RNNs.py:98-116); keys as in its state dict."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for i, c in enumerate((256, 128, 64, 16)):
+        sd["linear%d.1.weight" % i] = (torch.randn(64, c, 3, 3, generator=g) * (2.0 / (9 * c)) ** 0.5).to(dtype)
+        sd["linear%d.1.bias" % i] = (torch.randn(64, generator=g) * 0.01).to(dtype)
+    sd["mapping.1.weight"] = (torch.randn(16, 64, generator=g) * 0.5).to(dtype)
+    sd["mapping.1.bias"] = (torch.randn(16, generator=g) * 0.1).to(dtype)
+    sd["mapping.3.weight"] = (torch.randn(3, 16, generator=g) * 0.1).to(dtype)       # steps of ~0.1: tanh far from saturation
+    sd["mapping.3.bias"] = (torch.randn(3, generator=g) * 0.02).to(dtype)
+    return sd
+
+
+def nn_update(su, sv, th, sat_proj, grd_feat, nn_sd: dict):
+    """LM_S2GP.NN_update (models_kitti.py:1043-1054) with RNNs.NNrefine.forward (RNNs.py:118-126)."""
+    r = sat_proj - grd_feat
+    k = {256: 0, 128: 1, 64: 2, 16: 3}[r.shape[1]]
+    x = F.conv2d(F.relu(r), nn_sd["linear%d.1.weight" % k].to(r.dtype), nn_sd["linear%d.1.bias" % k].to(r.dtype), padding=1)
+    x = torch.mean(x, dim=[2, 3])
+    h = F.relu(F.linear(F.relu(x), nn_sd["mapping.1.weight"].to(r.dtype), nn_sd["mapping.1.bias"].to(r.dtype)))
+    y = torch.tanh(F.linear(h, nn_sd["mapping.3.weight"].to(r.dtype), nn_sd["mapping.3.bias"].to(r.dtype)))
+    zero = torch.zeros(y.shape[0], dtype=y.dtype)
+    return su + y[:, 0:1], sv + y[:, 1:2], th + y[:, 2:3], StepStats(torch.zeros(y.shape[0], 3, 3, dtype=y.dtype), y, zero, zero, zero, y)
+
+
 def resolve_damping(args: LMArgs, damping_param: Optional[torch.Tensor], n_dof: int, dtype=torch.float32):
     """models_kitti.py:958-966: trained lambda = 10^(-6 + 11*sigmoid(p)), else args.damping."""
     if args.train_damping:
@@ -390,6 +416,8 @@ def lm_one_step(kind: str, sf, gf, gc, tab, su, sv, th, args: LMArgs, lam, draws
         return su, sv, th, st
     if args.Optimizer == "GN":
         return gn_update(su, sv, th, sp, gfm, gcm, dj, args, draws)
+    if args.Optimizer == "NN":
+        return nn_update(su, sv, th, sp, gfm, adam["nn"])
     return lm_update(su, sv, th, sp, gfm, gcm, dj, args, lam, draws, always_3dof=(kind == "ford"))
 
 
@@ -419,7 +447,7 @@ def _step_order(n_iters: int, n_levels: int, level_first: int):
 def lm_loop(kind: str, sat_feats: Sequence[torch.Tensor], grd_feats: Sequence[torch.Tensor],
             grd_confs: Sequence[Optional[torch.Tensor]], args: LMArgs,
             damping_param: Optional[torch.Tensor] = None, reset_draws=None,
-            ford: Optional[dict] = None, pose0=None) -> LoopResult:
+            ford: Optional[dict] = None, pose0=None, nn_sd: Optional[dict] = None) -> LoopResult:
     """models_kitti.py:1141-1316 / :1318-1492 and models_ford.py:652-866 / :868-1026, mode='test'.
     kind: 'kitti' | 'ford'.  ford = dict(R_FL[B,3,3], T_FL[B,3], side_m).  `reset_draws`
     (optional) = list of (u,v) per executed step; default draws them from the CPU generator in
@@ -438,7 +466,7 @@ def lm_loop(kind: str, sat_feats: Sequence[torch.Tensor], grd_feats: Sequence[to
         ndof = 2 if args.rotation_range == 0 else 1
     lam = resolve_damping(args, damping_param, ndof, dt)
     draws_rng = ndof == 3 and args.Optimizer in ("LM", "GN")     # SGD_update / ADAM_update draw nothing
-    adam = dict(m=0, v=0, t=0)
+    adam = dict(m=0, v=0, t=0, nn=nn_sd)                        # per-run optimiser state (Adam moments, NNrefine weights)
     tabs = []
     for lv in range(L):
         tabs.append(tuple(t.to(dt) for t in ground_table(kind, lv, L, args.proj)))

@@ -38,11 +38,14 @@ LOOP_CASES = {
     "kat10_polar_kitti": ("kitti", "planted", dict(proj="polar", N_iters=3), {}),
     "kat10_polar_ford": ("ford", "planted", dict(proj="nn", N_iters=2), {}),
     "kat10_polar_sgd": ("kitti", "rand", dict(proj="polar", Optimizer="SGD", N_iters=2), {}),
+    # Optimizer 'NN' (RNNs.NNrefine with seeded weights, O.nnrefine_state_dict(seed + 1000))
+    "kat10_nn": ("kitti", "planted_l2", dict(Optimizer="NN", N_iters=2), dict(nn=True)),
+    "kat10_nn_level4_polar": ("kitti", "planted_l2", dict(Optimizer="NN", level=4, proj="polar", N_iters=1), dict(nn=True)),
 }
 # the cases cheap enough for the CPU suite (the rest are exercised by the gpu parity tests)
 CPU_LOOP_CASES = ["kat3_random_kitti", "kat4_planted_kitti", "kat4_planted_ford", "kat5_weight", "kat5_shiftonly",
                   "kat5_rotonly", "kat5_level4", "kat6_reset", "kat10_sgd", "kat10_adam_level4", "kat10_gn_ford",
-                  "kat10_polar_ford"]
+                  "kat10_polar_ford", "kat10_nn_level4_polar"]
 
 
 def csum(*ts) -> np.ndarray:
@@ -77,8 +80,9 @@ def build_loop_case(name):
     if extra.get("pose0_from_golden"):
         p0 = torch.from_numpy(gold["pose_in"][:, 0, 0])
         pose0 = (p0[:, 0:1].clone(), p0[:, 1:2].clone(), p0[:, 2:3].clone())
+    nn_sd = O.nnrefine_state_dict(seed + 1000) if extra.get("nn") else None
     return dict(kind=kind, args=args, sat=sat, grd=grd, conf=conf, ford=ford,
-                damping_param=extra.get("damping_param"), pose0=pose0, gold=gold, B=B, A=A, L=L)
+                damping_param=extra.get("damping_param"), pose0=pose0, gold=gold, B=B, A=A, L=L, nn_sd=nn_sd)
 
 
 RESET_SEED = 4242    # oracle/make_golden.py seeds the CPU generator with this before every loop

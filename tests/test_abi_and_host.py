@@ -111,9 +111,15 @@ def test_out_of_scope_flags_raise_at_construction():
     """flags outside the accelerated path raise NotImplementedError instead of silently running
     something else (the Ford model used to accept --dropout)."""
     for cls in (LM_S2GP, LM_S2GP_Ford):
-        for kw in (dict(dropout=1), dict(Optimizer="NN"), dict(Optimizer="RMSprop")):
+        for kw in (dict(dropout=1), dict(Optimizer="RMSprop")):
             with pytest.raises(NotImplementedError):
                 cls(K.ref_args(**kw))
+    with pytest.raises(NotImplementedError):
+        LM_S2GP_Ford(K.ref_args(Optimizer="NN"))                       # models_ford.py:600-607 adds a [B] row to a [B,1] column
+    nn_net = LM_S2GP(K.ref_args(Optimizer="NN"))                      # RNNs.NNrefine's parameters under the reference's names
+    keys = set(nn_net.state_dict())
+    assert {"NNrefine.linear0.1.weight", "NNrefine.linear3.1.bias", "NNrefine.mapping.1.weight", "NNrefine.mapping.3.bias"} <= keys
+    assert len(keys) == 49 + 12 and tuple(nn_net.state_dict()["NNrefine.linear1.1.weight"].shape) == (64, 128, 3, 3)
     with pytest.raises(NotImplementedError):
         LM_S2GP_Ford(K.ref_args(estimate_depth=1))
     # the reference's own Ford SGD_update / ADAM branch cannot run (models_ford.py:609-628 indexes a 2-D tensor with three

@@ -31,6 +31,9 @@ def make_net(c):
     if c["damping_param"] is not None:
         with torch.no_grad():
             net.damping.copy_(c["damping_param"])
+    if c.get("nn_sd") is not None:
+        net.NNrefine.load_state_dict(c["nn_sd"])
+        net = net.to(DEV)
     return net
 
 
