@@ -30,6 +30,8 @@ def _conf(cin):
 class VGGUnet(nn.Module):
     """VGG.py:13.  `level` selects the returned pyramid: 3 -> [x15,x18,x21], 4 -> +x24 (VGG.py:192-203)."""
 
+    G2S = False       # VGGUnet_G2S: decoders on the folded [2H, W/2] maps
+
     def __init__(self, level, estimate_depth=0):
         super().__init__()
         if estimate_depth:
@@ -92,7 +94,7 @@ class VGGUnet(nn.Module):
         `want_scale=False` leaves the L2-norm scales out (callers whose LM step renormalises: they cancel)."""
         if self._named is None:
             self._named = dict(self.named_parameters())
-        p = self._runner(self._named, x, self.n_levels(), want_conf, self.precision, want_scale)
+        p = self._runner(self._named, x, self.n_levels(), want_conf, self.precision, want_scale, g2s=self.G2S)
         sl = self.level_slice()
         return engine.Pyramid(p.feats[sl], p.scales[sl], p.confs[sl])
 
@@ -146,6 +148,25 @@ class VGGUnet(nn.Module):
         confs = [torch.sigmoid(-heads[i](f)) for i, f in enumerate(feats)]      # VGG.py:160-163
         sl = self.level_slice()
         return [L2_norm(f) for f in feats][sl], confs[sl]
+
+
+class VGGUnet_G2S(VGGUnet):
+    """VGG.py:206-345: the ground branch of `LM_G2SP --proj nn`.  Same parameters (and state-dict keys) as VGGUnet; every map
+    the decoders see is folded from [H, W] to [2H, W/2], so a 256 x 1024 image yields square 64 / 128 / 256 (/ 512) feature
+    maps.  Runs ha_vgg_g2s_forward (same tcgen05 kernels, the decoder schedule on the folded geometry).  Levels 3 and 4."""
+
+    G2S = True
+
+    def __init__(self, level):
+        super().__init__(level)
+        if level not in (3, 4):
+            raise NotImplementedError("VGGUnet_G2S: levels 3 and 4 are on the accelerated path")
+
+    def forward_autograd(self, x):
+        raise NotImplementedError("VGGUnet_G2S runs in test mode only on the accelerated path")
+
+    def forward_train(self, x):
+        raise NotImplementedError("VGGUnet_G2S runs in test mode only on the accelerated path")
 
 
 def L2_norm(x):

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libha_b200.so")
 HA_MAX_LEVELS = 4
 HA_STATS = 24
 HA_VGG_N_CONV = 17
-HA_GEOM_KITTI, HA_GEOM_FORD, HA_GEOM_G2SP = 0, 1, 2
+HA_GEOM_KITTI, HA_GEOM_FORD, HA_GEOM_G2SP, HA_GEOM_G2SP_NN = 0, 1, 2, 3
 HA_OPT_LM, HA_OPT_SGD, HA_OPT_ADAM, HA_OPT_GN = 0, 1, 2, 3
 HA_CONV_FP32_SIMT, HA_CONV_F16X3, HA_CONV_F16, HA_CONV_F16X3_1CTA = 0, 1, 2, 3
 HA_STATUS_NO_INRANGE, HA_STATUS_NAN_POSE, HA_STATUS_RESET, HA_STATUS_SAMPLE_EMPTY = 1, 2, 4, 8
@@ -32,7 +32,7 @@ EXPORTS = ["ha_version", "ha_error_string", "ha_last_cuda_error", "ha_device_che
            "ha_pose_loss", "ha_pose_loss_backward", "ha_img_affine_u8", "ha_img_resize_workspace_bytes",
            "ha_img_resize_to_tensor", "ha_vgg_train_workspace_bytes", "ha_vgg_forward_train",
            "ha_vgg_backward_workspace_bytes", "ha_vgg_backward", "ha_conv3x3_backward_workspace_bytes",
-           "ha_conv3x3_backward_nhwc", "ha_lm_residual", "ha_nn_pose_update"]
+           "ha_conv3x3_backward_nhwc", "ha_lm_residual", "ha_nn_pose_update", "ha_vgg_g2s_forward"]
 
 
 class HaLevel(C.Structure):
@@ -101,6 +101,7 @@ def lib() -> C.CDLL:
     L.ha_conv3x3_backward_workspace_bytes.restype = sz
     L.ha_conv3x3_backward_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.ha_conv3x3_backward_nhwc.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    L.ha_vgg_g2s_forward.argtypes = [vp, vp, i32, i32, i32, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, sz, vp]
     L.ha_conv3x3_workspace_bytes.restype = sz
     L.ha_conv3x3_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.ha_conv3x3_nhwc.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]

@@ -268,7 +268,7 @@ extern "C" int ha_lm_step_backward(const HaLmParams* p, int level, const HaLevel
   a.mpp = p->meter_per_pixel[level]; a.inv_mpp = p->inv_meter_per_pixel[level]; a.center = p->sat_center[level];
   for (int i = 0; i < 3; ++i) a.damping[i] = p->damping[i];
   a.ori_h = p->ori_grd_h; a.ori_w = p->ori_grd_w; a.variant = 0;
-  a.row0 = grd->H / 2; a.optimizer = HA_OPT_LM; a.adam_t = 0; a.adam_b1 = a.adam_b2 = 0.f; a.adam_mv = nullptr;
+  a.row0 = grd->H / 2; a.optimizer = HA_OPT_LM; a.adam_t = 0; a.adam_b1 = a.adam_b2 = 0.f; a.adam_mv = nullptr; a.g2sp_nn = 0;
   const int P = (grd->H - grd->H / 2) * grd->W;
   int ctas = (kNumSMs * 8 + B - 1) / B;
   if (ctas > kLmMaxCtasPerSample) ctas = kLmMaxCtasPerSample;

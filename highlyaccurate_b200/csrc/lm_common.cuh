@@ -51,6 +51,7 @@ struct LmStepArgs {
   int adam_t;              // HA_OPT_ADAM: t of this step (iter * args.level + level, models_kitti.py:1241)
   float adam_b1, adam_b2;  // HA_OPT_ADAM: args.beta1 / args.beta2
   float* adam_mv;          // HA_OPT_ADAM: [B][6] first / second moments, carried between the steps of a run
+  int g2sp_nn;             // HA_GEOM_G2SP_NN: the in-plane warp of models_kitti.py:289-331 instead of the camera projection
 };
 
 // Per-sample constants of the warp, evaluated in the reference's fp32 operation order.
@@ -125,11 +126,23 @@ struct G2spPose {
   float P[3][4];        // projection of (X, 0, Z, 1); column 1 multiplies Y = 0 and is dropped
   float dPt[3][2];      // dP/dtheta columns 0 (X) and 2 (Z); its last column is 0
   float du[3], dv[3];   // dP/dsu, dP/dsv: only the last column is non-zero -> duv1/dshift are per-sample constants
+  float nn_c, nn_s, nn_tx, nn_ty, nn_ju, nn_jv, nn_k;   // proj 'nn' (inplane_grd_to_map): R(theta), T in pixels, d/dsu, d/dsv, k
 };
 
 __device__ __forceinline__ G2spPose g2sp_pose(const LmStepArgs& a, int b, float su, float sv, float th) {
   G2spPose g;
   const float pi_f = 3.14159265358979323846f;
+  if (a.g2sp_nn) {
+    // models_kitti.py:294-303: T = (-lon su, lat sv) / mpp pixels, R = [[cos, -sin], [sin, cos]] of +heading
+    const float heading_nn = __fmul_rn(__fdiv_rn(__fmul_rn(th, a.rot), 180.f), pi_f);
+    sincosf(heading_nn, &g.nn_s, &g.nn_c);
+    g.nn_tx = -__fdiv_rn(__fmul_rn(a.lon, su), a.mpp);
+    g.nn_ty = __fdiv_rn(__fmul_rn(a.lat, sv), a.mpp);
+    g.nn_ju = -__fdiv_rn(a.lon, a.mpp);                                                  // :316-318
+    g.nn_jv = __fdiv_rn(a.lat, a.mpp);                                                   // :319-321
+    g.nn_k = (float)((double)a.rot / 180.0 * 3.14159265358979323846);                    // :322
+    return g;
+  }
   const float shu = __fmul_rn(a.lon, su), shv = __fmul_rn(a.lat, sv);                  // :92-93
   const float heading = __fmul_rn(__fdiv_rn(__fmul_rn(th, a.rot), 180.f), pi_f);       // :94
   float sn, cs;
@@ -227,7 +240,21 @@ __device__ __forceinline__ PixelScalars pixel_scalars(const LmStepArgs& a, const
   if (q >= q_end) return r;
   float x, y;
   int IW, IH;
-  if (GEOM == HA_GEOM_G2SP) {
+  if (GEOM == HA_GEOM_G2SP && a.g2sp_nn) {
+    // proj 'nn' (models_kitti.py:289-331): uv = R (p - A/2) + T + A/2 on the square ground feature map, mask all ones
+    const int i = q / a.A, j = q - i * a.A;
+    const float half = a.center;
+    const float u2 = (float)j - half, v2 = (float)i - half;
+    x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(gp.nn_c, u2), __fmul_rn(-gp.nn_s, v2)), gp.nn_tx), half);
+    y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(gp.nn_s, u2), __fmul_rn(gp.nn_c, v2)), gp.nn_ty), half);
+    IW = a.W; IH = a.H;
+    if (!((x >= 0.f) && (x <= (float)(IW - 1)) && (y >= 0.f) && (y <= (float)(IH - 1)))) return r;
+    r.goff = q * c4;
+    r.d0x = gp.nn_ju; r.d0y = 0.f; r.d1x = 0.f; r.d1y = gp.nn_jv;
+    // dR = k [[-sin, -cos], [cos, -sin]]  (:322-327)
+    r.tx = __fmul_rn(gp.nn_k, __fadd_rn(__fmul_rn(-gp.nn_s, u2), __fmul_rn(-gp.nn_c, v2)));
+    r.ty = __fmul_rn(gp.nn_k, __fadd_rn(__fmul_rn(gp.nn_c, u2), __fmul_rn(-gp.nn_s, v2)));
+  } else if (GEOM == HA_GEOM_G2SP) {
     // satellite pixel (row i, col j) -> ground-plane point (X south, 0, Z east)  (models_kitti.py:54-84)
     const int i = q / a.A, j = q - i * a.A;
     const float X = __fmul_rn(a.mpp, (float)(i - (int)a.center)), Z = __fmul_rn(a.mpp, (float)(j - (int)a.center));

@@ -823,7 +823,8 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
                         const float* ground_table, const float* extrinsics, float* pose, const float* reset_uv,
                         float* stats, float* traj_step, int traj_stride, uint32_t* status, void* ws, size_t ws_bytes,
                         int B, bool full, int iter, cudaStream_t st) {
-  const bool g2sp = p && p->geometry == HA_GEOM_G2SP;
+  const bool g2sp_nn = p && p->geometry == HA_GEOM_G2SP_NN;
+  const bool g2sp = p && (p->geometry == HA_GEOM_G2SP || g2sp_nn);
   if (!p || !sat || !grd || !pose || !status || !ws || (!ground_table && !g2sp)) return HA_EINVAL;
   if (level < 0 || level >= HA_MAX_LEVELS) return HA_EINVAL;
   if (sat->C != grd->C || sat->H != sat->W || (grd->H & 1)) return HA_EINVAL;
@@ -842,7 +843,8 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   if (first_order && (p->using_weight || p->dof != 3)) return HA_EINVAL;
   if (p->optimizer == HA_OPT_GN && p->dof != 3) return HA_EINVAL;
   if (p->dof == 3 && !reset_uv && !g2sp && !first_order) return HA_EINVAL;
-  if (g2sp && (p->dof != 3 || !extrinsics || p->ori_grd_h <= 0 || p->ori_grd_w <= 0)) return HA_EINVAL;
+  if (g2sp && p->dof != 3) return HA_EINVAL;
+  if (g2sp && !g2sp_nn && (!extrinsics || p->ori_grd_h <= 0 || p->ori_grd_w <= 0)) return HA_EINVAL;
   if (p->using_weight && !grd_conf) return HA_EINVAL;
   if (p->geometry == HA_GEOM_FORD && !extrinsics) return HA_EINVAL;
   if (ws_bytes < lm_ws_bytes(B)) return HA_ENOSPACE;
@@ -869,6 +871,7 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   a.adam_t = iter * p->adam_level_mult + level;
   a.adam_b1 = p->adam_beta1; a.adam_b2 = p->adam_beta2;
   a.adam_mv = w.adam_mv;
+  a.g2sp_nn = g2sp_nn ? 1 : 0;
   const int P = g2sp ? sat->H * sat->W : (grd->H - a.row0) * grd->W;
   a.px_per_cta = choose_px_per_cta(B, P);
   dim3 grid((P + a.px_per_cta - 1) / a.px_per_cta, B);
@@ -876,7 +879,7 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
     return full ? launch_by_channels<HA_GEOM_KITTI, true>(grd->C, grid, st, a) : launch_by_channels<HA_GEOM_KITTI, false>(grd->C, grid, st, a);
   if (p->geometry == HA_GEOM_FORD)
     return full ? launch_by_channels<HA_GEOM_FORD, true>(grd->C, grid, st, a) : launch_by_channels<HA_GEOM_FORD, false>(grd->C, grid, st, a);
-  if (p->geometry == HA_GEOM_G2SP) return launch_by_channels<HA_GEOM_G2SP, false>(grd->C, grid, st, a);
+  if (g2sp) return launch_by_channels<HA_GEOM_G2SP, false>(grd->C, grid, st, a);
   return HA_EINVAL;
 }
 

@@ -280,12 +280,12 @@ static int vgg_forward_simt(const char* packed, const PackedLayout& L, const flo
 
 static int vgg_run(const char* packed, const float* img, int B, int H, int W, int n_levels, int precision,
                    float* const* out_feat, float* const* out_scale, float* const* out_conf, Arena& ar, cudaStream_t st,
-                   TcSaved* saved = nullptr) {
+                   TcSaved* saved = nullptr, bool g2s = false) {
   const PackedLayout L = vgg_packed_layout();
   double* norm_part = (double*)ar.take((size_t)HA_MAX_LEVELS * B * kNormChunks * sizeof(double));
   int rc;
-  if (precision == HA_CONV_FP32_SIMT) rc = vgg_forward_simt(packed, L, img, B, H, W, n_levels, out_feat, ar, st);
-  else rc = vgg_forward_tc(packed, L, img, B, H, W, n_levels, precision, out_feat, ar, st, saved);
+  if (precision == HA_CONV_FP32_SIMT) rc = g2s ? HA_EINVAL : vgg_forward_simt(packed, L, img, B, H, W, n_levels, out_feat, ar, st);
+  else rc = vgg_forward_tc(packed, L, img, B, H, W, n_levels, precision, out_feat, ar, st, saved, g2s);
   if (rc != HA_OK || ar.dry) return rc;
   static const int chans[4] = {256, 128, 64, 16};
   NormArgs na;
@@ -304,7 +304,9 @@ static int vgg_run(const char* packed, const float* img, int B, int H, int W, in
     count_launches(2);
   }
   for (int l = 0; l < n_levels; ++l) {
-    const int h = H >> (3 - l), w = W >> (3 - l), C = chans[l];
+    int h = H >> (3 - l), w = W >> (3 - l);
+    const int C = chans[l];
+    if (g2s && l > 0) { h *= 2; w /= 2; }        // VGG.py:326-329: c0 is taken from the un-folded x15, c1.. from the folded decoder maps
     if (out_conf && out_conf[l]) {
       const size_t n_px = (size_t)B * h * w;
       conf_head_kernel<<<(unsigned)((n_px * 32 + 255) / 256), 256, 0, st>>>(
@@ -390,4 +392,17 @@ extern "C" int ha_vgg_forward_train(const void* packed_weights, const float* img
   ha::TcSaved sv;
   return ha::vgg_run(reinterpret_cast<const char*>(packed_weights), img_nchw, B, H, W, n_levels, HA_CONV_F16X3, out_feat,
                      out_scale, out_conf, ar, reinterpret_cast<cudaStream_t>(stream), &sv);
+}
+
+// ---- VGGUnet_G2S (VGG.py:206-345; the ground branch of LM_G2SP --proj nn): same weights and encoder, decoders on the folded maps
+extern "C" int ha_vgg_g2s_forward(const void* packed_weights, const float* img_nchw, int B, int H, int W, int n_levels, int precision,
+                                  float* const* out_feat, float* const* out_scale, float* const* out_conf, void* ws, size_t ws_bytes,
+                                  void* stream) {
+  if (!packed_weights || !img_nchw || !out_feat || !ws) return HA_EINVAL;
+  if (!vgg_shape_ok(B, H, W, n_levels, precision) || precision == HA_CONV_FP32_SIMT || (W % 128) || (H % 32)) return HA_EINVAL;
+  for (int l = 0; l < n_levels; ++l)
+    if (!out_feat[l]) return HA_EINVAL;
+  ha::Arena ar{reinterpret_cast<char*>(ws), 0, ws_bytes, false};
+  return ha::vgg_run(reinterpret_cast<const char*>(packed_weights), img_nchw, B, H, W, n_levels, precision, out_feat, out_scale,
+                     out_conf, ar, reinterpret_cast<cudaStream_t>(stream), nullptr, true);
 }

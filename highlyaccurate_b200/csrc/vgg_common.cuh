@@ -77,8 +77,9 @@ struct TcSaved {
 TcSaved vgg_tc_carve(Arena& ar, int B, int H, int W, int n_levels, bool train);
 TcSaved vgg_train_saved(char* ws, int B, int H, int W, int n_levels);
 // `saved` != nullptr = train mode: conv2 / conv7 / conv14 also keep their raw outputs and x15 is pooled by a kernel of its own
+// `g2s`: the decoder schedule of VGGUnet_G2S (VGG.py:275-345) on the folded [2H, W/2] maps
 int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, int B, int H, int W, int n_levels,
-                   int precision, float* const* out_feat, Arena& ar, cudaStream_t st, TcSaved* saved = nullptr);
+                   int precision, float* const* out_feat, Arena& ar, cudaStream_t st, TcSaved* saved = nullptr, bool g2s = false);
 
 constexpr float kLoScale = 2048.f;          // 2^11
 constexpr float kLoInvScale = 1.f / 2048.f;

@@ -1124,6 +1124,33 @@ __global__ void pool_x15_kernel(const float* __restrict__ x14, float* __restrict
   }
 }
 
+// VGGUnet_G2S (VGG.py:275-345): every map the decoders see is the [H, W] map re-interpreted as [2H, W/2] (row-major pixel
+// order unchanged, so in NHWC the re-shape is free); only the x2 nearest upsample depends on the folded geometry.
+// dst pixel (Y, X) of the folded fine map [2 hs][2 ws] = relu(src pixel (Y/2, X/2)) of the folded coarse map [hs][ws].
+__global__ void relu_up2x_fold_kernel(const float* __restrict__ src, __half* __restrict__ dst, int pitch, int coff, int C, int B, int hs,
+                                      int ws) {
+  const int C8 = C / 8;
+  const size_t total = (size_t)B * hs * ws * C8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    size_t p = i / C8;
+    const int x = (int)(p % ws); p /= ws;
+    const int y = (int)(p % hs); const size_t b = p / hs;
+    const float* s = src + ((b * hs + y) * ws + x) * C + c;
+    const float4 v0 = *reinterpret_cast<const float4*>(s), v1 = *reinterpret_cast<const float4*>(s + 4);
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split2(fmaxf(v[2 * e], 0.f), fmaxf(v[2 * e + 1], 0.f), hi[e], lo[e]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __half* o = dst + ((b * 2 * hs + 2 * y + (k >> 1)) * (size_t)(2 * ws) + 2 * x + (k & 1)) * (2 * pitch) + coff + c;
+      *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(o + pitch) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1348,7 +1375,7 @@ TcSaved vgg_tc_carve(Arena& ar, int B, int H, int W, int n_levels, bool train) {
 
 // Tensor-core schedule of the U-Net; buffer names follow vgg.cu / VGG.py:121-158.
 int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, int B, int H, int W, int n_levels,
-                   int precision, float* const* out_feat, Arena& ar, cudaStream_t st, TcSaved* saved) {
+                   int precision, float* const* out_feat, Arena& ar, cudaStream_t st, TcSaved* saved, bool g2s) {
   const bool split = precision == HA_CONV_F16X3 || precision == HA_CONV_F16X3_1CTA;
   const bool pair = precision == HA_CONV_F16X3;
   const size_t px1 = (size_t)B * H * W, px2 = px1 / 4, px4 = px1 / 16;
@@ -1388,6 +1415,16 @@ int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, 
   HA_TRY(conv(L_CONV10, cat1, 384, 256, o, H / 4, W / 4));
   o = TcOut(); o.act_full = a12; o.af_pitch = 256;
   HA_TRY(conv(L_CONV12, a10, 256, 0, o, H / 4, W / 4));
+  auto up_fold = [&](const float* src, __half* dst, int pitch, int C, int hs, int ws) {      // folded coarse dims
+    const size_t n = (size_t)B * hs * ws * (C / 8);
+    relu_up2x_fold_kernel<<<(unsigned)((n + 255) / 256 < (size_t)kNumSMs * 16 ? (n + 255) / 256 : (size_t)kNumSMs * 16), 256, 0, st>>>(
+        src, dst, pitch, 0, C, B, hs, ws);
+    count_launches(1);
+  };
+  // decoder geometry: VGGUnet runs on [H/4, W/4], [H/2, W/2], [H, W]; VGGUnet_G2S on the folded maps [H/2, W/8], [H, W/4], [2H, W/2]
+  const int h4 = g2s ? H / 2 : H / 4, w4 = g2s ? W / 8 : W / 4;
+  const int h2 = 2 * h4, w2 = 2 * w4, h1 = 4 * h4, w1 = 4 * w4;
+  if (g2s && saved) return HA_EINVAL;
   if (saved) {                                                                          // x14 kept; x15 and its upsample by a kernel
     o = TcOut(); o.feat = x14;
     HA_TRY(conv(L_CONV14, a12, 256, 0, o, H / 4, W / 4));
@@ -1395,24 +1432,31 @@ int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, 
     pool_x15_kernel<<<(unsigned)((n + 255) / 256 < (size_t)kNumSMs * 16 ? (n + 255) / 256 : (size_t)kNumSMs * 16), 256, 0, st>>>(
         x14, out_feat[0], cat1, B, H / 4, W / 4);
     count_launches(1);
+  } else if (g2s) {
+    o = TcOut(); o.feat = out_feat[0]; o.feat_pooled = 1;                                                     // x15, no upsample here
+    HA_TRY(conv(L_CONV14, a12, 256, 0, o, H / 4, W / 4));
+    up_fold(out_feat[0], cat1, 384, 256, h4 / 2, w4 / 2);                                                     // x16 = up(x15_)  (VGG.py:303)
   } else {
     o = TcOut(); o.feat = out_feat[0]; o.feat_pooled = 1; o.act_up = cat1; o.au_pitch = 384; o.au_coff = 0;   // x15
     HA_TRY(conv(L_CONV14, a12, 256, 0, o, H / 4, W / 4));
   }
   o = TcOut(); o.act_full = d1; o.af_pitch = 128;
-  HA_TRY(conv(L_DEC1A, cat1, 384, 0, o, H / 4, W / 4));
-  o = TcOut(); o.feat = out_feat[1]; o.act_up = cat2; o.au_pitch = 192; o.au_coff = 0;                      // x18
-  HA_TRY(conv(L_DEC1B, d1, 128, 0, o, H / 4, W / 4));
+  HA_TRY(conv(L_DEC1A, cat1, 384, 0, o, h4, w4));
+  o = TcOut(); o.feat = out_feat[1];                                                                          // x18
+  if (!g2s) { o.act_up = cat2; o.au_pitch = 192; o.au_coff = 0; }
+  HA_TRY(conv(L_DEC1B, d1, 128, 0, o, h4, w4));
+  if (g2s) up_fold(out_feat[1], cat2, 192, 128, h4, w4);                                                      // x19 (:308)
   o = TcOut(); o.act_full = d2; o.af_pitch = 64;
-  HA_TRY(conv(L_DEC2A, cat2, 192, 0, o, H / 2, W / 2));
-  o = TcOut(); o.feat = out_feat[2];                                                                        // x21
-  if (n_levels == 4) { o.act_up = cat3; o.au_pitch = 128; o.au_coff = 0; }
-  HA_TRY(conv(L_DEC2B, d2, 64, 0, o, H / 2, W / 2));
+  HA_TRY(conv(L_DEC2A, cat2, 192, 0, o, h2, w2));
+  o = TcOut(); o.feat = out_feat[2];                                                                          // x21
+  if (n_levels == 4 && !g2s) { o.act_up = cat3; o.au_pitch = 128; o.au_coff = 0; }
+  HA_TRY(conv(L_DEC2B, d2, 64, 0, o, h2, w2));
   if (n_levels == 4) {
+    if (g2s) up_fold(out_feat[2], cat3, 128, 64, h2, w2);                                                     // x22 (:312)
     o = TcOut(); o.act_full = d3; o.af_pitch = 32;
-    HA_TRY(conv(L_DEC3A, cat3, 128, 0, o, H, W));
-    o = TcOut(); o.feat = out_feat[3];                                                                      // x24
-    HA_TRY(conv(L_DEC3B, d3, 32, 0, o, H, W));
+    HA_TRY(conv(L_DEC3A, cat3, 128, 0, o, h1, w1));
+    o = TcOut(); o.feat = out_feat[3];                                                                        // x24
+    HA_TRY(conv(L_DEC3B, d3, 32, 0, o, h1, w1));
   }
 #undef HA_TRY
   return HA_OK;

@@ -138,7 +138,7 @@ def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
 @dataclass
 class LmSetup:
     """Everything about one LM run that does not depend on the batch content."""
-    kind: str                  # 'kitti' | 'ford' | 'g2sp'
+    kind: str                  # 'kitti' | 'ford' | 'g2sp' | 'g2sp_nn' (LM_G2SP --proj nn: in-plane warp, models_kitti.py:289-331)
     n_iters: int
     level_first: int
     dof: int
@@ -157,7 +157,7 @@ class LmSetup:
 
 def dof_of(args, kind: str) -> int:
     """models_kitti.py:954-957; the Ford model always refines all three (models_ford.py:380)."""
-    if kind in ("ford", "g2sp"):               # LM_G2SP.LM_update always refines all three (models_kitti.py:375-377)
+    if kind in ("ford", "g2sp", "g2sp_nn"):    # LM_G2SP.LM_update always refines all three (models_kitti.py:375-377)
         return 3
     if args.rotation_range == 0:
         return 2
@@ -174,7 +174,7 @@ def setup_from_args(args, kind: str, level_first: int = 0) -> LmSetup:
                    use_hessian=int(bool(getattr(args, "use_hessian", 0))),
                    rotation_range=float(args.rotation_range), shift_range_lat=float(args.shift_range_lat),
                    shift_range_lon=float(args.shift_range_lon), optimizer=opt,
-                   full_height=int(kind != "g2sp" and getattr(args, "proj", "geo") != "geo"),
+                   full_height=int(not kind.startswith("g2sp") and getattr(args, "proj", "geo") != "geo"),
                    adam_level_mult=int(args.level), adam_beta1=float(getattr(args, "beta1", 0.9)),
                    adam_beta2=float(getattr(args, "beta2", 0.999)))
 
@@ -182,7 +182,7 @@ def setup_from_args(args, kind: str, level_first: int = 0) -> LmSetup:
 def resolve_damping(args, damping_param: Optional[torch.Tensor], dof: int, kind: str = "kitti") -> List[float]:
     """models_kitti.py:958-966: trained lambda = 10^(-6 + 11*sigmoid(p)) else args.damping.
     LM_G2SP uses the trained parameter as is (models_kitti.py:356-359)."""
-    if kind == "g2sp":
+    if kind.startswith("g2sp"):
         if getattr(args, "train_damping", 0):
             return [float(v) for v in damping_param.detach().float().reshape(-1).tolist()]
         return [float(np.float32(args.damping))] * 3
@@ -231,7 +231,8 @@ def make_params(setup: LmSetup, sat: Pyramid, damping: Sequence[float], side_m: 
                 ori_grd_hw: Tuple[int, int] = (256, 1024)) -> HaLmParams:
     n = len(sat.feats)
     p = HaLmParams()
-    p.geometry = {"kitti": _lib.HA_GEOM_KITTI, "ford": _lib.HA_GEOM_FORD, "g2sp": _lib.HA_GEOM_G2SP}[setup.kind]
+    p.geometry = {"kitti": _lib.HA_GEOM_KITTI, "ford": _lib.HA_GEOM_FORD, "g2sp": _lib.HA_GEOM_G2SP,
+                  "g2sp_nn": _lib.HA_GEOM_G2SP_NN}[setup.kind]
     p.ori_grd_h, p.ori_grd_w = int(ori_grd_hw[0]), int(ori_grd_hw[1])
     p.kernel_variant, p.reserved = int(setup.kernel_variant), 0
     p.optimizer = OPTIMIZERS[setup.optimizer]
@@ -250,6 +251,9 @@ def make_params(setup: LmSetup, sat: Pyramid, damping: Sequence[float], side_m: 
         elif setup.kind == "g2sp":
             mpp = kitti_meter_per_pixel() * (SAT_PROCESS_SIDE / A)      # models_kitti.py:69-70
             center = A // 2                                             # :65
+        elif setup.kind == "g2sp_nn":
+            mpp = kitti_meter_per_pixel() * (SAT_PROCESS_SIDE / A)      # models_kitti.py:291-292
+            center = A / 2                                              # :307,312
         else:
             mpp = side_m / A                                            # models_ford.py:230
             center = A // 2                                             # :231
@@ -266,7 +270,7 @@ OPTIMIZERS = {"LM": _lib.HA_OPT_LM, "SGD": _lib.HA_OPT_SGD, "ADAM": _lib.HA_OPT_
 def draws_reset(setup: LmSetup) -> bool:
     """Whether a step consumes the two [B,1] CPU-RNG draws: the 3-DOF LM / GN updates of the S2GP models do
     (models_kitti.py:1028-1029, models_ford.py:453-454, :583-584); SGD / ADAM and LM_G2SP never draw."""
-    return setup.dof == 3 and setup.kind != "g2sp" and setup.optimizer in ("LM", "GN")
+    return setup.dof == 3 and not setup.kind.startswith("g2sp") and setup.optimizer in ("LM", "GN")
 
 
 class LmWorkspace:
@@ -364,7 +368,7 @@ def lm_run(setup: LmSetup, sat: Pyramid, grd: Pyramid, tables: Sequence[torch.Te
         if setup.using_weight and c is None:
             raise _lib.HaError("using_weight needs ground confidence maps")
         confs[i] = c.data_ptr() if (c is not None and setup.using_weight) else None
-        if setup.kind == "g2sp":
+        if setup.kind.startswith("g2sp"):
             tabs[i] = None                            # the satellite-plane points are computed in the kernel
         else:
             assert tables[i].is_cuda and tables[i].shape[:2] == grd.feats[i].shape[1:3], "ground table / feature shape mismatch"
@@ -406,7 +410,7 @@ def lm_step(setup: LmSetup, level: int, sat: Pyramid, grd: Pyramid, tables: Sequ
     sl, gl = _levels(sat, n), _levels(grd, n)
     rc = L.ha_lm_step(C.byref(params), level, C.byref(sl[level]), C.byref(gl[level]),
                       c.data_ptr() if c is not None else None,
-                      tables[level].data_ptr() if setup.kind != "g2sp" else None,
+                      tables[level].data_ptr() if not setup.kind.startswith("g2sp") else None,
                       extrinsics.data_ptr() if extrinsics is not None else None, pose.data_ptr(),
                       reset_uv.data_ptr() if reset_uv is not None else None, stats.data_ptr(), status.data_ptr(),
                       ws.data_ptr(), ws.numel(), _stream_ptr())
@@ -556,7 +560,7 @@ class VggRunner:
         self._keep = keep
 
     def __call__(self, named: dict, img: torch.Tensor, n_levels: int, want_conf: bool, precision: str,
-                 want_scale: bool = True) -> Pyramid:
+                 want_scale: bool = True, g2s: bool = False) -> Pyramid:
         """`want_scale=False` skips the L2-norm pass (VGG.py:172-175): the S2GP LM step renormalises the sampled and the
         ground vectors itself (models_kitti.py:982-989), so the per-sample scale cancels there exactly."""
         _require_cuda(img, "image")
@@ -590,8 +594,12 @@ class VggRunner:
                 pf[l] = feats[l][b0:].data_ptr()
                 ps[l] = scales[l][b0:].data_ptr() if want_scale else None
                 pc[l] = confs[l][b0:].data_ptr() if want_conf else None
-            check(L.ha_vgg_forward(self.packed.data_ptr(), img[b0:].data_ptr(), nb, H, W, n_levels, prec, pf, ps, pc,
-                                   self.ws.data_ptr(), self.ws.numel(), st), "ha_vgg_forward")
+            fn, what = (L.ha_vgg_g2s_forward, "ha_vgg_g2s_forward") if g2s else (L.ha_vgg_forward, "ha_vgg_forward")
+            check(fn(self.packed.data_ptr(), img[b0:].data_ptr(), nb, H, W, n_levels, prec, pf, ps, pc,
+                     self.ws.data_ptr(), self.ws.numel(), st), what)
+        if g2s:      # VGG.py:283-299: the features are the [h, w] maps read as [2h, w/2]; c0 stays un-folded (:326)
+            feats = [f.view(B, 2 * f.shape[1], f.shape[2] // 2, f.shape[3]) for f in feats]
+            confs = [c if (c is None or l == 0) else c.view(B, 2 * c.shape[1], c.shape[2] // 2) for l, c in enumerate(confs)]
         return Pyramid(feats, scales, confs)
 
 

@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from . import compat, engine
-from .VGG import VGGUnet
+from .VGG import VGGUnet, VGGUnet_G2S
 from .models_ford import loss_func, train_forward, _TrajectoryOutputs  # noqa: F401  (the reference re-exports loss_func too, :16)
 
 
@@ -153,12 +153,19 @@ class LM_G2SP(nn.Module):
         self.N_iters = args.N_iters
         self.using_weight = args.using_weight
         self.loss_method = args.loss_method
-        if getattr(args, "proj", "geo") != "geo":
-            raise NotImplementedError("LM_G2SP: only --proj geo is on the accelerated path (VGGUnet_G2S / 'nn' is out of scope)")
+        self.proj = getattr(args, "proj", "geo")
+        if self.proj not in ("geo", "nn"):
+            # models_kitti.py:176-233: project_grd_to_map knows 'geo' and 'nn' only ('polar' leaves uv undefined there)
+            raise NotImplementedError("LM_G2SP: --proj geo and nn are defined by the reference (models_kitti.py:176,232)")
         if self.level not in (3, 4):
             raise NotImplementedError("LM_G2SP: levels 3 and 4 are on the accelerated path")
         self.SatFeatureNet = VGGUnet(self.level)
-        self.GrdFeatureNet = VGGUnet(self.level)
+        self.GrdFeatureNet = VGGUnet_G2S(self.level) if self.proj == "nn" else VGGUnet(self.level)     # :36-39
+        self.KIND = "g2sp_nn" if self.proj == "nn" else "g2sp"
+        if self.proj == "nn" and self.using_weight:
+            # VGG.py:326 takes c0 from the UN-folded x15 ([B,1,32,128]) while the level-0 feature is the folded [B,256,64,64]; the
+            # reference then samples that 32 x 128 map with the 64 x 64 map's coordinates (models_kitti.py:280-282)
+            raise NotImplementedError("LM_G2SP --proj nn --using_weight 1: the reference pairs a 32x128 confidence with a 64x64 feature")
         self.damping = nn.Parameter(args.damping * torch.ones(size=(1, 3), dtype=torch.float32, requires_grad=True))   # :41
         self.meters_per_pixel = [engine.kitti_meter_per_pixel() * (2 ** (3 - lv)) for lv in range(4)]                     # :43-46
         self.last_result = None
@@ -174,7 +181,8 @@ class LM_G2SP(nn.Module):
         setup = engine.setup_from_args(self.args, self.KIND, 0)
         lam = engine.resolve_damping(self.args, self.damping, 3, self.KIND)
         B = sat.batch
-        res = engine.lm_run(setup, sat, grd, [None] * len(sat.feats), lam, extrinsics=left_camera_k.reshape(B, 9),
+        ext = left_camera_k.reshape(B, 9) if self.KIND == "g2sp" else None       # the in-plane warp of --proj nn ignores camera_k
+        res = engine.lm_run(setup, sat, grd, [None] * len(sat.feats), lam, extrinsics=ext,
                             pose0=pose0, want_stats=want_stats, ori_grd_hw=ori_grd_hw)
         self.last_result = res
         return res
@@ -182,6 +190,8 @@ class LM_G2SP(nn.Module):
     def project_grd_to_map(self, grd_f, grd_c, shift_u, shift_v, heading, camera_k, satmap_sidelength, ori_grdH, ori_grdW):
         """models_kitti.py:163-287: materialised warp of the ground features (and confidence) onto the satellite plane;
         returns (grd_f_trans, grd_c_trans, new_jac [3,B,C,A,A]).  Compatibility surface only (see LM_S2GP)."""
+        if self.proj != "geo":
+            raise NotImplementedError("the materialising compatibility method covers --proj geo")
         A = int(satmap_sidelength)
         a = self.args
         mpp = engine.kitti_meter_per_pixel() * (engine.SAT_PROCESS_SIDE / A)
@@ -224,6 +234,8 @@ class LM_G2SP(nn.Module):
                 mode='train', file_name=None, gt_depth=None):
         """models_kitti.py:381-499."""
         if mode == 'train':
+            if self.proj != "geo":
+                raise NotImplementedError("LM_G2SP --proj nn runs in test mode on the accelerated path")
             return self._train_forward(sat_map, grd_img_left, left_camera_k, gt_shift_u, gt_shift_v, gt_heading)
         want_conf = bool(self.using_weight)
         sat, grd = self.extract(sat_map, grd_img_left, want_conf)

@@ -40,9 +40,12 @@ enum {
 enum {
   HA_GEOM_KITTI = 0,   /* models_kitti.py:700-801  LM_S2GP.grd2cam2world2sat               */
   HA_GEOM_FORD = 1,    /* models_ford.py:173-264   LM_S2GP_Ford.cam2body2world2sat         */
-  HA_GEOM_G2SP = 2     /* models_kitti.py:54-160   LM_G2SP.get_warp_sat2real + seq_warp_real2camera:
+  HA_GEOM_G2SP = 2,    /* models_kitti.py:54-160   LM_G2SP.get_warp_sat2real + seq_warp_real2camera:
                           ground features warped onto the satellite plane, residual over the
                           whole satellite map, LM_update of :333-379 (no renormalisation)     */
+  HA_GEOM_G2SP_NN = 3  /* models_kitti.py:289-331  LM_G2SP.inplane_grd_to_map (--proj nn): the ground
+                          features (VGGUnet_G2S) already live on a square map; the warp is an in-plane
+                          rotation about its centre plus a shift in pixels; LM_update as for G2SP   */
 };
 
 /* update rule applied by a step to the reduced sums (args.Optimizer; the default everywhere is LM) */
@@ -243,6 +246,15 @@ size_t ha_vgg_workspace_bytes(int B, int H, int W, int n_levels, int precision);
 int ha_vgg_forward(const void* packed_weights, const float* img_nchw, int B, int H, int W, int n_levels,
                    int precision, float* const* out_feat, float* const* out_scale, float* const* out_conf,
                    void* ws, size_t ws_bytes, void* stream);
+
+/* VGGUnet_G2S (VGG.py:206-345; ground branch of LM_G2SP --proj nn): same weights, encoder and workspace as ha_vgg_forward, but
+ * the decoders run on the maps folded from [h, w] to [2h, w/2] (a re-interpretation of the row-major pixel order, VGG.py:283-299).
+ * out_feat[l] holds the same number of elements as for ha_vgg_forward; read it as [B][2 h_l][w_l / 2][C_l].  out_conf[0] is
+ * [B][h_0][w_0] (taken from the un-folded x15, VGG.py:326), out_conf[l >= 1] are [B][2 h_l][w_l / 2].  Tensor-core precisions
+ * only; W % 128 == 0, H % 32 == 0. */
+int ha_vgg_g2s_forward(const void* packed_weights, const float* img_nchw, int B, int H, int W, int n_levels, int precision,
+                       float* const* out_feat, float* const* out_scale, float* const* out_conf, void* ws, size_t ws_bytes,
+                       void* stream);
 
 /* ---- training: the same U-Net, keeping what its backward pass needs, and that backward pass ----------
  * Replaces what torch autograd does for VGGUnet.forward under `loss.backward()` (train_kitti.py:365, VGG.py:121-203).

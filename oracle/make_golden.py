@@ -609,6 +609,41 @@ def main():
         kat_g2sp(rk, "g2sp_random", g2sp_rand(82), N_iters=2)
         kat_g2sp(rk, "g2sp_weight", g2sp_planted(83, GT2), N_iters=2, using_weight=1)
 
+    if want("g2spnn"):  # LM_G2SP --proj nn: in-plane warp of square ground features (models_kitti.py:289-331)
+        def nn_planted(seed, gt, A=512, L=3):
+            def f(oa):
+                B = len(gt)
+                grd = [O.l2_norm(x) for x in O.smooth_pyramid(B, A, L, seed)]
+                g = torch.as_tensor(gt, dtype=torch.float32).reshape(B, 3)
+                sat = []
+                for lv in range(L):
+                    uv, *_ = O.g2sp_inplane_uv(grd[lv].shape[-1], g[:, 0:1], g[:, 1:2], g[:, 2:3], oa)
+                    sat.append(O.bilinear_sample(grd[lv], uv)[0].contiguous())
+                gg = torch.Generator().manual_seed(seed + 1)
+                conf = [torch.sigmoid(-torch.sigmoid(torch.randn(B, 1, *x.shape[-2:], generator=gg))) for x in grd]
+                return sat, grd, conf, dict(seed=seed, B=B, A=A, L=L, gt=np.array(gt, dtype=np.float32))
+            return f
+        kat_g2sp(rk, "g2sp_nn_planted", nn_planted(91, [[0.1, -0.08, 0.3], [-0.06, 0.12, -0.2]]), N_iters=3, proj="nn")
+        kat_g2sp(rk, "g2sp_nn_weight", nn_planted(92, [[0.05, 0.1, -0.25]]), N_iters=2, proj="nn", using_weight=1)
+        sd = O.vgg_state_dict(7)
+        for level in (3, 4):           # VGGUnet_G2S (VGG.py:206-345) on a small image
+            net = rv.VGGUnet_G2S(level)
+            net.load_state_dict(sd)
+            net.eval()
+            x = torch.rand(2, 3, 64, 128, generator=torch.Generator().manual_seed(170 + level))
+            with torch.no_grad():
+                rfe, rco = net(x)
+            ofe, oco = O.vgg_unet_g2s(sd, x, level)
+            out = {"in_csum": csum(x)}
+            for i in range(len(rfe)):
+                close(ofe[i], rfe[i], 1e-6, "g2s feat %d" % i)
+                close(oco[i], rco[i], 1e-6, "g2s conf %d" % i)
+                out["feat%d" % i] = rfe[i].numpy()
+                out["conf%d" % i] = rco[i].numpy()
+            np.savez_compressed(os.path.join(GOLD, "kat7_vgg_g2s_level%d.npz" % level), **out)
+        e2e_g2sp(rk, proj="nn", name="e2e_g2sp_nn")
+        print("G2SP nn ok")
+
     if want("kat7"):   # VGG U-Net: small image, all intermediate activations
         sd = O.vgg_state_dict(7)
         for level in (3, 4):
@@ -757,7 +792,7 @@ def planted_b32(rk):
     print("kat4_planted_b32 ok: max |final - gt| %.2e" % float((traj[:, -1, -1] - gt).abs().max()))
 
 
-def e2e_g2sp(rk):
+def e2e_g2sp(rk, proj="geo", name="e2e_g2sp"):
     """Whole LM_G2SP.forward (VGG + LM) through the reference nn.Module on CPU (Tensor.cuda patched)."""
     sd = {}
     sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
@@ -766,7 +801,7 @@ def e2e_g2sp(rk):
     sat = torch.rand(2, 3, 512, 512, generator=g)
     grd = torch.rand(2, 3, 256, 1024, generator=g)
     cam_k = torch.tensor([O._KITTI_K], dtype=torch.float32).repeat(2, 1, 1)
-    a = ref_args()
+    a = ref_args(proj=proj)
     orig_cuda = torch.Tensor.cuda
     torch.Tensor.cuda = lambda self, *x, **k: self
     try:
@@ -781,11 +816,11 @@ def e2e_g2sp(rk):
         torch.Tensor.cuda = orig_cuda
     oa = o_args(a)
     sf, _ = O.vgg_unet(sd, sat, 3, "SatFeatureNet.")
-    gf, gc = O.vgg_unet(sd, grd, 3, "GrdFeatureNet.")
+    gf, gc = (O.vgg_unet_g2s if proj == "nn" else O.vgg_unet)(sd, grd, 3, "GrdFeatureNet.")
     res = O.lm_loop_g2sp(sf, gf, gc, cam_k, oa)
     of = torch.stack([res.lats[:, -1, -1], res.lons[:, -1, -1], res.thetas[:, -1, -1]], dim=-1)
     d = close(of, r, 1e-5, "e2e g2sp")
-    np.savez_compressed(os.path.join(GOLD, "e2e_g2sp.npz"), final=r.numpy(), lats=res.lats.numpy(), lons=res.lons.numpy(),
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), final=r.numpy(), lats=res.lats.numpy(), lons=res.lons.numpy(),
                         thetas=res.thetas.numpy(), in_csum=csum(sat, grd), cam_k=cam_k.numpy())
     print("e2e g2sp ok (max|d| %.2e) final=%s" % (d, r.tolist()))
 

@@ -544,6 +544,32 @@ def g2sp_cam_uv(xyz1: torch.Tensor, su, sv, th, cam_k: torch.Tensor, gh: int, gw
     return uv, out[0], out[1], out[2], mask
 
 
+def g2sp_inplane_uv(A: int, su, sv, th, args: LMArgs):
+    """models_kitti.py:289-331 (inplane_grd_to_map, proj == 'nn'): the ground features live on a square map of the
+    satellite's size already (VGGUnet_G2S), so the warp is an in-plane rotation about the map centre A / 2 plus a shift in
+    pixels.  Returns uv[B,A,A,2] and (duv/dsu, duv/dsv, duv/dth); the mask is all ones."""
+    dt = su.dtype
+    B = th.shape[0]
+    mpp = meter_per_pixel_base()
+    mpp *= SAT_PROCESS_SIDE / A
+    shu_px = args.shift_range_lon * su / mpp
+    shv_px = args.shift_range_lat * sv / mpp
+    T = torch.cat([-shu_px, shv_px], dim=-1)
+    heading = th * args.rotation_range / 180 * np.pi
+    c, s = torch.cos(heading), torch.sin(heading)
+    R = torch.cat([c, -s, s, c], dim=-1).view(B, 2, 2)
+    i = torch.arange(0, A)
+    vv, uu = torch.meshgrid(i, i, indexing="ij")
+    uv2 = torch.stack([uu, vv], dim=-1).unsqueeze(0).repeat(B, 1, 1, 1).to(dt)
+    uv2 = uv2 - A / 2
+    uv = torch.einsum("bij, bhwj->bhwi", R, uv2) + T[:, None, None, :] + A / 2
+    ju = (args.shift_range_lon / mpp * torch.tensor([-1.0, 0.0], dtype=dt).view(1, 2).repeat(B, 1))[:, None, None, :].repeat(1, A, A, 1)
+    jv = (args.shift_range_lat / mpp * torch.tensor([0.0, 1.0], dtype=dt).view(1, 2).repeat(B, 1))[:, None, None, :].repeat(1, A, A, 1)
+    dR = args.rotation_range / 180 * np.pi * torch.cat([-s, -c, c, -s], dim=-1).view(B, 2, 2)
+    jt = torch.einsum("bij, bhwj->bhwi", dR, uv2)
+    return uv, ju, jv, jt
+
+
 def g2sp_lm_update(su, sv, th, grd_proj, grd_conf_proj, sat_feat, dfeat, args: LMArgs, damping: torch.Tensor):
     """models_kitti.py:333-379 (LM_G2SP.LM_update): r = grd_proj - sat, NO renormalisation, identity
     damping, always 3 DOF, no out-of-range reset."""
@@ -568,8 +594,11 @@ def g2sp_one_step(sf, gf, gc, cam_k, su, sv, th, ori_h: int, ori_w: int, args: L
     project_grd_to_map (:163-177,276-287) -> LM_update."""
     A = sf.shape[-1]
     gh, gw = gf.shape[-2:]
-    xyz1 = g2sp_sat_table(A, sf.dtype)
-    uv, ju, jv, jt, mask = g2sp_cam_uv(xyz1, su, sv, th, cam_k.to(sf.dtype), gh, gw, ori_h, ori_w, args)
+    if args.proj == "nn":                                   # models_kitti.py:232-233
+        uv, ju, jv, jt = g2sp_inplane_uv(A, su, sv, th, args)
+    else:
+        xyz1 = g2sp_sat_table(A, sf.dtype)
+        uv, ju, jv, jt, mask = g2sp_cam_uv(xyz1, su, sv, th, cam_k.to(sf.dtype), gh, gw, ori_h, ori_w, args)
     gp, dj = bilinear_sample(gf, uv, torch.stack([ju, jv, jt], dim=0))
     gcp = bilinear_sample(gc, uv)[0] if gc is not None else None
     return g2sp_lm_update(su, sv, th, gp, gcp, sf, dj, args, lam)
@@ -641,6 +670,37 @@ def vgg_unet(sd: dict, x: torch.Tensor, level: int, prefix: str = "", keep: Opti
         return feats[:1], confs[:1]
     if level == 2:
         return feats[1:3], confs[1:3]
+    raise ValueError("unsupported level %r" % level)
+
+
+def vgg_unet_g2s(sd: dict, x: torch.Tensor, level: int, prefix: str = ""):
+    """VGG.py:275-345 (VGGUnet_G2S.forward): the encoder of VGGUnet, but every skip / bottleneck map is re-shaped from
+    [H, W] to [2H, W/2] (a reinterpretation of the row-major pixel order, :283-299) before the decoders run on it; the
+    features come out square (64 / 128 / 256 / 512 for a 256 x 1024 image).  c0 is computed on the un-reshaped x15 (:326)."""
+    w = lambda n: sd[prefix + n]
+    conv = lambda t, n, bias=True: F.conv2d(t, w(n + ".weight"), w(n + ".bias") if bias else None, padding=1)
+    pool = lambda t: F.max_pool2d(t, 2, 2)
+    fold = lambda t: t.reshape(t.shape[0], t.shape[1], t.shape[2] * 2, t.shape[3] // 2)
+    x1 = F.relu(conv(x, "conv0"))
+    x2 = conv(x1, "conv2")
+    x4 = F.relu(pool(x2))                       # x3 / x3_ share storage with the in-place ReLU's output (:281,289)
+    x7 = conv(F.relu(conv(x4, "conv5")), "conv7")
+    x9 = F.relu(pool(x7))
+    x15 = pool(conv(F.relu(conv(F.relu(conv(x9, "conv10")), "conv12")), "conv14"))
+    x2_, x3_, x8_, x15_ = fold(x2), fold(x4), fold(x9), fold(x15)
+    up = lambda t, ref: F.interpolate(t, [ref.shape[2], ref.shape[3]], mode="nearest")
+    dec = lambda t, n: F.conv2d(F.relu(F.conv2d(F.relu(t), w(n + ".1.weight"), None, padding=1)),
+                                w(n + ".3.weight"), None, padding=1)
+    x18 = dec(torch.cat([up(x15_, x8_), x8_], dim=1), "conv_dec1")
+    x21 = dec(torch.cat([up(x18, x3_), x3_], dim=1), "conv_dec2")
+    feats, heads = [x15_, x18, x21], [x15, x18, x21]
+    if level == 4:
+        x24 = dec(torch.cat([up(x21, x2_), x2_], dim=1), "conv_dec3")
+        feats.append(x24); heads.append(x24)
+    confs = [torch.sigmoid(-torch.sigmoid(F.conv2d(F.relu(h), w("conf%d.1.weight" % i), None, padding=1))) for i, h in enumerate(heads)]
+    feats = [l2_norm(f) for f in feats]
+    if level in (3, 4):
+        return feats, confs
     raise ValueError("unsupported level %r" % level)
 
 

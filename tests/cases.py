@@ -107,7 +107,10 @@ def args_from_lmargs(a: "O.LMArgs"):
 
 
 G2SP_CASES = {"g2sp_planted": ("planted", dict(N_iters=3)), "g2sp_random": ("rand", dict(N_iters=2)),
-              "g2sp_weight": ("planted", dict(N_iters=2, using_weight=1))}
+              "g2sp_weight": ("planted", dict(N_iters=2, using_weight=1)),
+              # LM_G2SP --proj nn (models_kitti.py:289-331): square ground features, in-plane warp
+              "g2sp_nn_planted": ("nn_planted", dict(N_iters=3, proj="nn")),
+              "g2sp_nn_weight": ("nn_planted", dict(N_iters=2, proj="nn", using_weight=1))}
 
 
 def build_g2sp_case(name):
@@ -117,6 +120,15 @@ def build_g2sp_case(name):
     seed, B, A, L = int(gold["seed"]), int(gold["B"]), int(gold["A"]), int(gold["L"])
     if fam == "rand":
         sat, grd, conf = O.random_pyramid(B, A, L, seed)
+    elif fam == "nn_planted":          # square L2-normalised ground pyramids; the satellite side is their in-plane warp at gt
+        grd = [O.l2_norm(x) for x in O.smooth_pyramid(B, A, L, seed)]
+        gt = torch.as_tensor(gold["gt"], dtype=torch.float32).reshape(B, 3)
+        sat = []
+        for lv in range(L):
+            uv, *_ = O.g2sp_inplane_uv(grd[lv].shape[-1], gt[:, 0:1], gt[:, 1:2], gt[:, 2:3], args)
+            sat.append(O.bilinear_sample(grd[lv], uv)[0].contiguous())
+        g = torch.Generator().manual_seed(seed + 1)
+        conf = [torch.sigmoid(-torch.sigmoid(torch.randn(B, 1, *x.shape[-2:], generator=g))) for x in grd]
     else:
         sat, grd = O.planted_case("kitti", B, A, L, seed, gold["gt"], args)
         g = torch.Generator().manual_seed(seed + 1)

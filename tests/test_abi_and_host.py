@@ -264,7 +264,7 @@ def test_vggunet_level_selection(level, n_compute, want):
     net = VGGUnet(level)
     seen = {}
 
-    def fake_runner(named, x, n_levels, want_conf, precision, want_scale=True):
+    def fake_runner(named, x, n_levels, want_conf, precision, want_scale=True, g2s=False):
         seen["n"] = n_levels
         feats = [torch.full((1, 2, 2, 4), float(i)) for i in range(n_levels)]
         return engine.Pyramid(feats, [torch.full((1,), float(i)) for i in range(n_levels)],

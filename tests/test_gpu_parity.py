@@ -162,16 +162,22 @@ def test_g2sp_vs_reference(name):
     reference's pose state, against the reference's outputs and the float64 truth."""
     c = K.build_g2sp_case(name)
     g = c["gold"]
-    net = LM_G2SP(K.args_from_lmargs(c["args"])).to(DEV)
+    nn_proj = c["args"].proj == "nn"                       # --proj nn: in-plane warp (HA_GEOM_G2SP_NN), no camera matrix
+    kind = "g2sp_nn" if nn_proj else "g2sp"
     sat = engine.Pyramid.from_nchw([s.to(DEV) for s in c["sat"]])
     grd = engine.Pyramid.from_nchw([x.to(DEV) for x in c["grd"]], [x.to(DEV) for x in c["conf"]])
-    res = net.refine(sat, grd, c["cam_k"].to(DEV))
+    if nn_proj:      # the C ABI pairs features and confidences of one size; the module refuses weights + nn (VGG.py:326)
+        setup0 = engine.setup_from_args(K.args_from_lmargs(c["args"]), kind, 0)
+        res = engine.lm_run(setup0, sat, grd, [None] * c["L"], [c["args"].damping] * 3)
+    else:
+        net = LM_G2SP(K.args_from_lmargs(c["args"])).to(DEV)
+        res = net.refine(sat, grd, c["cam_k"].to(DEV))
     got, want, truth = res.traj.cpu().numpy(), g["traj"], g["traj64"]
     assert not int(res.status.item()) & _lib.HA_STATUS_NAN_POSE
     ok = (np.abs(got - want) <= 5e-5) | (np.abs(got - truth) <= 1.5 * np.abs(want - truth) + 2e-6)
     assert ok.all(), (np.abs(got - want).max(), np.abs(got - truth).max())
-    setup = engine.setup_from_args(K.args_from_lmargs(c["args"]), "g2sp", 0)
-    kmat = c["cam_k"].reshape(-1, 9).to(DEV)
+    setup = engine.setup_from_args(K.args_from_lmargs(c["args"]), kind, 0)
+    kmat = None if nn_proj else c["cam_k"].reshape(-1, 9).to(DEV)
     for it in range(c["args"].N_iters):
         for lv in range(c["L"]):
             pin = torch.from_numpy(g["pose_in"][:, it, lv])
@@ -328,6 +334,48 @@ def test_end_to_end_g2sp_forward_vs_reference():
     traj = net.last_result.traj.cpu().numpy()
     ref_traj = np.stack([g["lons"], g["lats"], g["thetas"]], -1)
     np.testing.assert_allclose(traj[:, 0], ref_traj[:, 0], atol=5e-5)
+
+
+@pytest.mark.parametrize("level", [3, 4])
+def test_vgg_g2s_vs_reference(level):
+    """VGGUnet_G2S (VGG.py:206-345: decoders on the folded [2H, W/2] maps; c0 from the un-folded x15) through
+    ha_vgg_g2s_forward against the unmodified reference's features and confidences."""
+    from highlyaccurate_b200.VGG import VGGUnet_G2S
+    g = K.load_golden("kat7_vgg_g2s_level%d" % level)
+    net = VGGUnet_G2S(level).to(DEV)
+    net.load_state_dict(O.vgg_state_dict(7))
+    x = torch.rand(2, 3, 64, 128, generator=torch.Generator().manual_seed(170 + level))
+    np.testing.assert_allclose(K.csum(x), g["in_csum"], rtol=1e-6)
+    feats, confs = net(x.to(DEV))
+    for i in range(level):
+        want = g["feat%d" % i]
+        got = feats[i].cpu().numpy()
+        assert got.shape == want.shape, (got.shape, want.shape)
+        assert np.abs(got - want).max() <= VGG_TOL["f16x3"] * np.abs(want).max(), (i, np.abs(got - want).max() / np.abs(want).max())
+        assert confs[i].shape == g["conf%d" % i].shape
+        np.testing.assert_allclose(confs[i].cpu().numpy(), g["conf%d" % i], atol=VGG_TOL["f16x3"])
+
+
+def test_end_to_end_g2sp_nn_forward_vs_reference():
+    """LM_G2SP --proj nn: VGGUnet_G2S ground branch + in-plane warp, whole forward against the unmodified reference."""
+    g = K.load_golden("e2e_g2sp_nn")
+    sd = {}
+    sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+    sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+    gen = torch.Generator().manual_seed(2022)
+    sat = torch.rand(2, 3, 512, 512, generator=gen)
+    grd = torch.rand(2, 3, 256, 1024, generator=gen)
+    np.testing.assert_allclose(K.csum(sat, grd), g["in_csum"], rtol=1e-6)
+    net = LM_G2SP(K.ref_args(proj="nn")).to(DEV)
+    sd["damping"] = net.damping.detach().clone()
+    net.load_state_dict(sd)
+    out = net(sat.to(DEV), grd.to(DEV), torch.from_numpy(g["cam_k"]).to(DEV), mode="test")
+    got = torch.stack([o.detach() for o in out], dim=-1).cpu().numpy()
+    np.testing.assert_allclose(got, g["final"], atol=3e-4)
+    traj = net.last_result.traj.cpu().numpy()
+    ref_traj = np.stack([g["lons"], g["lats"], g["thetas"]], -1)
+    np.testing.assert_allclose(traj[:, 0], ref_traj[:, 0], atol=5e-5)
+    print("e2e_g2sp_nn: final max|d| %.2e, first sweep max|d| %.2e" % (np.abs(got - g["final"]).max(), np.abs(traj[:, 0] - ref_traj[:, 0]).max()))
 
 
 def _e2e_state_dict():

@@ -82,7 +82,20 @@ def test_kat7_vgg(level):
         np.testing.assert_allclose(confs[i].numpy(), g["conf%d" % i], atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["g2sp_random", "g2sp_weight"])
+@pytest.mark.parametrize("level", [3, 4])
+def test_kat7_vgg_g2s(level):
+    """VGGUnet_G2S (VGG.py:206-345) restated: folded decoder maps, c0 from the un-folded x15."""
+    g = K.load_golden("kat7_vgg_g2s_level%d" % level)
+    x = torch.rand(2, 3, 64, 128, generator=torch.Generator().manual_seed(170 + level))
+    np.testing.assert_allclose(K.csum(x), g["in_csum"], rtol=1e-6)
+    feats, confs = O.vgg_unet_g2s(O.vgg_state_dict(7), x, level)
+    for i in range(len(feats)):
+        np.testing.assert_allclose(feats[i].numpy(), g["feat%d" % i], atol=1e-6)
+        np.testing.assert_allclose(confs[i].numpy(), g["conf%d" % i], atol=1e-6)
+    assert feats[0].shape[-2:] == (16, 8) and confs[0].shape[-2:] == (8, 16)
+
+
+@pytest.mark.parametrize("name", ["g2sp_random", "g2sp_weight", "g2sp_nn_weight"])
 def test_g2sp_loop_matches_reference(name):
     c = K.build_g2sp_case(name)
     res = O.lm_loop_g2sp(c["sat"], c["grd"], c["conf"], c["cam_k"], c["args"])
