@@ -54,6 +54,10 @@ class HaVggStateDict(C.Structure):
     _fields_ = [("weight", C.c_void_p * HA_VGG_N_CONV), ("bias", C.c_void_p * HA_VGG_N_CONV)]
 
 
+class HaVggGrads(C.Structure):
+    _fields_ = [("weight", C.c_void_p * HA_VGG_N_CONV), ("bias", C.c_void_p * HA_VGG_N_CONV)]
+
+
 class HaError(RuntimeError):
     pass
 
@@ -96,7 +100,7 @@ def lib() -> C.CDLL:
     L.ha_vgg_forward_train.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, sz, vp]
     L.ha_vgg_backward_workspace_bytes.restype = sz
     L.ha_vgg_backward_workspace_bytes.argtypes = [i32, i32, i32, i32]
-    L.ha_vgg_backward.argtypes = [C.POINTER(HaVggStateDict), vp, i32, i32, i32, i32, vp, C.POINTER(vp), C.POINTER(HaVggStateDict),
+    L.ha_vgg_backward.argtypes = [C.POINTER(HaVggStateDict), vp, i32, i32, i32, i32, vp, C.POINTER(vp), C.POINTER(HaVggGrads),
                                   vp, sz, vp]
     L.ha_conv3x3_backward_workspace_bytes.restype = sz
     L.ha_conv3x3_backward_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]

@@ -518,7 +518,7 @@ extern "C" size_t ha_vgg_backward_workspace_bytes(int B, int H, int W, int n_lev
 }
 
 extern "C" int ha_vgg_backward(const HaVggStateDict* sd, const float* img_nchw, int B, int H, int W, int n_levels, void* fwd_ws,
-                               const float* const* g_feat, const HaVggStateDict* grads, void* ws, size_t ws_bytes, void* stream) {
+                               const float* const* g_feat, const HaVggGrads* grads, void* ws, size_t ws_bytes, void* stream) {
   using namespace ha;
   if (!sd || !img_nchw || !fwd_ws || !g_feat || !grads || !ws) return HA_EINVAL;
   if (n_levels != 3 || B <= 0 || (W % 64) || (H % 32)) return HA_EINVAL;
@@ -536,10 +536,10 @@ extern "C" int ha_vgg_backward(const HaVggStateDict* sd, const float* img_nchw, 
   // ---- building blocks (BwdOps) bound to this network's layer table ---------------------------------------------------
   BwdOps ops{B, st, w, 0};
   auto prep = [&](const float* gy, int C, int h, int wd, int li) -> const unsigned* {
-    return ops.prep(gy, C, h, wd, kVggConvs[li].has_bias ? const_cast<float*>(grads->bias[li]) : nullptr);
+    return ops.prep(gy, C, h, wd, kVggConvs[li].has_bias ? grads->bias[li] : nullptr);
   };
   auto wgrad = [&](int li, const __half* x, int pitch, int coff, int h, int wd, const unsigned* bits) -> int {
-    return ops.wgrad(kVggConvs[li].cin, kVggConvs[li].cout, const_cast<float*>(grads->weight[li]), x, pitch, coff, h, wd, bits);
+    return ops.wgrad(kVggConvs[li].cin, kVggConvs[li].cout, grads->weight[li], x, pitch, coff, h, wd, bits);
   };
   auto dgrad = [&](int li, int ci0, int n, int h, int wd, float* R) -> int {
     return ops.dgrad(sd->weight[li], kVggConvs[li].cin, kVggConvs[li].cout, ci0, n, h, wd, R);
@@ -616,7 +616,7 @@ extern "C" int ha_vgg_backward(const HaVggStateDict* sd, const float* img_nchw, 
   mask(b0, bits, sv.a1, 64, 0, nullptr, b1, 64, px1);
   bits = prep(b1, 64, H, W, L_CONV0);
   if (grads->weight[L_CONV0]) {
-    float* dw = const_cast<float*>(grads->weight[L_CONV0]);
+    float* dw = grads->weight[L_CONV0];
     const size_t Pp = padded_pixels(B, H, W);
     image_pad_kernel<<<ew_grid(3 * Pp), 256, 0, st>>>(img_nchw, B, H, W, w.xT, Pp);
     zero_f32_kernel<<<ew_grid(64 * 3 * 9), 256, 0, st>>>(dw, 64 * 3 * 9);

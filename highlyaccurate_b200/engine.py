@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import HaLevel, HaLmParams, HaVggStateDict, check
+from ._lib import HaLevel, HaLmParams, HaVggGrads, HaVggStateDict, check
 
 CAMERA_HEIGHT = 1.65           # utils.py:7
 SAT_PROCESS_SIDE = 512         # utils.py:11
@@ -647,7 +647,7 @@ class VggTrain(torch.autograd.Function):
         for l, g in enumerate((g0, g1, g2)):
             shape = (B, H >> (3 - l), W >> (3 - l), PYRAMID_CHANNELS[l])
             gs.append(torch.zeros(shape, dtype=torch.float32, device=dev) if g is None else g.float().contiguous())
-        sd, gd = HaVggStateDict(), HaVggStateDict()
+        sd, gd = HaVggStateDict(), HaVggGrads()
         keep, gw, gb = [], [], []
         for i, n in enumerate(VGG_CONV_NAMES):
             wt = named[n + ".weight"].detach().float().contiguous()

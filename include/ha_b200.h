@@ -262,18 +262,22 @@ int ha_vgg_g2s_forward(const void* packed_weights, const float* img_nchw, int B,
  *   every convolution (fp16 hi / lo planes) and the raw conv outputs in front of the three max-pools; keep `ws` untouched
  *   until ha_vgg_backward has run.
  * ha_vgg_backward: g_feat[l] = gradient w.r.t. out_feat[l] of the forward (fp32 NHWC, all n_levels required, zeros where a
- *   level is unused) -> grads->weight[i] ([Cout][Cin][3][3] fp32, torch layout) and grads->bias[i] ([Cout]) for the 13
+ *   level is unused) -> grads->weight[i] ([Cout][Cin][3][3] fp32, torch layout) and grads->bias[i] ([Cout]) (HaVggGrads) for the 13
  *   feature convolutions (entries may be NULL to skip; the confidence heads are not differentiated: they only matter with
  *   using_weight, which keeps the torch path).  sd = the raw OIHW weights (device), img_nchw = the forward's input.
  *   Data gradients run on the forward's tcgen05 convolution kernels with flipped weights, weight gradients on a tcgen05
  *   split-K GEMM over the pixels (csrc/vgg_backward.cu).  n_levels = 3 (level 3 / -1 / 2 models); W % 64 == 0, H % 32 == 0. */
+typedef struct {             /* where ha_vgg_backward writes: same order as HaVggStateDict, entries may be NULL */
+  float* weight[HA_VGG_N_CONV];
+  float* bias[HA_VGG_N_CONV];
+} HaVggGrads;
 size_t ha_vgg_train_workspace_bytes(int B, int H, int W, int n_levels);
 int ha_vgg_forward_train(const void* packed_weights, const float* img_nchw, int B, int H, int W, int n_levels,
                          float* const* out_feat, float* const* out_scale, float* const* out_conf, void* ws, size_t ws_bytes,
                          void* stream);
 size_t ha_vgg_backward_workspace_bytes(int B, int H, int W, int n_levels);
 int ha_vgg_backward(const HaVggStateDict* sd, const float* img_nchw, int B, int H, int W, int n_levels, void* fwd_ws,
-                    const float* const* g_feat, const HaVggStateDict* grads, void* ws, size_t ws_bytes, void* stream);
+                    const float* const* g_feat, const HaVggGrads* grads, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- one 3x3 / pad 1 / stride 1 convolution layer (the building block of ha_vgg_forward) ----
  * Replaces a single nn.Conv2d call of VGG.py:123-155.  fp32 NHWC in ([B][H][W][cin]) and out

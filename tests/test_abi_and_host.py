@@ -78,6 +78,7 @@ def test_struct_layouts_match_header():
     assert ctypes_fields(_lib.HaLmParams) == header_struct_fields("HaLmParams")
     assert ctypes_fields(_lib.HaLevel) == header_struct_fields("HaLevel")
     assert ctypes_fields(_lib.HaVggStateDict) == header_struct_fields("HaVggStateDict")
+    assert ctypes_fields(_lib.HaVggGrads) == header_struct_fields("HaVggGrads")
     assert ctypes.sizeof(_lib.HaLevel) == 32
     assert ctypes.sizeof(_lib.HaLmParams) == 8 * 4 + (3 + 3 + 4 + 4 + 4) * 4 + 4 * 4 + 6 * 4
     assert ctypes.sizeof(_lib.HaVggStateDict) == 2 * 17 * 8
