@@ -117,8 +117,9 @@ class VGGUnet(nn.Module):
         names = engine.VGG_CONV_NAMES
         params = [self._named[n + ".weight"] for n in names[:engine.N_FEATURE_CONVS]] + \
                  [self._named[n + ".bias"] for n in names[:engine.N_BIASED_CONVS]]
-        out = engine.VggTrain.apply(self._runner, self._named, x, *params)
-        raw, confs = out[:3], out[3:]
+        n = self.n_levels()
+        out = engine.VggTrain.apply(self._runner, self._named, n, x, *params)
+        raw, confs = out[:n], out[n:]
         feats = []
         for f in raw:                                                  # VGG.py:172-175 / :511-514, on the NHWC tensor
             nrm = f.reshape(f.shape[0], -1).norm(p=2, dim=-1).clamp_min(1e-12)

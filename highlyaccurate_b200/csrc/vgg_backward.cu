@@ -230,6 +230,15 @@ __global__ void flip_weights_kernel(const float* __restrict__ w, int cout, int c
   }
 }
 
+__global__ void add_kernel(float* __restrict__ a, const float* __restrict__ b, size_t n) {       // a += b, n % 4 == 0
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n / 4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 x = reinterpret_cast<float4*>(a)[i];
+    const float4 y = reinterpret_cast<const float4*>(b)[i];
+    x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    reinterpret_cast<float4*>(a)[i] = x;
+  }
+}
+
 __global__ void zero_f32_kernel(float* __restrict__ p, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
@@ -431,7 +440,7 @@ static PackedConv dgrad_layout(int cin, int cout, size_t* total) {
 }
 
 struct BwdWs {
-  float* buf[5];          // gradient tensors, each up to B H W 64 floats
+  float* buf[6];          // gradient tensors, each up to B H W 64 floats
   __half* hs;             // scaled hi / lo planes of the current dy: [P][2][C]
   __half* gT;             // dy transposed: [2][CoutPad][Ppad]
   __half* xT;             // x transposed:  [2][CinPad][Ppad]
@@ -440,18 +449,19 @@ struct BwdWs {
   unsigned* bits;         // one abs-max word per layer (16)
   size_t total;
 };
-static BwdWs bwd_carve(void* ws, int B, int H, int W) {
+static BwdWs bwd_carve(void* ws, int B, int H, int W, int n_levels = 3) {
   BwdWs r;
   char* p = reinterpret_cast<char*>(ws);
   size_t off = 0;
   auto take = [&](size_t bytes) { char* q = p + off; off = align_up(off + bytes, 256); return q; };
   const size_t px1 = (size_t)B * H * W, P1 = padded_pixels(B, H, W);
-  for (int i = 0; i < 5; ++i) r.buf[i] = reinterpret_cast<float*>(take(px1 * 64 * sizeof(float)));
+  for (int i = 0; i < 6; ++i) r.buf[i] = reinterpret_cast<float*>(take(px1 * 64 * sizeof(float)));
   const size_t P2 = padded_pixels(B, H / 2, W / 2), P4 = padded_pixels(B, H / 4, W / 4);
   auto max3 = [](size_t a, size_t b, size_t c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); };
   r.hs = reinterpret_cast<__half*>(take(px1 * 2 * 64 * sizeof(__half)));
   r.gT = reinterpret_cast<__half*>(take(max3(P1 * 128, P2 * 128, P4 * 256) * 2 * sizeof(__half)));   // dy^T: CoutPad rows per plane
-  r.xT = reinterpret_cast<__half*>(take(max3(P1 * 64, P2 * 192, P4 * 384) * 6 * sizeof(__half)));    // x^T: 3 shifts x 2 planes x CinPad rows
+  // x^T: 3 shifts x 2 planes x CinPad rows (level 4 adds cat3: 128 channels at full resolution)
+  r.xT = reinterpret_cast<__half*>(take(max3(P1 * (n_levels == 4 ? 128 : 64), P2 * 192, P4 * 384) * 6 * sizeof(__half)));
   r.wflip = reinterpret_cast<float*>(take((size_t)256 * 256 * 9 * sizeof(float)));
   size_t wp;
   dgrad_layout(256, 256, &wp);
@@ -513,18 +523,18 @@ struct BwdOps {
 }  // namespace ha
 
 extern "C" size_t ha_vgg_backward_workspace_bytes(int B, int H, int W, int n_levels) {
-  if (B <= 0 || H <= 0 || W <= 0 || n_levels != 3) return 0;
-  return ha::bwd_carve(nullptr, B, H, W).total;
+  if (B <= 0 || H <= 0 || W <= 0 || (n_levels != 3 && n_levels != 4)) return 0;
+  return ha::bwd_carve(nullptr, B, H, W, n_levels).total;
 }
 
 extern "C" int ha_vgg_backward(const HaVggStateDict* sd, const float* img_nchw, int B, int H, int W, int n_levels, void* fwd_ws,
                                const float* const* g_feat, const HaVggGrads* grads, void* ws, size_t ws_bytes, void* stream) {
   using namespace ha;
   if (!sd || !img_nchw || !fwd_ws || !g_feat || !grads || !ws) return HA_EINVAL;
-  if (n_levels != 3 || B <= 0 || (W % 64) || (H % 32)) return HA_EINVAL;
-  for (int l = 0; l < 3; ++l)
+  if ((n_levels != 3 && n_levels != 4) || B <= 0 || (W % 64) || (H % 32)) return HA_EINVAL;
+  for (int l = 0; l < n_levels; ++l)
     if (!g_feat[l]) return HA_EINVAL;
-  const BwdWs w = bwd_carve(ws, B, H, W);
+  const BwdWs w = bwd_carve(ws, B, H, W, n_levels);
   if (ws_bytes < w.total) return HA_ENOSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const TcSaved sv = vgg_train_saved(reinterpret_cast<char*>(fwd_ws), B, H, W, n_levels);
@@ -558,12 +568,27 @@ extern "C" int ha_vgg_backward(const HaVggStateDict* sd, const float* img_nchw, 
     unpool_kernel<<<ew_grid((size_t)B * h * wd * C), 256, 0, st>>>(gp, raw, out, C, B, h, wd);
     count_launches(1);
   };
-  float *b0 = w.buf[0], *b1 = w.buf[1], *b2 = w.buf[2], *b3 = w.buf[3], *b4 = w.buf[4];
+  float *b0 = w.buf[0], *b1 = w.buf[1], *b2 = w.buf[2], *b3 = w.buf[3], *b4 = w.buf[4], *b5 = w.buf[5];
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
   const unsigned* bits;
 
+  // ---- decoder 3 (level 4 only, VGG.py:154-157): x24 = dec3b(d3), d3 = relu(dec3a(cat3)), cat3 = [relu(up(x21)) | relu(x2)] ----
+  const float* g21 = g_feat[2];
+  if (n_levels == 4) {
+    bits = prep(g_feat[3], 16, H, W, L_DEC3B);
+    HA_TRY(wgrad(L_DEC3B, sv.d3, 32, 0, H, W, bits));
+    HA_TRY(dgrad(L_DEC3B, 0, 32, H, W, b0));
+    mask(b0, bits, sv.d3, 32, 0, nullptr, b1, 32, px1);
+    bits = prep(b1, 32, H, W, L_DEC3A);
+    HA_TRY(wgrad(L_DEC3A, sv.cat3, 128, 0, H, W, bits));
+    HA_TRY(dgrad(L_DEC3A, 0, 64, H, W, b0));
+    sumpool(b0, bits, sv.cat3, 128, 0, g_feat[2], b4, 64, H2, W2);                     // b4 = total gradient of x21 (b4 is free until decoder 1)
+    HA_TRY(dgrad(L_DEC3A, 64, 64, H, W, b0));
+    mask(b0, bits, sv.cat3, 128, 64, nullptr, b5, 64, px1);                            // b5 = gradient of x2 through the relu(x2) skip
+    g21 = b4;
+  }
   // ---- decoder 2 (VGG.py:149-152): x21 = dec2b(d2), d2 = relu(dec2a(cat2)), cat2 = [relu(up(x18)) | x4] ---------------
-  bits = prep(g_feat[2], 64, H2, W2, L_DEC2B);
+  bits = prep(g21, 64, H2, W2, L_DEC2B);
   HA_TRY(wgrad(L_DEC2B, sv.d2, 64, 0, H2, W2, bits));
   HA_TRY(dgrad(L_DEC2B, 0, 64, H2, W2, b0));
   mask(b0, bits, sv.d2, 64, 0, nullptr, b1, 64, px2);                                  // b1 = d loss / d (dec2a output)
@@ -610,6 +635,10 @@ extern "C" int ha_vgg_backward(const HaVggStateDict* sd, const float* img_nchw, 
   mask(b0, bits, sv.cat2, 192, 128, b3, b1, 64, px2);                                  // b1 = total gradient of x4 = relu(pool(x2))
   // ---- encoder block 0 (:123-128) -------------------------------------------------------------------------------
   unpool(b1, sv.x2, b2, 64, H2, W2);
+  if (n_levels == 4) {                                                                   // + the skip into decoder 3
+    add_kernel<<<ew_grid(px1 * 16), 256, 0, st>>>(b2, b5, px1 * 64);
+    count_launches(1);
+  }
   bits = prep(b2, 64, H, W, L_CONV2);
   HA_TRY(wgrad(L_CONV2, sv.a1, 64, 0, H, W, bits));
   HA_TRY(dgrad(L_CONV2, 0, 64, H, W, b0));

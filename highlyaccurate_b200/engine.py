@@ -611,49 +611,52 @@ class VggTrain(torch.autograd.Function):
     """The U-Net with a native backward (second slice): forward = ha_vgg_forward_train (the tcgen05
     schedule of the eval path, keeping the activations in its workspace), backward = ha_vgg_backward (data gradients on the
     same tcgen05 convolution kernels with flipped weights, weight gradients on a tcgen05 split-K GEMM over the pixels).
-    apply(runner, named, img, *params) with params = the 13 feature-conv weights then the 7 encoder biases (autograd inputs);
-    returns the three raw NHWC feature maps x15 / x18 / x21 (VGG.py:141,147,152); the caller L2-normalises and slices."""
+    apply(runner, named, n_levels, img, *params) with params = the 13 feature-conv weights then the 7 encoder biases
+    (autograd inputs); returns the raw NHWC feature maps x15 / x18 / x21 (/ x24) (VGG.py:141,147,152,157) followed by the
+    confidence maps (not differentiated); the caller L2-normalises and slices."""
 
     @staticmethod
     def supports(img: torch.Tensor, n_levels: int, precision: str) -> bool:
-        return img.is_cuda and n_levels == 3 and precision == "f16x3" and img.shape[-1] % 64 == 0 and img.shape[-2] % 32 == 0
+        return img.is_cuda and n_levels in (3, 4) and precision == "f16x3" and img.shape[-1] % 64 == 0 and img.shape[-2] % 32 == 0
 
     @staticmethod
-    def forward(ctx, runner, named, img, *params):
+    def forward(ctx, runner, named, n_levels, img, *params):
         L = _lib.lib()
         dev = img.device
         img = img.float().contiguous()
         B, _, H, W = img.shape
+        n = int(n_levels)
         runner._pack(named, dev)
-        need = L.ha_vgg_train_workspace_bytes(B, H, W, 3)
+        need = L.ha_vgg_train_workspace_bytes(B, H, W, n)
         ws = torch.empty(need, dtype=torch.uint8, device=dev)          # owned by this call's graph until backward
-        feats = [torch.empty(B, H >> (3 - l), W >> (3 - l), PYRAMID_CHANNELS[l], dtype=torch.float32, device=dev) for l in range(3)]
-        confs = [torch.empty(B, H >> (3 - l), W >> (3 - l), dtype=torch.float32, device=dev) for l in range(3)]
-        pf, pc = (C.c_void_p * 3)(*[f.data_ptr() for f in feats]), (C.c_void_p * 3)(*[c.data_ptr() for c in confs])
-        check(L.ha_vgg_forward_train(runner.packed.data_ptr(), img.data_ptr(), B, H, W, 3, pf, None, pc, ws.data_ptr(), need,
+        feats = [torch.empty(B, H >> (3 - l), W >> (3 - l), PYRAMID_CHANNELS[l], dtype=torch.float32, device=dev) for l in range(n)]
+        confs = [torch.empty(B, H >> (3 - l), W >> (3 - l), dtype=torch.float32, device=dev) for l in range(n)]
+        pf, pc = (C.c_void_p * n)(*[f.data_ptr() for f in feats]), (C.c_void_p * n)(*[c.data_ptr() for c in confs])
+        check(L.ha_vgg_forward_train(runner.packed.data_ptr(), img.data_ptr(), B, H, W, n, pf, None, pc, ws.data_ptr(), need,
                                      _stream_ptr()), "ha_vgg_forward_train")
-        ctx.ws, ctx.img, ctx.named, ctx.shape = ws, img, named, (B, H, W)
-        ctx.confs = confs
+        ctx.ws, ctx.img, ctx.named, ctx.shape, ctx.n = ws, img, named, (B, H, W), n
         ctx.mark_non_differentiable(*confs)
         return (*feats, *confs)
 
     @staticmethod
-    def backward(ctx, g0, g1, g2, *_gconf):
+    def backward(ctx, *grads_out):
         L = _lib.lib()
         B, H, W = ctx.shape
+        n = ctx.n
         dev = ctx.img.device
         named = ctx.named
         gs = []
-        for l, g in enumerate((g0, g1, g2)):
+        for l, g in enumerate(grads_out[:n]):
             shape = (B, H >> (3 - l), W >> (3 - l), PYRAMID_CHANNELS[l])
             gs.append(torch.zeros(shape, dtype=torch.float32, device=dev) if g is None else g.float().contiguous())
         sd, gd = HaVggStateDict(), HaVggGrads()
         keep, gw, gb = [], [], []
-        for i, n in enumerate(VGG_CONV_NAMES):
-            wt = named[n + ".weight"].detach().float().contiguous()
+        n_convs = 11 if n == 3 else N_FEATURE_CONVS                  # conv_dec3 only exists in the 4-level pyramid
+        for i, name in enumerate(VGG_CONV_NAMES):
+            wt = named[name + ".weight"].detach().float().contiguous()
             keep.append(wt)
             sd.weight[i] = wt.data_ptr()
-            if i < N_FEATURE_CONVS and i < 11:                      # conv_dec3 only exists at level 4 (not on this path)
+            if i < n_convs:
                 g = torch.empty_like(wt)
                 gw.append(g)
                 gd.weight[i] = g.data_ptr()
@@ -663,13 +666,13 @@ class VggTrain(torch.autograd.Function):
                 g = torch.empty(wt.shape[0], dtype=torch.float32, device=dev)
                 gb.append(g)
                 gd.bias[i] = g.data_ptr()
-        need = L.ha_vgg_backward_workspace_bytes(B, H, W, 3)
+        need = L.ha_vgg_backward_workspace_bytes(B, H, W, n)
         ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        pg = (C.c_void_p * 3)(*[g.data_ptr() for g in gs])
-        check(L.ha_vgg_backward(C.byref(sd), ctx.img.data_ptr(), B, H, W, 3, ctx.ws.data_ptr(), pg, C.byref(gd), ws.data_ptr(), need,
+        pg = (C.c_void_p * n)(*[g.data_ptr() for g in gs])
+        check(L.ha_vgg_backward(C.byref(sd), ctx.img.data_ptr(), B, H, W, n, ctx.ws.data_ptr(), pg, C.byref(gd), ws.data_ptr(), need,
                                 _stream_ptr()), "ha_vgg_backward")
         ctx.ws = None
-        return (None, None, None, *gw, *gb)
+        return (None, None, None, None, *gw, *gb)
 
 
 def conv3x3(x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: str) -> torch.Tensor:
