@@ -804,19 +804,26 @@ static LmWs lm_ws_carve(void* ws, int B) {
 }
 static size_t lm_ws_bytes(int B) { return lm_ws_carve(nullptr, B).total; }
 
-// Work split: a CTA takes px_per_cta consecutive bottom-half pixels of one sample, a multiple of
-// 32 * warps so that every warp gets the same number of 32-pixel groups (no barrier skew).  Enough
-// CTAs to fill 148 SMs several times over, never more than kLmMaxCtasPerSample per sample.
-static int choose_px_per_cta(int B, int P) {
+// Work split: a CTA takes px_per_cta consecutive residual pixels of one sample, a multiple of 32 * warps so that every warp
+// gets the same number of 32-pixel groups (no barrier skew); never more than kLmMaxCtasPerSample CTAs per sample.
+// The grid runs in rounds of `slots` = 148 SMs x resident CTAs, and a launch costs about rounds x (units per CTA + a fixed
+// per-CTA overhead): B200, B = 256 showed 3.46 / 4.04 / 4.04 waves with the old "about 12 CTAs per SM" rule, i.e. a fifth
+// round that was 4 % full (profiles/r02_lm_full.csv: launch__waves_per_multiprocessor).  Pick the split that minimises that cost.
+static int choose_px_per_cta(int B, int P, int resident_per_sm) {
   const int unit = kLmWarps * 32;
   const int units = (P + unit - 1) / unit;                     // whole-CTA units in one sample
-  int want = (kNumSMs * 12 + B - 1) / B;                       // ~12 CTAs per SM over the batch
-  if (want > kLmMaxCtasPerSample) want = kLmMaxCtasPerSample;
-  if (want < 1) want = 1;
-  int upc = (units + want - 1) / want;                         // units per CTA
-  if (upc < 1) upc = 1;
-  while ((units + upc - 1) / upc > kLmMaxCtasPerSample) ++upc;
-  return upc * unit;
+  const long long slots = (long long)kNumSMs * resident_per_sm;
+  double best_cost = 1e300;
+  int best_upc = units;
+  for (int upc = 1; upc <= units; ++upc) {
+    const int n = (units + upc - 1) / upc;
+    if (n > kLmMaxCtasPerSample) continue;
+    const long long total = (long long)n * B;
+    const long long rounds = (total + slots - 1) / slots;
+    const double cost = (double)rounds * ((double)upc + 0.5);   // 0.5 unit: prologue (barriers, pose constants) + reduction tail
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_upc = upc; }
+  }
+  return best_upc * unit;
 }
 
 static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, const HaLevel* grd, const float* grd_conf,
@@ -873,7 +880,8 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   a.adam_mv = w.adam_mv;
   a.g2sp_nn = g2sp_nn ? 1 : 0;
   const int P = g2sp ? sat->H * sat->W : (grd->H - a.row0) * grd->W;
-  a.px_per_cta = choose_px_per_cta(B, P);
+  // resident CTAs per SM: 3 for the v4 kernel (160 registers, ring), HA_LM_MIN_CTAS for the register-staged kernel
+  a.px_per_cta = choose_px_per_cta(B, P, (g2sp || p->kernel_variant == 1) ? HA_LM_MIN_CTAS : 3);
   dim3 grid((P + a.px_per_cta - 1) / a.px_per_cta, B);
   if (p->geometry == HA_GEOM_KITTI)
     return full ? launch_by_channels<HA_GEOM_KITTI, true>(grd->C, grid, st, a) : launch_by_channels<HA_GEOM_KITTI, false>(grd->C, grid, st, a);
