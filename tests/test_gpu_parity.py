@@ -920,3 +920,44 @@ def test_train_mode_level4_native_vs_torch_path():
         print("train mode level 4: native vs torch path, worst max|d|/max|g| %.2e" % worst)
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def test_training_loop_native_vs_torch_path():
+    """The loop of train_kitti.py:333-368 (Adam, lr 1e-4: zero_grad -> forward(mode='train') -> loss.backward() ->
+    optimizer.step()) for three steps from the same initialisation, fully native against the reference-equivalent torch
+    path: the loss after every update must follow the same curve (Adam normalises the gradients, so this checks signs and
+    relative magnitudes of every parameter's gradient, not just its largest entry)."""
+    import copy
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        base = LM_S2GP(K.ref_args(N_iters=2))
+        sd = {}
+        sd.update(O.vgg_state_dict(100, "SatFeatureNet."))
+        sd.update(O.vgg_state_dict(101, "GrdFeatureNet."))
+        sd["damping"] = torch.zeros(1, 3)
+        base.load_state_dict(sd)
+        g = torch.Generator().manual_seed(77)
+        sat = torch.rand(2, 3, 512, 512, generator=g).to(DEV)
+        grd = torch.rand(2, 3, 256, 1024, generator=g).to(DEV)
+        gt = torch.tensor([[0.2, -0.1, 0.3], [-0.3, 0.25, -0.15]], device=DEV)
+        curves = {}
+        for mode in ("native", "torch"):
+            net = copy.deepcopy(base).to(DEV)
+            net.SatFeatureNet.native_train = net.GrdFeatureNet.native_train = mode == "native"
+            net.fused_backward = mode == "native"
+            opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+            losses = []
+            for _ in range(3):
+                opt.zero_grad()
+                torch.manual_seed(4242)
+                out = net(sat, grd, gt[:, 0:1], gt[:, 1:2], gt[:, 2:3], mode="train")
+                out[0].backward()
+                opt.step()
+                losses.append(float(out[0].detach()))
+            curves[mode] = losses
+        print("training loop losses: native %s  torch %s" % (curves["native"], curves["torch"]))
+        assert curves["native"][0] != curves["native"][2]                       # the parameters did move
+        np.testing.assert_allclose(curves["native"], curves["torch"], rtol=2e-3)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
