@@ -17,7 +17,7 @@ HA_VGG_N_CONV = 17
 HA_GEOM_KITTI, HA_GEOM_FORD, HA_GEOM_G2SP, HA_GEOM_G2SP_NN = 0, 1, 2, 3
 HA_OPT_LM, HA_OPT_SGD, HA_OPT_ADAM, HA_OPT_GN = 0, 1, 2, 3
 HA_CONV_FP32_SIMT, HA_CONV_F16X3, HA_CONV_F16, HA_CONV_F16X3_1CTA = 0, 1, 2, 3
-HA_STATUS_NO_INRANGE, HA_STATUS_NAN_POSE, HA_STATUS_RESET, HA_STATUS_SAMPLE_EMPTY = 1, 2, 4, 8
+HA_STATUS_NO_INRANGE, HA_STATUS_NAN_POSE, HA_STATUS_RESET, HA_STATUS_SAMPLE_EMPTY, HA_STATUS_TIMEOUT = 1, 2, 4, 8, 16
 HA_COMM_ID_BYTES = 128
 HA_ABI_VERSION = 3
 STAT_H, STAT_GRAD, STAT_SAT_NORM, STAT_GRD_NORM, STAT_RES_SQ, STAT_DELTA, STAT_N_INRANGE = 0, 9, 12, 13, 14, 15, 18

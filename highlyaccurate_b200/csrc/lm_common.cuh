@@ -52,6 +52,8 @@ struct LmStepArgs {
   float adam_b1, adam_b2;  // HA_OPT_ADAM: args.beta1 / args.beta2
   float* adam_mv;          // HA_OPT_ADAM: [B][6] first / second moments, carried between the steps of a run
   int g2sp_nn;             // HA_GEOM_G2SP_NN: the in-plane warp of models_kitti.py:289-331 instead of the camera projection
+  int* done;               // chained launches (ha_lm_run): [B] steps finished per sample; null = plain stream order
+  int step_index;          // chained launches: index of this step in the run (it waits for done[b] >= step_index)
 };
 
 // Per-sample constants of the warp, evaluated in the reference's fp32 operation order.

@@ -63,11 +63,33 @@ struct PixelLoads {            // one 128-bit channel slice of one pixel: ground
   V4 g, nw, ne, sw, se;
 };
 
-// CTA reduction + (last CTA of the sample) ordered combine, damped solve and pose update; shared by both step kernels.
+// What the reduce-and-solve tail needs beyond the level's LmStepArgs: which of the sample's CTAs this is and the
+// per-step outputs, built from the launch (block indices, the argument block: all constants).
+struct LmTail {
+  int cta_x, n_ctas;               // this CTA among the n_ctas CTAs of the sample
+  const float* reset_uv;           // [2][B] draws of this step or null
+  float* stats;                    // [B][HA_STATS] of this step or null
+  float* traj;                     // &traj[0][it][lv][0] or null
+  unsigned long long* step_word;   // batch-level arrival word of this step
+  int adam_t;                      // HA_OPT_ADAM: t of this step
+  int* done;                       // chained launches (ha_lm_run): [B] steps finished per sample, else null
+  int done_val;                    // value released into done[b] once the pose of this step is written
+};
+__device__ __forceinline__ LmTail lm_tail_of_launch(const LmStepArgs& a) {
+  LmTail t;
+  t.cta_x = blockIdx.x; t.n_ctas = gridDim.x; t.reset_uv = a.reset_uv; t.stats = a.stats; t.traj = a.traj;
+  t.step_word = a.step_word; t.adam_t = a.adam_t; t.done = a.done; t.done_val = a.step_index + 1;
+  return t;
+}
+
+// CTA reduction + (last CTA of the sample) ordered combine, damped solve and pose update; shared by the step kernels.
 // v[]: this lane's sixteen running sums {Gaa, Gab, Gbb, Bx, By, Ctt, Sa, Sb, St, Ga, Gb, Gt, SS, GG, SG, count}.
+// Chained launches (ha_lm_run) overlap consecutive steps, so whatever an earlier step wrote (pose, |g|^2 cache, Adam
+// moments) is read with ld.global.cg after the sample's `done` flag was acquired: there is no kernel boundary in between.
 template <int GEOM, bool FULL>
-__device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const int b, const double (&v)[kLmAcc], const KittiPose& kp,
-                                                    const FordPose& fp, const float su, const float sv, const float th) {
+__device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const LmTail& tc, const int b, const double (&v)[kLmAcc],
+                                                    const KittiPose& kp, const FordPose& fp, const float su, const float sv,
+                                                    const float th) {
   constexpr bool G2SP = (GEOM == HA_GEOM_G2SP);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // ---- CTA reduction: lanes -> warp (fp64 shuffles) -> shared -> one partial row per CTA
@@ -81,7 +103,7 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const i
     }
   }
   __syncthreads();
-  double* part = a.partial + ((size_t)b * kLmMaxCtasPerSample + blockIdx.x) * kLmAcc;
+  double* part = a.partial + ((size_t)b * kLmMaxCtasPerSample + tc.cta_x) * kLmAcc;
   if (threadIdx.x < kLmAcc) {
     double r = 0;
 #pragma unroll
@@ -92,7 +114,7 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const i
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t prev = atomicAdd(a.ticket + b, 1u);
-    is_last = (prev == gridDim.x - 1);
+    is_last = (prev == (uint32_t)tc.n_ctas - 1u);
   }
   __syncthreads();
   if (!is_last) return;
@@ -103,7 +125,7 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const i
   if (threadIdx.x < kLmAcc) {
     const volatile double* pp = a.partial + (size_t)b * kLmMaxCtasPerSample * kLmAcc + threadIdx.x;
     double r = 0;
-    for (unsigned c = 0; c < gridDim.x; ++c) r += pp[(size_t)c * kLmAcc];
+    for (int c = 0; c < tc.n_ctas; ++c) r += pp[(size_t)c * kLmAcc];
     tot[threadIdx.x] = r;
   }
   __syncthreads();
@@ -122,7 +144,7 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const i
     for (int i = 0; i < 3; ++i) gr[i] = tot[6 + i] * f2 - tot[9 + i] * fsg;
   } else {
     if (FULL) { if (a.gg_cache) a.gg_cache[b] = tot[13]; }
-    else tot[13] = a.gg_cache[b];                    // sum g^2 over the unmasked bottom half, from this level's first visit
+    else tot[13] = __ldcg(a.gg_cache + b);           // sum g^2 over the unmasked bottom half, from this level's first visit
 
     // assemble J^T W J, J^T W s, J^T W g from the split sums with the per-sample constant rows of D
     const double d0x = (GEOM == HA_GEOM_KITTI) ? kp.jux : fp.jux, d0y = (GEOM == HA_GEOM_KITTI) ? kp.juy : fp.juy;
@@ -179,9 +201,9 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const i
     if (a.optimizer == HA_OPT_ADAM) {
       float* mv = a.adam_mv + (size_t)b * 6;
       const double b1 = (double)a.adam_b1, b2 = (double)a.adam_b2;
-      const float c1 = (float)(1.0 - pow(b1, (double)(a.adam_t + 1))), c2 = (float)(1.0 - pow(b2, (double)(a.adam_t + 1)));
+      const float c1 = (float)(1.0 - pow(b1, (double)(tc.adam_t + 1))), c2 = (float)(1.0 - pow(b2, (double)(tc.adam_t + 1)));
       for (int i = 0; i < 3; ++i) {
-        const float m0 = a.adam_t == 0 ? 0.f : mv[i], v0 = a.adam_t == 0 ? 0.f : mv[3 + i];      // :1242-1244
+        const float m0 = tc.adam_t == 0 ? 0.f : __ldcg(mv + i), v0 = tc.adam_t == 0 ? 0.f : __ldcg(mv + 3 + i);   // :1242-1244
         const float m = __fadd_rn(__fmul_rn((float)b1, m0), __fmul_rn((float)(1.0 - b1), stepv[i]));
         const float v = __fadd_rn(__fmul_rn((float)b2, v0), __fmul_rn((float)(1.0 - b2), __fmul_rn(stepv[i], stepv[i])));
         mv[i] = m; mv[3 + i] = v;
@@ -218,8 +240,8 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const i
     nsu = su + (float)delta[0]; nsv = sv + (float)delta[1]; nth = th + (float)delta[2];
     // models_kitti.py:1028-1033: shifts outside (-2.5, 2.5) (or NaN) are re-drawn (S2GP models only)
     if (!G2SP) {
-      if (!(nsu > -2.5f && nsu < 2.5f)) { nsu = a.reset_uv[b]; st |= HA_STATUS_RESET; reset_mask |= 1; }
-      if (!(nsv > -2.5f && nsv < 2.5f)) { nsv = a.reset_uv[a.B + b]; st |= HA_STATUS_RESET; reset_mask |= 2; }
+      if (!(nsu > -2.5f && nsu < 2.5f)) { nsu = tc.reset_uv[b]; st |= HA_STATUS_RESET; reset_mask |= 1; }
+      if (!(nsv > -2.5f && nsv < 2.5f)) { nsv = tc.reset_uv[a.B + b]; st |= HA_STATUS_RESET; reset_mask |= 2; }
     }
   } else if (n == 2) {
     nsu = su + (float)delta[0]; nsv = sv + (float)delta[1];
@@ -230,20 +252,25 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const i
   const bool any_inrange = tot[15] != 0.0;
   if (!any_inrange) st |= HA_STATUS_SAMPLE_EMPTY;
   // jacobian.py:172 asserts that SOME sample point of the whole batch is in range: the last sample to finish this step
-  // sees how many samples had one (the word is reset for the next step of the stream)
-  const unsigned long long prev = atomicAdd(a.step_word, (1ull << 32) | (any_inrange ? 1ull : 0ull));
+  // sees how many samples had one (the word is reset for the next step of the stream; chained launches have one word per step)
+  const unsigned long long prev = atomicAdd(tc.step_word, (1ull << 32) | (any_inrange ? 1ull : 0ull));
   if ((unsigned)(prev >> 32) == (unsigned)a.B - 1u) {
     if ((unsigned)(prev & 0xffffffffull) + (any_inrange ? 1u : 0u) == 0u) st |= HA_STATUS_NO_INRANGE;
-    *a.step_word = 0ull;
+    *tc.step_word = 0ull;
   }
   if (st) atomicOr(a.status, st);
   a.pose[b * 3 + 0] = nsu; a.pose[b * 3 + 1] = nsv; a.pose[b * 3 + 2] = nth;
-  if (a.traj) {
-    float* tr = a.traj + (size_t)b * a.traj_stride;
+  if (tc.traj) {
+    float* tr = tc.traj + (size_t)b * a.traj_stride;
     tr[0] = nsu; tr[1] = nsv; tr[2] = nth;
   }
-  if (a.stats) {
-    float* s = a.stats + (size_t)b * HA_STATS;
+  if (tc.done) {
+    // chained launches: the pose of this step is out; the CTAs of the sample's next step (already resident) may go on
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(tc.done + b), "r"(tc.done_val) : "memory");
+  }
+  if (tc.stats) {
+    float* s = tc.stats + (size_t)b * HA_STATS;
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) s[HA_STAT_H + i * 3 + j] = (float)Hm[i][j];
     for (int i = 0; i < 3; ++i) s[HA_STAT_GRAD + i] = (float)gr[i];
@@ -421,7 +448,7 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
   {
     double v[kLmAcc] = {sum2(A_aa), sum2(A_ab), sum2(A_bb), sum2(B_x), sum2(B_y), sum2(C_tt), sum2(S_a), sum2(S_b),
                         sum2(S_t), sum2(G_a), sum2(G_b), sum2(G_t), sum2(SS), sum2(GG), sum2(SG), cnt / (float)LPP};
-    lm_reduce_and_solve<GEOM, FULL>(a, b, v, kp, fp, su, sv, th);
+    lm_reduce_and_solve<GEOM, FULL>(a, lm_tail_of_launch(a), b, v, kp, fp, su, sv, th);
   }
 }
 
@@ -445,34 +472,71 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
 extern __shared__ __align__(128) uint8_t lm_dyn_smem[];
 
 constexpr int kLmIterBytes = 2048;   // one warp pixel-iteration streams PPW pixels x C channels x 4 B = 2 KB for every C
+constexpr int kLmChainMaxSteps = 128;  // chained launches: arrival words in the workspace (1 KB)
 constexpr int kLmRecBytes = 48;      // per-pixel record: (wx, ny, tx, ty) | (&nw, &sw) | (east bytes, has ground, weight, -)
 
+// Ring slot layout.  A lane reads its 16 bytes of channel quarter k of its pixel with one LDS.128, and a quarter-warp (one
+// shared-memory wavefront) holds 8 / LPP pixels whose quarters sit 4C bytes apart: for C <= 64 that is a multiple of
+// 128 B (C = 16: of 64 B), so the lanes of a wavefront hit the same banks (ncu, C = 64: 17 M bank conflicts per launch,
+// 8 wavefronts per LDS.128 instead of 4).  The chunk is therefore copied as NS sub-copies, sub-copy j shifted by j * C
+// bytes, and a quarter-warp takes its pixels from all NS sub-copies: every wavefront covers 128 distinct bytes mod 128.
+template <int C> constexpr int lm_ring_ns() { return C > 64 ? 1 : (C == 64 ? 2 : 4); }
+constexpr int kLmSlotBytes = kLmIterBytes + 128;          // room for the (NS - 1) * C <= 96 bytes of shift, 128-byte aligned
+
 template <int NSLOT>
-constexpr int lm_ring_bytes() { return kLmWarps * NSLOT * kLmIterBytes + kLmWarps * NSLOT * 8 + 1024; }
+constexpr int lm_ring_bytes() {     // rings, mbarriers, 1 KB of zeros, per-warp pixel records
+  return kLmWarps * NSLOT * kLmSlotBytes + kLmWarps * NSLOT * 8 + 1024 + kLmWarps * 32 * kLmRecBytes;
+}
 
 // Loop-invariant addresses the compiler would otherwise re-derive from %tid / %ctaid inside the loop (it treats them as
 // "cheap to rematerialise" under register pressure; ncu showed ~100 such instructions per iteration): make them opaque.
 #define HA_KEEP32(x) asm volatile("" : "+r"(x))
 #define HA_KEEP64(x) asm volatile("" : "+l"(x))
 
-template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF, bool WEIGHTED, int UNR = 1, bool SCAL = false>
-__global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmStepArgs a) {
+// once per kernel: the per-warp mbarriers and the zero vector (followed by __syncthreads in the caller)
+template <int NSLOT>
+__device__ __forceinline__ void lm_v4_smem_init() {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t dyn = smem_u32(lm_dyn_smem);
+  const uint32_t bar_w = dyn + kLmWarps * NSLOT * kLmSlotBytes + warp * (NSLOT * 8);
+  const uint32_t zero_s = dyn + kLmWarps * NSLOT * kLmSlotBytes + kLmWarps * NSLOT * 8;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_w + s * 8));
+    fence_barrier_init();
+  }
+  asm volatile("st.shared.v2.b32 [%0], {%1, %1};" ::"r"(zero_s + threadIdx.x * 8), "r"(0) : "memory");
+}
+
+// One CTA's share of one LM step of sample b: pixels [cta_x * px_per_cta, ...) of the residual.
+template <int GEOM, int C, bool FULL, int NSLOT, int PF, bool WEIGHTED, int UNR, bool SCAL>
+__device__ __forceinline__ void lm_v4_body(const LmStepArgs& a, const int b, const int cta_x) {
   constexpr int LPP = C / 16;                      // lanes per pixel: every lane owns 4 x 4 channels
   constexpr int PPW = 32 / LPP;                    // pixels processed together by one warp
   constexpr int IPG = LPP;                         // pixel-iterations per 32-pixel group
   constexpr int C4 = C / 4;
+  constexpr int NS = lm_ring_ns<C>();              // sub-copies per chunk
+  constexpr int PPS = PPW / NS;                    // pixels per sub-copy
   static_assert(C % 16 == 0 && LPP >= 1 && LPP <= 32 && PPW * LPP == 32, "channel count");
   static_assert(GEOM != HA_GEOM_G2SP, "G2SP streams only the visible satellite pixels: it stays on lm_step_kernel");
   static_assert(4 * C <= 1024, "zero vectors cover four channel quarters");
 
-  const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPP, cl = lane % LPP;     // pixel slot within the warp, channel lane
+  const int cl = lane % LPP;                       // channel lane
+  int sub = lane / LPP;                            // pixel slot within the warp
+  if constexpr (NS > 1) {
+    // quarter-warp qw holds PPQ pixels; R of them come from each sub-copy (see the ring slot layout above)
+    constexpr int PPQ = 8 / LPP, R = PPQ / NS;
+    static_assert(PPQ % NS == 0 && R >= 1, "sub-copy split");
+    const int i = sub % PPQ, qw = sub / PPQ;
+    sub = (i / R) * PPS + qw * R + (i % R);
+  }
   const int P = (a.H - a.row0) * a.W;              // the residual lives on the bottom half (models_kitti.py:1195-1199; row0 = H/2)
-  const int q_begin = blockIdx.x * a.px_per_cta;
+  const int q_begin = cta_x * a.px_per_cta;
   const int q_end = min(P, q_begin + a.px_per_cta);
 
-  const float su = a.pose[b * 3 + 0], sv = a.pose[b * 3 + 1], th = a.pose[b * 3 + 2];
+  // through L2: with chained launches the previous step's CTA wrote it while this kernel was already running
+  const float su = __ldcg(a.pose + b * 3 + 0), sv = __ldcg(a.pose + b * 3 + 1), th = __ldcg(a.pose + b * 3 + 2);
   KittiPose kp;
   FordPose fp;
   G2spPose gq;                                     // unused (pixel_scalars signature)
@@ -485,25 +549,15 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
   const float4* tab = a.table + (size_t)a.row0 * a.W;
   const float* conf = a.conf ? a.conf + px_base : nullptr;
 
-  // per-warp pixel records: phase A (one lane per pixel) writes 32 of them, the pixel's channel lanes read them back
-  __shared__ __align__(16) uint8_t ps_s[kLmWarps][32 * kLmRecBytes];
-
-  // dynamic shared memory: [warp][NSLOT][2 KB] rings, [warp][NSLOT] mbarriers, 1 KB of zeros (masked ground pixels)
+  // dynamic shared memory: [warp][NSLOT] ring slots, [warp][NSLOT] mbarriers, 1 KB of zeros (masked ground pixels),
+  // [warp][32] pixel records: phase A (one lane per pixel) writes 32 of them, the pixel's channel lanes read them back
   const uint32_t dyn = smem_u32(lm_dyn_smem);
-  const uint32_t ring_w = dyn + warp * (NSLOT * kLmIterBytes);
-  const uint32_t bar_w = dyn + kLmWarps * NSLOT * kLmIterBytes + warp * (NSLOT * 8);
-  const uint32_t zero_s = dyn + kLmWarps * NSLOT * kLmIterBytes + kLmWarps * NSLOT * 8;
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_w + s * 8));
-    fence_barrier_init();
-  }
-  asm volatile("st.shared.v2.b32 [%0], {%1, %1};" ::"r"(zero_s + threadIdx.x * 8), "r"(0) : "memory");
-  __syncthreads();
-
-  uint32_t ring_lane = ring_w + sub * (C * 4) + cl * 16;           // this lane's slice of slot 0
+  const uint32_t ring_w = dyn + warp * (NSLOT * kLmSlotBytes);
+  const uint32_t bar_w = dyn + kLmWarps * NSLOT * kLmSlotBytes + warp * (NSLOT * 8);
+  const uint32_t zero_s = dyn + kLmWarps * NSLOT * kLmSlotBytes + kLmWarps * NSLOT * 8;
+  const uint32_t ps_w = zero_s + 1024 + warp * (32 * kLmRecBytes);
+  uint32_t ring_lane = ring_w + sub * (C * 4) + (sub / PPS) * C + cl * 16;   // this lane's slice of slot 0
   uint32_t zero_lane = zero_s + cl * 16;
-  const uint32_t ps_w = smem_u32(&ps_s[warp][0]);
   uint32_t ps_lane = ps_w + sub * kLmRecBytes;
   uint32_t ps_wr = ps_w + lane * kLmRecBytes;                      // the record this lane writes in phase A
   const uint32_t cl16 = cl * 16;
@@ -525,10 +579,17 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
     if (iss_left > 0)                              // warp-uniform; the warp is converged here (after __syncwarp)
       asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(leader));
     if (leader) {
-      const uint32_t bar = bar_keep + slot * 8, bytes = (uint32_t)min(iss_left, PPW) * (C * 4);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(ring_bar + slot * kLmIterBytes), "l"(grd_w + iss_off), "r"(bytes), "r"(bar) : "memory");
+      const uint32_t bar = bar_keep + slot * 8, npx = (uint32_t)min(iss_left, PPW);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(npx * (C * 4)) : "memory");
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        if (j == 0 || npx > (uint32_t)(j * PPS)) {
+          const uint32_t bytes = (NS == 1 ? npx : min(npx - j * PPS, (uint32_t)PPS)) * (C * 4);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(ring_bar + slot * kLmSlotBytes + j * (PPS * C * 4 + C)), "l"(grd_w + iss_off + j * (PPS * C * 4)),
+                         "r"(bytes), "r"(bar) : "memory");
+        }
+      }
     }
     iss_off += kLmIterBytes; iss_left -= PPW; --to_issue;
     if (++iss_it == IPG) { iss_it = 0; iss_off += (kLmWarps - 1) * 32 * C * 4; iss_left -= (kLmWarps - 1) * 32; }
@@ -659,7 +720,7 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(east), "=r"(has_g) : "r"(ps_rd + 32));
     p_nw = reinterpret_cast<const char*>(an) + cl16; p_sw = reinterpret_cast<const char*>(as_) + cl16;
     p_ne = p_nw + east; p_se = p_sw + east;
-    g_addr = has_g ? ring_lane + slot * kLmIterBytes : zero_lane;  // masked ground pixels read zeros
+    g_addr = has_g ? ring_lane + slot * kLmSlotBytes : zero_lane;  // masked ground pixels read zeros
     ps_cur = ps_rd;
     // advance to the pixel-iteration after this one
     ps_rd += PPW * kLmRecBytes; nxt_px += PPW;
@@ -709,18 +770,47 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
 #pragma unroll
       for (int i = 0; i < 12; ++i) v[i] = rs[i];
     }
-    lm_reduce_and_solve<GEOM, FULL>(a, b, v, kp, fp, su, sv, th);
+    lm_reduce_and_solve<GEOM, FULL>(a, lm_tail_of_launch(a), b, v, kp, fp, su, sv, th);
   }
 }
 
+// Chained launches (ha_lm_run).  Per-step launches leave the machine idle between the first CTA that finishes a step
+// and the last one (B = 32: 15 launches of 40-110 us, 0.44 of the HBM roofline against 0.61 at B = 256), although step
+// k + 1 of a sample needs nothing but ITS OWN pose of step k.  So every step kernel of a run is launched with
+// programmatic stream serialization and signals `launch_dependents` at once: the next step's CTAs become resident as soon
+// as every CTA of this step has started and SM slots free up.  They never execute griddepcontrol.wait; a CTA of
+// sample b waits for `done[b] >= step` instead, which the CTA that solves the sample's previous step releases after
+// writing the pose.  A kernel starts only when all CTAs of its predecessor are resident, and those wait only on CTAs
+// of still earlier kernels that are resident too, so the chain cannot deadlock; a waiter gives up after ~1 s
+// (HA_STATUS_TIMEOUT) rather than hang the GPU.
+__device__ __forceinline__ void lm_chain_enter(const LmStepArgs& a, int b) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (a.done != nullptr && threadIdx.x == 0) {
+    int seen, spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(a.done + b) : "memory");
+      if (seen >= a.step_index) break;
+      __nanosleep(64);
+      if (++spins > (1 << 21)) { atomicOr(a.status, HA_STATUS_TIMEOUT); break; }   // ~1 s
+    }
+  }
+}
+
+template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF, bool WEIGHTED, int UNR = 1, bool SCAL = false>
+__global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmStepArgs a) {
+  lm_chain_enter(a, blockIdx.y);
+  lm_v4_smem_init<NSLOT>();
+  __syncthreads();
+  lm_v4_body<GEOM, C, FULL, NSLOT, PF, WEIGHTED, UNR, SCAL>(a, blockIdx.y, blockIdx.x);
+}
+
 // Kernel selection: HaLmParams.kernel_variant 0 (default) = lm_step_v4_kernel with a 4-slot x 2 KB ring per warp, tap rows
-// prefetched to L1, 3 CTAs per SM, pixel loop unrolled by two; 1 = lm_step_kernel (register-staged ground stream; the
-// validation twin, and always the kernel for G2SP).  Other ring depths (3, 5, 6, 8 slots), L2-only prefetch, no prefetch,
-// 2 and 4 CTAs per SM and the non-unrolled loop were measured and dropped.
-template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF, bool WEIGHTED, int UNR, bool SCAL = false>
-static int launch_v4w(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
-  auto kern = lm_step_v4_kernel<GEOM, C, FULL, NSLOT, MINB, PF, WEIGHTED, UNR, SCAL>;
-  constexpr int smem = lm_ring_bytes<NSLOT>();
+// prefetched to L1, 3 CTAs per SM, pixel loop unrolled by two; ha_lm_run chains its launches (above).  1 = lm_step_kernel
+// (register-staged ground stream; the validation twin, and always the kernel for G2SP); 2 = the default kernel without
+// chaining (one stream-ordered launch per step: the A/B twin of the chain).  Other ring depths (3, 5, 6, 8 slots),
+// L2-only prefetch, no prefetch, 2 and 4 CTAs per SM and the non-unrolled loop were measured and dropped.
+template <typename K>
+static int lm_configure_smem(K kern, int smem, int minb) {
   // function attributes are per (device function, device): one bit per device ordinal, per instantiation
   static std::atomic<unsigned long long> configured{0};
   int dev = 0;
@@ -728,16 +818,32 @@ static int launch_v4w(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
   const unsigned long long bit = 1ull << (dev & 63);
   if (!(configured.load(std::memory_order_acquire) & bit)) {
     HA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    // shared-memory carve-out: exactly what MINB resident CTAs need (ring + static + 1 KB reserved each); the rest of
+    // shared-memory carve-out: exactly what `minb` resident CTAs need (ring + static + 1 KB reserved each); the rest of
     // the 228 KB stays L1 for the satellite taps
     cudaFuncAttributes fa;
     HA_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
-    const int want = MINB * (smem + (int)fa.sharedSizeBytes + 1024);
+    const int want = minb * (smem + (int)fa.sharedSizeBytes + 1024);
     const int pct = want >= 228 * 1024 ? 100 : (want * 100 + 228 * 1024 - 1) / (228 * 1024);
     HA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     configured.fetch_or(bit, std::memory_order_release);
   }
-  kern<<<grid, kLmThreads, smem, st>>>(a);
+  return HA_OK;
+}
+
+template <int GEOM, int C, bool FULL, int NSLOT, int MINB, int PF, bool WEIGHTED, int UNR, bool SCAL = false>
+static int launch_v4w(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
+  auto kern = lm_step_v4_kernel<GEOM, C, FULL, NSLOT, MINB, PF, WEIGHTED, UNR, SCAL>;
+  constexpr int smem = lm_ring_bytes<NSLOT>();
+  const int rc = lm_configure_smem(kern, smem, MINB);
+  if (rc != HA_OK) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kLmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  // steps after the first of a chained run may start before their predecessor has finished (lm_chain_enter)
+  if (a.done != nullptr && a.step_index > 0) { cfg.attrs = attr; cfg.numAttrs = 1; }
+  HA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
   return HA_OK;
 }
 
@@ -754,12 +860,7 @@ static int launch_variant(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
     return HA_OK;
   } else {
     if (a.variant == 1) { lm_step_kernel<GEOM, C, FULL><<<grid, kLmThreads, 0, st>>>(a); return HA_OK; }
-#ifdef HA_LM_DEV_VARIANTS      // A/B builds only (tools/bench_lm.py); measured at B = 256 on B200, per level 0 / 1 / 2 in us:
-    if (a.variant == 2) return launch_v4<GEOM, C, FULL, 4, 3, 2, 2, false>(grid, st, a);  // packed per-pixel fold: 256 / 414 / 759
-    if (a.variant == 3) return launch_v4<GEOM, C, FULL, 4, 4, 2, 2, true>(grid, st, a);   // 4 CTAs/SM, 128 regs, spills: 265 / 415 / 756
-    if (a.variant == 4) return launch_v4<GEOM, C, FULL, 3, 4, 2, 2, true>(grid, st, a);   // same with a 3-slot ring: 253 / 403 / 739
-#endif
-    return launch_v4<GEOM, C, FULL, 4, 3, 2, 2, true>(grid, st, a);                       // scalar per-pixel fold: 252 / 407 / 748
+    return launch_v4<GEOM, C, FULL, 4, 3, 2, 2, true>(grid, st, a);
   }
 }
 
@@ -779,10 +880,12 @@ static int launch_by_channels(int C, dim3 grid, cudaStream_t st, const LmStepArg
   return check_launch("lm_step_kernel");
 }
 
-// Workspace layout: [partials B x 256 x 16 fp64][tickets B x u32, padded to 256 B][step word, 256 B][zero vector 2 KB]
-// [|g|^2 cache HA_MAX_LEVELS x B fp64][Adam moments B x 6 fp32].  Tickets, step word and zero vector are contiguous: one kernel clears them.
+// Workspace layout: [partials B x 256 x 16 fp64][tickets B x u32, padded to 256 B][done B x s32, padded to 256 B]
+// [step region 1 KB: 64 step words (u64) for chained launches][zero vector 2 KB]
+// [|g|^2 cache HA_MAX_LEVELS x B fp64][Adam moments B x 6 fp32].  Tickets ... zero vector are contiguous: one kernel clears them.
 struct LmWs {
-  double* partial; uint32_t* ticket; unsigned long long* step_word; const float4* zeros; double* gg; float* adam_mv;
+  double* partial; uint32_t* ticket; int* done; unsigned long long* step_word; const float4* zeros;
+  double* gg; float* adam_mv;
   size_t clear_words;      // u32 words from `ticket` that must be zero when a run starts
   size_t total;
 };
@@ -791,15 +894,18 @@ static LmWs lm_ws_carve(void* ws, int B) {
   char* p = reinterpret_cast<char*>(ws);
   const size_t part = (size_t)B * kLmMaxCtasPerSample * kLmAcc * sizeof(double);
   const size_t tick = ((size_t)B * sizeof(uint32_t) + 255) / 256 * 256;
+  const size_t step = 1024;
+  static_assert(kLmChainMaxSteps * 8 <= step, "step words");
   w.partial = reinterpret_cast<double*>(p);
   w.ticket = reinterpret_cast<uint32_t*>(p + part);
-  w.step_word = reinterpret_cast<unsigned long long*>(p + part + tick);
-  w.zeros = reinterpret_cast<const float4*>(p + part + tick + 256);
-  w.gg = reinterpret_cast<double*>(p + part + tick + 256 + kLmZeroBytes);
-  w.clear_words = (tick + 256 + kLmZeroBytes) / 4;
+  w.done = reinterpret_cast<int*>(p + part + tick);
+  w.step_word = reinterpret_cast<unsigned long long*>(p + part + 2 * tick);
+  w.zeros = reinterpret_cast<const float4*>(p + part + 2 * tick + step);
+  w.gg = reinterpret_cast<double*>(p + part + 2 * tick + step + kLmZeroBytes);
+  w.clear_words = (2 * tick + step + kLmZeroBytes) / 4;
   const size_t gg = (size_t)HA_MAX_LEVELS * B * sizeof(double);
-  w.adam_mv = reinterpret_cast<float*>(p + part + tick + 256 + kLmZeroBytes + gg);     // [B][6], HA_OPT_ADAM only
-  w.total = part + tick + 256 + kLmZeroBytes + gg + (size_t)B * 6 * sizeof(float);
+  w.adam_mv = reinterpret_cast<float*>(p + part + 2 * tick + step + kLmZeroBytes + gg);     // [B][6], HA_OPT_ADAM only
+  w.total = part + 2 * tick + step + kLmZeroBytes + gg + (size_t)B * 6 * sizeof(float);
   return w;
 }
 static size_t lm_ws_bytes(int B) { return lm_ws_carve(nullptr, B).total; }
@@ -826,21 +932,18 @@ static int choose_px_per_cta(int B, int P, int resident_per_sm) {
   return best_upc * unit;
 }
 
-static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, const HaLevel* grd, const float* grd_conf,
+// Validates one (level, step) and fills its argument block and grid; shared by the per-step launches and the loop kernel.
+static int lm_step_args(const HaLmParams* p, int level, const HaLevel* sat, const HaLevel* grd, const float* grd_conf,
                         const float* ground_table, const float* extrinsics, float* pose, const float* reset_uv,
                         float* stats, float* traj_step, int traj_stride, uint32_t* status, void* ws, size_t ws_bytes,
-                        int B, bool full, int iter, cudaStream_t st) {
+                        int B, int iter, int chain_step, LmStepArgs& a, dim3& grid) {
   const bool g2sp_nn = p && p->geometry == HA_GEOM_G2SP_NN;
   const bool g2sp = p && (p->geometry == HA_GEOM_G2SP || g2sp_nn);
   if (!p || !sat || !grd || !pose || !status || !ws || (!ground_table && !g2sp)) return HA_EINVAL;
   if (level < 0 || level >= HA_MAX_LEVELS) return HA_EINVAL;
   if (sat->C != grd->C || sat->H != sat->W || (grd->H & 1)) return HA_EINVAL;
   if (p->dof < 1 || p->dof > 3) return HA_EINVAL;
-#ifdef HA_LM_DEV_VARIANTS
-  if (p->kernel_variant < 0 || p->kernel_variant > 4 || p->reserved != 0) return HA_EINVAL;
-#else
-  if (p->kernel_variant < 0 || p->kernel_variant > 1 || p->reserved != 0) return HA_EINVAL;
-#endif
+  if (p->kernel_variant < 0 || p->kernel_variant > 2 || p->reserved != 0) return HA_EINVAL;
   if (p->optimizer < HA_OPT_LM || p->optimizer > HA_OPT_GN || (p->full_height != 0 && p->full_height != 1)) return HA_EINVAL;
   const bool first_order = p->optimizer == HA_OPT_SGD || p->optimizer == HA_OPT_ADAM;
   // the ablation update rules exist for the models that define them: SGD / ADAM in LM_S2GP, GN in LM_S2GP_Ford; they
@@ -858,13 +961,17 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   if (((uintptr_t)sat->data | (uintptr_t)grd->data | (uintptr_t)ground_table) & 15) return HA_EINVAL;
   if (sat->H * sat->W >= (1 << 24) || grd->H * grd->W >= (1 << 24)) return HA_EINVAL;
 
-  LmStepArgs a;
+  a = LmStepArgs{};
   a.sat = sat->data; a.grd = grd->data; a.sat_scale = sat->scale; a.grd_scale = grd->scale;
   a.conf = grd_conf; a.table = reinterpret_cast<const float4*>(ground_table); a.extr = extrinsics;
   a.pose = pose; a.reset_uv = reset_uv; a.stats = stats; a.traj = traj_step; a.traj_stride = traj_stride;
   a.status = status;
   const LmWs w = lm_ws_carve(ws, B);
-  a.partial = w.partial; a.ticket = w.ticket; a.step_word = w.step_word; a.zeros = w.zeros;
+  a.partial = w.partial; a.ticket = w.ticket; a.zeros = w.zeros;
+  // chained run (ha_lm_run): the steps overlap, so each has its own arrival word and waits on the samples' done flags
+  a.step_word = w.step_word + (chain_step >= 0 ? chain_step : 0);
+  a.done = chain_step >= 0 ? w.done : nullptr;
+  a.step_index = chain_step >= 0 ? chain_step : 0;
   a.gg_cache = w.gg + (size_t)level * B;
   a.B = B; a.A = sat->H; a.H = grd->H; a.W = grd->W;
   a.dof = p->dof; a.using_weight = p->using_weight; a.use_hessian = p->use_hessian;
@@ -882,7 +989,21 @@ static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, cons
   const int P = g2sp ? sat->H * sat->W : (grd->H - a.row0) * grd->W;
   // resident CTAs per SM: 3 for the v4 kernel (160 registers, ring), HA_LM_MIN_CTAS for the register-staged kernel
   a.px_per_cta = choose_px_per_cta(B, P, (g2sp || p->kernel_variant == 1) ? HA_LM_MIN_CTAS : 3);
-  dim3 grid((P + a.px_per_cta - 1) / a.px_per_cta, B);
+  a.grd_C = grd->C;
+  grid = dim3((P + a.px_per_cta - 1) / a.px_per_cta, B);
+  return HA_OK;
+}
+
+static int lm_step_impl(const HaLmParams* p, int level, const HaLevel* sat, const HaLevel* grd, const float* grd_conf,
+                        const float* ground_table, const float* extrinsics, float* pose, const float* reset_uv,
+                        float* stats, float* traj_step, int traj_stride, uint32_t* status, void* ws, size_t ws_bytes,
+                        int B, bool full, int iter, int chain_step, cudaStream_t st) {
+  LmStepArgs a;
+  dim3 grid;
+  const int rc = lm_step_args(p, level, sat, grd, grd_conf, ground_table, extrinsics, pose, reset_uv, stats, traj_step,
+                              traj_stride, status, ws, ws_bytes, B, iter, chain_step, a, grid);
+  if (rc != HA_OK) return rc;
+  const bool g2sp = p->geometry == HA_GEOM_G2SP || p->geometry == HA_GEOM_G2SP_NN;
   if (p->geometry == HA_GEOM_KITTI)
     return full ? launch_by_channels<HA_GEOM_KITTI, true>(grd->C, grid, st, a) : launch_by_channels<HA_GEOM_KITTI, false>(grd->C, grid, st, a);
   if (p->geometry == HA_GEOM_FORD)
@@ -1025,7 +1146,7 @@ extern "C" int ha_lm_step(const HaLmParams* p, int level, const HaLevel* sat, co
   if (ws_bytes < ha::lm_ws_bytes(B)) return HA_ENOSPACE;
   ha::lm_begin(ws, B, status, st);        // tickets / step word / zero vector / *status start at zero (cheap, async)
   return ha::lm_step_impl(p, level, sat, grd, grd_conf, ground_table, extrinsics, pose, reset_uv, stats, nullptr, 0,
-                          status, ws, ws_bytes, B, /*full=*/true, p->adam_iter, st);
+                          status, ws, ws_bytes, B, /*full=*/true, p->adam_iter, /*chain_step=*/-1, st);
 }
 
 extern "C" int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel* grd, const float* const* grd_conf,
@@ -1038,6 +1159,9 @@ extern "C" int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel*
   if (ws_bytes < ha::lm_ws_bytes(B)) return HA_ENOSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ha::lm_begin(ws, B, status, st);
+  // the default step kernel of the S2GP geometries chains its launches (lm_chain_enter): one arrival word per step
+  const bool chain = p->kernel_variant == 0 && (p->geometry == HA_GEOM_KITTI || p->geometry == HA_GEOM_FORD) &&
+                     (long long)N * L <= ha::kLmChainMaxSteps;
   int k = 0;
   const int outer = p->level_first ? L : N, inner = p->level_first ? N : L;
   for (int o = 0; o < outer; ++o) {
@@ -1049,7 +1173,7 @@ extern "C" int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel*
       // the first visit of a level also reduces |g|^2 (pose independent) and caches it; later visits skip it
       const bool full = (it == 0) || stats != nullptr;
       int rc = ha::lm_step_impl(p, lv, sat + lv, grd + lv, grd_conf ? grd_conf[lv] : nullptr, ground_tables[lv],
-                                extrinsics, pose, ruv, stp, tr, N * L * 3, status, ws, ws_bytes, B, full, it, st);
+                                extrinsics, pose, ruv, stp, tr, N * L * 3, status, ws, ws_bytes, B, full, it, chain ? k : -1, st);
       if (rc != HA_OK) return rc;
     }
   }

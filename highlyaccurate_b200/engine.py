@@ -147,7 +147,8 @@ class LmSetup:
     rotation_range: float
     shift_range_lat: float
     shift_range_lon: float
-    kernel_variant: int = 0    # HaLmParams.kernel_variant: 0 = default kernels, 1 = register-staged validation kernel
+    kernel_variant: int = 0    # HaLmParams.kernel_variant: 0 = default kernels (lm_run chains its step launches), 1 = register-staged
+                               # validation kernel, 2 = default kernel with plain stream-ordered launches
     optimizer: str = "LM"      # args.Optimizer: 'LM' | 'SGD' | 'ADAM' (LM_S2GP) | 'GN' (LM_S2GP_Ford)
     full_height: int = 0       # 1: residual over the whole ground image (args.proj != 'geo', models_kitti.py:1200-1205)
     adam_level_mult: int = 0   # args.level: the reference's Adam step count is iter * args.level + level (:1241)
@@ -318,6 +319,9 @@ def check_status(status: torch.Tensor, where: str = "LM loop") -> int:
     if bits & _lib.HA_STATUS_NO_INRANGE:
         raise LmStatusError("%s: no sample point of the batch lands inside the satellite map (jacobian.py:172 asserts "
                             "torch.sum(mask) > 0)" % where)
+    if bits & _lib.HA_STATUS_TIMEOUT:
+        # the chained step launches of ha_lm_run gave up waiting for a sample's previous step: the poses are invalid
+        raise RuntimeError("%s: a step of the chained LM loop timed out waiting for its predecessor (HA_STATUS_TIMEOUT)" % where)
     if bits & _lib.HA_STATUS_NAN_POSE:
         print('theta_new is nan')               # models_kitti.py:1037-1039 prints and carries on
     return bits

@@ -2,7 +2,8 @@
 """Micro-benchmark of the fused LM step per pyramid level (random features, B pairs, KITTI shapes).
     python tools/bench_lm.py [B] [reps] [levels] [variants, e.g. 0,1,2]
 Prints per-level time, algorithmic GB/s and fraction of the measured HBM peak for every kernel variant
-(HaLmParams.kernel_variant: 0 = default ring kernel, 1 = register-staged validation kernel)."""
+(HaLmParams.kernel_variant: 0 = default ring kernel, whole loop with chained launches; 1 = register-staged validation
+kernel; 2 = default kernel, whole loop with plain stream-ordered launches)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -55,16 +56,18 @@ for variant in VARIANTS:
               % (lv, PYR_C[lv], t, byt / t / 1e3, byt / t / 1e3 / pk["hbm"], pk["src"]))
 
     # whole loop (5 iterations x L levels): exercises the cached-|g|^2 (FAST) launches too
+    kv = {} if variant is None else {"kernel_variant": variant}
     for _ in range(2):
-        res = net.refine(sat, grd, reset_uv=torch.zeros(5 * L, 2, B))
+        res = net.refine(sat, grd, reset_uv=torch.zeros(5 * L, 2, B), **kv)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     draws = torch.zeros(5 * L, 2, B, device=dev)
     e0.record()
     for _ in range(reps):
-        res = net.refine(sat, grd, reset_uv=draws)
+        res = net.refine(sat, grd, reset_uv=draws, **kv)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     byt = sum(4 * PYR_C[l] * (((256 >> (3 - l)) // 2) * (1024 >> (3 - l)) + SAT_TEXELS_TOUCHED[l]) for l in range(L)) * 5 * B
-    print("whole LM loop (5 iters x %d levels, B=%d): %.3f ms  -> %.1f GB/s algorithmic = %.3f of HBM peak" % (L, B, ms, byt / ms / 1e6, byt / ms / 1e6 / pk["hbm"]))
+    print("whole LM loop (5 iters x %d levels, B=%d): %.3f ms  -> %.1f GB/s algorithmic = %.3f of HBM peak  (status %d)"
+          % (L, B, ms, byt / ms / 1e6, byt / ms / 1e6 / pk["hbm"], int(res.status.item())))

@@ -74,8 +74,8 @@ while [ $# -gt 0 ]; do
         --clock-control none -k regex:conv3x3 --csv --log-file $OUT/convab_$TAG.csv python tools/bench_conv.py 32 1 > $OUT/convab_$TAG.log 2>&1
       python tools/convab_report.py $OUT/convab_$TAG.csv ;;
     lm_ab)
-      timeout 400 python tools/bench_lm.py 256 10 3 0,1 > $OUT/bench_lm_b256_$TAG.log 2>&1
-      timeout 400 python tools/bench_lm.py 32 20 3 0 > $OUT/bench_lm_b32_$TAG.log 2>&1
+      timeout 400 python tools/bench_lm.py 256 10 3 0,2 > $OUT/bench_lm_b256_$TAG.log 2>&1
+      timeout 400 python tools/bench_lm.py 32 20 3 0,2 > $OUT/bench_lm_b32_$TAG.log 2>&1
       grep -h "variant\|level\|whole" $OUT/bench_lm_b256_$TAG.log $OUT/bench_lm_b32_$TAG.log | cut -c1-200 ;;
     pipeline)        # input pipeline on the GPU vs PIL on the host, plus its ncu launch list
       timeout 300 python tools/bench_input_pipeline.py 32 20 8 > $OUT/pipeline_$TAG.json 2> $OUT/pipeline_$TAG.err
