@@ -480,7 +480,13 @@ constexpr int kLmRecBytes = 48;      // per-pixel record: (wx, ny, tx, ty) | (&n
 // 128 B (C = 16: of 64 B), so the lanes of a wavefront hit the same banks (ncu, C = 64: 17 M bank conflicts per launch,
 // 8 wavefronts per LDS.128 instead of 4).  The chunk is therefore copied as NS sub-copies, sub-copy j shifted by j * C
 // bytes, and a quarter-warp takes its pixels from all NS sub-copies: every wavefront covers 128 distinct bytes mod 128.
-template <int C> constexpr int lm_ring_ns() { return C > 64 ? 1 : (C == 64 ? 2 : 4); }
+// Measured on B200 (C = 64, B = 256): the conflicts disappear but the launch is 4 % SLOWER (763 vs 734 us) — the kernel is
+// bound by per-warp latency, not by the shared-memory pipe, and the elected lane now issues two copies per chunk.  The
+// split therefore stays off (HA_LM_RING_SPLIT = 1 builds it).
+#ifndef HA_LM_RING_SPLIT
+#define HA_LM_RING_SPLIT 0
+#endif
+template <int C> constexpr int lm_ring_ns() { return !HA_LM_RING_SPLIT || C > 64 ? 1 : (C == 64 ? 2 : 4); }
 constexpr int kLmSlotBytes = kLmIterBytes + 128;          // room for the (NS - 1) * C <= 96 bytes of shift, 128-byte aligned
 
 template <int NSLOT>
@@ -915,7 +921,13 @@ static size_t lm_ws_bytes(int B) { return lm_ws_carve(nullptr, B).total; }
 // The grid runs in rounds of `slots` = 148 SMs x resident CTAs, and a launch costs about rounds x (units per CTA + a fixed
 // per-CTA overhead): B200, B = 256 showed 3.46 / 4.04 / 4.04 waves with the old "about 12 CTAs per SM" rule, i.e. a fifth
 // round that was 4 % full (profiles/r02_lm_full.csv: launch__waves_per_multiprocessor).  Pick the split that minimises that cost.
-static int choose_px_per_cta(int B, int P, int resident_per_sm) {
+//
+// Chained launches (ha_lm_run) have no rounds: the next step's CTAs fill the slots as they free up.  A step then costs
+// the larger of (a) the sample's critical path, one CTA share plus the fixed latency between two steps of a sample
+// (reduction, ticket, solve, release / acquire, prologue, first ring fill: ~10 us = 4.3 units at 2.3 us per unit), and
+// (b) the machine's throughput, all CTAs of the step times (share + the ~1.7 units a CTA is busy outside its pixel
+// loop) over the slots.  B = 32 was bound by (a) with 13 CTAs per sample (0.97 ms for 15 steps, chained or not).
+static int choose_px_per_cta(int B, int P, int resident_per_sm, bool chained) {
   const int unit = kLmWarps * 32;
   const int units = (P + unit - 1) / unit;                     // whole-CTA units in one sample
   const long long slots = (long long)kNumSMs * resident_per_sm;
@@ -928,6 +940,18 @@ static int choose_px_per_cta(int B, int P, int resident_per_sm) {
     const long long rounds = (total + slots - 1) / slots;
     const double cost = (double)rounds * ((double)upc + 0.5);   // 0.5 unit: prologue (barriers, pose constants) + reduction tail
     if (cost < best_cost - 1e-9) { best_cost = cost; best_upc = upc; }
+  }
+  if (chained) {
+    // never coarser than the per-step choice (the end of the run is still a tail of whole CTA shares)
+    const int cap = best_upc;
+    best_cost = 1e300;
+    for (int upc = 1; upc <= cap; ++upc) {
+      const int n = (units + upc - 1) / upc;
+      if (n > kLmMaxCtasPerSample) continue;
+      const double critical = (double)upc + 4.3, throughput = (double)n * B * ((double)upc + 1.7) / (double)slots;
+      const double cost = critical > throughput ? critical : throughput;
+      if (cost < best_cost - 1e-9) { best_cost = cost; best_upc = upc; }
+    }
   }
   return best_upc * unit;
 }
@@ -988,7 +1012,7 @@ static int lm_step_args(const HaLmParams* p, int level, const HaLevel* sat, cons
   a.g2sp_nn = g2sp_nn ? 1 : 0;
   const int P = g2sp ? sat->H * sat->W : (grd->H - a.row0) * grd->W;
   // resident CTAs per SM: 3 for the v4 kernel (160 registers, ring), HA_LM_MIN_CTAS for the register-staged kernel
-  a.px_per_cta = choose_px_per_cta(B, P, (g2sp || p->kernel_variant == 1) ? HA_LM_MIN_CTAS : 3);
+  a.px_per_cta = choose_px_per_cta(B, P, (g2sp || p->kernel_variant == 1) ? HA_LM_MIN_CTAS : 3, chain_step >= 0);
   a.grd_C = grd->C;
   grid = dim3((P + a.px_per_cta - 1) / a.px_per_cta, B);
   return HA_OK;
