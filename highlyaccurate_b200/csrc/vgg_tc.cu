@@ -1085,24 +1085,28 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const float* __restrict__
 // utilisation) although its real floor is the 2.1 GB it writes (0.35 ms).  Here the contraction runs on tcgen05 like
 // every other layer: K = 27 im2col values per pixel (padded to 32 = two K = 16 steps), f16x3 split of image and
 // weights, M = 128 consecutive pixels of one image row per tile.  Nothing is staged in global memory:
-//   warps 0 and 3 (64 threads, two pixels each) read the 3 x 3 x 3 neighbourhood straight from the fp32 image, split it
-//     into fp16 hi / lo and write the pixel's K-major row into the SWIZZLE_128B operand tiles (generic stores +
-//     fence.proxy.async, then an arrive on the tile's `full` barrier);
-//   warp 1 issues A_hi x [B_hi | B_lo] (N = 128) and A_lo x B_hi (N = 64) for the two K steps; the 16 KB weight tile
-//     is built once per CTA;
-//   warps 4-7 read the three accumulators of their TMEM lane quarter, add bias, ReLU, split, park each pixel's
-//     256-byte record [hi 64 | lo 64] in a warp-private XOR-swizzled staging tile and write whole records, 512
-//     contiguous bytes per store instruction.
+//   warps 0-3 (128 threads, one pixel each, one warp per SM sub-partition) read the 3 x 3 x 3 neighbourhood straight
+//     from the fp32 image, split it into fp16 hi / lo and write the pixel's K-major row into the SWIZZLE_128B operand
+//     tiles (generic stores + fence.proxy.async, then an arrive on the tile's `full` barrier).  The image loads of the
+//     tiles one and two ahead are in flight meanwhile (three register buffers): under the kernel's own 3 TB/s of
+//     writes a load takes longer than a tile (ncu: with one tile of lead the epilogue warps starved, 695-870 us).
+//   warp 12 allocates TMEM and issues A_hi x [B_hi | B_lo] (N = 128) and A_lo x B_hi (N = 64) for the two K steps; the
+//     16 KB weight tile is built once per CTA;
+//   warps 4-11 are the epilogue, two per TMEM lane quarter (channels 0-31 and 32-63: one warp per quarter was the
+//     critical path, ~600 dependent instructions per tile): the three accumulators -> bias, ReLU, split -> the pixel's
+//     [hi 64 B | lo 64 B] half-record in a warp-private XOR-swizzled staging tile -> global, 64-byte segments that the
+//     sibling warp completes to whole 128-byte lines in L2.
 // The earlier tensor-core attempt (an im2col tensor in global memory + the generic 1 x 1 kernel) lost to the CUDA-core
 // kernel on exactly those two points: the extra round trip of the im2col tensor and 64-byte store segments.
 constexpr int kC0tTile = 128;                            // pixels per tile = UMMA M
 constexpr int kC0tABytes = kC0tTile * 128;               // one operand plane of a tile: 128 rows x 128 B
 constexpr int kC0tBBytes = 2 * 64 * 128;                 // [B_hi 64 rows | B_lo 64 rows] x 128 B
-constexpr int kC0tStaging = 4 * 32 * 256;                // 32 pixel records of 256 B per epilogue warp
-constexpr int kC0tProducers = 64;
+constexpr int kC0tStaging = 8 * 32 * 128;                // 32 pixel half-records of 128 B per epilogue warp
+constexpr int kC0tProducers = 128;
+constexpr int kC0tThreads = 13 * 32;                     // 4 producer warps, 8 epilogue warps, the MMA warp
 constexpr int kC0tSmem = 1024 + 2 * 2 * kC0tABytes + kC0tBBytes + kC0tStaging + 256 /*barriers*/ + 256 /*bias*/;
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kC0tThreads, 1)
 conv0_tc_kernel(const float* __restrict__ img, const float* __restrict__ w /*[27][64]*/, const float* __restrict__ bias,
                 __half* __restrict__ out, int B, int H, int W) {
   extern __shared__ uint8_t smem_raw[];
@@ -1120,28 +1124,30 @@ conv0_tc_kernel(const float* __restrict__ img, const float* __restrict__ w /*[27
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_x = W / kC0tTile, n_tiles = B * H * tiles_x;
-  if (warp == 1 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(a_full + s, kC0tProducers); mbar_init(a_empty + s, 1);
-      mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4);
+      mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 8);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc_512(tmem_slot);
+  if (warp == 12) tmem_alloc_512(tmem_slot);
   {
     // weight tile: row n = output channel, 32 K values (k = tap * 3 + c, zero from 27 on) = four 16-byte chunks at
     // (chunk ^ (n & 7)) of the 128-byte row; thread = (n, chunk)
-    const int n = threadIdx.x & 63, j = threadIdx.x >> 6;
-    uint32_t hi[4], lo[4];
+    if (threadIdx.x < 256) {
+      const int n = threadIdx.x & 63, j = threadIdx.x >> 6;
+      uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int k0 = j * 8 + 2 * e;
-      const float v0 = k0 < 27 ? __ldg(w + k0 * 64 + n) : 0.f, v1 = k0 + 1 < 27 ? __ldg(w + (k0 + 1) * 64 + n) : 0.f;
-      split2(v0, v1, hi[e], lo[e]);
+      for (int e = 0; e < 4; ++e) {
+        const int k0 = j * 8 + 2 * e;
+        const float v0 = k0 < 27 ? __ldg(w + k0 * 64 + n) : 0.f, v1 = k0 + 1 < 27 ? __ldg(w + (k0 + 1) * 64 + n) : 0.f;
+        split2(v0, v1, hi[e], lo[e]);
+      }
+      const uint32_t row = smem_u32(smem_b) + n * 128 + ((j ^ (n & 7)) << 4);
+      st_shared_v4(row, hi[0], hi[1], hi[2], hi[3]);
+      st_shared_v4(row + 64 * 128, lo[0], lo[1], lo[2], lo[3]);
     }
-    const uint32_t row = smem_u32(smem_b) + n * 128 + ((j ^ (n & 7)) << 4);
-    st_shared_v4(row, hi[0], hi[1], hi[2], hi[3]);
-    st_shared_v4(row + 64 * 128, lo[0], lo[1], lo[2], lo[3]);
     if (threadIdx.x < 64) bias_s[threadIdx.x] = bias[threadIdx.x];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic stores -> the MMA's (async proxy) reads
   }
@@ -1150,65 +1156,63 @@ conv0_tc_kernel(const float* __restrict__ img, const float* __restrict__ w /*[27
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 || warp == 3) {
+  if (warp < 4) {
     // ===================== im2col producers =====================
-    const int pt = (warp == 3 ? 32 : 0) + lane;                      // this thread's pixels of a tile: pt and pt + 64
-    auto load_tile = [&](int tile, float (&v)[2][27]) {
+    const int m = threadIdx.x;                                       // this thread's pixel of every tile
+    auto load_tile = [&](int tile, float (&v)[27]) {
+      if (tile >= n_tiles) return;
       const int xt = tile % tiles_x; int r = tile / tiles_x;
       const int y = r % H, b = r / H;
       const float* base = img + (size_t)b * 3 * H * W;
+      const int x = xt * kC0tTile + m;
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const int x = xt * kC0tTile + pt + p * 64;
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        const bool yok = yy >= 0 && yy < H;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int yy = y + ky - 1;
-          const bool yok = yy >= 0 && yy < H;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = x + kx - 1;
+          const bool ok = yok && xx >= 0 && xx < W;
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int xx = x + kx - 1;
-            const bool ok = yok && xx >= 0 && xx < W;
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-              v[p][(ky * 3 + kx) * 3 + c] = ok ? __ldg(base + ((size_t)c * H + yy) * W + xx) : 0.f;
-          }
+          for (int c = 0; c < 3; ++c)
+            v[(ky * 3 + kx) * 3 + c] = ok ? __ldg(base + ((size_t)c * H + yy) * W + xx) : 0.f;
         }
       }
     };
-    float cur[2][27], nxt[2][27];
     int sa = 0; uint32_t pa = 0;
-    if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x, cur);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int tn = tile + gridDim.x;
-      if (tn < n_tiles) load_tile(tn, nxt);                          // the next tile's loads fly while this one is converted
+    auto put_tile = [&](const float (&cur)[27]) {                    // split + store this thread's row of the operand tiles
       mbar_wait(a_empty + sa, pa ^ 1);
-      const uint32_t a_hi = smem_u32(smem_a) + sa * 2 * kC0tABytes;
+      const uint32_t row = smem_u32(smem_a) + sa * 2 * kC0tABytes + m * 128;
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const int m = pt + p * 64;
-        const uint32_t row = a_hi + m * 128;
+      for (int j = 0; j < 4; ++j) {
+        uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int k0 = j * 8 + 2 * e;
-            split2(k0 < 27 ? cur[p][k0 < 27 ? k0 : 0] : 0.f, k0 + 1 < 27 ? cur[p][k0 + 1 < 27 ? k0 + 1 : 0] : 0.f, hi[e], lo[e]);
-          }
-          const uint32_t off = (uint32_t)((j ^ (m & 7)) << 4);
-          st_shared_v4(row + off, hi[0], hi[1], hi[2], hi[3]);
-          st_shared_v4(row + kC0tABytes + off, lo[0], lo[1], lo[2], lo[3]);
+        for (int e = 0; e < 4; ++e) {
+          const int k0 = j * 8 + 2 * e;
+          split2(k0 < 27 ? cur[k0 < 27 ? k0 : 0] : 0.f, k0 + 1 < 27 ? cur[k0 + 1 < 27 ? k0 + 1 : 0] : 0.f, hi[e], lo[e]);
         }
+        const uint32_t off = (uint32_t)((j ^ (m & 7)) << 4);
+        st_shared_v4(row + off, hi[0], hi[1], hi[2], hi[3]);
+        st_shared_v4(row + kC0tABytes + off, lo[0], lo[1], lo[2], lo[3]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(a_full + sa);
       if (++sa == 2) { sa = 0; pa ^= 1; }
-#pragma unroll
-      for (int p = 0; p < 2; ++p)
-#pragma unroll
-        for (int k = 0; k < 27; ++k) cur[p][k] = nxt[p][k];
+    };
+    // three register buffers rotate statically (the loop body handles three tiles): a tile's loads are issued two
+    // tiles before its values are converted
+    float t0[27], t1[27], t2[27];
+    const int step = gridDim.x;
+    int tile = blockIdx.x;
+    load_tile(tile, t0); load_tile(tile + step, t1);
+    while (tile < n_tiles) {
+      load_tile(tile + 2 * step, t2); put_tile(t0); tile += step;
+      if (tile >= n_tiles) break;
+      load_tile(tile + 2 * step, t0); put_tile(t1); tile += step;
+      if (tile >= n_tiles) break;
+      load_tile(tile + 2 * step, t1); put_tile(t2); tile += step;
     }
-  } else if (warp == 1) {
+  } else if (warp == 12) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_n128 = umma_idesc_f16(128);             // A_hi x [B_hi | B_lo]
     constexpr uint32_t idesc_n64 = umma_idesc_f16(64);               // A_lo x B_hi
@@ -1234,22 +1238,25 @@ conv0_tc_kernel(const float* __restrict__ img, const float* __restrict__ w /*[27
       __syncwarp();
       if (++sa == 2) { sa = 0; pa ^= 1; }
     }
-  } else if (warp >= 4) {
+  } else {
     // ===================== epilogue =====================
     const int q = warp & 3;                                          // TMEM lane quarter = pixels [32 q, 32 q + 32) of the tile
-    const uint32_t stg = smem_u32(staging) + q * (32 * 256);
+    const int c0 = warp >= 8 ? 32 : 0;                               // this warp's 32 output channels
+    const uint32_t stg = smem_u32(staging) + (warp - 4) * (32 * 128);
     int t = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int as = t & 1; const uint32_t aphase = (t >> 1) & 1;
       mbar_wait(tmem_full + as, aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
-      const uint32_t rec = stg + lane * 256;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
+      const uint32_t rec = stg + lane * 128;
+      {
         uint32_t r0[32], r1[32], r2[32];
         tmem_ld_x32(taddr + c0, r0); tmem_ld_x32(taddr + 64 + c0, r1); tmem_ld_x32(taddr + 128 + c0, r2);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + as);                 // the accumulators are in registers: the next tile's MMAs may run
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                                // 8 channels = one 16-byte piece of hi and of lo
           uint32_t hi[4], lo[4];
@@ -1260,23 +1267,20 @@ conv0_tc_kernel(const float* __restrict__ img, const float* __restrict__ w /*[27
             const float v1 = fmaf(__uint_as_float(r1[i0 + 1]) + __uint_as_float(r2[i0 + 1]), kLoInvScale, __uint_as_float(r0[i0 + 1])) + bias_s[c0 + i0 + 1];
             split2(fmaxf(v0, 0.f), fmaxf(v1, 0.f), hi[e], lo[e]);
           }
-          const uint32_t off = (uint32_t)((((c0 >> 3) + j) ^ (lane & 7)) << 4);
-          st_shared_v4(rec + off, hi[0], hi[1], hi[2], hi[3]);
-          st_shared_v4(rec + 128 + off, lo[0], lo[1], lo[2], lo[3]);
+          st_shared_v4(rec + ((j ^ (lane & 7)) << 4), hi[0], hi[1], hi[2], hi[3]);
+          st_shared_v4(rec + (((j + 4) ^ (lane & 7)) << 4), lo[0], lo[1], lo[2], lo[3]);
         }
       }
-      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + as);                   // the accumulators are free: the next tile's MMAs may run
-      // write-out: the tile's pixels are consecutive in memory, a warp instruction stores two whole records (512 B)
+      // write-out: four pixels per store instruction, each a 64-byte hi and a 64-byte lo segment of its record
       {
-        const int half_px = lane >> 4, piece = lane & 15;            // piece 0-7: hi, 8-15: lo
-        __half* gp = out + ((size_t)tile * kC0tTile + q * 32 + half_px) * 128 + piece * 8;
+        const int sub = lane >> 3, piece = lane & 7;                 // piece 0-3: hi, 4-7: lo
+        __half* gp = out + ((size_t)tile * kC0tTile + q * 32 + sub) * 128 + (piece >> 2) * 64 + c0 + (piece & 3) * 8;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int px = 2 * i + half_px;
-          const uint4 d = ld_shared_v4(stg + px * 256 + (piece >> 3) * 128 + (((piece & 7) ^ (px & 7)) << 4));
-          *reinterpret_cast<uint4*>(gp + (size_t)i * 256) = d;
+        for (int i = 0; i < 8; ++i) {
+          const int px = 4 * i + sub;
+          const uint4 d = ld_shared_v4(stg + px * 128 + ((piece ^ (px & 7)) << 4));
+          *reinterpret_cast<uint4*>(gp + (size_t)i * 512) = d;
         }
       }
       __syncwarp();                                                  // staging is rewritten by the next tile
@@ -1284,7 +1288,7 @@ conv0_tc_kernel(const float* __restrict__ img, const float* __restrict__ w /*[27
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc_512(tmem_base); }
+  if (warp == 12) { tc_fence_after(); tmem_dealloc_512(tmem_base); }
 }
 
 // fp32 NHWC -> hi/lo activation planes (used by ha_conv3x3_nhwc, the single-layer test entry)
@@ -1605,7 +1609,7 @@ int vgg_forward_tc(const char* packed, const PackedLayout& L, const float* img, 
     static std::atomic<unsigned long long> c0t_configured{0};
     if (int rc0 = set_smem_once(conv0_tc_kernel, kC0tSmem, c0t_configured)) return rc0;
     const long long n_tiles = (long long)B * H * (W / kC0tTile);
-    conv0_tc_kernel<<<(int)std::min<long long>(n_tiles, kNumSMs), kTcThreads, kC0tSmem, st>>>(img, w0, b0, a1, B, H, W);
+    conv0_tc_kernel<<<(int)std::min<long long>(n_tiles, kNumSMs), kC0tThreads, kC0tSmem, st>>>(img, w0, b0, a1, B, H, W);
     count_launches(1);
     HA_TRY(check_launch("conv0_tc_kernel"));
   } else {
