@@ -525,7 +525,7 @@ __device__ __forceinline__ void lm_v4_body(const LmStepArgs& a, const int b, con
   constexpr int PPS = PPW / NS;                    // pixels per sub-copy
   static_assert(C % 16 == 0 && LPP >= 1 && LPP <= 32 && PPW * LPP == 32, "channel count");
   static_assert(GEOM != HA_GEOM_G2SP, "G2SP streams only the visible satellite pixels: it stays on lm_step_kernel");
-  static_assert(4 * C <= 1024, "zero vectors cover four channel quarters");
+  static_assert(8 * C <= kLmZeroBytes, "the global zero vector covers two texels (west + east taps), the shared one a ground pixel");
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cl = lane % LPP;                       // channel lane
@@ -664,7 +664,7 @@ __device__ __forceinline__ void lm_v4_body(const LmStepArgs& a, const int b, con
   uint32_t slot = 0, parity = 0;                   // ring slot and mbarrier phase of the next pixel-iteration
   uint32_t ps_rd = ps_lane;                        // record of the next pixel-iteration
   uint32_t ps_cur = ps_lane;                       // record of the pixel-iteration whose loads were issued last
-  const char *p_nw = nullptr, *p_ne = nullptr, *p_sw = nullptr, *p_se = nullptr;   // this lane's 16 bytes of the four taps
+  const char *p_nw = nullptr, *p_sw = nullptr;     // this lane's 16 bytes of the north-west / south-west taps
   uint32_t g_addr = zero_lane;                     // this lane's 16 bytes of the ground vector (shared memory)
 
   float4 tab_next = make_float4(0.f, 0.f, 0.f, 0.f);   // table entry of this lane's pixel in the group phase A handles next
@@ -721,11 +721,12 @@ __device__ __forceinline__ void lm_v4_body(const LmStepArgs& a, const int b, con
       ps_rd = ps_lane;
     }
     uint64_t an, as_;
-    uint32_t east, has_g;
+    uint32_t has_g;
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(an), "=l"(as_) : "r"(ps_rd + 16));
-    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(east), "=r"(has_g) : "r"(ps_rd + 32));
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(has_g) : "r"(ps_rd + 36));
+    // the east taps sit one texel (4 C bytes) after the west ones: taps are read only when xe - xw == 1 (phase A), and
+    // the zero vector that stands in otherwise is two texels long, so east is an immediate offset, not a pointer
     p_nw = reinterpret_cast<const char*>(an) + cl16; p_sw = reinterpret_cast<const char*>(as_) + cl16;
-    p_ne = p_nw + east; p_se = p_sw + east;
     g_addr = has_g ? ring_lane + slot * kLmSlotBytes : zero_lane;  // masked ground pixels read zeros
     ps_cur = ps_rd;
     // advance to the pixel-iteration after this one
@@ -735,8 +736,8 @@ __device__ __forceinline__ void lm_v4_body(const LmStepArgs& a, const int b, con
   };
   auto load_quarter = [&](PixelLoads& L, int k) {  // k-th channel quarter: immediate offsets k * C bytes
     L.g = ld_ring(g_addr + k * C);
-    L.nw = ld_cached(reinterpret_cast<const float4*>(p_nw + k * C)); L.ne = ld_cached(reinterpret_cast<const float4*>(p_ne + k * C));
-    L.sw = ld_cached(reinterpret_cast<const float4*>(p_sw + k * C)); L.se = ld_cached(reinterpret_cast<const float4*>(p_se + k * C));
+    L.nw = ld_cached(reinterpret_cast<const float4*>(p_nw + k * C)); L.ne = ld_cached(reinterpret_cast<const float4*>(p_nw + k * C + 4 * C));
+    L.sw = ld_cached(reinterpret_cast<const float4*>(p_sw + k * C)); L.se = ld_cached(reinterpret_cast<const float4*>(p_sw + k * C + 4 * C));
   };
 
   // Software pipeline at quarter-pixel granularity (ping-pong buffers A / B): the five 128-bit loads of a quarter

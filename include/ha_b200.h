@@ -70,8 +70,8 @@ enum {
   HA_STATUS_RESET = 4u,      /* an out-of-range shift was re-drawn (models_kitti.py:1030)      */
   HA_STATUS_SAMPLE_EMPTY = 8u, /* some SAMPLE had no in-range point in some step (its H is 0 and
                                 its pose does not move; the reference carries on silently)     */
-  HA_STATUS_TIMEOUT = 16u    /* ha_lm_run's one-launch loop gave up waiting for a sample's previous step (never
-                                expected; the poses are then invalid).  No reference analogue.  */
+  HA_STATUS_TIMEOUT = 16u    /* a step of ha_lm_run's chained launches gave up waiting for a sample's previous step
+                                (never expected; the poses are then invalid).  No reference analogue.  */
 };
 
 /* One pyramid level of one branch. */
@@ -105,12 +105,12 @@ typedef struct {
   float sat_center[HA_MAX_LEVELS];      /* A/2 (KITTI) or A//2 (Ford, G2SP)                  */
   int32_t ori_grd_h, ori_grd_w;         /* G2SP: size of the ground image `left_camera_k` refers to
                                            (models_kitti.py:111-114); ignored otherwise              */
-  int32_t kernel_variant;               /* 0 = default kernels (ha_lm_run: the whole loop in ONE persistent launch when the
-                                           pyramid's channel counts are 256 / 128 / 64 / 16, else one launch per step);
-                                           1 = register-staged validation kernel for the S2GP geometries (same algorithm,
-                                           other schedule); 2 = the default step kernel with one launch per step also in
-                                           ha_lm_run.  The parity tests hold all three to the same bar.  No reference
-                                           analogue.                                                    */
+  int32_t kernel_variant;               /* 0 = default kernels; ha_lm_run chains its step launches for the S2GP geometries
+                                           (programmatic stream serialization + per-sample flags: a sample's next step
+                                           starts as soon as ITS previous step is solved); 1 = register-staged validation
+                                           kernel for the S2GP geometries (same algorithm, other schedule); 2 = the
+                                           default step kernel with plain stream-ordered launches also in ha_lm_run.
+                                           The parity tests hold all three to the same bar.  No reference analogue.  */
   int32_t optimizer;                    /* HA_OPT_*: the update rule of a step (args.Optimizer)       */
   int32_t full_height;                  /* 0: residual over the bottom half of the ground image (args.proj == 'geo',
                                            models_kitti.py:1194-1199); 1: over the whole image (any other proj:
