@@ -22,6 +22,7 @@
 // ng = max(|g|,1e-6)  — identical to normalising s, J and g first (models_kitti.py:982-992).
 #include <math.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "lm_common.cuh"
@@ -923,11 +924,18 @@ static size_t lm_ws_bytes(int B) { return lm_ws_carve(nullptr, B).total; }
 // per-CTA overhead): B200, B = 256 showed 3.46 / 4.04 / 4.04 waves with the old "about 12 CTAs per SM" rule, i.e. a fifth
 // round that was 4 % full (profiles/r02_lm_full.csv: launch__waves_per_multiprocessor).  Pick the split that minimises that cost.
 //
-// Chained launches (ha_lm_run) have no rounds: the next step's CTAs fill the slots as they free up.  A step then costs
-// the larger of (a) the sample's critical path, one CTA share plus the fixed latency between two steps of a sample
-// (reduction, ticket, solve, release / acquire, prologue, first ring fill: ~10 us = 4.3 units at 2.3 us per unit), and
-// (b) the machine's throughput, all CTAs of the step times (share + the ~1.7 units a CTA is busy outside its pixel
-// loop) over the slots.  B = 32 was bound by (a) with 13 CTAs per sample (0.97 ms for 15 steps, chained or not).
+// Chained launches (ha_lm_run) have no rounds: the next step's CTAs fill the slots as they free up, and what counts is
+// (a) the sample's critical path (15 x (one CTA share + the fixed latency between two steps of a sample: reduction,
+// ticket, solve, release / acquire, prologue, first ring fill)), which small batches are bound by, against (b) the
+// per-CTA cost that fine splits multiply, the tail of one share at the end of the run, and L2: with few CTAs per
+// sample more samples are resident at once and their satellite footprints stop fitting.  Measured on B200 (whole
+// loop, KITTI pyramid, fraction of the HBM peak; shares in 128-pixel units at levels 0 / 1 / 2):
+//   B = 32 : (1,5,13) 0.533  (1,4,10) 0.562  (1,3,8) 0.570  (1,3,6) 0.567  (1,2,4) 0.546  (2,8,16) 0.422
+//   B = 64 : (1,5,13) 0.630  (1,4,10) 0.623  (1,3,8) 0.614  (4,11,16) 0.571  (8,32,32) 0.347
+//   B = 128: (4,8,22) 0.671  (4,11,16) 0.671  (4,11,32) 0.668  (2,5,10) 0.648  (8,32,32) 0.562
+//   B = 256: (8,32,32) 0.699  (8,32,52) 0.696  (8,32,64) 0.695  (4,32,37) 0.693  (8,32,16) 0.690  (2,13,10) 0.664
+//            (8,64,37) 0.613 and (16,32,37) 0.652: ONE CTA per sample at a level puts the whole share on the critical path
+// i.e. the best split keeps about 2.5 CTAs per slot in a step, at least two CTAs per sample, shares of at most 64 units.
 static int choose_px_per_cta(int B, int P, int resident_per_sm, bool chained) {
   const int unit = kLmWarps * 32;
   const int units = (P + unit - 1) / unit;                     // whole-CTA units in one sample
@@ -943,16 +951,9 @@ static int choose_px_per_cta(int B, int P, int resident_per_sm, bool chained) {
     if (cost < best_cost - 1e-9) { best_cost = cost; best_upc = upc; }
   }
   if (chained) {
-    // never coarser than the per-step choice (the end of the run is still a tail of whole CTA shares)
-    const int cap = best_upc;
-    best_cost = 1e300;
-    for (int upc = 1; upc <= cap; ++upc) {
-      const int n = (units + upc - 1) / upc;
-      if (n > kLmMaxCtasPerSample) continue;
-      const double critical = (double)upc + 4.3, throughput = (double)n * B * ((double)upc + 1.7) / (double)slots;
-      const double cost = critical > throughput ? critical : throughput;
-      if (cost < best_cost - 1e-9) { best_cost = cost; best_upc = upc; }
-    }
+    const long long n_target = std::max<long long>(2, (5 * slots / 2 + B - 1) / B);
+    best_upc = (int)std::min<long long>(64, std::max<long long>(1, (units + n_target - 1) / n_target));
+    while ((units + best_upc - 1) / best_upc > kLmMaxCtasPerSample) ++best_upc;
   }
   return best_upc * unit;
 }
