@@ -106,6 +106,17 @@ def test_status_word_follows_the_reference_error_convention(capsys):
         engine.check_status(torch.tensor([_lib.HA_STATUS_NO_INRANGE], dtype=torch.int32))
     engine.check_status(torch.tensor([_lib.HA_STATUS_NAN_POSE], dtype=torch.int32))
     assert "theta_new is nan" in capsys.readouterr().out
+    # a chained LM step that gave up waiting for its predecessor leaves invalid poses: never silent
+    with pytest.raises(RuntimeError):
+        engine.check_status(torch.tensor([_lib.HA_STATUS_TIMEOUT], dtype=torch.int32))
+
+
+def test_status_bits_match_the_header():
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "ha_b200.h")).read()
+    for name in ("NO_INRANGE", "NAN_POSE", "RESET", "SAMPLE_EMPTY", "TIMEOUT"):
+        m = re.search(r"HA_STATUS_%s\s*=\s*(\d+)u" % name, hdr)
+        assert m and int(m.group(1)) == getattr(_lib, "HA_STATUS_" + name), name
 
 
 def test_out_of_scope_flags_raise_at_construction():

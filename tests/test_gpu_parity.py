@@ -336,6 +336,25 @@ def test_end_to_end_g2sp_forward_vs_reference():
     np.testing.assert_allclose(traj[:, 0], ref_traj[:, 0], atol=5e-5)
 
 
+def test_conv0_tensor_core_path_vs_cuda_core_path():
+    """conv0 runs on tcgen05 (conv0_tc_kernel: in-kernel im2col, f16x3) in the split-operand modes and on the CUDA cores
+    (conv0_kernel, fp32) in the validation mode.  An input wide and tall enough that every CTA walks several tiles
+    (2 x 192 x 4 = 1536 tiles of 128 pixels for 148 CTAs: the producers' three-deep load pipeline and both operand
+    stages wrap), image borders on both sides of a row and rows at the top / bottom edge: the full-resolution level-2
+    features (conv0 -> conv2 -> ... -> dec2) of the two paths agree to the f16x3 bar."""
+    from highlyaccurate_b200.VGG import VGGUnet
+    sd = O.vgg_state_dict(11)
+    x = torch.rand(2, 3, 192, 512, generator=torch.Generator().manual_seed(12)).to(DEV)
+    feats = {}
+    for prec in ("f16x3", "fp32"):
+        net = VGGUnet(3).to(DEV)
+        net.load_state_dict(sd)
+        net.precision = prec
+        feats[prec] = [f.detach().cpu().numpy() for f in net(x)[0]]
+    for a, b in zip(feats["f16x3"], feats["fp32"]):
+        assert np.abs(a - b).max() <= VGG_TOL["f16x3"] * np.abs(b).max(), np.abs(a - b).max() / np.abs(b).max()
+
+
 @pytest.mark.parametrize("level", [3, 4])
 def test_vgg_g2s_vs_reference(level):
     """VGGUnet_G2S (VGG.py:206-345: decoders on the folded [2H, W/2] maps; c0 from the un-folded x15) through
