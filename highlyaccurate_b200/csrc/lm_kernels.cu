@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kLmThreads, HA_LM_MIN_CTAS) lm_step_kernel(con
   static_assert(C % 8 == 0 && LPP >= 1 && LPP <= 32 && PPW * LPP == 32, "channel count");
 
   const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (see lm_v4_body)
   const int sub = lane / LPP, cl = lane % LPP;     // pixel slot within the warp, channel lane
   constexpr bool G2SP = (GEOM == HA_GEOM_G2SP);
   // S2GP: the residual lives on the bottom half of the ground image (models_kitti.py:1195-1199), the ground
@@ -528,7 +528,10 @@ __device__ __forceinline__ void lm_v4_body(const LmStepArgs& a, const int b, con
   static_assert(GEOM != HA_GEOM_G2SP, "G2SP streams only the visible satellite pixels: it stays on lm_step_kernel");
   static_assert(8 * C <= kLmZeroBytes, "the global zero vector covers two texels (west + east taps), the shared one a ground pixel");
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the warp index through a shuffle: the compiler then knows that everything derived from it (trip counts, ring and
+  // stream positions, the producer's bookkeeping) is warp-uniform and moves it to the uniform datapath: 158 -> 142
+  // registers, 17 -> 6 BSSY / BSYNC pairs and 10 fewer branches per two pixel-iterations (C = 64)
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int cl = lane % LPP;                       // channel lane
   int sub = lane / LPP;                            // pixel slot within the warp
   if constexpr (NS > 1) {
@@ -813,10 +816,10 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_step_v4_kernel(const LmSt
 }
 
 // Kernel selection: HaLmParams.kernel_variant 0 (default) = lm_step_v4_kernel with a 4-slot x 2 KB ring per warp, tap rows
-// prefetched to L1, 3 CTAs per SM, pixel loop unrolled by two; ha_lm_run chains its launches (above).  1 = lm_step_kernel
+// prefetched to L1, 4 CTAs per SM (128 registers), pixel loop unrolled by two; ha_lm_run chains its launches (above).  1 = lm_step_kernel
 // (register-staged ground stream; the validation twin, and always the kernel for G2SP); 2 = the default kernel without
 // chaining (one stream-ordered launch per step: the A/B twin of the chain).  Other ring depths (3, 5, 6, 8 slots),
-// L2-only prefetch, no prefetch, 2 and 4 CTAs per SM and the non-unrolled loop were measured and dropped.
+// L2-only prefetch, no prefetch, 2 and 3 CTAs per SM and the non-unrolled loop were measured and dropped.
 template <typename K>
 static int lm_configure_smem(K kern, int smem, int minb) {
   // function attributes are per (device function, device): one bit per device ordinal, per instantiation
@@ -868,7 +871,14 @@ static int launch_variant(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
     return HA_OK;
   } else {
     if (a.variant == 1) { lm_step_kernel<GEOM, C, FULL><<<grid, kLmThreads, 0, st>>>(a); return HA_OK; }
-    return launch_v4<GEOM, C, FULL, 4, 3, 2, 2, true>(grid, st, a);
+    // Measured on B200 with the warp-uniform bookkeeping (whole chained loop, fraction of the HBM peak, B = 256 / 128 / 32):
+    // 3 CTAs / SM (142 registers) 0.750 / 0.719 / 0.611; 4 CTAs / SM (128 registers, no spills in the unweighted kernels,
+    // 8-16 bytes in the weighted FULL ones) 0.760 / 0.757 / 0.632; 4 CTAs / SM with a 3-slot ring 0.725 / 0.743 / 0.636.
+#ifdef HA_LM_DEV_VARIANTS      // A/B builds only (tools/lm_profile_batches.py)
+    if (a.variant == 3) return launch_v4<GEOM, C, FULL, 4, 3, 2, 2, true>(grid, st, a);   // 3 CTAs / SM
+    if (a.variant == 4) return launch_v4<GEOM, C, FULL, 3, 4, 2, 2, true>(grid, st, a);   // 4 CTAs / SM, 3-slot ring (more L1 for the taps)
+#endif
+    return launch_v4<GEOM, C, FULL, 4, 4, 2, 2, true>(grid, st, a);
   }
 }
 
@@ -969,7 +979,11 @@ static int lm_step_args(const HaLmParams* p, int level, const HaLevel* sat, cons
   if (level < 0 || level >= HA_MAX_LEVELS) return HA_EINVAL;
   if (sat->C != grd->C || sat->H != sat->W || (grd->H & 1)) return HA_EINVAL;
   if (p->dof < 1 || p->dof > 3) return HA_EINVAL;
+#ifdef HA_LM_DEV_VARIANTS
+  if (p->kernel_variant < 0 || p->kernel_variant > 4 || p->reserved != 0) return HA_EINVAL;
+#else
   if (p->kernel_variant < 0 || p->kernel_variant > 2 || p->reserved != 0) return HA_EINVAL;
+#endif
   if (p->optimizer < HA_OPT_LM || p->optimizer > HA_OPT_GN || (p->full_height != 0 && p->full_height != 1)) return HA_EINVAL;
   const bool first_order = p->optimizer == HA_OPT_SGD || p->optimizer == HA_OPT_ADAM;
   // the ablation update rules exist for the models that define them: SGD / ADAM in LM_S2GP, GN in LM_S2GP_Ford; they
@@ -1013,8 +1027,7 @@ static int lm_step_args(const HaLmParams* p, int level, const HaLevel* sat, cons
   a.adam_mv = w.adam_mv;
   a.g2sp_nn = g2sp_nn ? 1 : 0;
   const int P = g2sp ? sat->H * sat->W : (grd->H - a.row0) * grd->W;
-  // resident CTAs per SM: 3 for the v4 kernel (160 registers, ring), HA_LM_MIN_CTAS for the register-staged kernel
-  a.px_per_cta = choose_px_per_cta(B, P, (g2sp || p->kernel_variant == 1) ? HA_LM_MIN_CTAS : 3, chain_step >= 0);
+  a.px_per_cta = choose_px_per_cta(B, P, p->kernel_variant == 3 ? 3 : 4, chain_step >= 0);   // resident CTAs per SM of the kernel that runs
   a.grd_C = grd->C;
   grid = dim3((P + a.px_per_cta - 1) / a.px_per_cta, B);
   return HA_OK;
@@ -1186,7 +1199,7 @@ extern "C" int ha_lm_run(const HaLmParams* p, const HaLevel* sat, const HaLevel*
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ha::lm_begin(ws, B, status, st);
   // the default step kernel of the S2GP geometries chains its launches (lm_chain_enter): one arrival word per step
-  const bool chain = p->kernel_variant == 0 && (p->geometry == HA_GEOM_KITTI || p->geometry == HA_GEOM_FORD) &&
+  const bool chain = (p->kernel_variant == 0 || p->kernel_variant >= 3) && (p->geometry == HA_GEOM_KITTI || p->geometry == HA_GEOM_FORD) &&
                      (long long)N * L <= ha::kLmChainMaxSteps;
   int k = 0;
   const int outer = p->level_first ? L : N, inner = p->level_first ? N : L;

@@ -11,13 +11,14 @@ from bench import ref_args, PYR_C, peaks, SAT_TEXELS_TOUCHED
 dev = torch.device("cuda:0")
 pk = peaks()
 L = 3
+VARIANTS = [int(v) for v in os.environ.get("HA_LM_VARIANTS", "0,2").split(",")]
 for B in [int(b) for b in sys.argv[1:]] or [32, 64, 128, 256, 512]:
     net = LM_S2GP(ref_args(5, L)).to(dev)
     g = torch.Generator(device=dev).manual_seed(1)
     sat = engine.Pyramid([torch.randn(B, 512 >> (3 - l), 512 >> (3 - l), PYR_C[l], device=dev, generator=g) for l in range(L)], [None] * L)
     grd = engine.Pyramid([torch.randn(B, 256 >> (3 - l), 1024 >> (3 - l), PYR_C[l], device=dev, generator=g) for l in range(L)], [None] * L)
     draws = torch.zeros(5 * L, 2, B, device=dev)
-    for v in (0, 2):
+    for v in VARIANTS:
         for _ in range(3):
             res = net.refine(sat, grd, reset_uv=draws, kernel_variant=v)
         torch.cuda.synchronize()
