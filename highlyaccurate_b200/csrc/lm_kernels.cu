@@ -121,12 +121,25 @@ __device__ __forceinline__ void lm_reduce_and_solve(const LmStepArgs& a, const L
   if (!is_last) return;
 
   // ---- last CTA of this sample: ordered combine of the partials, damped solve, pose update
+  // (all threads take part: sixteen threads adding up to 256 partial rows one dependent L2 load after the other were
+  // ~10 us of a small batch's ~45-us step, which is bound by exactly this per-sample chain.  Fixed order: eight strided
+  // subsets, then the subsets in index order — bit-deterministic for a given CTA split.)
   __threadfence();
+  __shared__ double tot8[kLmThreads / kLmAcc][kLmAcc];
   __shared__ double tot[kLmAcc];
-  if (threadIdx.x < kLmAcc) {
-    const volatile double* pp = a.partial + (size_t)b * kLmMaxCtasPerSample * kLmAcc + threadIdx.x;
+  {
+    static_assert(kLmThreads % kLmAcc == 0, "subsets");
+    const int i = threadIdx.x % kLmAcc, j = threadIdx.x / kLmAcc;
+    const double* pp = a.partial + (size_t)b * kLmMaxCtasPerSample * kLmAcc + i;
     double r = 0;
-    for (int c = 0; c < tc.n_ctas; ++c) r += pp[(size_t)c * kLmAcc];
+    for (int c = j; c < tc.n_ctas; c += kLmThreads / kLmAcc) r += __ldcg(pp + (size_t)c * kLmAcc);
+    tot8[j][i] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < kLmAcc) {
+    double r = 0;
+#pragma unroll
+    for (int j = 0; j < kLmThreads / kLmAcc; ++j) r += tot8[j][threadIdx.x];
     tot[threadIdx.x] = r;
   }
   __syncthreads();

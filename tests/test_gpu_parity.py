@@ -492,6 +492,29 @@ def test_full_size_properties():
     assert torch.equal(r2.pose.cpu(), final[perm])
 
 
+def test_long_schedule_falls_back_to_plain_launches():
+    """ha_lm_run chains its step launches through per-step arrival words in the workspace (128 of them); a schedule
+    with more steps (45 iterations x 3 levels = 135) runs the same kernel with plain stream-ordered launches instead:
+    identical bits to kernel_variant 2, and a 42-iteration run (126 steps, chained) follows the same trajectory."""
+    B = 2
+    args = O.LMArgs()
+    gt = torch.tensor([[0.3, -0.2, 0.25], [-0.15, 0.1, -0.3]])
+    sat, grd = O.planted_case("kitti", B, 512, 3, 78, gt, args)
+    ps = engine.Pyramid.from_nchw([s.to(DEV) for s in sat])
+    pg = engine.Pyramid.from_nchw([x.to(DEV) for x in grd])
+    got = {}
+    for n_iters, variants in ((45, (0, 2)), (42, (0,))):
+        net = LM_S2GP(K.ref_args(N_iters=n_iters)).to(DEV)
+        draws = torch.zeros(n_iters * 3, 2, B)
+        for v in variants:
+            r = net.refine(ps, pg, reset_uv=draws, kernel_variant=v)
+            assert not int(r.status.item()) & (_lib.HA_STATUS_TIMEOUT | _lib.HA_STATUS_NAN_POSE)
+            got[(n_iters, v)] = r.traj.cpu()
+    assert torch.equal(got[(45, 0)], got[(45, 2)])
+    np.testing.assert_allclose(got[(42, 0)].numpy(), got[(45, 0)][:, :42].numpy(), atol=2e-6)
+    assert float((got[(45, 0)][:, -1, -1] - gt).abs().max()) < 2e-4
+
+
 def test_ford_config3_shapes_run_and_are_deterministic():
     """BASELINE config-3 shapes (Ford geometry, satellite 1280 x 1280, ground 256 x 1024) through the whole
     forward on the tensor-core path: finite poses, bit-identical on a re-run, per-sample independence."""
