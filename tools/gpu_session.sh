@@ -76,6 +76,7 @@ while [ $# -gt 0 ]; do
     lm_ab)
       timeout 400 python tools/bench_lm.py 256 10 3 0,2 > $OUT/bench_lm_b256_$TAG.log 2>&1
       timeout 400 python tools/bench_lm.py 32 20 3 0,2 > $OUT/bench_lm_b32_$TAG.log 2>&1
+      timeout 300 python tools/lm_profile_batches.py 32 64 128 256 512 > $OUT/lm_batches_$TAG.txt 2>&1; cat $OUT/lm_batches_$TAG.txt
       grep -h "variant\|level\|whole" $OUT/bench_lm_b256_$TAG.log $OUT/bench_lm_b32_$TAG.log | cut -c1-200 ;;
     pipeline)        # input pipeline on the GPU vs PIL on the host, plus its ncu launch list
       timeout 300 python tools/bench_input_pipeline.py 32 20 8 > $OUT/pipeline_$TAG.json 2> $OUT/pipeline_$TAG.err
