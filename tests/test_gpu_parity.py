@@ -492,6 +492,35 @@ def test_full_size_properties():
     assert torch.equal(r2.pose.cpu(), final[perm])
 
 
+def test_chained_loops_on_two_streams_do_not_interfere():
+    """The C ABI is re-entrant per (device, stream) with caller-owned workspaces: two chained LM loops enqueued on two
+    streams at the same time (their step kernels interleave on the GPU, each waiting on its OWN workspace's per-sample
+    flags) give the bits of the same loops run one after the other."""
+    B = 4
+    args = O.LMArgs()
+    gen = torch.Generator().manual_seed(11)
+    nets, pyrs, want = [], [], []
+    for k in range(2):
+        gt = (torch.rand(B, 3, generator=gen) - 0.5) * 0.6
+        sat, grd = O.planted_case("kitti", B, 512, 3, 90 + k, gt, args)
+        pyrs.append((engine.Pyramid.from_nchw([s.to(DEV) for s in sat]), engine.Pyramid.from_nchw([x.to(DEV) for x in grd])))
+        nets.append(LM_S2GP(K.ref_args()).to(DEV))
+    draws = torch.zeros(15, 2, B)
+    for k in range(2):
+        want.append(nets[k].refine(*pyrs[k], reset_uv=draws).traj.clone())
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = [None, None]
+    for rep in range(3):
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                got[k] = nets[k].refine(*pyrs[k], reset_uv=draws)
+    torch.cuda.synchronize()
+    for k in range(2):
+        assert int(got[k].status.item()) & _lib.HA_STATUS_TIMEOUT == 0
+        assert torch.equal(got[k].traj, want[k])
+
+
 def test_long_schedule_falls_back_to_plain_launches():
     """ha_lm_run chains its step launches through per-step arrival words in the workspace (128 of them); a schedule
     with more steps (45 iterations x 3 levels = 135) runs the same kernel with plain stream-ordered launches instead:
