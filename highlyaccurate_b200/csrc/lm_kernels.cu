@@ -887,9 +887,11 @@ static int launch_variant(dim3 grid, cudaStream_t st, const LmStepArgs& a) {
     // Measured on B200 with the warp-uniform bookkeeping (whole chained loop, fraction of the HBM peak, B = 256 / 128 / 32):
     // 3 CTAs / SM (142 registers) 0.750 / 0.719 / 0.611; 4 CTAs / SM (128 registers, no spills in the unweighted kernels,
     // 8-16 bytes in the weighted FULL ones) 0.760 / 0.757 / 0.632; 4 CTAs / SM with a 3-slot ring 0.725 / 0.743 / 0.636.
+    // Tap-row prefetch at 4 CTAs / SM (B = 256 / 32, two rounds in one process): to L1 0.762, 0.696 / 0.620, 0.635; to L2
+    // only 0.692, 0.673 / 0.620, 0.632; none 0.678, 0.656 / 0.596, 0.600.
 #ifdef HA_LM_DEV_VARIANTS      // A/B builds only (tools/lm_profile_batches.py)
-    if (a.variant == 3) return launch_v4<GEOM, C, FULL, 4, 3, 2, 2, true>(grid, st, a);   // 3 CTAs / SM
-    if (a.variant == 4) return launch_v4<GEOM, C, FULL, 3, 4, 2, 2, true>(grid, st, a);   // 4 CTAs / SM, 3-slot ring (more L1 for the taps)
+    if (a.variant == 3) return launch_v4<GEOM, C, FULL, 4, 4, 1, 2, true>(grid, st, a);   // tap rows prefetched to L2 only
+    if (a.variant == 4) return launch_v4<GEOM, C, FULL, 4, 4, 0, 2, true>(grid, st, a);   // no tap prefetch
 #endif
     return launch_v4<GEOM, C, FULL, 4, 4, 2, 2, true>(grid, st, a);
   }
@@ -1040,7 +1042,7 @@ static int lm_step_args(const HaLmParams* p, int level, const HaLevel* sat, cons
   a.adam_mv = w.adam_mv;
   a.g2sp_nn = g2sp_nn ? 1 : 0;
   const int P = g2sp ? sat->H * sat->W : (grd->H - a.row0) * grd->W;
-  a.px_per_cta = choose_px_per_cta(B, P, p->kernel_variant == 3 ? 3 : 4, chain_step >= 0);   // resident CTAs per SM of the kernel that runs
+  a.px_per_cta = choose_px_per_cta(B, P, 4, chain_step >= 0);   // resident CTAs per SM of the kernel that runs
   a.grd_C = grd->C;
   grid = dim3((P + a.px_per_cta - 1) / a.px_per_cta, B);
   return HA_OK;
